@@ -1,0 +1,122 @@
+/* lbfgsb_b200 -- C ABI of the B200-native L-BFGS-B iteration engine.
+ *
+ * Drop-in boundary for ONE path of jacobwilliams/lbfgsb: everything `mainlb`
+ * does between two returns to the caller, behind the reference's own
+ * reverse-communication entry point
+ *
+ *     subroutine setulb(n,m,x,l,u,Nbd,f,g,Factr,Pgtol,Wa,Iwa,Task,Iprint,
+ *                       Csave,Lsave,Isave,Dsave,iteration_file)      src/lbfgsb.f90:88-89
+ *
+ * Same `task` protocol ('START' -> 'FG_START' -> 'FG_LNSRCH'* -> 'NEW_X' -> ... ->
+ * 'CONVERGENCE: ...' | 'ABNORMAL_TERMINATION_IN_LNSRCH' | 'ERROR: ...'; user 'STOP...'),
+ * same meaning of isave(22:44), dsave(1:29), lsave(1:4)   (src/lbfgsb.f90:194-242, :904-947).
+ * All arguments are passed by reference, strings are blank-padded character(60),
+ * logicals are 4-byte, so a Fortran `bind(C)` interface forwards 1:1
+ * (see fortran/lbfgsb_b200_module.f90 and INTEGRATION.md).
+ *
+ * There is no CPU fallback: every entry point needs a CUDA device and fails with
+ * task = 'ERROR: ...' / a non-zero return code when there is none.
+ */
+#ifndef LBFGSB_B200_H
+#define LBFGSB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBFGSB_B200_MMAX 20   /* largest history size m (reference recommends 3 <= m <= 20, src/lbfgsb.f90:95-97) */
+
+typedef struct lbfgsb_dev lbfgsb_dev_t;   /* opaque device workspace: replaces wa/iwa (src/lbfgsb.f90:146-149) */
+
+int lbfgsb_b200_version(void);
+/* last error text of the calling thread's most recent failing call ("" if none) */
+const char* lbfgsb_b200_last_error(void);
+
+/* ---- (1) host twin of setulb: host arrays in, host arrays out -------------------------------
+ * replaces: setulb, src/lbfgsb.f90:88-286 (REAL64 build) / the -DREAL32 build (lbfgsb_kinds_module.F90:29-37).
+ * x,l,u,nbd are staged to the GPU at task='START'; g (and f) on every 'FG' re-entry; x is copied
+ * back whenever the engine changed it.  wa/iwa are accepted for signature compatibility and are
+ * not used as workspace (the state lives on the device); the handle is kept in isave(17:19),
+ * which the reference leaves unused.  itfile/itfile_len = iteration_file (may be NULL/0).   */
+void lbfgsb_setulb_f64(const int32_t* n, const int32_t* m, double* x, const double* l, const double* u,
+                       const int32_t* nbd, double* f, double* g, const double* factr, const double* pgtol,
+                       double* wa, int32_t* iwa, char* task, const int32_t* iprint, char* csave,
+                       int32_t* lsave, int32_t* isave, double* dsave, const char* itfile, int32_t itfile_len);
+void lbfgsb_setulb_f32(const int32_t* n, const int32_t* m, float* x, const float* l, const float* u,
+                       const int32_t* nbd, float* f, float* g, const float* factr, const float* pgtol,
+                       float* wa, int32_t* iwa, char* task, const int32_t* iprint, char* csave,
+                       int32_t* lsave, int32_t* isave, float* dsave, const char* itfile, int32_t itfile_len);
+/* frees the device workspace bound to this isave (needed when the caller leaves its loop on a
+ * user 'STOP' without calling setulb again, as test/driver2.f90:174-190 does) */
+void lbfgsb_host_release(int32_t* isave);
+/* copies the previous iterate t (= wa(lt:lt+n-1), read by test/driver3.f90:173-175) to the host */
+int lbfgsb_host_previous_x_f64(const int32_t* isave, double* t_out);
+int lbfgsb_host_previous_x_f32(const int32_t* isave, float* t_out);
+
+/* ---- (2) device-pointer variant --------------------------------------------------------------
+ * x, g, l, u, nbd are CUDA device pointers (16-byte aligned); f and the state arrays stay on the
+ * host.  The caller's f/g evaluation and every O(n), O(mn) step of the iteration stay on the GPU.
+ * real_kind: 8 (REAL64) or 4 (REAL32).  cuda_stream: a cudaStream_t (NULL = a private stream).
+ * n is the number of variables held by this process.                                         */
+lbfgsb_dev_t* lbfgsb_dev_create(int64_t n, int32_t m, int32_t real_kind, void* cuda_stream);
+/* sharded over `world` GPUs by variable index (contiguous blocks): n_local variables starting at
+ * global index `offset` of n_global; nccl_comm is an initialised ncclComm_t (see
+ * lbfgsb_dev_nccl_unique_id / lbfgsb_dev_nccl_init).                                            */
+lbfgsb_dev_t* lbfgsb_dev_create_sharded(int64_t n_local, int64_t offset, int64_t n_global, int32_t m,
+                                        int32_t real_kind, void* cuda_stream, void* nccl_comm,
+                                        int32_t rank, int32_t world);
+void lbfgsb_dev_destroy(lbfgsb_dev_t* h);
+void lbfgsb_setulb_dev_f64(lbfgsb_dev_t* h, double* x_dev, const double* l_dev, const double* u_dev,
+                           const int32_t* nbd_dev, double* f, double* g_dev, const double* factr,
+                           const double* pgtol, char* task, const int32_t* iprint, char* csave,
+                           int32_t* lsave, int32_t* isave, double* dsave);
+void lbfgsb_setulb_dev_f32(lbfgsb_dev_t* h, float* x_dev, const float* l_dev, const float* u_dev,
+                           const int32_t* nbd_dev, float* f, float* g_dev, const float* factr,
+                           const float* pgtol, char* task, const int32_t* iprint, char* csave,
+                           int32_t* lsave, int32_t* isave, float* dsave);
+
+/* NCCL plumbing for the sharded variant (128-byte unique id made on rank 0, broadcast by the caller) */
+int lbfgsb_dev_nccl_unique_id(void* id128);
+void* lbfgsb_dev_nccl_init(const void* id128, int32_t rank, int32_t world);
+void lbfgsb_dev_nccl_destroy(void* comm);
+
+/* ---- diagnostics used by the parity tests and the benchmark -------------------------------- */
+/* 64-bit identity of the active set {i : iwhere(i) > 0} (freev, src/lbfgsb.f90:2047) and its size */
+int lbfgsb_dev_active_set_hash(lbfgsb_dev_t* h, uint64_t* hash, int64_t* count);
+/* device pointer of a work vector: 0 z, 1 r, 2 d, 3 t, 4 xp, 5 ws, 6 wy, 7 iwhere */
+void* lbfgsb_dev_vector(lbfgsb_dev_t* h, int32_t which);
+/* counters since creation: kernels launched, host syncs, device ms per kernel family */
+int lbfgsb_dev_counters(lbfgsb_dev_t* h, int64_t* launches, int64_t* syncs);
+/* per-kernel timing: when enabled every streaming kernel is bracketed by CUDA events on the
+ * engine's stream; names/ms/bytes/calls are returned for up to `cap` kernel families          */
+void lbfgsb_dev_profile(lbfgsb_dev_t* h, int32_t enable);
+int lbfgsb_dev_profile_read(lbfgsb_dev_t* h, int32_t cap, char* names /* cap*32 */, double* ms, double* bytes,
+                            int64_t* calls);
+void lbfgsb_dev_profile_reset(lbfgsb_dev_t* h);
+
+/* ---- sample problem of the reference drivers, evaluated on the device -----------------------
+ * test/driver1.f90:274-289: f = 4[ 1/4 (x1-1)^2 + sum_{i>=2} (x_i - x_{i-1}^2)^2 ] and its gradient.
+ * xl / xr are the neighbours' boundary values on a shard (ignored when first / last).          */
+int lbfgsb_problem_rosenbrock_f64(int64_t n, const double* x_dev, double* g_dev, double* f_out, void* cuda_stream,
+                                  int32_t first, int32_t last, double xl, double xr, void* scratch_dev);
+int lbfgsb_problem_rosenbrock_f32(int64_t n, const float* x_dev, float* g_dev, float* f_out, void* cuda_stream,
+                                  int32_t first, int32_t last, float xl, float xr, void* scratch_dev);
+int64_t lbfgsb_problem_scratch_bytes(void);
+
+/* ---- single-kernel entry points for the per-routine parity tests (device pointers) ---------- */
+int lbfgsb_test_projgr_f64(int64_t n, const double* l, const double* u, const int32_t* nbd, const double* x,
+                           const double* g, double* sbgnrm_out);
+int lbfgsb_test_sum_f64(int64_t n, const double* a, const double* b, double* out);      /* fixed-shape sum of a*b */
+int lbfgsb_test_sum_f32(int64_t n, const float* a, const float* b, float* out);
+int lbfgsb_test_sort_f64(int64_t n, const double* t_dev, int32_t* order_out_dev, double* sorted_out_dev);
+int lbfgsb_test_dense_f64(int32_t op, int32_t m, int32_t col, double theta, double* a, double* b, double* c,
+                          int32_t* info);   /* op 0 dpofa(a,lda=m,n=col) 1 dtrsl job01 2 dtrsl job11 3 bmv 4 formt */
+int lbfgsb_test_dcsrch_f64(double f, double g, double* stp, double stpmax, int32_t* task, int32_t* isave2,
+                           double* dsave13);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -13,9 +13,9 @@
  *     lives across all of the block's tiles;
  *   - lanes combine by xor-butterfly shuffles (offsets 16,8,4,2,1), the warp
  *     sums are added serially in warp order by one thread -> block partial;
- *   - the GRID block partials are combined by one block of LBFGSB_FINAL_BLOCK
- *     threads: thread t adds partials t, t+FINAL_BLOCK, ... serially, then the
- *     same butterfly and serial warp sum.
+ *   - the GRID block partials of one sum are combined by one warp
+ *     (LBFGSB_FINAL_BLOCK = 32 threads): lane t adds partials t, t+32, ...
+ *     serially, then the same butterfly.
  *
  * No floating-point atomics anywhere.
  */
@@ -24,7 +24,7 @@
 
 #define LBFGSB_BLOCK 256        /* threads per streaming block                  */
 #define LBFGSB_UNROLL 4         /* 128-bit loads in flight per thread per stream */
-#define LBFGSB_GRID 1184        /* 148 SMs x 8 resident blocks                   */
-#define LBFGSB_FINAL_BLOCK 256  /* threads of the finishing block                */
+#define LBFGSB_GRID 592         /* 148 SMs x 4 blocks                            */
+#define LBFGSB_FINAL_BLOCK 32   /* one warp finishes one reduction slot          */
 
 #endif

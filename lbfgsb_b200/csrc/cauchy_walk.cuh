@@ -1,0 +1,749 @@
+// The generalized-Cauchy-point search when the first breakpoint is reached
+// (src/lbfgsb.f90:1378-1497).  The reference pops breakpoints one at a time from a
+// heap (hpsolb :2079) and updates f1, f2, p, c sequentially.  Here:
+//
+//   1. ordered compaction of the breakpoints (t_i, i)                (k_flag_count/k_tile_scan/k_bp_write)
+//   2. stable LSD radix sort on the bit pattern of t (t > 0)          (k_rs_*)  -> ties stay in index order
+//   3. the loop-carried recurrences as prefix scans over the sorted list, in chunks:
+//        p_j   = p_0 - sum_{i<j} d_i w_i                      (2col-vector prefix sum A)
+//        c_j+1 = t_j p_j + sum_{i<j} z_i w_i                  (2col-vector prefix sum B, Abel summation)
+//        f2_j+1 = max(eps f2_org, f2_j + g2_j)                ((max,+) scan)
+//        f1_j+1 = f1_j + dt_j f2_j + g1_j                     (prefix sum)
+//      exit at the first j with -f1_j/f2_j < dt_j  (:1416)
+//   4. scatter of the fixed variables (xcp = bound, iwhere = 1/2, d = 0)  (k_walk_fix)
+//
+// Decisions are the reference's decisions up to the rounding of the re-associated
+// sums; see DESIGN.md "Cauchy walk" for the tie-order caveat.
+#pragma once
+#include "kernels_dense.cuh"
+
+#define LB_WB 256                 // threads (= breakpoints) per walk block
+#define LB_RS_GRID 592            // blocks of the radix sort (one contiguous chunk each)
+#define LB_RS_ITEMS 16            // keys per thread per sub-tile
+#define LB_RS_TILE (256 * LB_RS_ITEMS)
+
+template <typename T> struct KeyBits;
+template <> struct KeyBits<double> {
+    __device__ static unsigned long long to(double t) { return (unsigned long long)__double_as_longlong(t); }
+    __device__ static double from(unsigned long long k) { return __longlong_as_double((long long)k); }
+};
+template <> struct KeyBits<float> {
+    __device__ static unsigned int to(float t) { return __float_as_uint(t); }
+    __device__ static float from(unsigned int k) { return __uint_as_float(k); }
+};
+
+// small device block shared by the sort / compaction kernels
+struct SortCtl {
+    i64 count;        // number of items
+    int cur;          // which of the two (key,val) buffers holds the current order
+    int skip;         // current pass is a no-op (all keys share the digit)
+};
+
+// ---- block scans -----------------------------------------------------------
+// exclusive prefix of v over the block (thread order); total returned to all threads.
+// smem: 33 elements.
+template <typename V>
+__device__ __forceinline__ V block_excl_scan(V v, V* smem, V& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    V inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { V o = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc = inc + o; }
+    if (lane == 31) smem[wid] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        V run = (V)0;
+        for (int q = 0; q < nw; ++q) { V t = smem[q]; smem[q] = run; run = run + t; }
+        smem[32] = run;
+    }
+    __syncthreads();
+    V excl = smem[wid] + (inc - v);
+    total = smem[32];
+    __syncthreads();
+    return excl;
+}
+
+// breakpoint of variable i, recomputed from the classify pass outputs (:1305-1322)
+template <typename T>
+__device__ __forceinline__ bool bp_of(T d, T x, T l, T u, int nb, T& t) {
+    if (nb <= 2 && nb != 0 && d < (T)0) { t = (x - l) / (-d); return true; }
+    if (nb >= 2 && d > (T)0) { t = (u - x) / d; return true; }
+    return false;
+}
+__device__ __forceinline__ bool el_of(int st) { return ((st & 1) != 0) != ((st & 2) != 0); }
+
+// ---------------------------------------------------------------------------
+// Ordered compaction.  MODE 0: breakpoints -> (key = bits of t, val = variable);
+// MODE 1: entering / leaving variables -> val = variable (state bits tell which).
+// ---------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_count(Wk<T> w, int* tile_counts) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body) return;
+    if (MODE == 0 && !s->need_walk) return;
+    if (MODE == 1 && !s->do_delta) return;
+    const i64 n = w.n;
+    const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
+    const i64 ntiles = (n + tile - 1) / tile;
+    __shared__ i64 smi[LBFGSB_BLOCK / 32];
+    for (i64 tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        i64 c = 0;
+#pragma unroll
+        for (int k = 0; k < LBFGSB_UNROLL; ++k) {
+            const i64 base = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC) + (i64)threadIdx.x * VEC;
+            if (base >= n) continue;
+            if (MODE == 0) {
+                T d[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC];
+                ldv<T>(w.d, base, n, d); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
+                ldvi<T>(w.nbd, base, n, nb);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { T t; if (base + v < n && bp_of<T>(d[v], x[v], l[v], u[v], nb[v], t)) c++; }
+            } else {
+                int st[VEC];
+                ldvb<T>(w.state, base, n, st);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) if (base + v < n && el_of(st[v])) c++;
+            }
+        }
+        i64 r = block_isum(c, smi);
+        if (threadIdx.x == 0) tile_counts[tl] = (int)r;
+    }
+}
+
+// exclusive scan of tile_counts -> offsets; total -> ctl->count.  One block of 1024.
+template <typename T>
+__global__ void __launch_bounds__(1024) k_tile_scan(Wk<T> w, int mode, const int* counts, i64* offsets, i64 ntiles,
+                                                   SortCtl* ctl) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body) return;
+    if (mode == 0 && !s->need_walk) return;
+    if (mode == 1 && !s->do_delta) return;
+    __shared__ i64 sm[33];
+    i64 carry = 0;
+    for (i64 b0 = 0; b0 < ntiles; b0 += 1024) {
+        const i64 i = b0 + threadIdx.x;
+        i64 v = (i < ntiles) ? (i64)counts[i] : 0;
+        i64 tot;
+        i64 ex = block_excl_scan<i64>(v, sm, tot);
+        if (i < ntiles) offsets[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) { ctl->count = carry; ctl->cur = 0; ctl->skip = 0; }
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_write(Wk<T> w, const i64* tile_offsets,
+                                                            typename Real<T>::key_t* keys, int* vals) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body) return;
+    if (MODE == 0 && !s->need_walk) return;
+    if (MODE == 1 && !s->do_delta) return;
+    const i64 n = w.n;
+    const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
+    const i64 ntiles = (n + tile - 1) / tile;
+    __shared__ i64 sm[33];
+    for (i64 tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        i64 run = tile_offsets[tl];
+#pragma unroll 1
+        for (int k = 0; k < LBFGSB_UNROLL; ++k) {
+            const i64 base = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC) + (i64)threadIdx.x * VEC;
+            bool fl[VEC]; T tv[VEC];
+            i64 c = 0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { fl[v] = false; tv[v] = (T)0; }
+            if (base < n) {
+                if (MODE == 0) {
+                    T d[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC];
+                    ldv<T>(w.d, base, n, d); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
+                    ldvi<T>(w.nbd, base, n, nb);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+                        if (base + v < n && bp_of<T>(d[v], x[v], l[v], u[v], nb[v], tv[v])) { fl[v] = true; c++; }
+                } else {
+                    int st[VEC];
+                    ldvb<T>(w.state, base, n, st);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) if (base + v < n && el_of(st[v])) { fl[v] = true; c++; }
+                }
+            }
+            i64 tot;
+            i64 pos = run + block_excl_scan<i64>(c, sm, tot);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (fl[v]) {
+                    if (MODE == 0) keys[pos] = KeyBits<T>::to(tv[v]);
+                    vals[pos] = (int)(base + v);
+                    pos++;
+                }
+            run += tot;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Stable LSD radix sort, 8-bit digits.  LB_RS_GRID blocks, each owning one
+// contiguous chunk of the input; counts are laid out [digit][block] so that one
+// exclusive scan of the flattened array gives every (digit, block) its output base.
+// ---------------------------------------------------------------------------
+template <typename K>
+__global__ void __launch_bounds__(256) k_rs_hist(const K* k0, const K* k1, const SortCtl* ctl, int shift, int* counts) {
+    const i64 nitems = ctl->count;
+    const K* keys = ctl->cur ? k1 : k0;
+    const i64 chunk = ((nitems + LB_RS_GRID - 1) / LB_RS_GRID + LB_RS_TILE - 1) / LB_RS_TILE * LB_RS_TILE;
+    const i64 beg = (i64)blockIdx.x * chunk;
+    i64 end = beg + chunk; if (end > nitems) end = nitems;
+    __shared__ int h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    for (i64 i = beg + threadIdx.x; i < end; i += 256) atomicAdd(&h[(int)((keys[i] >> shift) & 0xff)], 1);
+    __syncthreads();
+    counts[threadIdx.x * LB_RS_GRID + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of counts[256*GRID] in place; sets ctl->skip if one digit holds everything
+__global__ void __launch_bounds__(1024) k_rs_scan(int* counts, SortCtl* ctl) {
+    __shared__ i64 sm[33];
+    __shared__ int allsame;
+    const i64 total = 256 * LB_RS_GRID;
+    if (threadIdx.x == 0) allsame = 0;
+    __syncthreads();
+    // digit totals: thread d < 256 sums its row
+    if (threadIdx.x < 256) {
+        i64 t = 0;
+        for (int b = 0; b < LB_RS_GRID; ++b) t += counts[threadIdx.x * LB_RS_GRID + b];
+        if (t == ctl->count) allsame = 1;
+    }
+    __syncthreads();
+    if (allsame) { if (threadIdx.x == 0) ctl->skip = 1; return; }
+    i64 carry = 0;
+    for (i64 b0 = 0; b0 < total; b0 += 1024) {
+        const i64 i = b0 + threadIdx.x;
+        i64 v = (i < total) ? (i64)counts[i] : 0;
+        i64 tot;
+        i64 ex = block_excl_scan<i64>(v, sm, tot);
+        if (i < total) counts[i] = (int)(carry + ex);
+        carry += tot;
+    }
+    if (threadIdx.x == 0) ctl->skip = 0;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(256) k_rs_scatter(K* k0, K* k1, int* v0, int* v1, SortCtl* ctl, int shift,
+                                                   const int* offsets) {
+    if (ctl->skip) return;
+    const i64 nitems = ctl->count;
+    const K* kin = ctl->cur ? k1 : k0; K* kout = ctl->cur ? k0 : k1;
+    const int* vin = ctl->cur ? v1 : v0; int* vout = ctl->cur ? v0 : v1;
+    const i64 chunk = ((nitems + LB_RS_GRID - 1) / LB_RS_GRID + LB_RS_TILE - 1) / LB_RS_TILE * LB_RS_TILE;
+    const i64 beg = (i64)blockIdx.x * chunk;
+    i64 end = beg + chunk; if (end > nitems) end = nitems;
+    __shared__ int cnt[8][257];
+    __shared__ int dig_off[256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    dig_off[threadIdx.x] = offsets[threadIdx.x * LB_RS_GRID + blockIdx.x];
+    __syncthreads();
+    for (i64 t0 = beg; t0 < end; t0 += LB_RS_TILE) {
+        for (int q = threadIdx.x; q < 8 * 257; q += 256) (&cnt[0][0])[q] = 0;
+        __syncthreads();
+        K key[LB_RS_ITEMS]; int val[LB_RS_ITEMS]; int dg[LB_RS_ITEMS]; int rk[LB_RS_ITEMS];
+        const i64 wbase = t0 + (i64)wid * (32 * LB_RS_ITEMS);
+#pragma unroll
+        for (int k = 0; k < LB_RS_ITEMS; ++k) {
+            const i64 i = wbase + k * 32 + lane;
+            const bool ok = i < end;
+            key[k] = ok ? kin[i] : (K)0; val[k] = ok ? vin[i] : 0;
+            dg[k] = ok ? (int)((key[k] >> shift) & 0xff) : 256;
+        }
+#pragma unroll
+        for (int k = 0; k < LB_RS_ITEMS; ++k) {
+            const unsigned peers = __match_any_sync(0xffffffffu, dg[k]);
+            const int below = __popc(peers & lt);
+            const int pre = cnt[wid][dg[k]];
+            __syncwarp();
+            if (below == 0) cnt[wid][dg[k]] = pre + __popc(peers);
+            __syncwarp();
+            rk[k] = pre + below;
+        }
+        __syncthreads();
+        // per digit: exclusive offsets over the warps, then the sub-tile total
+        {
+            const int d = threadIdx.x;
+            int run = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { int t = cnt[q][d]; cnt[q][d] = run; run += t; }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < LB_RS_ITEMS; ++k) {
+                if (dg[k] < 256) {
+                    const i64 pos = (i64)dig_off[dg[k]] + cnt[wid][dg[k]] + rk[k];
+                    kout[pos] = key[k]; vout[pos] = val[k];
+                }
+            }
+            __syncthreads();
+            dig_off[d] += run;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_rs_flip(SortCtl* ctl) { if (threadIdx.x == 0 && !ctl->skip) ctl->cur ^= 1; }
+
+// ---------------------------------------------------------------------------
+// Walk scratch (one chunk of sorted breakpoints)
+// ---------------------------------------------------------------------------
+template <typename T>
+struct WalkBuf {
+    i64 cap;                 // chunk capacity (breakpoints)
+    T* wj;                   // [2*MMAX][cap]  rows of W at the breakpoints (theta applied to the S half)
+    T* vj;                   // [2*MMAX][cap]  M * w_j
+    T *delta, *zeta, *omega, *g2, *g1, *f1a, *f2a;   // [cap]
+    T *blkA, *blkB;          // [nblk][2*MMAX] block totals -> exclusive prefixes
+    T *blk_a, *blk_b;        // (max,+) block operators -> f2 at block starts (blk_a reused)
+    T *blkH;                 // block sums of h -> f1 at block starts
+    typename Real<T>::key_t *k0, *k1; int *v0, *v1;   // sorted breakpoints (two buffers)
+    SortCtl* ctl;
+};
+
+template <typename T>
+__device__ __forceinline__ const typename Real<T>::key_t* cur_keys(const WalkBuf<T>& b) { return b.ctl->cur ? b.k1 : b.k0; }
+template <typename T>
+__device__ __forceinline__ const int* cur_vals(const WalkBuf<T>& b) { return b.ctl->cur ? b.v1 : b.v0; }
+
+// (a) gather: w_j, v_j = M w_j, omega_j, delta_j, zeta_j; block totals of delta*w and zeta*w
+template <typename T>
+__global__ void __launch_bounds__(LB_WB) k_walk_gather(Wk<T> w, WalkBuf<T> b, i64 start, i64 len) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_J >= 0) return;
+    const int col = s->col, col2 = 2 * col, m = s->m, head0 = s->head - 1;
+    const T theta = s->theta;
+    __shared__ T ssy[LB_MMAX * LB_MMAX], swt[LB_MMAX * LB_MMAX];
+    __shared__ T red[LB_WB / 32];
+    for (int q = threadIdx.x; q < m * m; q += LB_WB) { ssy[q] = s->sy[q]; swt[q] = s->wt[q]; }
+    __syncthreads();
+    const i64 j = (i64)blockIdx.x * LB_WB + threadIdx.x;
+    const bool ok = j < len;
+    T dl = (T)0, ze = (T)0;
+    T wl[2 * LB_MMAX], vl[2 * LB_MMAX];
+    if (ok) {
+        const int var = cur_vals<T>(b)[start + j];
+        dl = w.d[var];
+        ze = (dl > (T)0) ? (w.u[var] - w.x[var]) : (w.l[var] - w.x[var]);   // zibp (:1427,:1431)
+        b.delta[j] = dl; b.zeta[j] = ze;
+        if (col > 0) {
+            int pj = head0;
+            for (int c = 0; c < col; ++c) {
+                wl[c] = w.wy[(i64)pj * w.ldw + var];
+                wl[col + c] = theta * w.ws[(i64)pj * w.ldw + var];   // :1463-1464
+                pj = (pj + 1 == m) ? 0 : pj + 1;
+            }
+            dense::bmv<T>(m, ssy, swt, col, wl, vl);   // singular T was already excluded by the first bmv (:1360)
+            T om = (T)0;
+            for (int c = 0; c < col2; ++c) { om = om + wl[c] * vl[c]; b.wj[(i64)c * b.cap + j] = wl[c]; b.vj[(i64)c * b.cap + j] = vl[c]; }
+            b.omega[j] = om;
+        } else b.omega[j] = (T)0;
+    }
+    // block totals (fixed order: butterfly + serial over warps)
+    for (int c = 0; c < col2; ++c) {
+        for (int which = 0; which < 2; ++which) {
+            T v = ok ? ((which == 0 ? dl : ze) * wl[c]) : (T)0;
+            v = warp_sum<T>(v);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                T t = red[0];
+                for (int q = 1; q < LB_WB / 32; ++q) t = t + red[q];
+                (which == 0 ? b.blkA : b.blkB)[(i64)blockIdx.x * (2 * LB_MMAX) + c] = t;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// (b) exclusive scan of the block totals over the blocks, with the carry from earlier chunks.
+//     One warp per sequence.  Leaves the chunk totals (incl. carry) in s->walkA/B *candidates*
+//     (tmpA/tmpB), committed by s_walk_chunk_end if no exit was found in this chunk.
+template <typename T>
+__global__ void __launch_bounds__(1024) k_walk_scan_vec(Wk<T> w, WalkBuf<T> b, i64 nblk, T* tmpAB) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_J >= 0) return;
+    const int col2 = 2 * s->col;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int seq = wid; seq < 2 * col2; seq += nw) {
+        const int which = seq / col2, c = seq % col2;
+        T* arr = which == 0 ? b.blkA : b.blkB;
+        T carry = which == 0 ? s->walkA[c] : s->walkB[c];
+        for (i64 b0 = 0; b0 < nblk; b0 += 32) {
+            const i64 i = b0 + lane;
+            T v = (i < nblk) ? arr[i * (2 * LB_MMAX) + c] : (T)0;
+            T inc = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { T o = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc = inc + o; }
+            if (i < nblk) arr[i * (2 * LB_MMAX) + c] = carry + (inc - v);
+            carry = carry + __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) tmpAB[which * (2 * LB_MMAX) + c] = carry;
+    }
+}
+
+// (max,+) operator: x -> max(a, x + b); compose(first, then)
+template <typename T> struct MaxPlus { T a, b; };
+template <typename T>
+__device__ __forceinline__ MaxPlus<T> mp_compose(MaxPlus<T> f, MaxPlus<T> g) {   // g after f
+    MaxPlus<T> r;
+    r.a = dense::tmax(g.a, f.a + g.b);
+    r.b = f.b + g.b;
+    return r;
+}
+template <typename T>
+__device__ __forceinline__ T mp_apply(MaxPlus<T> f, T x) { return dense::tmax(f.a, x + f.b); }
+
+// inclusive scan of (max,+) operators over the block; returns the exclusive operator of
+// this thread and the block aggregate.  smem: 2*(33) T.
+template <typename T>
+__device__ __forceinline__ MaxPlus<T> block_excl_scan_mp(MaxPlus<T> v, T* sma, T* smb, MaxPlus<T>& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const T NEG = -LB_INF(T);
+    MaxPlus<T> inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        MaxPlus<T> o; o.a = __shfl_up_sync(0xffffffffu, inc.a, off); o.b = __shfl_up_sync(0xffffffffu, inc.b, off);
+        if (lane >= off) inc = mp_compose<T>(o, inc);
+    }
+    // exclusive within warp
+    MaxPlus<T> ex; ex.a = __shfl_up_sync(0xffffffffu, inc.a, 1); ex.b = __shfl_up_sync(0xffffffffu, inc.b, 1);
+    if (lane == 0) { ex.a = NEG; ex.b = (T)0; }
+    if (lane == 31) { sma[wid] = inc.a; smb[wid] = inc.b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MaxPlus<T> run; run.a = NEG; run.b = (T)0;
+        for (int q = 0; q < nw; ++q) {
+            MaxPlus<T> t; t.a = sma[q]; t.b = smb[q];
+            sma[q] = run.a; smb[q] = run.b;
+            run = mp_compose<T>(run, t);
+        }
+        sma[32] = run.a; smb[32] = run.b;
+    }
+    __syncthreads();
+    MaxPlus<T> pre; pre.a = sma[wid]; pre.b = smb[wid];
+    MaxPlus<T> r = mp_compose<T>(pre, ex);
+    total.a = sma[32]; total.b = smb[32];
+    __syncthreads();
+    return r;
+}
+
+// (c) wmp_j, wmc_j via the prefix sums; g2_j, g1_j; block (max,+) aggregates
+template <typename T>
+__global__ void __launch_bounds__(LB_WB) k_walk_dots(Wk<T> w, WalkBuf<T> b, i64 start, i64 len) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_J >= 0) return;
+    const int col = s->col, col2 = 2 * col;
+    const T theta = s->theta, two = (T)2;
+    __shared__ T sm[33], sma[33], smb[33];
+    const i64 j = (i64)blockIdx.x * LB_WB + threadIdx.x;
+    const bool ok = j < len;
+    const T dl = ok ? b.delta[j] : (T)0, ze = ok ? b.zeta[j] : (T)0;
+    const T tj = ok ? KeyBits<T>::from(cur_keys<T>(b)[start + j]) : (T)0;
+    T wmp = (T)0, wmc = (T)0;
+    for (int c = 0; c < col2; ++c) {
+        const T wv_ = ok ? b.wj[(i64)c * b.cap + j] : (T)0;
+        const T vv = ok ? b.vj[(i64)c * b.cap + j] : (T)0;
+        T tot;
+        const T exA = block_excl_scan<T>(dl * wv_, sm, tot);
+        const T exB = block_excl_scan<T>(ze * wv_, sm, tot);
+        const T Aj = b.blkA[(i64)blockIdx.x * (2 * LB_MMAX) + c] + exA;
+        const T Bj = b.blkB[(i64)blockIdx.x * (2 * LB_MMAX) + c] + exB;
+        const T pj = s->p0[c] - Aj;            // p at the start of segment j
+        const T cj = tj * pj + Bj;             // c after "c = c + dt*p" (:1457)
+        wmp = wmp + pj * vv;                   // :1472
+        wmc = wmc + cj * vv;                   // :1471
+    }
+    const T d2 = dl * dl;
+    T g2 = -theta * d2, g1 = d2 - theta * dl * ze;   // :1452-1453
+    if (col > 0 && ok) {
+        g1 = g1 + dl * wmc;                    // :1479
+        g2 = g2 + two * dl * wmp - d2 * b.omega[j];   // :1480
+    }
+    if (ok) { b.g2[j] = g2; b.g1[j] = g1; }
+    MaxPlus<T> op; op.a = ok ? s->epsmch * s->f2_org : -LB_INF(T); op.b = ok ? g2 : (T)0;   // :1483
+    MaxPlus<T> total;
+    block_excl_scan_mp<T>(op, sma, smb, total);
+    if (threadIdx.x == 0) { b.blk_a[blockIdx.x] = total.a; b.blk_b[blockIdx.x] = total.b; }
+}
+
+// (d) f2 at the block starts: serial composition over the blocks by one warp
+template <typename T>
+__global__ void __launch_bounds__(32) k_walk_scan_f2(Wk<T> w, WalkBuf<T> b, i64 nblk, T* tmpF) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_J >= 0) return;
+    const int lane = threadIdx.x;
+    const T NEG = -LB_INF(T);
+    T f2 = s->walk_f2;
+    for (i64 b0 = 0; b0 < nblk; b0 += 32) {
+        const i64 i = b0 + lane;
+        MaxPlus<T> v; v.a = (i < nblk) ? b.blk_a[i] : NEG; v.b = (i < nblk) ? b.blk_b[i] : (T)0;
+        MaxPlus<T> inc = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            MaxPlus<T> o; o.a = __shfl_up_sync(0xffffffffu, inc.a, off); o.b = __shfl_up_sync(0xffffffffu, inc.b, off);
+            if (lane >= off) inc = mp_compose<T>(o, inc);
+        }
+        MaxPlus<T> ex; ex.a = __shfl_up_sync(0xffffffffu, inc.a, 1); ex.b = __shfl_up_sync(0xffffffffu, inc.b, 1);
+        if (lane == 0) { ex.a = NEG; ex.b = (T)0; }
+        if (i < nblk) b.blk_a[i] = mp_apply<T>(ex, f2);   // f2 at the start of block i
+        MaxPlus<T> last; last.a = __shfl_sync(0xffffffffu, inc.a, 31); last.b = __shfl_sync(0xffffffffu, inc.b, 31);
+        f2 = mp_apply<T>(last, f2);
+    }
+    if (lane == 0) tmpF[1] = f2;   // f2 after the whole chunk
+}
+
+// (e) f2_j, h_j = dt_j f2_j + g1_j, block sums of h
+template <typename T>
+__global__ void __launch_bounds__(LB_WB) k_walk_f2(Wk<T> w, WalkBuf<T> b, i64 start, i64 len) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_J >= 0) return;
+    __shared__ T sma[33], smb[33], red[LB_WB / 32];
+    const i64 j = (i64)blockIdx.x * LB_WB + threadIdx.x;
+    const bool ok = j < len;
+    MaxPlus<T> op; op.a = ok ? s->epsmch * s->f2_org : -LB_INF(T); op.b = ok ? b.g2[j] : (T)0;
+    MaxPlus<T> total;
+    MaxPlus<T> ex = block_excl_scan_mp<T>(op, sma, smb, total);
+    const T f2j = mp_apply<T>(ex, b.blk_a[blockIdx.x]);
+    T h = (T)0;
+    if (ok) {
+        const typename Real<T>::key_t* keys = cur_keys<T>(b);
+        const T tj = KeyBits<T>::from(keys[start + j]);
+        const T tp = (start + j > 0) ? KeyBits<T>::from(keys[start + j - 1]) : (T)0;
+        const T dt = tj - tp;
+        h = dt * f2j + b.g1[j];
+        b.f2a[j] = f2j;
+        b.g2[j] = dt;       // g2 no longer needed: keep dt_j for the test
+        b.g1[j] = h;
+    }
+    T v = warp_sum<T>(h);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { T t = red[0]; for (int q = 1; q < LB_WB / 32; ++q) t = t + red[q]; b.blkH[blockIdx.x] = t; }
+}
+
+// (f) f1 at the block starts
+template <typename T>
+__global__ void __launch_bounds__(32) k_walk_scan_f1(Wk<T> w, WalkBuf<T> b, i64 nblk, T* tmpF) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_J >= 0) return;
+    const int lane = threadIdx.x;
+    T carry = s->walk_f1;
+    for (i64 b0 = 0; b0 < nblk; b0 += 32) {
+        const i64 i = b0 + lane;
+        T v = (i < nblk) ? b.blkH[i] : (T)0;
+        T inc = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { T o = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc = inc + o; }
+        if (i < nblk) b.blkH[i] = carry + (inc - v);
+        carry = carry + __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) tmpF[0] = carry;   // f1 after the whole chunk
+}
+
+// (g) f1_j and the exit test (:1416)
+template <typename T>
+__global__ void __launch_bounds__(LB_WB) k_walk_test(Wk<T> w, WalkBuf<T> b, i64 start, i64 len, unsigned long long* jmin) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_J >= 0) return;
+    __shared__ T sm[33];
+    const i64 j = (i64)blockIdx.x * LB_WB + threadIdx.x;
+    const bool ok = j < len;
+    T tot;
+    const T ex = block_excl_scan<T>(ok ? b.g1[j] : (T)0, sm, tot);
+    if (ok) {
+        const T f1j = b.blkH[blockIdx.x] + ex;
+        const T f2j = b.f2a[j];
+        b.f1a[j] = f1j;
+        const T dtm = -f1j / f2j;
+        if (dtm < b.g2[j]) atomicMin(jmin, (unsigned long long)(start + j));
+    }
+}
+
+// end of a chunk: commit the exit position or the carries
+template <typename T>
+__global__ void k_walk_chunk_end(Wk<T> w, WalkBuf<T> b, i64 start, i64 len, const T* tmpAB, const T* tmpF,
+                                 const unsigned long long* jmin) {
+    DevState<T>* s = w.s;
+    if (threadIdx.x != 0) return;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_J >= 0) return;
+    if (*jmin != 0xffffffffffffffffULL) { s->walk_J = (i64)*jmin; return; }
+    const int col2 = 2 * s->col;
+    for (int c = 0; c < col2; ++c) { s->walkA[c] = tmpAB[c]; s->walkB[c] = tmpAB[2 * LB_MMAX + c]; }
+    s->walk_f1 = tmpF[0]; s->walk_f2 = tmpF[1];
+    s->walk_done = start + len;
+}
+
+// After all chunks: state at the exit, GCP scalars (:1436-1442, :1484-1495, :1509-1526).
+// One block; if the exit is inside a chunk, re-derives A_J, B_J from that chunk's scratch.
+template <typename T>
+__global__ void __launch_bounds__(LB_WB) k_walk_final(Wk<T> w, WalkBuf<T> b, i64 chunk_cap, i64 n_global) {
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk) return;
+    __shared__ T AJ[2 * LB_MMAX], BJ[2 * LB_MMAX];
+    __shared__ T sm[33];
+    const int col = s->col, col2 = 2 * col;
+    const i64 nb = b.ctl->count;
+    const i64 J = s->walk_J;
+    const typename Real<T>::key_t* keys = cur_keys<T>(b);
+    if (J >= 0) {
+        // prefix sums at J: block prefix + in-block partial sums of the chunk that holds J
+        const i64 start = (J / chunk_cap) * chunk_cap;
+        const i64 jl = J - start;
+        const i64 blk = jl / LB_WB;
+        const i64 j = blk * LB_WB + threadIdx.x;
+        const bool in = j < jl;
+        for (int c = 0; c < col2; ++c) {
+            const T wv_ = in ? b.wj[(i64)c * b.cap + j] : (T)0;
+            T tot;
+            block_excl_scan<T>(in ? b.delta[j] * wv_ : (T)0, sm, tot);
+            if (threadIdx.x == 0) AJ[c] = b.blkA[blk * (2 * LB_MMAX) + c] + tot;
+            block_excl_scan<T>(in ? b.zeta[j] * wv_ : (T)0, sm, tot);
+            if (threadIdx.x == 0) BJ[c] = b.blkB[blk * (2 * LB_MMAX) + c] + tot;
+        }
+        __syncthreads();
+        if (threadIdx.x != 0) return;
+        const T f1 = b.f1a[jl], f2 = b.f2a[jl];
+        const T tprev = KeyBits<T>::from(keys[J - 1]);   // J >= 1: the first test is done by s_cauchy
+        T dtm = -f1 / f2;
+        if (dtm <= (T)0) dtm = (T)0;
+        s->f1 = f1; s->f2 = f2; s->dtm = dtm;
+        s->tsum = tprev + dtm;
+        s->nseg = 1 + J;
+        for (int c = 0; c < col2; ++c) {
+            const T pJ = s->p0[c] - AJ[c];
+            s->p[c] = pJ;
+            s->c[c] = (tprev * pJ + BJ[c]) + dtm * pJ;
+        }
+    } else {
+        if (threadIdx.x != 0) return;
+        // every breakpoint was passed
+        const T tlast = KeyBits<T>::from(keys[nb - 1]);
+        T dtm;
+        if (nb == n_global) {   // all n variables fixed (:1436-1442)
+            const T tprev = (nb > 1) ? KeyBits<T>::from(keys[nb - 2]) : (T)0;
+            dtm = tlast - tprev;
+            s->nseg = nb;
+            s->tsum = tlast;
+            for (int c = 0; c < col2; ++c) { const T pJ = s->p0[c] - s->walkA[c]; s->p[c] = pJ; s->c[c] = tlast * pJ + s->walkB[c]; }
+            s->dtm = dtm;
+        } else {
+            s->nseg = nb + 1;
+            T f1 = s->walk_f1, f2 = s->walk_f2;
+            if (s->bnded) { f1 = (T)0; f2 = (T)0; dtm = (T)0; }
+            else dtm = -f1 / f2;
+            if (dtm <= (T)0) dtm = (T)0;
+            s->f1 = f1; s->f2 = f2; s->dtm = dtm;
+            s->tsum = tlast + dtm;
+            for (int c = 0; c < col2; ++c) {
+                const T pJ = s->p0[c] - s->walkA[c];
+                s->p[c] = pJ;
+                s->c[c] = (tlast * pJ + s->walkB[c]) + dtm * pJ;
+            }
+        }
+        s->walk_J = nb;
+    }
+}
+
+// fix the variables whose breakpoints were passed (:1424-1434)
+template <typename T>
+__global__ void __launch_bounds__(256) k_walk_fix(Wk<T> w, WalkBuf<T> b) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk) return;
+    const i64 J = s->walk_J;
+    const int* vals = cur_vals<T>(b);
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < J; j += (i64)gridDim.x * blockDim.x) {
+        const int var = vals[j];
+        const T dl = w.d[var];
+        if (dl > (T)0) { w.z[var] = w.u[var]; w.iwhere[var] = 2; }
+        else { w.z[var] = w.l[var]; w.iwhere[var] = 1; }
+        w.d[var] = (T)0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// formk: corrections of the old blocks of WN1 for the variables that entered or
+// left the free set (:1801-1851).  The reference re-gathers the lists for every
+// (iy, jy) pair; here every listed row is read once into shared memory and all
+// 3 col^2 products are accumulated from it (enter and leave sums kept apart).
+// out: [gridDim][6][MMAX*MMAX] partials, finished by k_formk_delta_final.
+// ---------------------------------------------------------------------------
+#define LB_FD_GRID 592
+#define LB_FD_ROWS 32
+template <typename T>
+__global__ void __launch_bounds__(256) k_formk_delta(Wk<T> w, const int* list, const SortCtl* ctl, T* out) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_delta) return;
+    const int col = s->col, m = s->m, head0 = s->head - 1, col2 = 2 * col;
+    const i64 nel = ctl->count;
+    const i64 chunk = (nel + gridDim.x - 1) / gridDim.x;
+    const i64 beg = (i64)blockIdx.x * chunk;
+    i64 end = beg + chunk; if (end > nel) end = nel;
+    __shared__ T tile[LB_FD_ROWS][2 * LB_MMAX + 1];
+    __shared__ int ent[LB_FD_ROWS];
+    constexpr int PMAX = (3 * LB_MMAX * LB_MMAX + 255) / 256;
+    T accE[PMAX], accL[PMAX];
+#pragma unroll
+    for (int q = 0; q < PMAX; ++q) { accE[q] = (T)0; accL[q] = (T)0; }
+    const int npairs = 3 * col * col;
+    for (i64 r0 = beg; r0 < end; r0 += LB_FD_ROWS) {
+        const int nr = (int)((end - r0 < LB_FD_ROWS) ? (end - r0) : LB_FD_ROWS);
+        for (int e = threadIdx.x; e < nr * col2; e += 256) {
+            const int r = e % nr, c = e / nr;
+            const int var = list[r0 + r];
+            const int ring = c < col ? c : c - col;
+            int pj = head0 + ring; if (pj >= m) pj -= m;
+            tile[r][c] = (c < col) ? w.wy[(i64)pj * w.ldw + var] : w.ws[(i64)pj * w.ldw + var];
+        }
+        for (int r = threadIdx.x; r < nr; r += 256) ent[r] = (w.state[list[r0 + r]] & 1);   // free now => entering
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PMAX; ++q) {
+            const int pr = threadIdx.x + q * 256;
+            if (pr < npairs) {
+                const int blk = pr / (col * col), ij = pr % (col * col);
+                const int i = ij % col, j = ij / col;
+                // blk 0: Wy_i*Wy_j ; 1: Ws_i*Ws_j ; 2: Ws_i*Wy_j
+                const int ca = (blk == 0) ? i : col + i;
+                const int cb = (blk == 1) ? col + j : j;
+                for (int r = 0; r < nr; ++r) {
+                    const T pv = tile[r][ca] * tile[r][cb];
+                    if (ent[r]) accE[q] = accE[q] + pv; else accL[q] = accL[q] + pv;
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < PMAX; ++q) {
+        const int pr = threadIdx.x + q * 256;
+        if (pr < npairs) {
+            const int blk = pr / (col * col), ij = pr % (col * col);
+            const int i = ij % col, j = ij / col;
+            T* o = out + (i64)blockIdx.x * (6 * LB_MMAX * LB_MMAX);
+            o[(blk)*LB_MMAX * LB_MMAX + i + j * LB_MMAX] = accE[q];
+            o[(3 + blk) * LB_MMAX * LB_MMAX + i + j * LB_MMAX] = accL[q];
+        }
+    }
+}
+
+// sum the per-block partials in block order (one thread per entry, serial: fixed order)
+template <typename T>
+__global__ void __launch_bounds__(256) k_formk_delta_final(Wk<T> w, const T* parts, int nparts, T* delta) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_delta) return;
+    const int col = s->col;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 6 * LB_MMAX * LB_MMAX) return;
+    const int ij = e % (LB_MMAX * LB_MMAX);
+    const int i = ij % LB_MMAX, j = ij / LB_MMAX;
+    if (i >= col || j >= col) return;
+    T acc = (T)0;
+    for (int p = 0; p < nparts; ++p) acc = acc + parts[(i64)p * (6 * LB_MMAX * LB_MMAX) + e];
+    delta[e] = acc;
+}

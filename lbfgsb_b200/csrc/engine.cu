@@ -1,0 +1,943 @@
+// Host side of the B200 L-BFGS-B engine: device workspace, the kernel pipeline
+// enqueued for each `task` entry of the reverse-communication protocol
+// (src/lbfgsb.f90:552-577), and the C ABI of include/lbfgsb_b200.h.
+//
+// One status read-back per return to the caller (plus one after the Cauchy
+// classify pass when bounds are present, to size the breakpoint walk).  All
+// data-dependent branches of mainlb are taken on the device (kernels_dense.cuh).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/lbfgsb_b200.h"
+#include "cauchy_walk.cuh"
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static void set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+#define CK(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #call); \
+            return false;                                                                    \
+        }                                                                                    \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// NCCL through dlopen (the process may already hold torch's bundled libnccl.so.2)
+// ---------------------------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+    int (*GetUniqueId)(ncclUniqueId*);
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    int (*CommDestroy)(ncclComm_t);
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
+    const char* (*GetErrorString)(int);
+    bool ok;
+};
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        api.ok = false;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+            api.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+            api.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+            api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather;
+        }
+    }
+    return &api;
+}
+
+// ---------------------------------------------------------------------------
+// kernel families (profiling / launch accounting)
+// ---------------------------------------------------------------------------
+enum Fam {
+    F_ERRCLB, F_ACTIVE, F_PROJGR, F_CLASSIFY, F_GCP_FREEV, F_FORMK_GRAM, F_FORMK_DELTA, F_CMPRLB_WV,
+    F_SUBSM_STEP, F_BACKTRACK, F_LS_INIT, F_LS_STEP, F_LS_TRIAL, F_UPDATE, F_RESTORE, F_WALK_COMPACT,
+    F_WALK_SORT, F_WALK_SCAN, F_WALK_FIX, F_SCALAR, F_HASH, F_COUNT
+};
+static const char* fam_name[F_COUNT] = {
+    "errclb", "active", "projgr", "cauchy_classify", "gcp_freev", "formk_gram", "formk_delta", "cmprlb_wv",
+    "subsm_step", "backtrack", "ls_init", "ls_step", "ls_trial", "update", "restore", "walk_compact",
+    "walk_sort", "walk_scan", "walk_fix", "scalar", "hash"};
+
+struct EngineBase {
+    virtual ~EngineBase() {}
+    int real_kind;
+};
+
+template <typename T>
+struct Engine : EngineBase {
+    i64 n = 0, n_global = 0, offset = 0;
+    int m = 0, mt = 0;
+    cudaStream_t stream = 0;
+    bool own_stream = false;
+    Wk<T> w;
+    WalkBuf<T> wb;
+    DevState<T>* s_dev = nullptr;
+    DevState<T>* s_host = nullptr;   // pinned mirror (scalar header only is copied)
+    size_t header_bytes = 0;
+    int* tile_counts = nullptr; i64* tile_offsets = nullptr; i64 ntiles = 0;
+    int* rs_counts = nullptr;
+    SortCtl* ctl_el = nullptr;
+    SortCtl* ctl_host = nullptr;     // pinned
+    T* tmpAB = nullptr; T* tmpF = nullptr; unsigned long long* jmin = nullptr;
+    T* fd_parts = nullptr; T* delta = nullptr;
+    std::vector<void*> allocs;
+    // sharding
+    int R = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    Red<T>* rec_local = nullptr; Red<T>* rec_all = nullptr;
+    // accounting
+    i64 launches = 0, syncs = 0;
+    bool profile = false;
+    struct Ev { int fam; cudaEvent_t a, b; };
+    std::vector<Ev> pending;
+    std::vector<cudaEvent_t> pool;
+    double fam_ms[F_COUNT]; i64 fam_calls[F_COUNT];
+    bool x_changed = false, g_changed = false;
+
+    Dist<T> dist() const { Dist<T> d; d.R = R; d.all = rec_all; return d; }
+
+    template <typename P> bool dalloc(P** p, size_t bytes) {
+        void* q = nullptr;
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return false; }
+        allocs.push_back(q);
+        *p = (P*)q;
+        return true;
+    }
+
+    bool init(i64 n_, i64 off_, i64 ng_, int m_, cudaStream_t st, ncclComm_t cm, int rank_, int world_) {
+        n = n_; offset = off_; n_global = ng_; m = m_; R = world_; rank = rank_; comm = cm;
+        real_kind = (int)sizeof(T);
+        mt = (m <= 5) ? 5 : (m <= 10 ? 10 : 20);
+        for (int q = 0; q < F_COUNT; ++q) { fam_ms[q] = 0; fam_calls[q] = 0; }
+        if (st) stream = st;
+        else { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
+        memset(&w, 0, sizeof w);
+        w.n = n; w.m = m;
+        w.ldw = (n + 31) / 32 * 32;
+        const size_t vb = (size_t)w.ldw * sizeof(T);
+        if (!dalloc(&w.ws, vb * m) || !dalloc(&w.wy, vb * m)) return false;
+        if (!dalloc(&w.z, vb) || !dalloc(&w.r, vb) || !dalloc(&w.d, vb) || !dalloc(&w.t, vb) || !dalloc(&w.xp, vb)) return false;
+        if (!dalloc(&w.iwhere, (size_t)w.ldw * 4) || !dalloc(&w.state, (size_t)w.ldw)) return false;
+        if (!dalloc(&w.part, sizeof(T) * LB_KMAX * LBFGSB_GRID) || !dalloc(&w.ipart, sizeof(i64) * LB_IMAX * LBFGSB_GRID)) return false;
+        if (!dalloc(&s_dev, sizeof(DevState<T>))) return false;
+        CK(cudaMemsetAsync(s_dev, 0, sizeof(DevState<T>), stream));
+        CK(cudaMemsetAsync(w.ws, 0, vb * m, stream));
+        CK(cudaMemsetAsync(w.wy, 0, vb * m, stream));
+        w.s = s_dev;
+        CK(cudaMallocHost((void**)&s_host, sizeof(DevState<T>)));
+        memset(s_host, 0, sizeof(DevState<T>));
+        CK(cudaMallocHost((void**)&ctl_host, sizeof(SortCtl)));
+        header_bytes = offsetof(DevState<T>, sy);
+        // walk / compaction buffers
+        const i64 tile = (i64)LBFGSB_BLOCK * Real<T>::VEC * LBFGSB_UNROLL;
+        ntiles = (n + tile - 1) / tile;
+        if (!dalloc(&tile_counts, sizeof(int) * (size_t)(ntiles + 1)) || !dalloc(&tile_offsets, sizeof(i64) * (size_t)(ntiles + 1))) return false;
+        if (!dalloc(&rs_counts, sizeof(int) * 256 * LB_RS_GRID)) return false;
+        typedef typename Real<T>::key_t K;
+        memset(&wb, 0, sizeof wb);
+        if (!dalloc(&wb.k0, sizeof(K) * (size_t)w.ldw) || !dalloc(&wb.k1, sizeof(K) * (size_t)w.ldw)) return false;
+        if (!dalloc(&wb.v0, 4 * (size_t)w.ldw) || !dalloc(&wb.v1, 4 * (size_t)w.ldw)) return false;
+        if (!dalloc(&wb.ctl, sizeof(SortCtl)) || !dalloc(&ctl_el, sizeof(SortCtl))) return false;
+        i64 cap = n < (i64)(1 << 22) ? n : (i64)(1 << 22);   // 4M breakpoints per chunk
+        cap = (cap + LB_WB - 1) / LB_WB * LB_WB;
+        wb.cap = cap;
+        const size_t cb = (size_t)cap * sizeof(T);
+        if (!dalloc(&wb.wj, cb * 2 * m) || !dalloc(&wb.vj, cb * 2 * m)) return false;
+        if (!dalloc(&wb.delta, cb) || !dalloc(&wb.zeta, cb) || !dalloc(&wb.omega, cb) || !dalloc(&wb.g2, cb) ||
+            !dalloc(&wb.g1, cb) || !dalloc(&wb.f1a, cb) || !dalloc(&wb.f2a, cb)) return false;
+        const i64 nblk = cap / LB_WB;
+        if (!dalloc(&wb.blkA, sizeof(T) * (size_t)nblk * 2 * LB_MMAX) || !dalloc(&wb.blkB, sizeof(T) * (size_t)nblk * 2 * LB_MMAX)) return false;
+        if (!dalloc(&wb.blk_a, sizeof(T) * (size_t)nblk) || !dalloc(&wb.blk_b, sizeof(T) * (size_t)nblk) || !dalloc(&wb.blkH, sizeof(T) * (size_t)nblk)) return false;
+        if (!dalloc(&tmpAB, sizeof(T) * 4 * LB_MMAX) || !dalloc(&tmpF, sizeof(T) * 2) || !dalloc(&jmin, 8)) return false;
+        if (!dalloc(&fd_parts, sizeof(T) * (size_t)LB_FD_GRID * 6 * LB_MMAX * LB_MMAX) || !dalloc(&delta, sizeof(T) * 6 * LB_MMAX * LB_MMAX)) return false;
+        CK(cudaMemsetAsync(delta, 0, sizeof(T) * 6 * LB_MMAX * LB_MMAX, stream));
+        if (R > 1) {
+            if (!dalloc(&rec_local, sizeof(Red<T>)) || !dalloc(&rec_all, sizeof(Red<T>) * R)) return false;
+        }
+        CK(cudaStreamSynchronize(stream));
+        return true;
+    }
+
+    ~Engine() {
+        for (void* p : allocs) cudaFree(p);
+        if (s_host) cudaFreeHost(s_host);
+        if (ctl_host) cudaFreeHost(ctl_host);
+        for (auto e : pool) cudaEventDestroy(e);
+        for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+
+    // ---- launch helpers ----------------------------------------------------
+    cudaEvent_t get_event() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void begin(int fam) {
+        if (profile) { Ev ev; ev.fam = fam; ev.a = get_event(); ev.b = get_event(); cudaEventRecord(ev.a, stream); pending.push_back(ev); }
+    }
+    void end(int fam, int nlaunch = 1) {
+        launches += nlaunch;
+        if (profile) cudaEventRecord(pending.back().b, stream);
+        else fam_calls[fam] += 1;
+    }
+    void resolve_events() {
+        for (auto& p : pending) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, p.a, p.b);
+            fam_ms[p.fam] += ms; fam_calls[p.fam] += 1;
+            pool.push_back(p.a); pool.push_back(p.b);
+        }
+        pending.clear();
+    }
+    bool sync_state() {
+        CK(cudaMemcpyAsync(s_host, s_dev, header_bytes, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        syncs++;
+        if (profile) resolve_events();
+        return true;
+    }
+    // finish + all-gather of a reduction site on sharded runs
+    bool site(const SiteSpec& sp) {
+        if (R <= 1) return true;
+        k_rank_finish<T><<<1, LB_SCALAR_THREADS, 0, stream>>>(w, sp, rec_local);
+        launches++;
+        int rc = nccl_api()->AllGather(rec_local, rec_all, sizeof(Red<T>), 0 /*ncclChar*/, comm, stream);
+        if (rc != 0) { set_error("ncclAllGather failed: %d", rc); return false; }
+        return true;
+    }
+#define LG LBFGSB_GRID, LBFGSB_BLOCK, 0, stream
+#define LS 1, LB_SCALAR_THREADS, 0, stream
+#define MTCALL(kern, ...)                                                     \
+    do {                                                                      \
+        if (mt == 5) kern<T, 5><<<LG>>>(__VA_ARGS__);                         \
+        else if (mt == 10) kern<T, 10><<<LG>>>(__VA_ARGS__);                  \
+        else kern<T, 20><<<LG>>>(__VA_ARGS__);                                \
+    } while (0)
+
+    // ---- the breakpoint walk ------------------------------------------------
+    bool enqueue_walk(i64 nbreak) {
+        typedef typename Real<T>::key_t K;
+        begin(F_WALK_COMPACT);
+        k_flag_count<T, 0><<<LG>>>(w, tile_counts);
+        k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 0, tile_counts, tile_offsets, ntiles, wb.ctl);
+        k_flag_write<T, 0><<<LG>>>(w, tile_offsets, wb.k0, wb.v0);
+        end(F_WALK_COMPACT, 3);
+        begin(F_WALK_SORT);
+        for (int pass = 0; pass < (int)sizeof(K); ++pass) {
+            k_rs_hist<K><<<LB_RS_GRID, 256, 0, stream>>>(wb.k0, wb.k1, wb.ctl, pass * 8, rs_counts);
+            k_rs_scan<<<1, 1024, 0, stream>>>(rs_counts, wb.ctl);
+            k_rs_scatter<K><<<LB_RS_GRID, 256, 0, stream>>>(wb.k0, wb.k1, wb.v0, wb.v1, wb.ctl, pass * 8, rs_counts);
+            k_rs_flip<<<1, 32, 0, stream>>>(wb.ctl);
+            launches += 4;
+        }
+        end(F_WALK_SORT, 0);
+        begin(F_WALK_SCAN);
+        for (i64 start = 0; start < nbreak; start += wb.cap) {
+            const i64 len = (nbreak - start < wb.cap) ? (nbreak - start) : wb.cap;
+            const i64 nblk = (len + LB_WB - 1) / LB_WB;
+            CK(cudaMemsetAsync(jmin, 0xff, 8, stream));
+            k_walk_gather<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wb, start, len);
+            k_walk_scan_vec<T><<<1, 1024, 0, stream>>>(w, wb, nblk, tmpAB);
+            k_walk_dots<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wb, start, len);
+            k_walk_scan_f2<T><<<1, 32, 0, stream>>>(w, wb, nblk, tmpF);
+            k_walk_f2<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wb, start, len);
+            k_walk_scan_f1<T><<<1, 32, 0, stream>>>(w, wb, nblk, tmpF);
+            k_walk_test<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wb, start, len, jmin);
+            k_walk_chunk_end<T><<<1, 32, 0, stream>>>(w, wb, start, len, tmpAB, tmpF, jmin);
+            launches += 8;
+        }
+        k_walk_final<T><<<1, LB_WB, 0, stream>>>(w, wb, wb.cap, n_global);
+        end(F_WALK_SCAN, 1);
+        begin(F_WALK_FIX);
+        k_walk_fix<T><<<LBFGSB_GRID, 256, 0, stream>>>(w, wb);
+        end(F_WALK_FIX);
+        return true;
+    }
+
+    // ---- prelims + first lnsrlb (:601-773) ----------------------------------
+    bool enqueue_body() {
+        for (;;) {
+            begin(F_CLASSIFY); MTCALL(k_cauchy_classify, w); end(F_CLASSIFY);
+            if (!site(site_cauchy(mt))) return false;
+            begin(F_SCALAR); s_cauchy<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);
+            if (s_host->cnstnd) {
+                if (!sync_state()) return false;
+                if (s_host->go && s_host->in_body && s_host->need_walk) {
+                    if (R > 1) { set_error("breakpoint walk on a sharded problem is not implemented yet"); return false; }
+                    if (!enqueue_walk(s_host->nbreak)) return false;
+                }
+            }
+            begin(F_GCP_FREEV); k_gcp_freev<T><<<LG>>>(w); end(F_GCP_FREEV);
+            if (!site(site_freev())) return false;
+            begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global); end(F_SCALAR);
+            begin(F_FORMK_GRAM); MTCALL(k_formk_gram, w); end(F_FORMK_GRAM);
+            begin(F_FORMK_DELTA);
+            k_flag_count<T, 1><<<LG>>>(w, tile_counts);
+            k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 1, tile_counts, tile_offsets, ntiles, ctl_el);
+            k_flag_write<T, 1><<<LG>>>(w, tile_offsets, wb.k0, wb.v0);
+            k_formk_delta<T><<<LB_FD_GRID, 256, 0, stream>>>(w, wb.v0, ctl_el, fd_parts);
+            k_formk_delta_final<T><<<(6 * LB_MMAX * LB_MMAX + 255) / 256, 256, 0, stream>>>(w, fd_parts, LB_FD_GRID, delta);
+            end(F_FORMK_DELTA, 5);
+            if (!site(site_formk(mt))) return false;
+            begin(F_SCALAR); s_formk_dense<T><<<LS>>>(w, dist(), mt, delta); end(F_SCALAR);
+            begin(F_CMPRLB_WV); MTCALL(k_cmprlb_wv, w); end(F_CMPRLB_WV);
+            if (!site(site_wv(mt))) return false;
+            begin(F_SCALAR); s_subsm_dense<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);
+            begin(F_SUBSM_STEP); MTCALL(k_subsm_step, w); end(F_SUBSM_STEP);
+            if (!site(site_subsm())) return false;
+            begin(F_SCALAR); s_subsm_post<T><<<LS>>>(w, dist()); end(F_SCALAR);
+            begin(F_BACKTRACK);
+            k_bt_alpha<T><<<LG>>>(w);
+            if (!site(site_bt())) return false;
+            s_bt<T><<<LS>>>(w, dist(), offset);
+            k_bt_apply<T><<<LG>>>(w);
+            end(F_BACKTRACK, 3);
+            begin(F_LS_INIT); k_ls_init<T><<<LG>>>(w); end(F_LS_INIT);
+            if (!site(site_lsinit())) return false;
+            begin(F_SCALAR); s_ls_init<T><<<LS>>>(w, dist()); end(F_SCALAR);
+            begin(F_LS_STEP); k_ls_step<T><<<LG>>>(w); end(F_LS_STEP);
+            if (!sync_state()) return false;
+            if (s_host->do_step) x_changed = true;
+            if (!s_host->restart) break;
+            // "refresh the lbfgs memory and restart the iteration": run the prelims again
+            begin(F_SCALAR); s_restart_body<T><<<1, 32, 0, stream>>>(w); end(F_SCALAR);
+        }
+        return true;
+    }
+
+    bool check_launch() {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("kernel launch failed: %s", cudaGetErrorString(e)); return false; }
+        return true;
+    }
+
+    // ---- one setulb call (device pointers) ----------------------------------
+    // entry: 0 START, 1 FG_START, 2 FG_LNSRCH, 3 NEW_X, 4 STOP (cpu restore flag in aux), 5 other
+    bool call(int entry, int aux, T* x, const T* l, const T* u, const int* nbd, T* f, T* g, T factr, T pgtol) {
+        w.x = x; w.l = l; w.u = u; w.nbd = nbd; w.g = g;
+        x_changed = false; g_changed = false;
+        if (entry == 0) {
+            int host_err = 0;
+            if (factr < (T)0) host_err = TK_ERR_FACTR;
+            s_start<T><<<1, 32, 0, stream>>>(w, factr, pgtol, host_err); launches++;
+            begin(F_ERRCLB); k_errclb<T><<<LG>>>(w); end(F_ERRCLB);
+            if (!site(site_errclb())) return false;
+            s_errclb<T><<<LS>>>(w, dist(), offset); launches++;
+            begin(F_ACTIVE); k_active<T><<<LG>>>(w); end(F_ACTIVE);
+            if (!site(site_active())) return false;
+            s_active<T><<<LS>>>(w, dist()); launches++;
+            if (!sync_state()) return false;
+            x_changed = true;
+            return check_launch();
+        }
+        if (entry == 4) {   // user STOP (:565-572)
+            if (aux) {
+                CK(cudaMemcpyAsync(x, w.t, sizeof(T) * n, cudaMemcpyDeviceToDevice, stream));
+                CK(cudaMemcpyAsync(g, w.r, sizeof(T) * n, cudaMemcpyDeviceToDevice, stream));
+                CK(cudaStreamSynchronize(stream));
+                *f = s_host->fold;
+                s_host->f = s_host->fold;
+                x_changed = true; g_changed = true;
+            }
+            s_host->task = TK_STOP;
+            return true;
+        }
+        if (entry == 5) {   // any other task: start() (:573-575)
+            s_host->task = TK_FG_START;
+            return true;
+        }
+        s_call_begin<T><<<1, 32, 0, stream>>>(w, *f, entry); launches++;
+        if (entry == 1) {
+            begin(F_PROJGR); k_projgr<T><<<LG>>>(w); end(F_PROJGR);
+            if (!site(site_projgr())) return false;
+            begin(F_SCALAR); s_fg_start<T><<<LS>>>(w, dist()); end(F_SCALAR);
+            if (!enqueue_body()) return false;
+        } else if (entry == 2) {
+            begin(F_LS_TRIAL); k_ls_trial<T><<<LG>>>(w); end(F_LS_TRIAL);
+            if (!site(site_lstrial())) return false;
+            begin(F_SCALAR); s_ls_trial<T><<<LS>>>(w, dist()); end(F_SCALAR);
+            begin(F_LS_STEP); k_ls_step<T><<<LG>>>(w); end(F_LS_STEP);
+            begin(F_RESTORE); k_restore<T><<<LG>>>(w); end(F_RESTORE);
+            if (!sync_state()) return false;
+            if (s_host->do_step) x_changed = true;
+            if (s_host->do_restore) { x_changed = true; g_changed = true; }
+            if (s_host->restart) {
+                begin(F_SCALAR); s_restart_body<T><<<1, 32, 0, stream>>>(w); end(F_SCALAR);
+                if (!enqueue_body()) return false;
+            }
+        } else {   // NEW_X
+            begin(F_SCALAR); s_newx_tests<T><<<1, 32, 0, stream>>>(w); end(F_SCALAR);
+            begin(F_UPDATE); MTCALL(k_update, w); end(F_UPDATE);
+            if (!site(site_update(mt))) return false;
+            begin(F_SCALAR); s_update_dense<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);
+            if (!enqueue_body()) return false;
+        }
+        *f = s_host->f;
+        return check_launch();
+    }
+
+    bool active_hash(uint64_t* hash, i64* count) {
+        begin(F_HASH); k_active_hash<T><<<LG>>>(w, offset); end(F_HASH);
+        // finish on the host: 2 x GRID integers
+        std::vector<i64> hp(2 * LBFGSB_GRID);
+        CK(cudaMemcpyAsync(hp.data(), w.ipart, sizeof(i64) * 2 * LBFGSB_GRID, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        uint64_t h = 0; i64 c = 0;
+        for (int b = 0; b < LBFGSB_GRID; ++b) { h += (uint64_t)hp[b]; c += hp[LBFGSB_GRID + b]; }
+        *hash = h; *count = c;
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// task strings
+// ---------------------------------------------------------------------------
+static void put60(char* s, const char* lit) {
+    size_t k = strlen(lit);
+    if (k > 60) k = 60;
+    memcpy(s, lit, k);
+    for (size_t i = k; i < 60; ++i) s[i] = ' ';
+}
+static bool pre60(const char* s, const char* lit) { return memcmp(s, lit, strlen(lit)) == 0; }
+static bool eq60(const char* s, const char* lit) {
+    size_t k = strlen(lit);
+    if (memcmp(s, lit, k) != 0) return false;
+    for (size_t i = k; i < 60; ++i) if (s[i] != ' ') return false;
+    return true;
+}
+static const char* task_text(int code) {
+    switch (code) {
+        case TK_FG_START: return "FG_START";
+        case TK_FG_LNSRCH: return "FG_LNSRCH";
+        case TK_NEW_X: return "NEW_X";
+        case TK_CONV_PG: return "CONVERGENCE: NORM_OF_PROJECTED_GRADIENT_<=_PGTOL";
+        case TK_CONV_F: return "CONVERGENCE: REL_REDUCTION_OF_F_<=_FACTR*EPSMCH";
+        case TK_ABNORMAL: return "ABNORMAL_TERMINATION_IN_LNSRCH";
+        case TK_RESTART: return "RESTART_FROM_LNSRCH";
+        case TK_ERR_N: return "ERROR: N <= 0";
+        case TK_ERR_M: return "ERROR: M <= 0";
+        case TK_ERR_FACTR: return "ERROR: FACTR < 0";
+        case TK_ERR_NBD: return "ERROR: INVALID NBD";
+        case TK_ERR_INFEAS: return "ERROR: NO FEASIBLE SOLUTION";
+        default: return "START";
+    }
+}
+static const char* csave_text(int code) {
+    switch (code) {
+        case CS_START: return "START";
+        case CS_FG: return "FG";
+        case CS_CONV: return "CONVERGENCE";
+        case CS_WARN_ROUND: return "WARNING: ROUNDING ERRORS PREVENT PROGRESS";
+        case CS_WARN_XTOL: return "WARNING: XTOL TEST SATISFIED";
+        case CS_WARN_STPMAX: return "WARNING: STP = STPMAX";
+        case CS_WARN_STPMIN: return "WARNING: STP = STPMIN";
+        case CS_ERR_STP_LT_MIN: return "ERROR: STP < STPMIN";
+        case CS_ERR_STP_GT_MAX: return "ERROR: STP > STPMAX";
+        case CS_ERR_G_GE_0: return "ERROR: INITIAL G >= ZERO";
+        case CS_ERR_FTOL: return "ERROR: FTOL < ZERO";
+        case CS_ERR_GTOL: return "ERROR: GTOL < ZERO";
+        case CS_ERR_XTOL: return "ERROR: XTOL < ZERO";
+        case CS_ERR_STPMIN: return "ERROR: STPMIN < ZERO";
+        case CS_ERR_STPMAX: return "ERROR: STPMAX < STPMIN";
+        default: return "";
+    }
+}
+
+// save_locals (:904-947): device mirror -> the caller's isave / dsave / lsave
+template <typename T>
+static void export_state(const Engine<T>* e, char* task, char* csave, int32_t* lsave, int32_t* isave, T* dsave) {
+    const DevState<T>* s = e->s_host;
+    const i64 ng = e->n_global;
+    auto clamp32 = [](i64 v) { return (int32_t)(v > 2147483647LL ? 2147483647LL : v); };
+    lsave[0] = s->prjctd; lsave[1] = s->cnstnd; lsave[2] = s->boxed; lsave[3] = s->updatd;
+    isave[21] = clamp32(s->nintol);
+    isave[23] = 0;                      // itfile: no Fortran unit on this path
+    isave[24] = s->iback; isave[25] = s->nskip; isave[26] = s->head; isave[27] = s->col; isave[28] = s->itail;
+    isave[29] = s->iter; isave[30] = s->iupdat;
+    isave[32] = clamp32(s->nseg); isave[33] = s->nfgv; isave[34] = s->info; isave[35] = s->ifun; isave[36] = s->iword;
+    isave[37] = clamp32(s->nfree); isave[38] = clamp32(s->nact);
+    isave[39] = clamp32(ng + 1 - s->nleave);   // ileave
+    isave[40] = clamp32(s->nenter);
+    isave[42] = s->brackt; isave[43] = s->stage;
+    dsave[0] = s->theta; dsave[1] = s->fold; dsave[2] = s->tol; dsave[3] = s->dnorm; dsave[4] = s->epsmch;
+    dsave[5] = 0; dsave[6] = 0; dsave[7] = 0; dsave[8] = 0; dsave[9] = 0;
+    dsave[10] = s->gd; dsave[11] = s->stpmx; dsave[12] = s->sbgnrm; dsave[13] = s->stp; dsave[14] = s->gdold; dsave[15] = s->dtd;
+    for (int q = 0; q < 13; ++q) dsave[16 + q] = s->ls[q];
+    put60(task, task_text(s->task));
+    if (s->csave != CS_BLANK) put60(csave, csave_text(s->csave));
+}
+
+template <typename T>
+static void setulb_dev_impl(lbfgsb_dev_t* hh, T* x, const T* l, const T* u, const int32_t* nbd, T* f, T* g,
+                            const T* factr, const T* pgtol, char* task, const int32_t* iprint, char* csave,
+                            int32_t* lsave, int32_t* isave, T* dsave) {
+    (void)iprint;
+    Engine<T>* e = (Engine<T>*)hh;
+    if (!e || e->real_kind != (int)sizeof(T)) { put60(task, "ERROR: INVALID LBFGSB_B200 HANDLE"); set_error("invalid handle"); return; }
+    int entry, aux = 0;
+    if (eq60(task, "START")) entry = 0;
+    else if (pre60(task, "FG_LN")) entry = 2;
+    else if (pre60(task, "NEW_X")) entry = 3;
+    else if (pre60(task, "FG_ST")) entry = 1;
+    else if (pre60(task, "STOP")) { entry = 4; aux = (memcmp(task + 6, "CPU", 3) == 0); }
+    else entry = 5;
+    if (entry == 0) {
+        // isave(1:16): sizes/offsets of the reference's wa partition (:250-265), informational here
+        const i64 n = e->n_global, m = e->m;
+        const i64 mn = m * n, m2 = m * m, m24 = 4 * m2;
+        i64 v[16]; v[0] = mn; v[1] = m2; v[2] = m24; v[3] = 1; v[4] = v[3] + mn; v[5] = v[4] + mn; v[6] = v[5] + m2;
+        v[7] = v[6] + m2; v[8] = v[7] + m2; v[9] = v[8] + m24; v[10] = v[9] + m24; v[11] = v[10] + n; v[12] = v[11] + n;
+        v[13] = v[12] + n; v[14] = v[13] + n; v[15] = v[14] + n;
+        for (int q = 0; q < 16; ++q) isave[q] = (v[q] <= 2147483647LL) ? (int32_t)v[q] : -1;
+    }
+    if (entry == 4 && !aux) { return; }   // finish(): nothing changes on this path
+    bool ok = e->call(entry, aux, x, l, u, nbd, f, g, *factr, *pgtol);
+    if (!ok) {
+        char buf[61];
+        snprintf(buf, sizeof buf, "ERROR: CUDA FAILURE (see lbfgsb_b200_last_error)");
+        put60(task, buf);
+        return;
+    }
+    if (entry == 4) return;               // the caller's STOP text stays in task
+    if (entry == 5) { put60(task, "FG_START"); return; }
+    export_state<T>(e, task, csave, lsave, isave, dsave);
+    if (entry == 0 && pre60(task, "ERROR")) { isave[34] = e->s_host->info; isave[41] = (int32_t)e->s_host->errk; }
+}
+
+// ---------------------------------------------------------------------------
+// host twin: device copies of the caller's vectors, handle in isave(17:19)
+// ---------------------------------------------------------------------------
+struct HostProblem {
+    EngineBase* eng;
+    void *x, *l, *u, *g; int32_t* nbd;
+    i64 n; int kind;
+};
+static std::mutex g_reg_mu;
+static std::unordered_set<HostProblem*> g_registry;
+#define LB_MAGIC 0x4C424232   /* 'LBB2' */
+
+static HostProblem* hp_from_isave(const int32_t* isave) {
+    if (isave[18] != LB_MAGIC) return nullptr;
+    uint64_t v = (uint64_t)(uint32_t)isave[16] | ((uint64_t)(uint32_t)isave[17] << 32);
+    HostProblem* p = (HostProblem*)(uintptr_t)v;
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    return g_registry.count(p) ? p : nullptr;
+}
+static void hp_free(HostProblem* p) {
+    {
+        std::lock_guard<std::mutex> lk(g_reg_mu);
+        if (!g_registry.erase(p)) return;
+    }
+    delete p->eng;
+    cudaFree(p->x); cudaFree(p->l); cudaFree(p->u); cudaFree(p->g); cudaFree(p->nbd);
+    delete p;
+}
+
+template <typename T>
+static void setulb_host_impl(const int32_t* n, const int32_t* m, T* x, const T* l, const T* u, const int32_t* nbd, T* f,
+                             T* g, const T* factr, const T* pgtol, char* task, const int32_t* iprint, char* csave,
+                             int32_t* lsave, int32_t* isave, T* dsave) {
+    HostProblem* p = nullptr;
+    if (eq60(task, "START")) {
+        HostProblem* old = hp_from_isave(isave);
+        if (old) hp_free(old);
+        isave[18] = 0;
+        // errclb's scalar checks (:1618-1620) that cannot reach the device
+        if (*n <= 0) { put60(task, "ERROR: N <= 0"); if (*m <= 0) put60(task, "ERROR: M <= 0"); if (*factr < (T)0) put60(task, "ERROR: FACTR < 0"); return; }
+        if (*m <= 0) { put60(task, "ERROR: M <= 0"); if (*factr < (T)0) put60(task, "ERROR: FACTR < 0"); return; }
+        if (*m > LB_MMAX) { put60(task, "ERROR: M > 20 IS NOT SUPPORTED BY LBFGSB_B200"); return; }
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            put60(task, "ERROR: NO CUDA DEVICE (LBFGSB_B200 HAS NO CPU PATH)");
+            set_error("no CUDA device");
+            return;
+        }
+        Engine<T>* e = new Engine<T>();
+        if (!e->init(*n, 0, *n, *m, nullptr, nullptr, 0, 1)) { delete e; put60(task, "ERROR: CUDA FAILURE (see lbfgsb_b200_last_error)"); return; }
+        p = new HostProblem();
+        p->eng = e; p->n = *n; p->kind = (int)sizeof(T);
+        const size_t vb = (size_t)(*n) * sizeof(T);
+        if (cudaMalloc(&p->x, vb) || cudaMalloc(&p->l, vb) || cudaMalloc(&p->u, vb) || cudaMalloc(&p->g, vb) ||
+            cudaMalloc((void**)&p->nbd, (size_t)(*n) * 4)) {
+            set_error("cudaMalloc failed for the host twin's staging vectors");
+            put60(task, "ERROR: CUDA FAILURE (see lbfgsb_b200_last_error)");
+            delete e; delete p; return;
+        }
+        cudaMemcpyAsync(p->x, x, vb, cudaMemcpyHostToDevice, e->stream);
+        cudaMemcpyAsync(p->l, l, vb, cudaMemcpyHostToDevice, e->stream);
+        cudaMemcpyAsync(p->u, u, vb, cudaMemcpyHostToDevice, e->stream);
+        cudaMemcpyAsync(p->nbd, nbd, (size_t)(*n) * 4, cudaMemcpyHostToDevice, e->stream);
+        {
+            std::lock_guard<std::mutex> lk(g_reg_mu);
+            g_registry.insert(p);
+        }
+        uint64_t v = (uint64_t)(uintptr_t)p;
+        isave[16] = (int32_t)(uint32_t)(v & 0xffffffffu); isave[17] = (int32_t)(uint32_t)(v >> 32); isave[18] = LB_MAGIC;
+    } else {
+        p = hp_from_isave(isave);
+        if (!p || p->kind != (int)sizeof(T)) { put60(task, "ERROR: SETULB CALLED WITHOUT A VALID START (ISAVE ALTERED?)"); return; }
+    }
+    Engine<T>* e = (Engine<T>*)p->eng;
+    const size_t vb = (size_t)p->n * sizeof(T);
+    if (pre60(task, "FG")) cudaMemcpyAsync(p->g, g, vb, cudaMemcpyHostToDevice, e->stream);
+    setulb_dev_impl<T>((lbfgsb_dev_t*)e, (T*)p->x, (const T*)p->l, (const T*)p->u, p->nbd, f, (T*)p->g, factr, pgtol,
+                       task, iprint, csave, lsave, isave, dsave);
+    if (e->x_changed) cudaMemcpyAsync(x, p->x, vb, cudaMemcpyDeviceToHost, e->stream);
+    if (e->g_changed) cudaMemcpyAsync(g, p->g, vb, cudaMemcpyDeviceToHost, e->stream);
+    if (e->x_changed || e->g_changed) cudaStreamSynchronize(e->stream);
+    if (pre60(task, "CONV") || pre60(task, "ABNO") || pre60(task, "ERROR") || pre60(task, "STOP")) {
+        hp_free(p);
+        isave[18] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// sample problem (test/driver1.f90:274-289) on the device
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_rosenbrock(i64 n, const T* __restrict__ x, T* __restrict__ g,
+                                                            T* part, int first, int last, T xl, T xr) {
+    constexpr int VEC = Real<T>::VEC;
+    __shared__ T sm[LBFGSB_BLOCK / 32];
+    T acc[1]; acc[0] = (T)0;
+    LB_FOR_TILES(T, n, base) {
+        T xv[VEC], gv[VEC];
+        ldv<T>(x, base, n, xv);
+        T xm = (base > 0) ? x[base - 1] : xl;
+        T xp = (base + VEC < n) ? x[base + VEC] : xr;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const i64 i = base + v;
+            if (i < n) {
+                const T xi = xv[v];
+                const T xprev = (v == 0) ? xm : xv[v - 1];
+                const T xnext = (v == VEC - 1 || i + 1 >= n) ? ((i + 1 < n) ? ((v == VEC - 1) ? xp : xv[v + 1]) : xr) : xv[v + 1];
+                const bool is_first = first && i == 0, is_last = last && i == n - 1;
+                T t2 = xi - xprev * xprev;       // x(i) - x(i-1)^2
+                T t1 = xnext - xi * xi;          // x(i+1) - x(i)^2
+                if (is_first) {
+                    gv[v] = (T)2 * (xi - (T)1) - (T)16 * xi * t1;
+                    acc[0] = acc[0] + (T)0.25 * (xi - (T)1) * (xi - (T)1);
+                } else {
+                    acc[0] = acc[0] + t2 * t2;
+                    gv[v] = is_last ? (T)8 * t2 : ((T)8 * t2 - (T)16 * xi * t1);
+                }
+            } else gv[v] = (T)0;
+        }
+        stv<T>(g, base, n, gv);
+    }
+    block_sum_store<T, 1>(acc, 1, sm, part);
+}
+template <typename T>
+__global__ void k_rosenbrock_final(const T* part, T* out) {
+    T s = final_sum_warp<T>(part);
+    if (threadIdx.x == 0) out[0] = (T)4 * s;
+}
+template <typename T>
+static int rosenbrock_impl(i64 n, const T* x, T* g, T* f_out, void* st, int first, int last, T xl, T xr, void* scratch) {
+    cudaStream_t s = (cudaStream_t)st;
+    T* part = (T*)scratch;
+    T* out = part + LBFGSB_GRID;
+    k_rosenbrock<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, first, last, xl, xr);
+    k_rosenbrock_final<T><<<1, 32, 0, s>>>(part, out);
+    if (cudaMemcpyAsync(f_out, out, sizeof(T), cudaMemcpyDeviceToHost, s) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("rosenbrock kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// test-only single kernels
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_test_sum(i64 n, const T* a, const T* b, T* part) {
+    constexpr int VEC = Real<T>::VEC;
+    __shared__ T sm[LBFGSB_BLOCK / 32];
+    T acc[1]; acc[0] = (T)0;
+    LB_FOR_TILES(T, n, base) {
+        T av[VEC], bv[VEC];
+        ldv<T>(a, base, n, av); ldv<T>(b, base, n, bv);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) if (base + v < n) acc[0] = acc[0] + av[v] * bv[v];
+    }
+    block_sum_store<T, 1>(acc, 1, sm, part);
+}
+template <typename T>
+__global__ void k_test_sum_final(const T* part, T* out) {
+    T s = final_sum_warp<T>(part);
+    if (threadIdx.x == 0) out[0] = s;
+}
+template <typename T>
+static int test_sum_impl(i64 n, const T* a, const T* b, T* out) {
+    T* part = nullptr;
+    if (cudaMalloc(&part, sizeof(T) * (LBFGSB_GRID + 1)) != cudaSuccess) return 1;
+    k_test_sum<T><<<LBFGSB_GRID, LBFGSB_BLOCK>>>(n, a, b, part);
+    k_test_sum_final<T><<<1, 32>>>(part, part + LBFGSB_GRID);
+    cudaError_t e = cudaMemcpy(out, part + LBFGSB_GRID, sizeof(T), cudaMemcpyDeviceToHost);
+    cudaFree(part);
+    return e != cudaSuccess;
+}
+
+__global__ void k_test_dense(int op, int m, int col, double theta, double* a, double* b, double* c, int* info) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (op == 0) *info = dense::dpofa<double>(a, m, col);
+    else if (op == 1) *info = dense::dtrsl<double>(a, m, col, b, 1);
+    else if (op == 2) *info = dense::dtrsl<double>(a, m, col, b, 11);
+    else if (op == 3) *info = dense::bmv<double>(m, a, b, col, c, c + 2 * m);      // a=sy, b=wt, c=[v | p]
+    else if (op == 4) *info = dense::formt<double>(m, c, a, b, col, theta);         // a=sy, b=ss, c=wt
+}
+__global__ void k_test_dcsrch(double f, double g, double* stp, double stpmax, int* task, int* isave2, double* dsave13) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    dense::dcsrch<double>(f, g, *stp, 1.0e-3, 0.9, 0.1, 0.0, stpmax, *task, isave2[0], isave2[1], dsave13);
+}
+template <typename K>
+__global__ void k_test_iota(int* v, i64 n) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) v[i] = (int)i;
+}
+__global__ void k_test_setctl(SortCtl* c, i64 n) { if (threadIdx.x == 0) { c->count = n; c->cur = 0; c->skip = 0; } }
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int lbfgsb_b200_version(void) { return 100; }
+const char* lbfgsb_b200_last_error(void) { return g_last_error.c_str(); }
+
+lbfgsb_dev_t* lbfgsb_dev_create_sharded(int64_t n_local, int64_t offset, int64_t n_global, int32_t m, int32_t real_kind,
+                                        void* cuda_stream, void* nccl_comm, int32_t rank, int32_t world) {
+    if (n_local <= 0 || m <= 0 || m > LB_MMAX) { set_error("lbfgsb_dev_create: need n > 0 and 0 < m <= %d", LB_MMAX); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (lbfgsb_b200 has no CPU path)"); return nullptr; }
+    if (world > 1 && (!nccl_comm || !nccl_api()->ok)) { set_error("sharded engine needs an NCCL communicator"); return nullptr; }
+    if (real_kind == 8) {
+        Engine<double>* e = new Engine<double>();
+        if (!e->init(n_local, offset, n_global, m, (cudaStream_t)cuda_stream, (ncclComm_t)nccl_comm, rank, world)) { delete e; return nullptr; }
+        return (lbfgsb_dev_t*)e;
+    } else if (real_kind == 4) {
+        Engine<float>* e = new Engine<float>();
+        if (!e->init(n_local, offset, n_global, m, (cudaStream_t)cuda_stream, (ncclComm_t)nccl_comm, rank, world)) { delete e; return nullptr; }
+        return (lbfgsb_dev_t*)e;
+    }
+    set_error("real_kind must be 8 or 4");
+    return nullptr;
+}
+lbfgsb_dev_t* lbfgsb_dev_create(int64_t n, int32_t m, int32_t real_kind, void* cuda_stream) {
+    return lbfgsb_dev_create_sharded(n, 0, n, m, real_kind, cuda_stream, nullptr, 0, 1);
+}
+void lbfgsb_dev_destroy(lbfgsb_dev_t* h) { delete (EngineBase*)h; }
+
+void lbfgsb_setulb_dev_f64(lbfgsb_dev_t* h, double* x, const double* l, const double* u, const int32_t* nbd, double* f,
+                           double* g, const double* factr, const double* pgtol, char* task, const int32_t* iprint,
+                           char* csave, int32_t* lsave, int32_t* isave, double* dsave) {
+    setulb_dev_impl<double>(h, x, l, u, nbd, f, g, factr, pgtol, task, iprint, csave, lsave, isave, dsave);
+}
+void lbfgsb_setulb_dev_f32(lbfgsb_dev_t* h, float* x, const float* l, const float* u, const int32_t* nbd, float* f,
+                           float* g, const float* factr, const float* pgtol, char* task, const int32_t* iprint,
+                           char* csave, int32_t* lsave, int32_t* isave, float* dsave) {
+    setulb_dev_impl<float>(h, x, l, u, nbd, f, g, factr, pgtol, task, iprint, csave, lsave, isave, dsave);
+}
+
+void lbfgsb_setulb_f64(const int32_t* n, const int32_t* m, double* x, const double* l, const double* u, const int32_t* nbd,
+                       double* f, double* g, const double* factr, const double* pgtol, double* wa, int32_t* iwa, char* task,
+                       const int32_t* iprint, char* csave, int32_t* lsave, int32_t* isave, double* dsave,
+                       const char* itfile, int32_t itfile_len) {
+    (void)wa; (void)iwa; (void)itfile; (void)itfile_len;
+    setulb_host_impl<double>(n, m, x, l, u, nbd, f, g, factr, pgtol, task, iprint, csave, lsave, isave, dsave);
+}
+void lbfgsb_setulb_f32(const int32_t* n, const int32_t* m, float* x, const float* l, const float* u, const int32_t* nbd,
+                       float* f, float* g, const float* factr, const float* pgtol, float* wa, int32_t* iwa, char* task,
+                       const int32_t* iprint, char* csave, int32_t* lsave, int32_t* isave, float* dsave,
+                       const char* itfile, int32_t itfile_len) {
+    (void)wa; (void)iwa; (void)itfile; (void)itfile_len;
+    setulb_host_impl<float>(n, m, x, l, u, nbd, f, g, factr, pgtol, task, iprint, csave, lsave, isave, dsave);
+}
+void lbfgsb_host_release(int32_t* isave) {
+    HostProblem* p = hp_from_isave(isave);
+    if (p) { hp_free(p); isave[18] = 0; }
+}
+int lbfgsb_host_previous_x_f64(const int32_t* isave, double* t_out) {
+    HostProblem* p = hp_from_isave(isave);
+    if (!p || p->kind != 8) return 1;
+    Engine<double>* e = (Engine<double>*)p->eng;
+    return cudaMemcpy(t_out, e->w.t, sizeof(double) * p->n, cudaMemcpyDeviceToHost) != cudaSuccess;
+}
+int lbfgsb_host_previous_x_f32(const int32_t* isave, float* t_out) {
+    HostProblem* p = hp_from_isave(isave);
+    if (!p || p->kind != 4) return 1;
+    Engine<float>* e = (Engine<float>*)p->eng;
+    return cudaMemcpy(t_out, e->w.t, sizeof(float) * p->n, cudaMemcpyDeviceToHost) != cudaSuccess;
+}
+// the host twin's engine, for diagnostics (active-set hash) in tests
+lbfgsb_dev_t* lbfgsb_host_engine(const int32_t* isave) {
+    HostProblem* p = hp_from_isave(isave);
+    return p ? (lbfgsb_dev_t*)p->eng : nullptr;
+}
+
+int lbfgsb_dev_nccl_unique_id(void* id128) {
+    if (!nccl_api()->ok) { set_error("libnccl.so.2 not found"); return 1; }
+    return nccl_api()->GetUniqueId((ncclUniqueId*)id128);
+}
+void* lbfgsb_dev_nccl_init(const void* id128, int32_t rank, int32_t world) {
+    if (!nccl_api()->ok) { set_error("libnccl.so.2 not found"); return nullptr; }
+    ncclComm_t c = nullptr;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    int rc = nccl_api()->CommInitRank(&c, world, id, rank);
+    if (rc != 0) { set_error("ncclCommInitRank failed: %d", rc); return nullptr; }
+    return c;
+}
+void lbfgsb_dev_nccl_destroy(void* comm) { if (comm && nccl_api()->ok) nccl_api()->CommDestroy((ncclComm_t)comm); }
+
+int lbfgsb_dev_active_set_hash(lbfgsb_dev_t* h, uint64_t* hash, int64_t* count) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b) return 1;
+    i64 c = 0;
+    bool ok = (b->real_kind == 8) ? ((Engine<double>*)b)->active_hash(hash, &c) : ((Engine<float>*)b)->active_hash(hash, &c);
+    *count = c;
+    return ok ? 0 : 1;
+}
+void* lbfgsb_dev_vector(lbfgsb_dev_t* h, int32_t which) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b) return nullptr;
+#define VSEL(E)                                                                                          \
+    switch (which) { case 0: return E->w.z; case 1: return E->w.r; case 2: return E->w.d; case 3: return E->w.t; \
+                     case 4: return E->w.xp; case 5: return E->w.ws; case 6: return E->w.wy; case 7: return E->w.iwhere; default: return nullptr; }
+    if (b->real_kind == 8) { Engine<double>* e = (Engine<double>*)b; VSEL(e) }
+    else { Engine<float>* e = (Engine<float>*)b; VSEL(e) }
+}
+int lbfgsb_dev_counters(lbfgsb_dev_t* h, int64_t* launches, int64_t* syncs) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b) return 1;
+    if (b->real_kind == 8) { *launches = ((Engine<double>*)b)->launches; *syncs = ((Engine<double>*)b)->syncs; }
+    else { *launches = ((Engine<float>*)b)->launches; *syncs = ((Engine<float>*)b)->syncs; }
+    return 0;
+}
+void lbfgsb_dev_profile(lbfgsb_dev_t* h, int32_t enable) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b) return;
+    if (b->real_kind == 8) ((Engine<double>*)b)->profile = enable != 0; else ((Engine<float>*)b)->profile = enable != 0;
+}
+void lbfgsb_dev_profile_reset(lbfgsb_dev_t* h) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b) return;
+    for (int q = 0; q < F_COUNT; ++q) {
+        if (b->real_kind == 8) { ((Engine<double>*)b)->fam_ms[q] = 0; ((Engine<double>*)b)->fam_calls[q] = 0; }
+        else { ((Engine<float>*)b)->fam_ms[q] = 0; ((Engine<float>*)b)->fam_calls[q] = 0; }
+    }
+}
+int lbfgsb_dev_profile_read(lbfgsb_dev_t* h, int32_t cap, char* names, double* ms, double* bytes, int64_t* calls) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b) return 0;
+    int k = 0;
+    for (int q = 0; q < F_COUNT && k < cap; ++q, ++k) {
+        snprintf(names + 32 * k, 32, "%s", fam_name[q]);
+        if (b->real_kind == 8) { ms[k] = ((Engine<double>*)b)->fam_ms[q]; calls[k] = ((Engine<double>*)b)->fam_calls[q]; }
+        else { ms[k] = ((Engine<float>*)b)->fam_ms[q]; calls[k] = ((Engine<float>*)b)->fam_calls[q]; }
+        bytes[k] = 0;
+    }
+    return k;
+}
+
+int64_t lbfgsb_problem_scratch_bytes(void) { return (int64_t)sizeof(double) * (LBFGSB_GRID + 8); }
+int lbfgsb_problem_rosenbrock_f64(int64_t n, const double* x, double* g, double* f_out, void* st, int32_t first, int32_t last,
+                                  double xl, double xr, void* scratch) {
+    return rosenbrock_impl<double>(n, x, g, f_out, st, first, last, xl, xr, scratch);
+}
+int lbfgsb_problem_rosenbrock_f32(int64_t n, const float* x, float* g, float* f_out, void* st, int32_t first, int32_t last,
+                                  float xl, float xr, void* scratch) {
+    return rosenbrock_impl<float>(n, x, g, f_out, st, first, last, xl, xr, scratch);
+}
+
+int lbfgsb_test_projgr_f64(int64_t n, const double* l, const double* u, const int32_t* nbd, const double* x, const double* g,
+                           double* out) {
+    Wk<double> w; memset(&w, 0, sizeof w);
+    DevState<double>* s = nullptr; double* part = nullptr;
+    if (cudaMalloc(&s, sizeof(DevState<double>)) || cudaMalloc(&part, sizeof(double) * (LBFGSB_GRID + 1))) return 1;
+    int one = 1;
+    cudaMemcpy(&s->go, &one, sizeof(int), cudaMemcpyHostToDevice);
+    w.n = n; w.l = l; w.u = u; w.nbd = nbd; w.x = (double*)x; w.g = (double*)g; w.part = part; w.s = s;
+    k_projgr<double><<<LBFGSB_GRID, LBFGSB_BLOCK>>>(w);
+    std::vector<double> hp(LBFGSB_GRID);
+    cudaError_t e = cudaMemcpy(hp.data(), part, sizeof(double) * LBFGSB_GRID, cudaMemcpyDeviceToHost);
+    double r = 0; for (double v : hp) r = v > r ? v : r;
+    *out = r;
+    cudaFree(s); cudaFree(part);
+    return e != cudaSuccess;
+}
+int lbfgsb_test_sum_f64(int64_t n, const double* a, const double* b, double* out) { return test_sum_impl<double>(n, a, b, out); }
+int lbfgsb_test_sum_f32(int64_t n, const float* a, const float* b, float* out) { return test_sum_impl<float>(n, a, b, out); }
+
+int lbfgsb_test_sort_f64(int64_t n, const double* t, int32_t* order_out, double* sorted_out) {
+    typedef unsigned long long K;
+    K *k0, *k1; int *v0, *v1, *cnt; SortCtl* ctl;
+    if (cudaMalloc(&k0, 8 * n) || cudaMalloc(&k1, 8 * n) || cudaMalloc(&v0, 4 * n) || cudaMalloc(&v1, 4 * n) ||
+        cudaMalloc(&cnt, 4 * 256 * LB_RS_GRID) || cudaMalloc(&ctl, sizeof(SortCtl))) return 1;
+    cudaMemcpy(k0, t, 8 * n, cudaMemcpyDeviceToDevice);   // t > 0: bit pattern order == value order
+    k_test_iota<K><<<256, 256>>>(v0, n);
+    k_test_setctl<<<1, 32>>>(ctl, n);
+    for (int pass = 0; pass < 8; ++pass) {
+        k_rs_hist<K><<<LB_RS_GRID, 256>>>(k0, k1, ctl, pass * 8, cnt);
+        k_rs_scan<<<1, 1024>>>(cnt, ctl);
+        k_rs_scatter<K><<<LB_RS_GRID, 256>>>(k0, k1, v0, v1, ctl, pass * 8, cnt);
+        k_rs_flip<<<1, 32>>>(ctl);
+    }
+    SortCtl hc;
+    cudaMemcpy(&hc, ctl, sizeof hc, cudaMemcpyDeviceToHost);
+    cudaMemcpy(order_out, hc.cur ? v1 : v0, 4 * n, cudaMemcpyDeviceToDevice);
+    cudaError_t e = cudaMemcpy(sorted_out, hc.cur ? k1 : k0, 8 * n, cudaMemcpyDeviceToDevice);
+    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(cnt); cudaFree(ctl);
+    return e != cudaSuccess || cudaGetLastError() != cudaSuccess;
+}
+int lbfgsb_test_dense_f64(int32_t op, int32_t m, int32_t col, double theta, double* a, double* b, double* c, int32_t* info) {
+    int* dinfo;
+    if (cudaMalloc(&dinfo, 4)) return 1;
+    k_test_dense<<<1, 32>>>(op, m, col, theta, a, b, c, dinfo);
+    cudaError_t e = cudaMemcpy(info, dinfo, 4, cudaMemcpyDeviceToHost);
+    cudaFree(dinfo);
+    return e != cudaSuccess;
+}
+int lbfgsb_test_dcsrch_f64(double f, double g, double* stp, double stpmax, int32_t* task, int32_t* isave2, double* dsave13) {
+    double *dstp, *dds; int *dtask, *dis;
+    if (cudaMalloc(&dstp, 8) || cudaMalloc(&dds, 8 * 13) || cudaMalloc(&dtask, 4) || cudaMalloc(&dis, 8)) return 1;
+    cudaMemcpy(dstp, stp, 8, cudaMemcpyHostToDevice); cudaMemcpy(dds, dsave13, 8 * 13, cudaMemcpyHostToDevice);
+    cudaMemcpy(dtask, task, 4, cudaMemcpyHostToDevice); cudaMemcpy(dis, isave2, 8, cudaMemcpyHostToDevice);
+    k_test_dcsrch<<<1, 32>>>(f, g, dstp, stpmax, dtask, dis, dds);
+    cudaMemcpy(stp, dstp, 8, cudaMemcpyDeviceToHost); cudaMemcpy(dsave13, dds, 8 * 13, cudaMemcpyDeviceToHost);
+    cudaMemcpy(task, dtask, 4, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(isave2, dis, 8, cudaMemcpyDeviceToHost);
+    cudaFree(dstp); cudaFree(dds); cudaFree(dtask); cudaFree(dis);
+    return e != cudaSuccess;
+}
+
+}  // extern "C"

@@ -1,0 +1,634 @@
+// Single-CTA kernels: finish the block partials of the preceding streaming pass,
+// run the 2m x 2m dense algebra (bmv, formt, formk tail, subsm solves, dcsrch)
+// and take every data-dependent branch of mainlb (src/lbfgsb.f90:599-872) on the
+// device, writing the flags that predicate the kernels enqueued after them.
+//
+// In a sharded run (R ranks) the partials of every rank are finished locally
+// (k_rank_finish), all-gathered, and combined here in rank order, so every rank
+// takes bit-identical decisions.
+#pragma once
+#include "kernels_stream.cuh"
+
+#define LB_SCALAR_THREADS 256
+
+// Reduced values of one site.  rv[] real slots, iv[] integer slots.
+template <typename T>
+struct Red {
+    T rv[LB_KMAX];
+    i64 iv[LB_IMAX];
+};
+
+// op codes for the slots of a site
+enum { OP_SUM = 0, OP_MAX = 1, OP_MIN = 2, OP_ARGMIN = 3 /* real slot paired with iv[0] */ };
+
+// Per-site description: ops of the real slots come as (first, count, op) runs.
+struct SiteSpec {
+    int nreal;            // real slots in use
+    int nint;             // integer slots in use
+    int argmin_slot;      // real slot that carries the ARGMIN value (-1: none); its index is iv[0]
+    int max_from, max_to; // real slots [max_from, max_to) are OP_MAX
+    int min_from, min_to; // real slots [min_from, min_to) are OP_MIN (excluding argmin_slot)
+    int imin_from, imin_to;  // integer slots that are minima; others are sums; iv[0] is the argmin index if argmin_slot>=0
+    int imax_from, imax_to;  // integer slots that are maxima
+};
+
+// Finish the local block partials of a site into red (shared memory), using all warps.
+template <typename T>
+__device__ void site_finish_local(const Wk<T>& w, const SiteSpec sp, Red<T>* red) {
+    const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int k = wid; k < sp.nreal; k += nw) {
+        const T* p = LB_SLOT(w.part, k);
+        T r;
+        if (k == sp.argmin_slot) {
+            i64 idx;
+            final_argmin_warp<T>(p, LB_SLOT(w.ipart, 0), r, idx);
+            if (lane == 0) red->iv[0] = idx;
+        } else if (k >= sp.max_from && k < sp.max_to) r = final_max_warp<T>(p);
+        else if (k >= sp.min_from && k < sp.min_to) r = final_min_warp<T>(p);
+        else r = final_sum_warp<T>(p);
+        if (lane == 0) red->rv[k] = r;
+    }
+    for (int k = wid; k < sp.nint; k += nw) {
+        if (k == 0 && sp.argmin_slot >= 0) continue;
+        const i64* p = LB_SLOT(w.ipart, k);
+        i64 r;
+        if (k >= sp.imin_from && k < sp.imin_to) r = final_imin_warp(p);
+        else if (k >= sp.imax_from && k < sp.imax_to) r = final_imax_warp(p);
+        else r = final_isum_warp(p);
+        if (lane == 0) red->iv[k] = r;
+    }
+    __syncthreads();
+}
+
+// Combine the per-rank records (rank order) into red.
+template <typename T>
+__device__ void site_combine_ranks(const Red<T>* all, int R, const SiteSpec sp, Red<T>* red) {
+    for (int k = threadIdx.x; k < sp.nreal; k += blockDim.x) {
+        T r = all[0].rv[k];
+        if (k == sp.argmin_slot) {
+            i64 idx = all[0].iv[0];
+            for (int q = 1; q < R; ++q) {
+                T ov = all[q].rv[k]; i64 oi = all[q].iv[0];
+                if (ov < r || (ov == r && oi < idx)) { r = ov; idx = oi; }
+            }
+            red->iv[0] = idx;
+        } else if (k >= sp.max_from && k < sp.max_to) {
+            for (int q = 1; q < R; ++q) r = all[q].rv[k] > r ? all[q].rv[k] : r;
+        } else if (k >= sp.min_from && k < sp.min_to) {
+            for (int q = 1; q < R; ++q) r = all[q].rv[k] < r ? all[q].rv[k] : r;
+        } else {
+            for (int q = 1; q < R; ++q) r = r + all[q].rv[k];
+        }
+        red->rv[k] = r;
+    }
+    for (int k = threadIdx.x; k < sp.nint; k += blockDim.x) {
+        if (k == 0 && sp.argmin_slot >= 0) continue;
+        i64 r = all[0].iv[k];
+        if (k >= sp.imin_from && k < sp.imin_to) { for (int q = 1; q < R; ++q) r = all[q].iv[k] < r ? all[q].iv[k] : r; }
+        else if (k >= sp.imax_from && k < sp.imax_to) { for (int q = 1; q < R; ++q) r = all[q].iv[k] > r ? all[q].iv[k] : r; }
+        else { for (int q = 1; q < R; ++q) r += all[q].iv[k]; }
+        red->iv[k] = r;
+    }
+    __syncthreads();
+}
+
+// Distribution context passed to every scalar kernel.
+template <typename T>
+struct Dist {
+    int R;                 // ranks (1: single GPU)
+    const Red<T>* all;     // [R] gathered records (R > 1)
+};
+
+template <typename T>
+__device__ __forceinline__ void site_reduce(const Wk<T>& w, const Dist<T>& dist, const SiteSpec sp, Red<T>* red) {
+    if (dist.R <= 1) site_finish_local<T>(w, sp, red);
+    else site_combine_ranks<T>(dist.all, dist.R, sp, red);
+}
+
+// Rank-local finish of a site into a global record (sharded runs; followed by an all-gather).
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) k_rank_finish(Wk<T> w, SiteSpec sp, Red<T>* out) {
+    __shared__ Red<T> red;
+    site_finish_local<T>(w, sp, &red);
+    for (int k = threadIdx.x; k < LB_KMAX; k += blockDim.x) out->rv[k] = (k < sp.nreal) ? red.rv[k] : (T)0;
+    for (int k = threadIdx.x; k < LB_IMAX; k += blockDim.x) out->iv[k] = (k < sp.nint) ? red.iv[k] : 0;
+}
+
+__host__ __device__ inline SiteSpec make_site(int nreal, int nint) {
+    SiteSpec sp;
+    sp.nreal = nreal; sp.nint = nint; sp.argmin_slot = -1;
+    sp.max_from = sp.max_to = sp.min_from = sp.min_to = 0;
+    sp.imin_from = sp.imin_to = sp.imax_from = sp.imax_to = 0;
+    return sp;
+}
+// the sites
+__host__ __device__ inline SiteSpec site_errclb() { SiteSpec s = make_site(0, 2); s.imax_from = 0; s.imax_to = 2; return s; }
+__host__ __device__ inline SiteSpec site_active() { return make_site(0, 4); }
+__host__ __device__ inline SiteSpec site_projgr() { SiteSpec s = make_site(1, 0); s.max_from = 0; s.max_to = 1; return s; }
+__host__ __device__ inline SiteSpec site_cauchy(int mt) {
+    SiteSpec s = make_site(2 * mt + 2, 4); s.argmin_slot = 2 * mt + 1; s.imin_from = 3; s.imin_to = 4; return s;
+}
+__host__ __device__ inline SiteSpec site_freev() { return make_site(0, 3); }
+__host__ __device__ inline SiteSpec site_formk(int mt) { return make_site(4 * mt, 0); }
+__host__ __device__ inline SiteSpec site_wv(int mt) { return make_site(2 * mt, 0); }
+__host__ __device__ inline SiteSpec site_subsm() { return make_site(1, 1); }
+__host__ __device__ inline SiteSpec site_bt() { SiteSpec s = make_site(1, 1); s.argmin_slot = 0; return s; }
+__host__ __device__ inline SiteSpec site_lsinit() { SiteSpec s = make_site(3, 0); s.min_from = 2; s.min_to = 3; return s; }
+__host__ __device__ inline SiteSpec site_lstrial() { SiteSpec s = make_site(2, 0); s.max_from = 1; s.max_to = 2; return s; }
+__host__ __device__ inline SiteSpec site_update(int mt) { return make_site(2 * mt + 1, 0); }
+__host__ __device__ inline SiteSpec site_hash() { return make_site(0, 2); }
+
+// "refresh the lbfgs memory" (:625-630 and the four other sites)
+template <typename T> __device__ inline void reset_memory(DevState<T>* s) {
+    s->info = 0; s->col = 0; s->head = 1; s->theta = (T)1; s->iupdat = 0; s->updatd = 0;
+}
+// prepare the flags for the prelims block (:601-612)
+template <typename T> __device__ inline void begin_body(DevState<T>* s) {
+    s->in_body = 1; s->restart = 0; s->need_walk = 0;
+    s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0; s->do_step = 0;
+    s->iword = -1;
+    if (!s->cnstnd && s->col > 0) {  // :607-611
+        s->cauchy_mode = 1; s->wrk = s->updatd; s->nseg = 0;
+    } else if (s->sbgnrm <= (T)0) {  // :1245-1249
+        s->cauchy_mode = 2;
+    } else s->cauchy_mode = 0;
+    s->tsum = (T)0;
+}
+
+// ---------------------------------------------------------------------------
+// START, part 1: errclb (:1601-1643) result.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_errclb(Wk<T> w, Dist<T> dist, i64 index_offset) {
+    __shared__ Red<T> red;
+    site_reduce<T>(w, dist, site_errclb(), &red);
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    i64 k6 = red.iv[0], k7 = red.iv[1];
+    // Each offending i overwrites (task, info, k); the last one wins.  On a shard the
+    // indices are local, so they are globalised by the caller through index_offset.
+    if (dist.R <= 1) { if (k6 >= 0) k6 += index_offset; if (k7 >= 0) k7 += index_offset; }
+    if (k6 >= 0 || k7 >= 0) {
+        if (k6 > k7) { s->task = TK_ERR_NBD; s->info = -6; s->errk = k6 + 1; }
+        else { s->task = TK_ERR_INFEAS; s->info = -7; s->errk = k7 + 1; }
+        s->go = 0;
+    } else if (s->task >= TK_ERR_N) s->go = 0;   // factr < 0 stands when no array error overwrites it
+}
+
+// START, part 2: active (:965-1040) flags; then start() (:884-890).
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_active(Wk<T> w, Dist<T> dist) {
+    __shared__ Red<T> red;
+    if (!w.s->go) return;
+    site_reduce<T>(w, dist, site_active(), &red);
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    s->nbdd = red.iv[0];
+    s->prjctd = red.iv[1] > 0; s->cnstnd = red.iv[2] > 0; s->boxed = !(red.iv[3] > 0);
+    s->task = TK_FG_START;
+    s->go = 0;
+}
+
+// ---------------------------------------------------------------------------
+// FG_START entry (:579-596): sbgnrm, first termination test, open the body.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_fg_start(Wk<T> w, Dist<T> dist) {
+    __shared__ Red<T> red;
+    site_reduce<T>(w, dist, site_projgr(), &red);
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    s->nfgv = 1;
+    s->sbgnrm = red.rv[0];
+    if (s->sbgnrm <= s->pgtol) { s->task = TK_CONV_PG; s->go = 0; return; }
+    begin_body<T>(s);
+}
+
+// ---------------------------------------------------------------------------
+// NEW_X entry, part 1 (:795-834, :838-839, matupd :2303-2309): termination
+// tests, skip rule, ring pointers.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void s_newx_tests(Wk<T> w) {
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    const T one = (T)1;
+    if (s->sbgnrm <= s->pgtol) { s->task = TK_CONV_PG; s->go = 0; return; }
+    T ddum = dense::tmax(dense::tmax(fabs(s->fold), fabs(s->f)), one);
+    if ((s->fold - s->f) <= s->tol * ddum) {
+        s->task = TK_CONV_F;
+        if (s->iback >= 10) s->info = -5;
+        s->go = 0;
+        return;
+    }
+    if (s->stp == one) { s->dr = s->gd - s->gdold; s->ddum = -s->gdold; }
+    else { s->dr = (s->gd - s->gdold) * s->stp; s->ddum = -s->gdold * s->stp; }
+    if (s->dr <= s->epsmch * s->ddum) {
+        s->nskip = s->nskip + 1; s->updatd = 0; s->do_update = 0;
+    } else {
+        s->updatd = 1; s->iupdat = s->iupdat + 1; s->do_update = 1;
+        const int m = s->m;
+        if (s->iupdat <= m) { s->col = s->iupdat; s->itail = (s->head + s->iupdat - 2) % m + 1; }
+        else { s->itail = s->itail % m + 1; s->head = s->head % m + 1; }
+    }
+}
+
+// NEW_X entry, part 2: matupd's small matrices (:2318-2344) + formt (:1926-1963),
+// then open the body.
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_update_dense(Wk<T> w, Dist<T> dist, int mt) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    if (!s->go) return;
+    const bool upd = s->do_update;
+    if (upd) site_reduce<T>(w, dist, site_update(mt), &red);
+    if (threadIdx.x != 0) return;
+    if (upd) {
+        const int m = s->m, col = s->col;
+        s->rr = red.rv[0];
+        s->theta = s->rr / s->dr;
+        T* sy = s->sy; T* ss = s->ss;
+        if (s->iupdat > m) {  // :2324-2330
+            for (int j = 1; j <= col - 1; ++j) {
+                for (int q = 0; q < j; ++q) ss[q + (j - 1) * m] = ss[(1 + q) + j * m];             // dcopy(j,Ss(2,j+1),Ss(1,j))
+                for (int q = 0; q < col - j; ++q) sy[(j - 1 + q) + (j - 1) * m] = sy[(j + q) + j * m];  // dcopy(col-j,Sy(j+1,j+1),Sy(j,j))
+            }
+        }
+        for (int j = 1; j <= col - 1; ++j) {
+            sy[(col - 1) + (j - 1) * m] = red.rv[1 + (j - 1)];
+            ss[(j - 1) + (col - 1) * m] = red.rv[1 + mt + (j - 1)];
+        }
+        ss[(col - 1) + (col - 1) * m] = (s->stp == (T)1) ? s->dtd : s->stp * s->stp * s->dtd;
+        sy[(col - 1) + (col - 1) * m] = s->dr;
+        int info = dense::formt<T>(m, s->wt, sy, ss, col, s->theta);
+        if (info != 0) reset_memory<T>(s);   // :851-863
+    }
+    begin_body<T>(s);
+}
+
+// Host asked for another pass of the body after a memory reset ("cycle main_loop").
+template <typename T>
+__global__ void s_restart_body(Wk<T> w) {
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    s->go = 1;
+    begin_body<T>(s);
+}
+
+// ---------------------------------------------------------------------------
+// cauchy after the per-variable pass (:1337-1366) and the first-segment exit
+// test (:1384-1416 with iter == 1).
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> dist, int mt) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || s->cauchy_mode != 0) return;
+    site_reduce<T>(w, dist, site_cauchy(mt), &red);
+    if (threadIdx.x != 0) return;
+    const int col = s->col, col2 = 2 * col, m = s->m;
+    const T zero = (T)0, one = (T)1;
+    for (int j = 0; j < col; ++j) { s->p[j] = red.rv[j]; s->p[col + j] = red.rv[mt + j]; }
+    s->f1 = -red.rv[2 * mt];
+    s->bkmin = red.rv[2 * mt + 1];
+    s->ibkmin = red.iv[0];
+    s->nbreak = red.iv[1];
+    s->nfreec = red.iv[2];
+    s->bnded = red.iv[3] > 0;
+    if (s->theta != one) for (int j = 0; j < col; ++j) s->p[col + j] = s->theta * s->p[col + j];  // :1337
+    s->tsum = zero;
+    if (s->nbreak == 0 && s->nfreec == 0) return;   // d is the zero vector (:1343-1347); nseg untouched
+    for (int j = 0; j < col2; ++j) s->c[j] = zero;
+    s->f2 = -s->theta * s->f1;
+    s->f2_org = s->f2;
+    if (col > 0) {
+        int info = dense::bmv<T>(m, s->sy, s->wt, col, s->p, s->v);
+        if (info != 0) {   // :620-635
+            reset_memory<T>(s);
+            s->restart = 1; s->in_body = 0;
+            return;
+        }
+        s->f2 = s->f2 - dense::ddot<T>(col2, s->v, s->p);
+    }
+    s->dtm = -s->f1 / s->f2;
+    s->nseg = 1;
+    if (s->nbreak != 0 && !(s->dtm < s->bkmin)) {
+        // the first breakpoint is reached: the sorted walk takes over
+        s->need_walk = 1;
+        for (int j = 0; j < col2; ++j) { s->p0[j] = s->p[j]; s->walkA[j] = zero; s->walkB[j] = zero; }
+        s->walk_f1 = s->f1; s->walk_f2 = s->f2; s->walk_tlast = zero;
+        s->walk_J = -1; s->walk_done = 0;
+        return;
+    }
+    if (s->dtm <= zero) s->dtm = zero;   // :1509
+    s->tsum = s->tsum + s->dtm;
+    if (col > 0) dense::daxpy<T>(col2, s->dtm, s->p, s->c);  // :1526
+}
+
+// ---------------------------------------------------------------------------
+// after freev (:638-648): counters, wrk, what of the subspace phase runs.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_freev(Wk<T> w, Dist<T> dist, i64 n_global) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body) return;
+    const int mode = s->cauchy_mode;
+    if (mode != 1) site_reduce<T>(w, dist, site_freev(), &red);
+    if (threadIdx.x != 0) return;
+    if (mode != 1) {
+        s->nintol = s->nintol + s->nseg;
+        s->nfree = red.iv[0];
+        s->nenter = red.iv[1];
+        s->nleave = red.iv[2];
+        s->wrk = (s->nleave > 0) || (s->nenter > 0) || s->updatd;
+        s->nact = n_global - s->nfree;
+    }
+    s->do_subspace = !(s->nfree == 0 || s->col == 0);
+    s->do_formk = s->do_subspace && s->wrk;
+    s->do_delta = s->do_formk && (s->nenter + s->nleave > 0);
+}
+
+// ---------------------------------------------------------------------------
+// formk, everything after the long sums (:1735-1744 shift, :1772-1792 new
+// row/column, :1821-1847 corrections, :1853-1906 assembly and factorisation),
+// then cmprlb's bmv (:1569).
+// delta: [3][2m][2m] enter-minus-leave sums of Wy.Wy, Ws.Ws, Ws.Wy over ring positions
+//        (dE - dL kept separately: delta[0..2] enter, delta[3..5] leave)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist<T> dist, int mt, const T* delta) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_subspace) return;
+    const bool newrow = s->do_formk && s->updatd;
+    if (newrow) site_reduce<T>(w, dist, site_formk(mt), &red);
+    if (threadIdx.x != 0) return;
+    const int m = s->m, col = s->col, m2 = 2 * m;
+    T* wn = s->wn; T* wn1 = s->wn1;
+#define WN(i, j) wn[((i)-1) + ((j)-1) * m2]
+#define WN1(i, j) wn1[((i)-1) + ((j)-1) * m2]
+    if (s->do_formk) {
+        int upcl;
+        if (s->updatd) {
+            if (s->iupdat > m) {   // :1736-1744
+                for (int jy = 1; jy <= m - 1; ++jy) {
+                    int js = m + jy;
+                    for (int q = 0; q < m - jy; ++q) WN1(jy + q, jy) = WN1(jy + 1 + q, jy + 1);
+                    for (int q = 0; q < m - jy; ++q) WN1(js + q, js) = WN1(js + 1 + q, js + 1);
+                    for (int q = 0; q < m - 1; ++q) WN1(m + 1 + q, jy) = WN1(m + 2 + q, jy + 1);
+                }
+            }
+            const int iy = col, is = m + col;
+            for (int jy = 1; jy <= col; ++jy) {   // :1772-1774
+                const int js = m + jy;
+                WN1(iy, jy) = red.rv[jy - 1];
+                WN1(is, js) = red.rv[mt + jy - 1];
+                WN1(is, jy) = red.rv[2 * mt + jy - 1];
+            }
+            for (int i = 1; i <= col; ++i) WN1(m + i, col) = red.rv[3 * mt + i - 1];   // :1792
+            upcl = col - 1;
+        } else upcl = col;
+        if (s->do_delta) {
+            // delta layout: block b in 0..5, entry (i,j) ring positions, leading dimension LB_MMAX
+            const T* eYY = delta + 0 * LB_MMAX * LB_MMAX; const T* eSS = delta + 1 * LB_MMAX * LB_MMAX;
+            const T* eSY = delta + 2 * LB_MMAX * LB_MMAX; const T* lYY = delta + 3 * LB_MMAX * LB_MMAX;
+            const T* lSS = delta + 4 * LB_MMAX * LB_MMAX; const T* lSY = delta + 5 * LB_MMAX * LB_MMAX;
+            for (int iy = 1; iy <= upcl; ++iy) {   // :1802-1826
+                const int is = m + iy;
+                for (int jy = 1; jy <= iy; ++jy) {
+                    const int js = m + jy;
+                    const int e = (iy - 1) + (jy - 1) * LB_MMAX;
+                    WN1(iy, jy) = WN1(iy, jy) + eYY[e] - lYY[e];
+                    WN1(is, js) = WN1(is, js) - eSS[e] + lSS[e];
+                }
+            }
+            for (int is = m + 1; is <= m + upcl; ++is) {   // :1830-1851
+                for (int jy = 1; jy <= upcl; ++jy) {
+                    const int e = (is - m - 1) + (jy - 1) * LB_MMAX;
+                    if (is <= jy + m) WN1(is, jy) = WN1(is, jy) + eSY[e] - lSY[e];
+                    else WN1(is, jy) = WN1(is, jy) - eSY[e] + lSY[e];
+                }
+            }
+        }
+        const T theta = s->theta;
+        for (int iy = 1; iy <= col; ++iy) {   // :1857-1873
+            const int is = col + iy, is1 = m + iy;
+            for (int jy = 1; jy <= iy; ++jy) {
+                const int js = col + jy, js1 = m + jy;
+                WN(jy, iy) = WN1(iy, jy) / theta;
+                WN(js, is) = WN1(is1, js1) * theta;
+            }
+            for (int jy = 1; jy <= iy - 1; ++jy) WN(jy, is) = -WN1(is1, jy);
+            for (int jy = iy; jy <= col; ++jy) WN(jy, is) = WN1(is1, jy);
+            WN(iy, iy) = WN(iy, iy) + s->sy[(iy - 1) + (iy - 1) * m];
+        }
+        int info = dense::dpofa<T>(wn, m2, col);
+        if (info != 0) info = -1;
+        else {
+            const int col2 = 2 * col;
+            for (int js = col + 1; js <= col2; ++js) dense::dtrsl<T>(wn, m2, col, &WN(1, js), 11);
+            for (int is = col + 1; is <= col2; ++is)
+                for (int js = is; js <= col2; ++js)
+                    WN(is, js) = WN(is, js) + dense::ddot<T>(col, &WN(1, is), &WN(1, js));
+            info = dense::dpofa<T>(&WN(col + 1, col + 1), m2, col);
+            if (info != 0) info = -2;
+        }
+        if (info != 0) {   // :666-682
+            reset_memory<T>(s);
+            s->restart = 1; s->in_body = 0;
+            return;
+        }
+    }
+#undef WN
+#undef WN1
+    // cmprlb :1569 (not needed on the unconstrained shortcut :1560-1563)
+    if (!(!s->cnstnd && col > 0)) {
+        int info = dense::bmv<T>(m, s->sy, s->wt, col, s->c, s->a);
+        if (info != 0) {   // info = -8 -> :694-710
+            reset_memory<T>(s);
+            s->restart = 1; s->in_body = 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// subsm: wv = K^{-1} wv (:2751-2766)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_dense(Wk<T> w, Dist<T> dist, int mt) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_subspace) return;
+    site_reduce<T>(w, dist, site_wv(mt), &red);
+    if (threadIdx.x != 0) return;
+    const int m = s->m, col = s->col, m2 = 2 * m, col2 = 2 * col;
+    for (int i = 0; i < col; ++i) { s->wv[i] = red.rv[i]; s->wv[col + i] = s->theta * red.rv[mt + i]; }
+    int info = dense::dtrsl<T>(s->wn, m2, col2, s->wv, 11);
+    if (info == 0) {
+        for (int i = 0; i < col; ++i) s->wv[i] = -s->wv[i];
+        info = dense::dtrsl<T>(s->wn, m2, col2, s->wv, 1);
+    }
+    if (info != 0) {   // :694-710
+        reset_memory<T>(s);
+        s->restart = 1; s->in_body = 0; s->do_subspace = 0;
+    }
+}
+
+// subsm: projection outcome (:2820-2828)
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_post(Wk<T> w, Dist<T> dist) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_subspace) return;
+    site_reduce<T>(w, dist, site_subsm(), &red);
+    if (threadIdx.x != 0) return;
+    s->iword = red.iv[0] > 0 ? 1 : 0;
+    s->dd_p = red.rv[0];
+    s->do_backtrack = (s->iword == 1 && s->dd_p > (T)0);
+}
+
+// subsm: backtrack step length (:2836-2863)
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_bt(Wk<T> w, Dist<T> dist, i64 index_offset) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_backtrack) return;
+    site_reduce<T>(w, dist, site_bt(), &red);
+    if (threadIdx.x != 0) return;
+    T alpha = (T)1; i64 ibd = -1;
+    if (red.rv[0] < alpha) { alpha = red.rv[0]; ibd = red.iv[0]; }
+    s->alpha = alpha;
+    s->ibd = ibd;   // global index when sharded (the kernel globalises), local otherwise
+    (void)index_offset;
+}
+
+// ---------------------------------------------------------------------------
+// lnsrlb first entry (:2196-2273) and mainlb's handling of its outcome (:734-773)
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ inline void ls_failure(DevState<T>* s, bool at_first_entry) {
+    // :734-769 ; x = t, g = r, f = fold
+    if (!at_first_entry) s->do_restore = 1;   // at the first entry x, g are still the old iterate
+    s->do_step = 0;
+    s->f = s->fold;
+    if (s->col == 0) {
+        if (s->info == 0) { s->info = -9; s->nfgv -= 1; s->ifun -= 1; s->iback -= 1; }
+        s->task = TK_ABNORMAL;
+        s->iter += 1;
+        s->go = 0; s->in_body = 0;
+    } else {
+        if (s->info == 0) s->nfgv -= 1;
+        reset_memory<T>(s);
+        s->task = TK_RESTART;
+        s->restart = 1; s->in_body = 0;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_init(Wk<T> w, Dist<T> dist) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body) return;
+    site_reduce<T>(w, dist, site_lsinit(), &red);
+    if (threadIdx.x != 0) return;
+    const T zero = (T)0, one = (T)1, big = (T)1.0e+10, ftol = (T)1.0e-3, gtol = (T)0.9, xtol = (T)0.1;
+    s->dtd = red.rv[0];
+    s->dnorm = sqrt(s->dtd);
+    s->stpmx = big;
+    if (s->cnstnd) {
+        if (s->iter == 0) s->stpmx = one;
+        else s->stpmx = dense::tmin(big, red.rv[2]);
+    }
+    if (s->iter == 0 && !s->boxed) s->stp = dense::tmin(one / s->dnorm, s->stpmx);
+    else s->stp = one;
+    s->fold = s->f;
+    s->ifun = 0; s->iback = 0; s->csave = CS_START;
+    s->gd = red.rv[1];
+    s->gdold = s->gd;
+    if (s->gd >= zero) {   // :2247-2253
+        s->info = -4;
+        ls_failure<T>(s, true);
+        return;
+    }
+    dense::dcsrch<T>(s->f, s->gd, s->stp, ftol, gtol, xtol, zero, s->stpmx, s->csave, s->brackt, s->stage, s->ls);
+    s->xstep = s->stp * s->dnorm;
+    if (s->csave != CS_CONV && !cs_is_warn(s->csave)) {
+        s->task = TK_FG_LNSRCH;
+        s->ifun += 1; s->nfgv += 1; s->iback = s->ifun - 1;
+        s->do_step = 1;
+        s->go = 0; s->in_body = 0;   // return to the caller for f and g
+    } else {
+        // cannot happen on the first entry (dcsrch 'START' returns 'FG' or 'ERROR')
+        s->task = TK_NEW_X; s->iter += 1; s->go = 0; s->in_body = 0;
+    }
+}
+
+// lnsrlb re-entry (:2244-2273) and the outcome (:734-788)
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_trial(Wk<T> w, Dist<T> dist) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    site_reduce<T>(w, dist, site_lstrial(), &red);
+    if (threadIdx.x != 0) return;
+    const T zero = (T)0, ftol = (T)1.0e-3, gtol = (T)0.9, xtol = (T)0.1;
+    s->gd = red.rv[0];
+    if (s->ifun == 0) {   // only after a dcsrch input error on the first entry; kept for fidelity
+        s->gdold = s->gd;
+        if (s->gd >= zero) { s->info = -4; ls_failure<T>(s, false); return; }
+    }
+    dense::dcsrch<T>(s->f, s->gd, s->stp, ftol, gtol, xtol, zero, s->stpmx, s->csave, s->brackt, s->stage, s->ls);
+    s->xstep = s->stp * s->dnorm;
+    bool more = (s->csave != CS_CONV && !cs_is_warn(s->csave));
+    if (more) {
+        s->task = TK_FG_LNSRCH;
+        s->ifun += 1; s->nfgv += 1; s->iback = s->ifun - 1;
+    } else s->task = TK_NEW_X;
+    if (s->info != 0 || s->iback >= 20) {
+        ls_failure<T>(s, false);
+        return;
+    }
+    if (more) { s->do_step = 1; s->go = 0; return; }
+    // accepted: NEW_X (:775-787)
+    s->iter += 1;
+    s->sbgnrm = red.rv[1];
+    s->go = 0;
+}
+
+// clear the per-call flags at the start of every setulb call
+template <typename T>
+__global__ void s_call_begin(Wk<T> w, T f, int entry_task) {
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    s->go = 1; s->in_body = 0; s->restart = 0; s->need_walk = 0;
+    s->do_step = 0; s->do_restore = 0; s->do_update = 0;
+    s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0;
+    s->f = f;
+    (void)entry_task;
+}
+
+// START: initialise the state block (:436-480)
+template <typename T>
+__global__ void s_start(Wk<T> w, T factr, T pgtol, int host_err_task) {
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    const T zero = (T)0;
+    s->go = 1; s->in_body = 0; s->restart = 0; s->need_walk = 0; s->cauchy_mode = 0;
+    s->do_subspace = s->do_formk = s->do_delta = s->do_backtrack = s->do_update = s->do_step = s->do_restore = 0;
+    s->task = TK_START; s->csave = CS_BLANK; s->info = 0;
+    s->col = 0; s->head = 1; s->theta = (T)1; s->iupdat = 0; s->updatd = 0;
+    s->iback = 0; s->itail = 0; s->iword = 0; s->nact = 0; s->nleave = 0; s->nenter = 0;
+    s->fold = zero; s->dnorm = zero; s->gd = zero; s->stpmx = zero; s->sbgnrm = zero; s->stp = zero;
+    s->gdold = zero; s->dtd = zero; s->xstep = zero;
+    s->iter = 0; s->nfgv = 0; s->nseg = 0; s->nintol = 0; s->nskip = 0; s->nfree = w.n; s->ifun = 0;
+    s->epsmch = Real<T>::eps();
+    s->tol = factr * s->epsmch;
+    s->pgtol = pgtol; s->factr = factr;
+    s->brackt = 0; s->stage = 0;
+    s->prjctd = s->cnstnd = s->boxed = 0; s->wrk = 0; s->bnded = 0;
+    s->errk = 0; s->nbdd = 0; s->n = w.n; s->m = w.m;
+    s->nbreak = 0; s->nfreec = 0; s->ibkmin = 0; s->ibd = -1; s->walk_J = -1; s->walk_done = 0; s->n_el = 0;
+    for (int q = 0; q < 13; ++q) s->ls[q] = zero;
+    s->f = zero; s->rr = zero; s->dr = zero; s->ddum = zero; s->tsum = zero; s->dtm = zero;
+    if (host_err_task != 0) { s->task = host_err_task; }   // n<=0 / m<=0 / factr<0 (:1618-1620); array errors overwrite
+}

@@ -1,0 +1,743 @@
+// Streaming (HBM-bound) kernels of one L-BFGS-B iteration.  One pass over the
+// variables each, 128-bit loads, fixed-shape block reductions (common.cuh), no
+// floating-point atomics.  Every kernel is launched with LBFGSB_GRID blocks of
+// LBFGSB_BLOCK threads and predicates itself on the device state block, so the
+// host can enqueue a whole setulb call without reading anything back.
+//
+// Each kernel names the reference loop(s) it replaces (src/lbfgsb.f90).
+#pragma once
+#include "common.cuh"
+
+template <typename T>
+struct Wk {               // workspace + user vectors of one problem (device pointers)
+    i64 n, ldw;           // variables; leading dimension of ws/wy (multiple of 32)
+    int m;
+    T *ws, *wy;           // S, Y histories, column-major [m][ldw]        (:390-391)
+    T *z, *r, *d, *t, *xp;  // n-vectors of mainlb                         (:382-388)
+    int* iwhere;          // (:348-355)
+    unsigned char* state; // bit0: free at the GCP (freev :2047); bit1: free at the previous freev
+    T* part;              // [LB_KMAX][GRID] block partials
+    i64* ipart;           // [LB_IMAX][GRID]
+    DevState<T>* s;
+    T* x; const T* l; const T* u; const int* nbd; T* g;   // caller's vectors
+};
+
+#define LB_SLOT(part, k) ((part) + (i64)(k) * LBFGSB_GRID)
+#define LB_INF(T) ((T)INFINITY)
+#define LB_I64MAX 0x7fffffffffffffffLL
+
+// ---------------------------------------------------------------------------
+// errclb (:1601-1643): last offending index of each error kind.
+// ipart slot 0: max index with invalid nbd (-1 none); slot 1: max index with l>u.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_errclb(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    i64 k6 = -1, k7 = -1;
+    LB_FOR_TILES(T, w.n, base) {
+        T l[VEC], u[VEC]; int nb[VEC];
+        ldv<T>(w.l, base, w.n, l); ldv<T>(w.u, base, w.n, u); ldvi<T>(w.nbd, base, w.n, nb);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            i64 i = base + v;
+            if (i < w.n) {
+                if (nb[v] < 0 || nb[v] > 3) k6 = i;
+                if (nb[v] == 2 && l[v] > u[v]) k7 = i;
+            }
+        }
+    }
+    i64 m6 = k6, m7 = k7;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        i64 o6 = shfl_xor_t<i64>(m6, off), o7 = shfl_xor_t<i64>(m7, off);
+        m6 = o6 > m6 ? o6 : m6; m7 = o7 > m7 ? o7 : m7;
+    }
+    __shared__ i64 s6[LBFGSB_BLOCK / 32], s7[LBFGSB_BLOCK / 32];
+    if ((threadIdx.x & 31) == 0) { s6[threadIdx.x >> 5] = m6; s7[threadIdx.x >> 5] = m7; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < LBFGSB_BLOCK / 32; ++q) { m6 = s6[q] > m6 ? s6[q] : m6; m7 = s7[q] > m7 ? s7[q] : m7; }
+        LB_SLOT(w.ipart, 0)[blockIdx.x] = m6;
+        LB_SLOT(w.ipart, 1)[blockIdx.x] = m7;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// active (:965-1040): project x into the box, initialise iwhere, flags.
+// ipart: 0 nbdd (sum), 1 prjctd (sum>0), 2 cnstnd (sum>0), 3 not-boxed (sum>0)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_active(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    if (!w.s->go) return;
+    __shared__ i64 smi[LBFGSB_BLOCK / 32];
+    i64 nbdd = 0, prj = 0, cns = 0, nbx = 0;
+    LB_FOR_TILES(T, w.n, base) {
+        T x[VEC], l[VEC], u[VEC]; int nb[VEC], iw[VEC], st[VEC];
+        ldv<T>(w.x, base, w.n, x); ldv<T>(w.l, base, w.n, l); ldv<T>(w.u, base, w.n, u);
+        ldvi<T>(w.nbd, base, w.n, nb);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            iw[v] = 0; st[v] = 3;
+            if (base + v < w.n) {
+                if (nb[v] > 0) {
+                    if (nb[v] <= 2 && x[v] <= l[v]) {
+                        if (x[v] < l[v]) { prj = 1; x[v] = l[v]; }
+                        nbdd++;
+                    } else if (nb[v] >= 2 && x[v] >= u[v]) {
+                        if (x[v] > u[v]) { prj = 1; x[v] = u[v]; }
+                        nbdd++;
+                    }
+                }
+                if (nb[v] != 2) nbx = 1;
+                if (nb[v] == 0) iw[v] = -1;
+                else {
+                    cns = 1;
+                    iw[v] = (nb[v] == 2 && u[v] - l[v] <= (T)0) ? 3 : 0;
+                }
+            }
+        }
+        stv<T>(w.x, base, w.n, x);
+        stvi<T>(w.iwhere, base, w.n, iw);
+        stvb<T>(w.state, base, w.n, st);
+    }
+    i64 r0 = block_isum(nbdd, smi), r1 = block_isum(prj, smi), r2 = block_isum(cns, smi), r3 = block_isum(nbx, smi);
+    if (threadIdx.x == 0) {
+        LB_SLOT(w.ipart, 0)[blockIdx.x] = r0; LB_SLOT(w.ipart, 1)[blockIdx.x] = r1;
+        LB_SLOT(w.ipart, 2)[blockIdx.x] = r2; LB_SLOT(w.ipart, 3)[blockIdx.x] = r3;
+    }
+}
+
+// projected gradient of one variable (projgr :2611-2619)
+template <typename T>
+__device__ __forceinline__ T projg_one(T x, T g, T l, T u, int nb) {
+    T gi = g;
+    if (nb != 0) {
+        if (gi < (T)0) { if (nb >= 2) gi = dense::tmax(x - u, gi); }
+        else           { if (nb <= 2) gi = dense::tmin(x - l, gi); }
+    }
+    return fabs(gi);
+}
+
+// ---------------------------------------------------------------------------
+// projgr (:2594-2622).  part slot 0: max |proj g|.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_projgr(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    if (!w.s->go) return;
+    __shared__ T sm[LBFGSB_BLOCK / 32];
+    T acc = (T)0;
+    LB_FOR_TILES(T, w.n, base) {
+        T x[VEC], l[VEC], u[VEC], g[VEC]; int nb[VEC];
+        ldv<T>(w.x, base, w.n, x); ldv<T>(w.g, base, w.n, g); ldv<T>(w.l, base, w.n, l);
+        ldv<T>(w.u, base, w.n, u); ldvi<T>(w.nbd, base, w.n, nb);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            if (base + v < w.n) acc = dense::tmax(acc, projg_one<T>(x[v], g[v], l[v], u[v], nb[v]));
+    }
+    T r = block_max<T>(acc, sm);
+    if (threadIdx.x == 0) LB_SLOT(w.part, 0)[blockIdx.x] = r;
+}
+
+// ---------------------------------------------------------------------------
+// cauchy, per-variable pass (:1270-1341): classify iwhere, Cauchy direction d,
+// f1 = -sum d^2, p = W'd, smallest breakpoint; xcp = x.
+// part: [0,MT) sum Wy(:,j) d ; [MT,2MT) sum Ws(:,j) d ; 2MT: sum d^2 ; 2MT+1: bkmin
+// ipart: 0 argmin variable ; 1 nbreak ; 2 count of moving variables without breakpoint ;
+//        3 bnded (min over blocks)
+// ---------------------------------------------------------------------------
+template <typename T, int MT>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_cauchy_classify(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body) return;
+    const int mode = s->cauchy_mode;
+    const i64 n = w.n;
+    if (mode != 0) {  // xcp = x only (:609 or :1247)
+        LB_FOR_TILES(T, n, base) {
+            T x[VEC];
+            ldv<T>(w.x, base, n, x);
+            stv<T>(w.z, base, n, x);
+        }
+        return;
+    }
+    const int col = s->col, m = s->m, head0 = s->head - 1;
+    __shared__ T sm[(2 * MT + 1) * (LBFGSB_BLOCK / 32)];
+    __shared__ T smv[LBFGSB_BLOCK / 32];
+    __shared__ i64 smi[LBFGSB_BLOCK / 32];
+    T acc[2 * MT + 1];
+#pragma unroll
+    for (int k = 0; k < 2 * MT + 1; ++k) acc[k] = (T)0;
+    T bk = LB_INF(T);
+    i64 ibk = LB_I64MAX, nbr = 0, nfc = 0, bnd = 1;
+    LB_FOR_TILES_NU(T, n, base) {
+        T x[VEC], l[VEC], u[VEC], g[VEC], d[VEC]; int nb[VEC], iw[VEC];
+        ldv<T>(w.x, base, n, x); ldv<T>(w.g, base, n, g); ldv<T>(w.l, base, n, l);
+        ldv<T>(w.u, base, n, u); ldvi<T>(w.nbd, base, n, nb); ldvi<T>(w.iwhere, base, n, iw);
+        bool anymv = false;
+        bool mv[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            mv[v] = false; d[v] = (T)0;
+            if (base + v < n) {
+                const T neggi = -g[v];
+                T tl = (T)0, tu = (T)0;
+                if (iw[v] != 3 && iw[v] != -1) {
+                    if (nb[v] <= 2) tl = x[v] - l[v];
+                    if (nb[v] >= 2) tu = u[v] - x[v];
+                    const bool xlower = nb[v] <= 2 && tl <= (T)0;
+                    const bool xupper = nb[v] >= 2 && tu <= (T)0;
+                    iw[v] = 0;
+                    if (xlower) { if (neggi <= (T)0) iw[v] = 1; }
+                    else if (xupper) { if (neggi >= (T)0) iw[v] = 2; }
+                    else { if (fabs(neggi) <= (T)0) iw[v] = -3; }
+                }
+                if (iw[v] == 0 || iw[v] == -1) {
+                    mv[v] = true; anymv = true;
+                    d[v] = neggi;
+                    acc[2 * MT] = acc[2 * MT] + neggi * neggi;
+                    T tb; bool hasb = false;
+                    if (nb[v] <= 2 && nb[v] != 0 && neggi < (T)0) { tb = tl / (-neggi); hasb = true; }
+                    else if (nb[v] >= 2 && neggi > (T)0) { tb = tu / neggi; hasb = true; }
+                    if (hasb) {
+                        nbr++;
+                        if (tb < bk) { bk = tb; ibk = base + v; }   // strict <: lowest index among ties (:1310)
+                    } else {
+                        nfc++;
+                        if (fabs(neggi) > (T)0) bnd = 0;
+                    }
+                }
+            }
+        }
+        stvi<T>(w.iwhere, base, n, iw);
+        stv<T>(w.d, base, n, d);
+        stv<T>(w.z, base, n, x);
+        if (col > 0 && anymv) {
+            int pj = head0;
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                if (j < col) {
+                    T wy[VEC], wsv[VEC];
+                    ldv<T>(w.wy + (i64)pj * w.ldw, base, n, wy);
+                    ldv<T>(w.ws + (i64)pj * w.ldw, base, n, wsv);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+                        if (mv[v]) {
+                            acc[j] = acc[j] + wy[v] * d[v];
+                            acc[MT + j] = acc[MT + j] + wsv[v] * d[v];
+                        }
+                    pj = (pj + 1 == m) ? 0 : pj + 1;
+                }
+            }
+        }
+    }
+    block_sum_store<T, 2 * MT + 1>(acc, 2 * MT + 1, sm, w.part);
+    block_argmin<T>(bk, ibk, smv, smi);
+    i64 r1 = block_isum(nbr, smi), r2 = block_isum(nfc, smi);
+    i64 r3 = -block_isum(bnd ? 0 : 1, smi);  // <0 if any thread saw an unbounded moving variable
+    if (threadIdx.x == 0) {
+        LB_SLOT(w.part, 2 * MT + 1)[blockIdx.x] = bk;
+        LB_SLOT(w.ipart, 0)[blockIdx.x] = ibk;
+        LB_SLOT(w.ipart, 1)[blockIdx.x] = r1;
+        LB_SLOT(w.ipart, 2)[blockIdx.x] = r2;
+        LB_SLOT(w.ipart, 3)[blockIdx.x] = (r3 < 0) ? 0 : 1;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// cauchy tail (:1515) fused with freev (:1980-2059): xcp += tsum*d, then count
+// free / entering / leaving variables and refresh the per-variable state byte.
+// The reference's index lists are not materialised: every later "over the free
+// set" loop is a masked pass over the variables.
+// ipart: 0 nfree ; 1 nenter ; 2 nleave
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_gcp_freev(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || s->cauchy_mode == 1) return;
+    const i64 n = w.n;
+    const T tsum = s->tsum;
+    const bool axpy = (s->cauchy_mode == 0) && (tsum != (T)0);   // daxpy early-out (:49-50)
+    const bool cnt = (s->iter > 0 && s->cnstnd);
+    __shared__ i64 smi[LBFGSB_BLOCK / 32];
+    i64 nfr = 0, nen = 0, nle = 0;
+    LB_FOR_TILES(T, n, base) {
+        int iw[VEC], st[VEC];
+        ldvi<T>(w.iwhere, base, n, iw); ldvb<T>(w.state, base, n, st);
+        if (axpy) {
+            T d[VEC], z[VEC];
+            ldv<T>(w.d, base, n, d); ldv<T>(w.z, base, n, z);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) z[v] = z[v] + tsum * d[v];
+            stv<T>(w.z, base, n, z);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            if (base + v < n) {
+                const int fr = iw[v] <= 0 ? 1 : 0;
+                const int old = st[v] & 1;
+                nfr += fr;
+                if (cnt) { nen += (fr && !old); nle += (!fr && old); }
+                st[v] = fr | ((cnt ? old : fr) << 1);
+            }
+        }
+        stvb<T>(w.state, base, n, st);
+    }
+    i64 r0 = block_isum(nfr, smi), r1 = block_isum(nen, smi), r2 = block_isum(nle, smi);
+    if (threadIdx.x == 0) {
+        LB_SLOT(w.ipart, 0)[blockIdx.x] = r0; LB_SLOT(w.ipart, 1)[blockIdx.x] = r1;
+        LB_SLOT(w.ipart, 2)[blockIdx.x] = r2;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// formk, new row/column of WN1 (:1756-1793): one pass over all rows of S,Y.
+// part: [0,MT) A_j = sum_free Wy_last*Wy_j ; [MT,2MT) B_j = sum_act Ws_last*Ws_j ;
+//       [2MT,3MT) C_j = sum_act Ws_last*Wy_j ; [3MT,4MT) D_j = sum_free Ws_j*Wy_last
+// ---------------------------------------------------------------------------
+template <typename T, int MT>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_formk_gram(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_formk || !s->updatd) return;
+    const i64 n = w.n;
+    const int col = s->col, m = s->m, head0 = s->head - 1;
+    const int lastp = (head0 + col - 1) % m;
+    __shared__ T sm[4 * MT * (LBFGSB_BLOCK / 32)];
+    T acc[4 * MT];
+#pragma unroll
+    for (int k = 0; k < 4 * MT; ++k) acc[k] = (T)0;
+    LB_FOR_TILES_NU(T, n, base) {
+        int st[VEC];
+        ldvb<T>(w.state, base, n, st);
+        T wyl[VEC], wsl[VEC];
+        ldv<T>(w.wy + (i64)lastp * w.ldw, base, n, wyl);
+        ldv<T>(w.ws + (i64)lastp * w.ldw, base, n, wsl);
+        int pj = head0;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+            if (j < col) {
+                T wy[VEC], wsv[VEC];
+                ldv<T>(w.wy + (i64)pj * w.ldw, base, n, wy);
+                ldv<T>(w.ws + (i64)pj * w.ldw, base, n, wsv);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    if (base + v < n) {
+                        if (st[v] & 1) {
+                            acc[j] = acc[j] + wyl[v] * wy[v];
+                            acc[3 * MT + j] = acc[3 * MT + j] + wsv[v] * wyl[v];
+                        } else {
+                            acc[MT + j] = acc[MT + j] + wsl[v] * wsv[v];
+                            acc[2 * MT + j] = acc[2 * MT + j] + wsl[v] * wy[v];
+                        }
+                    }
+                }
+                pj = (pj + 1 == m) ? 0 : pj + 1;
+            }
+        }
+    }
+    block_sum_store<T, 4 * MT>(acc, 4 * MT, sm, w.part);
+}
+
+// ---------------------------------------------------------------------------
+// cmprlb (:1565-1583) fused with the first half of subsm (:2742-2754):
+//   r_k = -theta (z_k - x_k) - g_k + sum_j Wy(k,j) a1_j + Ws(k,j) a2_j   (free k)
+//   wv  = W' Z r
+// r is kept by variable (the reference keeps it compact over the free list).
+// part: [0,MT) sum Wy(:,j) r ; [MT,2MT) sum Ws(:,j) r
+// ---------------------------------------------------------------------------
+template <typename T, int MT>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_cmprlb_wv(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_subspace) return;
+    const i64 n = w.n;
+    const int col = s->col, m = s->m, head0 = s->head - 1;
+    const T theta = s->theta;
+    const bool uc = (!s->cnstnd && col > 0);   // :1560-1563
+    __shared__ T sm[2 * MT * (LBFGSB_BLOCK / 32)];
+    T a1[MT], a2[MT], acc[2 * MT];
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+        a1[j] = (j < col) ? s->a[j] : (T)0;
+        a2[j] = (j < col) ? theta * s->a[col + j] : (T)0;
+        acc[j] = (T)0; acc[MT + j] = (T)0;
+    }
+    LB_FOR_TILES_NU(T, n, base) {
+        int st[VEC];
+        ldvb<T>(w.state, base, n, st);
+        bool fr[VEC]; bool any = false;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { fr[v] = (base + v < n) && (st[v] & 1); any |= fr[v]; }
+        if (!any) continue;
+        T z[VEC], x[VEC], g[VEC], r[VEC];
+        ldv<T>(w.g, base, n, g);
+        if (!uc) { ldv<T>(w.z, base, n, z); ldv<T>(w.x, base, n, x); }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = uc ? -g[v] : (-theta * (z[v] - x[v]) - g[v]);
+        T wyv[MT][VEC], wsv[MT][VEC];
+        int pj = head0;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+            if (j < col) {
+                ldv<T>(w.wy + (i64)pj * w.ldw, base, n, wyv[j]);
+                ldv<T>(w.ws + (i64)pj * w.ldw, base, n, wsv[j]);
+                if (!uc) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) r[v] = r[v] + wyv[j][v] * a1[j] + wsv[j][v] * a2[j];
+                }
+                pj = (pj + 1 == m) ? 0 : pj + 1;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+            if (j < col) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (fr[v]) {
+                        acc[j] = acc[j] + wyv[j][v] * r[v];
+                        acc[MT + j] = acc[MT + j] + wsv[j][v] * r[v];
+                    }
+            }
+        }
+        // r of a non-free variable is never read (every later pass masks on the free set),
+        // so the whole vector is stored: no partial-sector writes.
+        stv<T>(w.r, base, n, r);
+    }
+    block_sum_store<T, 2 * MT>(acc, 2 * MT, sm, w.part);
+}
+
+// ---------------------------------------------------------------------------
+// subsm second half (:2770-2827): Newton direction on the free set, projected
+// step, xp = xcp backup, and the directional derivative dd_p over all variables.
+// part: 0 dd_p.  ipart: 0 iword (sum>0)
+// ---------------------------------------------------------------------------
+template <typename T, int MT>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_subsm_step(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_subspace) return;
+    const i64 n = w.n;
+    const int col = s->col, m = s->m, head0 = s->head - 1;
+    const T theta = s->theta, rtheta = (T)1 / theta;
+    __shared__ T sm[LBFGSB_BLOCK / 32];
+    __shared__ i64 smi[LBFGSB_BLOCK / 32];
+    T wv1[MT], wv2[MT];
+#pragma unroll
+    for (int j = 0; j < MT; ++j) { wv1[j] = (j < col) ? s->wv[j] : (T)0; wv2[j] = (j < col) ? s->wv[col + j] : (T)0; }
+    T acc[1]; acc[0] = (T)0;
+    i64 iwd = 0;
+    LB_FOR_TILES_NU(T, n, base) {
+        int st[VEC];
+        ldvb<T>(w.state, base, n, st);
+        bool fr[VEC]; bool any = false;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { fr[v] = (base + v < n) && (st[v] & 1); any |= fr[v]; }
+        T z[VEC], x[VEC], g[VEC];
+        ldv<T>(w.z, base, n, z); ldv<T>(w.x, base, n, x); ldv<T>(w.g, base, n, g);
+        stv<T>(w.xp, base, n, z);   // :2787
+        if (any) {
+            T dk[VEC], l[VEC], u[VEC]; int nb[VEC];
+            ldv<T>(w.r, base, n, dk); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
+            ldvi<T>(w.nbd, base, n, nb);
+            int pj = head0;
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                if (j < col) {
+                    T wy[VEC], wsv[VEC];
+                    ldv<T>(w.wy + (i64)pj * w.ldw, base, n, wy);
+                    ldv<T>(w.ws + (i64)pj * w.ldw, base, n, wsv);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) dk[v] = dk[v] + wy[v] * wv1[j] / theta + wsv[v] * wv2[j];
+                    pj = (pj + 1 == m) ? 0 : pj + 1;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                dk[v] = rtheta * dk[v];   // dscal(nsub, one/theta, d) :2780
+                if (fr[v]) {
+                    T xk = z[v];
+                    if (nb[v] != 0) {
+                        if (nb[v] == 1) { z[v] = dense::tmax(l[v], xk + dk[v]); if (z[v] == l[v]) iwd = 1; }
+                        else if (nb[v] == 2) {
+                            xk = dense::tmax(l[v], xk + dk[v]);
+                            z[v] = dense::tmin(u[v], xk);
+                            if (z[v] == l[v] || z[v] == u[v]) iwd = 1;
+                        } else if (nb[v] == 3) { z[v] = dense::tmin(u[v], xk + dk[v]); if (z[v] == u[v]) iwd = 1; }
+                    } else z[v] = xk + dk[v];
+                }
+            }
+            // direction (don't-care on non-free variables) and new point (unchanged there)
+            stv<T>(w.r, base, n, dk);
+            stv<T>(w.z, base, n, z);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            if (base + v < n) acc[0] = acc[0] + (z[v] - x[v]) * g[v];   // :2825-2827
+    }
+    block_sum_store<T, 1>(acc, 1, sm, w.part);
+    i64 r0 = block_isum(iwd, smi);
+    if (threadIdx.x == 0) LB_SLOT(w.ipart, 0)[blockIdx.x] = r0;
+}
+
+// ---------------------------------------------------------------------------
+// subsm backtrack (:2836-2863): largest feasible step along the Newton direction
+// from xp, first binding variable.  part 0: alpha candidate; ipart 0: its variable.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_bt_alpha(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_backtrack) return;
+    const i64 n = w.n;
+    __shared__ T smv[LBFGSB_BLOCK / 32];
+    __shared__ i64 smi[LBFGSB_BLOCK / 32];
+    T best = LB_INF(T); i64 ib = LB_I64MAX;
+    LB_FOR_TILES(T, n, base) {
+        int st[VEC], nb[VEC]; T dk[VEC], xk[VEC], l[VEC], u[VEC];
+        ldvb<T>(w.state, base, n, st); ldvi<T>(w.nbd, base, n, nb);
+        ldv<T>(w.r, base, n, dk); ldv<T>(w.xp, base, n, xk); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            if (base + v < n && (st[v] & 1) && nb[v] != 0) {
+                T cand = LB_INF(T);
+                if (dk[v] < (T)0 && nb[v] <= 2) {
+                    T t2 = l[v] - xk[v];
+                    cand = (t2 >= (T)0) ? (T)0 : t2 / dk[v];
+                } else if (dk[v] > (T)0 && nb[v] >= 2) {
+                    T t2 = u[v] - xk[v];
+                    cand = (t2 <= (T)0) ? (T)0 : t2 / dk[v];
+                }
+                if (cand < best) { best = cand; ib = base + v; }
+            }
+        }
+    }
+    block_argmin<T>(best, ib, smv, smi);
+    if (threadIdx.x == 0) { LB_SLOT(w.part, 0)[blockIdx.x] = best; LB_SLOT(w.ipart, 0)[blockIdx.x] = ib; }
+}
+
+// subsm backtrack apply (:2830, :2865-2879): x = xp + alpha d on the free set,
+// the binding variable pinned to its bound.
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_bt_apply(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_backtrack) return;
+    const i64 n = w.n;
+    const T alpha = s->alpha;
+    const i64 ibd = s->ibd;
+    LB_FOR_TILES(T, n, base) {
+        int st[VEC]; T dk[VEC], xk[VEC], l[VEC], u[VEC];
+        ldvb<T>(w.state, base, n, st);
+        ldv<T>(w.r, base, n, dk); ldv<T>(w.xp, base, n, xk); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            if (base + v < n) {
+                if (st[v] & 1) {
+                    if (alpha < (T)1 && base + v == ibd) {
+                        if (dk[v] > (T)0) { xk[v] = u[v]; dk[v] = (T)0; }
+                        else if (dk[v] < (T)0) { xk[v] = l[v]; dk[v] = (T)0; }
+                    }
+                    xk[v] = xk[v] + alpha * dk[v];
+                }
+            }
+        }
+        stv<T>(w.z, base, n, xk);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// d = z - x (:720-722) fused with the first entry of lnsrlb (:2196-2244):
+// dtd, stpmx candidates, t = x, r = g, gd = g.d
+// part: 0 dtd ; 1 gd ; 2 stpmx candidate (min)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_ls_init(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body) return;
+    const i64 n = w.n;
+    const bool bounds = (s->cnstnd && s->iter != 0);
+    __shared__ T sm[2 * (LBFGSB_BLOCK / 32)];
+    __shared__ T smm[LBFGSB_BLOCK / 32];
+    T acc[2]; acc[0] = (T)0; acc[1] = (T)0;
+    T smx = LB_INF(T);
+    LB_FOR_TILES(T, n, base) {
+        T z[VEC], x[VEC], g[VEC], d[VEC];
+        ldv<T>(w.z, base, n, z); ldv<T>(w.x, base, n, x); ldv<T>(w.g, base, n, g);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            d[v] = z[v] - x[v];
+            if (base + v < n) { acc[0] = acc[0] + d[v] * d[v]; acc[1] = acc[1] + g[v] * d[v]; }
+        }
+        stv<T>(w.d, base, n, d); stv<T>(w.t, base, n, x); stv<T>(w.r, base, n, g);
+        if (bounds) {
+            T l[VEC], u[VEC]; int nb[VEC];
+            ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u); ldvi<T>(w.nbd, base, n, nb);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if (base + v < n && nb[v] != 0) {
+                    const T a1 = d[v];
+                    if (a1 < (T)0 && nb[v] <= 2) {
+                        const T a2 = l[v] - x[v];
+                        const T cand = (a2 >= (T)0) ? (T)0 : a2 / a1;
+                        smx = dense::tmin(smx, cand);
+                    } else if (a1 > (T)0 && nb[v] >= 2) {
+                        const T a2 = u[v] - x[v];
+                        const T cand = (a2 <= (T)0) ? (T)0 : a2 / a1;
+                        smx = dense::tmin(smx, cand);
+                    }
+                }
+            }
+        }
+    }
+    block_sum_store<T, 2>(acc, 2, sm, w.part);
+    T r = block_min<T>(smx, smm);
+    if (threadIdx.x == 0) LB_SLOT(w.part, 2)[blockIdx.x] = r;
+}
+
+// ---------------------------------------------------------------------------
+// lnsrlb trial point (:2264-2270): x = z (stp == 1) or x = stp*d + t.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_ls_step(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->do_step) return;
+    const i64 n = w.n;
+    const T stp = s->stp;
+    if (stp == (T)1) {
+        LB_FOR_TILES(T, n, base) { T z[VEC]; ldv<T>(w.z, base, n, z); stv<T>(w.x, base, n, z); }
+    } else {
+        LB_FOR_TILES(T, n, base) {
+            T d[VEC], t[VEC], x[VEC];
+            ldv<T>(w.d, base, n, d); ldv<T>(w.t, base, n, t);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) x[v] = stp * d[v] + t[v];
+            stv<T>(w.x, base, n, x);
+        }
+    }
+}
+
+// restore the previous iterate (:736-738, :568-570): x = t, g = r
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_restore(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    if (!w.s->do_restore) return;
+    const i64 n = w.n;
+    LB_FOR_TILES(T, n, base) {
+        T t[VEC], r[VEC];
+        ldv<T>(w.t, base, n, t); ldv<T>(w.r, base, n, r);
+        stv<T>(w.x, base, n, t); stv<T>(w.g, base, n, r);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// lnsrlb re-entry (:2244): gd = g.d at the trial point, fused with a
+// speculative projgr (:781) that is used if the line search accepts the point.
+// part: 0 gd ; 1 max |proj g|
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_ls_trial(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    if (!w.s->go) return;
+    const i64 n = w.n;
+    __shared__ T sm[LBFGSB_BLOCK / 32];
+    __shared__ T smm[LBFGSB_BLOCK / 32];
+    T acc[1]; acc[0] = (T)0;
+    T pg = (T)0;
+    LB_FOR_TILES(T, n, base) {
+        T x[VEC], l[VEC], u[VEC], g[VEC], d[VEC]; int nb[VEC];
+        ldv<T>(w.g, base, n, g); ldv<T>(w.d, base, n, d); ldv<T>(w.x, base, n, x);
+        ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u); ldvi<T>(w.nbd, base, n, nb);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            if (base + v < n) {
+                acc[0] = acc[0] + g[v] * d[v];
+                pg = dense::tmax(pg, projg_one<T>(x[v], g[v], l[v], u[v], nb[v]));
+            }
+    }
+    block_sum_store<T, 1>(acc, 1, sm, w.part);
+    T r = block_max<T>(pg, smm);
+    if (threadIdx.x == 0) LB_SLOT(w.part, 1)[blockIdx.x] = r;
+}
+
+// ---------------------------------------------------------------------------
+// y/s preparation (:813-824) fused with matupd (:2313-2338): y = g - r,
+// s = stp*d written straight into the ring columns, rr = y.y, and the new row of
+// S'Y / column of S'S against the col-1 older pairs -- one pass.
+// part: 0 rr ; [1,1+MT) sum s*Wy(:,j) ; [1+MT,1+2MT) sum Ws(:,j)*s   (j = ring position, < col-1)
+// ---------------------------------------------------------------------------
+template <typename T, int MT>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_update(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->do_update) return;
+    const i64 n = w.n;
+    const int col = s->col, m = s->m, head0 = s->head - 1, itail0 = s->itail - 1;
+    const T stp = s->stp;
+    __shared__ T sm[(2 * MT + 1) * (LBFGSB_BLOCK / 32)];
+    T acc[2 * MT + 1];
+#pragma unroll
+    for (int k = 0; k < 2 * MT + 1; ++k) acc[k] = (T)0;
+    T* wsn = w.ws + (i64)itail0 * w.ldw;
+    T* wyn = w.wy + (i64)itail0 * w.ldw;
+    LB_FOR_TILES_NU(T, n, base) {
+        T g[VEC], r[VEC], d[VEC];
+        ldv<T>(w.g, base, n, g); ldv<T>(w.r, base, n, r); ldv<T>(w.d, base, n, d);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            r[v] = g[v] - r[v];
+            if (stp != (T)1) d[v] = stp * d[v];
+            if (base + v < n) acc[0] = acc[0] + r[v] * r[v];
+        }
+        int pj = head0;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+            if (j < col - 1) {
+                T wy[VEC], wsv[VEC];
+                ldv<T>(w.wy + (i64)pj * w.ldw, base, n, wy);
+                ldv<T>(w.ws + (i64)pj * w.ldw, base, n, wsv);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (base + v < n) {
+                        acc[1 + j] = acc[1 + j] + d[v] * wy[v];
+                        acc[1 + MT + j] = acc[1 + MT + j] + wsv[v] * d[v];
+                    }
+                pj = (pj + 1 == m) ? 0 : pj + 1;
+            }
+        }
+        stv<T>(wsn, base, n, d);
+        stv<T>(wyn, base, n, r);
+    }
+    block_sum_store<T, 2 * MT + 1>(acc, 2 * MT + 1, sm, w.part);
+}
+
+// ---------------------------------------------------------------------------
+// Identity of the active set {i : iwhere(i) > 0}: sum of splitmix64(i) mod 2^64
+// (order independent, integer).  ipart 0: hash, 1: count.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long lb_splitmix64(unsigned long long v) {
+    v += 0x9E3779B97F4A7C15ULL;
+    v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    v = (v ^ (v >> 27)) * 0x94D049BB133111EBULL;
+    return v ^ (v >> 31);
+}
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_active_hash(Wk<T> w, i64 index_offset) {
+    constexpr int VEC = Real<T>::VEC;
+    const i64 n = w.n;
+    __shared__ i64 smi[LBFGSB_BLOCK / 32];
+    i64 h = 0, c = 0;
+    LB_FOR_TILES(T, n, base) {
+        int iw[VEC];
+        ldvi<T>(w.iwhere, base, n, iw);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            if (base + v < n && iw[v] > 0) { h += (i64)lb_splitmix64((unsigned long long)(base + v + index_offset)); c++; }
+    }
+    i64 r0 = block_isum(h, smi), r1 = block_isum(c, smi);
+    if (threadIdx.x == 0) { LB_SLOT(w.ipart, 0)[blockIdx.x] = r0; LB_SLOT(w.ipart, 1)[blockIdx.x] = r1; }
+}
