@@ -54,6 +54,8 @@ void lbfgsb_host_release(int32_t* isave);
 /* copies the previous iterate t (= wa(lt:lt+n-1), read by test/driver3.f90:173-175) to the host */
 int lbfgsb_host_previous_x_f64(const int32_t* isave, double* t_out);
 int lbfgsb_host_previous_x_f32(const int32_t* isave, float* t_out);
+/* the device workspace behind a host-twin problem (NULL if none), for the diagnostics of section (4) */
+lbfgsb_dev_t* lbfgsb_host_engine(const int32_t* isave);
 
 /* ---- (2) device-pointer variant --------------------------------------------------------------
  * x, g, l, u, nbd are CUDA device pointers (16-byte aligned); f and the state arrays stay on the

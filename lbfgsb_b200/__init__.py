@@ -1,0 +1,288 @@
+"""lbfgsb_b200 -- host-side mirror of the reference's `setulb` interface over the C ABI.
+
+The product is the CUDA engine in csrc/ behind include/lbfgsb_b200.h.  This module is a thin
+ctypes binding that plays the role of the Fortran module `lbfgsb_module`
+(/root/reference/src/lbfgsb.f90:46-58): it exports
+
+    setulb(n, m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, iprint, csave, lsave, isave, dsave)
+        host arrays (numpy), same argument order and meaning as src/lbfgsb.f90:88-89;
+    setulb_dev(handle, x, l, u, nbd, f, g, factr, pgtol, task, iprint, csave, lsave, isave, dsave)
+        x, l, u, nbd, g are CUDA tensors (device pointers), the state arrays stay on the host.
+
+There is no CPU path: importing works anywhere (so the symbol table can be checked), every
+compute entry point needs a CUDA device and fails loudly without one or without the built
+library.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+SO_PATH = os.path.join(_HERE, "liblbfgsb_b200.so")
+_SOURCES = ["engine.cu", "common.cuh", "kernels_stream.cuh", "kernels_dense.cuh", "cauchy_walk.cuh"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              # no fused multiply-add: the dense 2m x 2m algebra and dcsrch/dcstep must round like the
+              # reference (gfortran x86-64 default has no FMA), see DESIGN.md "Numerics"
+              "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
+
+_LIB = None
+
+
+class LbfgsbB200Error(RuntimeError):
+    pass
+
+
+def _stale():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = [os.path.join(_HERE, "csrc", s) for s in _SOURCES]
+    deps += [os.path.join(_ROOT, "include", h) for h in ("lbfgsb_b200.h", "lbfgsb_b200_shape.h")]
+    return any(os.path.exists(p) and os.path.getmtime(p) > t for p in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/engine.cu for sm_100a into lbfgsb_b200/liblbfgsb_b200.so (in-tree)."""
+    if not (force or _stale()):
+        return SO_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", SO_PATH, os.path.join(_HERE, "csrc", "engine.cu"), "-ldl"]
+    subprocess.check_call(cmd)
+    return SO_PATH
+
+
+_REAL = {np.dtype(np.float64): ("f64", C.c_double), np.dtype(np.float32): ("f32", C.c_float)}
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built (no fallback of any kind)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise LbfgsbB200Error(
+                "lbfgsb_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU path)" % SO_PATH)
+        L = C.CDLL(SO_PATH)
+        L.lbfgsb_b200_last_error.restype = C.c_char_p
+        L.lbfgsb_dev_create.restype = C.c_void_p
+        L.lbfgsb_dev_create.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+        L.lbfgsb_dev_create_sharded.restype = C.c_void_p
+        L.lbfgsb_dev_create_sharded.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                                C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+        L.lbfgsb_dev_destroy.argtypes = [C.c_void_p]
+        L.lbfgsb_host_engine.restype = C.c_void_p
+        L.lbfgsb_host_engine.argtypes = [C.c_void_p]
+        L.lbfgsb_dev_vector.restype = C.c_void_p
+        L.lbfgsb_dev_vector.argtypes = [C.c_void_p, C.c_int32]
+        L.lbfgsb_dev_active_set_hash.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lbfgsb_dev_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lbfgsb_dev_profile.argtypes = [C.c_void_p, C.c_int32]
+        L.lbfgsb_dev_profile_reset.argtypes = [C.c_void_p]
+        L.lbfgsb_dev_profile_read.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lbfgsb_dev_nccl_init.restype = C.c_void_p
+        L.lbfgsb_dev_nccl_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.lbfgsb_dev_nccl_destroy.argtypes = [C.c_void_p]
+        L.lbfgsb_problem_scratch_bytes.restype = C.c_int64
+        for sfx, cr in (("f64", C.c_double), ("f32", C.c_float)):
+            getattr(L, "lbfgsb_setulb_" + sfx).restype = None
+            getattr(L, "lbfgsb_setulb_dev_" + sfx).restype = None
+            getattr(L, "lbfgsb_problem_rosenbrock_" + sfx).argtypes = [
+                C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, cr, cr, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def last_error():
+    return lib().lbfgsb_b200_last_error().decode()
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _check_task(task):
+    s = bytes(task[:60]).decode(errors="replace")
+    if s.startswith("ERROR: CUDA") or s.startswith("ERROR: NO CUDA") or s.startswith("ERROR: INVALID LBFGSB"):
+        raise LbfgsbB200Error(s.rstrip() + " -- " + last_error())
+
+
+def setulb(n, m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, iprint, csave, lsave, isave, dsave,
+           iteration_file=None):
+    """Host twin of the reference's setulb (src/lbfgsb.f90:88-89); numpy arrays, updated in place.
+
+    f is a 1-element array of x's dtype; task/csave are 60-byte uint8 arrays (blank padded);
+    lsave int32[4]; isave int32[44]; dsave real[29].  wa / iwa are accepted for signature
+    compatibility (the workspace lives on the device)."""
+    sfx, cr = _REAL[x.dtype]
+    fn = getattr(lib(), "lbfgsb_setulb_" + sfx)
+    n32, m32, ip = C.c_int32(n), C.c_int32(m), C.c_int32(iprint)
+    fa, pg = cr(factr), cr(pgtol)
+    itf = iteration_file.encode() if iteration_file else None
+    fn(C.byref(n32), C.byref(m32), _p(x), _p(l), _p(u), _p(nbd), _p(f), _p(g), C.byref(fa), C.byref(pg),
+       _p(wa) if wa is not None else None, _p(iwa) if iwa is not None else None, _p(task), C.byref(ip),
+       _p(csave), _p(lsave), _p(isave), _p(dsave), itf, C.c_int32(len(itf) if itf else 0))
+    _check_task(task)
+
+
+class HostSetulb:
+    """Callable with the calling convention of tests/harness.py (same as oracle_py.OracleSetulb)."""
+
+    def __init__(self, dtype=np.float64):
+        self.dtype = np.dtype(dtype)
+        self._isave = None
+
+    def workspace(self, n, m):
+        # the reference's sizes (src/lbfgsb.f90:146-148) are not needed: the state is on the device
+        return np.zeros(1, dtype=self.dtype), np.zeros(1, dtype=np.int32)
+
+    def __call__(self, n, m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, iprint, csave, lsave, isave, dsave):
+        self._isave = isave
+        setulb(n, m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, iprint, csave, lsave, isave, dsave)
+
+    def engine(self):
+        return lib().lbfgsb_host_engine(_p(self._isave))
+
+    def active_set_hash(self, n, iwa):
+        h, c = C.c_uint64(0), C.c_int64(0)
+        e = self.engine()
+        if not e:
+            return None, None
+        if lib().lbfgsb_dev_active_set_hash(e, C.byref(h), C.byref(c)) != 0:
+            raise LbfgsbB200Error(last_error())
+        return h.value, c.value
+
+    def previous_x(self, n):
+        t = np.zeros(n, dtype=self.dtype)
+        fn = lib().lbfgsb_host_previous_x_f64 if self.dtype == np.float64 else lib().lbfgsb_host_previous_x_f32
+        if fn(_p(self._isave), _p(t)) != 0:
+            raise LbfgsbB200Error("no live problem bound to this isave")
+        return t
+
+    def release(self, isave):
+        lib().lbfgsb_host_release(_p(isave))
+
+
+class DeviceProblem:
+    """Device-pointer variant (include/lbfgsb_b200.h section 2): the caller's x, g, l, u, nbd are CUDA
+    tensors; f/g evaluation and the whole iteration stay on the GPU.  `stream` is a raw cudaStream_t
+    (int) or None for the engine's private stream."""
+
+    def __init__(self, n, m, dtype, stream=None, shard=None):
+        import torch
+        self.torch = torch
+        self.n, self.m = int(n), int(m)
+        self.dtype = np.dtype(dtype)
+        kind = 8 if self.dtype == np.float64 else 4
+        if shard is None:
+            self.h = lib().lbfgsb_dev_create(self.n, self.m, kind, stream)
+        else:
+            off, n_global, comm, rank, world = shard
+            self.h = lib().lbfgsb_dev_create_sharded(self.n, off, n_global, self.m, kind, stream, comm, rank, world)
+        if not self.h:
+            raise LbfgsbB200Error("lbfgsb_dev_create failed: " + last_error())
+        self.task = np.full(60, ord(" "), dtype=np.uint8)
+        self.task[:5] = np.frombuffer(b"START", dtype=np.uint8)
+        self.csave = np.full(60, ord(" "), dtype=np.uint8)
+        self.lsave = np.zeros(4, dtype=np.int32)
+        self.isave = np.zeros(44, dtype=np.int32)
+        self.dsave = np.zeros(29, dtype=self.dtype)
+        self.f = np.zeros(1, dtype=self.dtype)
+        sfx, self._cr = _REAL[self.dtype]
+        self._fn = getattr(lib(), "lbfgsb_setulb_dev_" + sfx)
+        self._ip = C.c_int32(-1)
+
+    def task_str(self):
+        return bytes(self.task).decode().rstrip()
+
+    def set_task(self, s):
+        self.task[:] = ord(" ")
+        b = s.encode()
+        self.task[:len(b)] = np.frombuffer(b, dtype=np.uint8)
+
+    def setulb_dev(self, x, l, u, nbd, g, factr, pgtol):
+        fa, pg = self._cr(factr), self._cr(pgtol)
+        self._fn(C.c_void_p(self.h), C.c_void_p(x.data_ptr()), C.c_void_p(l.data_ptr()), C.c_void_p(u.data_ptr()),
+                 C.c_void_p(nbd.data_ptr()), _p(self.f), C.c_void_p(g.data_ptr()), C.byref(fa), C.byref(pg),
+                 _p(self.task), C.byref(self._ip), _p(self.csave), _p(self.lsave), _p(self.isave), _p(self.dsave))
+        _check_task(self.task)
+
+    def active_set_hash(self):
+        h, c = C.c_uint64(0), C.c_int64(0)
+        if lib().lbfgsb_dev_active_set_hash(C.c_void_p(self.h), C.byref(h), C.byref(c)) != 0:
+            raise LbfgsbB200Error(last_error())
+        return h.value, c.value
+
+    def counters(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        lib().lbfgsb_dev_counters(C.c_void_p(self.h), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def profile(self, on=True):
+        lib().lbfgsb_dev_profile(C.c_void_p(self.h), 1 if on else 0)
+
+    def profile_reset(self):
+        lib().lbfgsb_dev_profile_reset(C.c_void_p(self.h))
+
+    def profile_read(self):
+        cap = 64
+        names = C.create_string_buffer(32 * cap)
+        ms = (C.c_double * cap)()
+        by = (C.c_double * cap)()
+        calls = (C.c_int64 * cap)()
+        k = lib().lbfgsb_dev_profile_read(C.c_void_p(self.h), cap, names, ms, by, calls)
+        out = {}
+        for i in range(k):
+            nm = names.raw[32 * i:32 * (i + 1)].split(b"\0")[0].decode()
+            out[nm] = {"ms": ms[i], "bytes": by[i], "calls": calls[i]}
+        return out
+
+    def vector(self, which, count=None, dtype=None):
+        """Copy of a work vector: 0 z, 1 r, 2 d, 3 t, 4 xp, 7 iwhere (diagnostics)."""
+        import ctypes
+        ptr = lib().lbfgsb_dev_vector(C.c_void_p(self.h), which)
+        torch = self.torch
+        n = self.n if count is None else count
+        tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}[self.dtype]
+        if which == 7:
+            tdt = torch.int32
+        out = torch.empty(n, dtype=tdt, device="cuda")
+        cudart = torch.cuda.cudart()
+        torch.cuda.synchronize()
+        rc = cudart.cudaMemcpy(out.data_ptr(), ptr, out.numel() * out.element_size(), 3)  # D2D
+        torch.cuda.synchronize()
+        return out
+
+    def close(self):
+        if self.h:
+            lib().lbfgsb_dev_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RosenbrockDevice:
+    """f/g of the reference's sample problem (test/driver1.f90:274-289) evaluated on the device."""
+
+    def __init__(self, dtype, stream=None):
+        import torch
+        self.dtype = np.dtype(dtype)
+        self.scratch = torch.empty(int(lib().lbfgsb_problem_scratch_bytes()), dtype=torch.uint8, device="cuda")
+        sfx, self._cr = _REAL[self.dtype]
+        self._fn = getattr(lib(), "lbfgsb_problem_rosenbrock_" + sfx)
+        self._f = np.zeros(1, dtype=self.dtype)
+        self.stream = stream
+
+    def __call__(self, x, g, first=1, last=1, xl=0.0, xr=0.0):
+        rc = self._fn(C.c_int64(x.numel()), C.c_void_p(x.data_ptr()), C.c_void_p(g.data_ptr()), _p(self._f),
+                      self.stream, first, last, self._cr(xl), self._cr(xr), C.c_void_p(self.scratch.data_ptr()))
+        if rc != 0:
+            raise LbfgsbB200Error("rosenbrock kernel failed: " + last_error())
+        return self._f[0]

@@ -1866,4 +1866,15 @@ void oracle_dcsrch_f64(double* f, double* g, double* stp, double ftol, double gt
     LB<double>::dcsrch(*f, *g, *stp, ftol, gtol, xtol, stpmin, stpmax, task, isave, dsave);
 }
 
+// The fixed-shape ("device order") dot product on its own, for the reduction parity tests.
+double oracle_device_order_dot_f64(int64_t n, const double* a, const double* b) {
+    return device_order_sum<double>(n, [&](i64 i) { return a[i] * b[i]; });
+}
+float oracle_device_order_dot_f32(int64_t n, const float* a, const float* b) {
+    return device_order_sum<float>(n, [&](i64 i) { return a[i] * b[i]; });
+}
+int oracle_shape(int which) {
+    switch (which) { case 0: return LBFGSB_BLOCK; case 1: return LBFGSB_UNROLL; case 2: return LBFGSB_GRID; default: return LBFGSB_FINAL_BLOCK; }
+}
+
 }  // extern "C"

@@ -1,0 +1,189 @@
+"""Per-routine parity of the CUDA kernels against the CPU oracle, through the C ABI
+(include/lbfgsb_b200.h section 5).  Needs a B200: run with `-m gpu`.
+
+Bit-exact where the arithmetic is order-free or replays a fixed order (max, sort, the 2m x 2m
+dense algebra, dcsrch/dcstep, the fixed-shape long sums against the oracle's device-order mode).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import harness as H
+from oracle import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    import torch
+    assert torch.cuda.is_available()
+    import lbfgsb_b200
+    return lbfgsb_b200.lib()
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _vp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 255, 2048, 2049, 100003, 1 << 20, 3000017])
+def test_fixed_shape_sum_f64_bitwise(L, n):
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal(n) * np.exp(rng.uniform(-8, 8, n))
+    b = rng.standard_normal(n)
+    out = np.zeros(1)
+    assert L.lbfgsb_test_sum_f64(C.c_int64(n), _vp(_dev(a)), _vp(_dev(b)), out.ctypes.data_as(C.c_void_p)) == 0
+    lo = O.lib()
+    lo.oracle_device_order_dot_f64.restype = C.c_double
+    ref = lo.oracle_device_order_dot_f64(C.c_int64(n), a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+    assert out[0] == ref, (out[0], ref, float(a @ b))
+
+
+@pytest.mark.parametrize("n", [5, 4097, 777777])
+def test_fixed_shape_sum_f32_bitwise(L, n):
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal(n).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    out = np.zeros(1, np.float32)
+    assert L.lbfgsb_test_sum_f32(C.c_int64(n), _vp(_dev(a)), _vp(_dev(b)), out.ctypes.data_as(C.c_void_p)) == 0
+    lo = O.lib()
+    lo.oracle_device_order_dot_f32.restype = C.c_float
+    ref = lo.oracle_device_order_dot_f32(C.c_int64(n), a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+    assert out[0] == np.float32(ref)
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 123457, 2000003])
+def test_projgr_exact(L, n):
+    """projgr src/lbfgsb.f90:2594-2622 -- a max, so exact whatever the order."""
+    rng = np.random.default_rng(n + 1)
+    x = rng.uniform(-2, 2, n)
+    l = x - rng.uniform(0, 1, n) * (rng.random(n) < 0.7)
+    u = x + rng.uniform(0, 1, n) * (rng.random(n) < 0.7)
+    nbd = rng.integers(0, 4, n).astype(np.int32)
+    g = rng.standard_normal(n) * 3
+    out = np.zeros(1)
+    assert L.lbfgsb_test_projgr_f64(C.c_int64(n), _vp(_dev(l)), _vp(_dev(u)), _vp(_dev(nbd)), _vp(_dev(x)),
+                                    _vp(_dev(g)), out.ctypes.data_as(C.c_void_p)) == 0
+    ref = np.zeros(1)
+    O.lib().oracle_projgr_f64(C.c_int64(n), l.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p),
+                              nbd.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p),
+                              g.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p))
+    assert out[0] == ref[0]
+
+
+@pytest.mark.parametrize("n,ties", [(1, False), (100, False), (5000, True), (1 << 16, False), (1234567, True)])
+def test_breakpoint_sort_is_stable(L, n, ties):
+    """Replaces hpsolb (src/lbfgsb.f90:2079-2157): ascending t, ties in index order."""
+    import torch
+    rng = np.random.default_rng(n)
+    t = rng.uniform(1e-12, 10.0, n) * np.exp(rng.uniform(-20, 20, n))
+    if ties:
+        t = np.round(t, 1) + 0.5        # many exact ties
+        t[: n // 3] = 0.0               # breakpoints at t = 0 (variables sitting on a bound with g pointing out)
+    td = _dev(t)
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    srt = torch.empty(n, dtype=torch.float64, device="cuda")
+    assert L.lbfgsb_test_sort_f64(C.c_int64(n), _vp(td), _vp(order), _vp(srt)) == 0
+    ref = np.argsort(t, kind="stable")
+    assert np.array_equal(order.cpu().numpy(), ref.astype(np.int32))
+    assert np.array_equal(srt.cpu().numpy(), t[ref])
+
+
+def _spd(rng, m, col):
+    a = rng.standard_normal((col, col))
+    s = a @ a.T + col * np.eye(col)
+    full = np.zeros((m, m))
+    full[:col, :col] = s
+    return np.asfortranarray(full)
+
+
+@pytest.mark.parametrize("m,col", [(5, 1), (5, 5), (10, 7), (20, 20)])
+def test_dpofa_dtrsl_bitwise(L, m, col):
+    """dpofa / dtrsl, src/lbfgsb_linpack_module.f90:30-67, :87-165."""
+    rng = np.random.default_rng(m * 100 + col)
+    a = _spd(rng, m, col)
+    ref = a.copy(order="F")
+    info_ref = np.zeros(1, np.int32)
+    O.lib().oracle_dpofa_f64(ref.ctypes.data_as(C.c_void_p), m, col, info_ref.ctypes.data_as(C.c_void_p))
+    ad = _dev(a.T)     # column-major bytes
+    info = np.zeros(1, np.int32)
+    dummy = _dev(np.zeros(4 * m))
+    assert L.lbfgsb_test_dense_f64(0, m, col, C.c_double(1.0), _vp(ad), _vp(dummy), _vp(dummy),
+                                   info.ctypes.data_as(C.c_void_p)) == 0
+    got = ad.cpu().numpy().T
+    assert info[0] == info_ref[0] == 0
+    assert np.array_equal(np.triu(got[:col, :col]), np.triu(ref[:col, :col]))
+    for job, op in ((1, 1), (11, 2)):
+        b = rng.standard_normal(col)
+        bref = b.copy()
+        O.lib().oracle_dtrsl_f64(ref.ctypes.data_as(C.c_void_p), m, col, bref.ctypes.data_as(C.c_void_p), job,
+                                 info_ref.ctypes.data_as(C.c_void_p))
+        bd = _dev(b)
+        assert L.lbfgsb_test_dense_f64(op, m, col, C.c_double(1.0), _vp(ad), _vp(bd), _vp(dummy),
+                                       info.ctypes.data_as(C.c_void_p)) == 0
+        assert info[0] == info_ref[0] == 0
+        assert np.array_equal(bd.cpu().numpy(), bref)
+
+
+def test_dpofa_reports_non_positive_pivot(L):
+    m = col = 4
+    a = np.asfortranarray(np.eye(4))
+    a[2, 2] = -1.0
+    ref = a.copy(order="F")
+    ir = np.zeros(1, np.int32)
+    O.lib().oracle_dpofa_f64(ref.ctypes.data_as(C.c_void_p), m, col, ir.ctypes.data_as(C.c_void_p))
+    ad = _dev(a.T)
+    dummy = _dev(np.zeros(16))
+    info = np.zeros(1, np.int32)
+    L.lbfgsb_test_dense_f64(0, m, col, C.c_double(1.0), _vp(ad), _vp(dummy), _vp(dummy), info.ctypes.data_as(C.c_void_p))
+    assert info[0] == ir[0] == 3
+
+
+def test_dcsrch_sequence_bitwise(L):
+    """dcsrch / dcstep (src/lbfgsb.f90:2942-3415) on a 1-D function with a bracketing phase."""
+    def phi(s):
+        return -s / (s * s + 2.0), (s * s - 2.0) / (s * s + 2.0) ** 2
+
+    for stp0, stpmax in ((1e-3, 10.0), (10.0, 50.0), (0.1, 1.0)):
+        # oracle
+        task = H.make_task("START")
+        isv = np.zeros(2, np.int32)
+        dsv = np.zeros(13)
+        stp = np.array([stp0])
+        f0, g0 = phi(0.0)
+        f = np.array([f0]); g = np.array([g0])
+        ref_steps = []
+        for _ in range(40):
+            O.lib().oracle_dcsrch_f64(f.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p),
+                                      stp.ctypes.data_as(C.c_void_p), C.c_double(1e-3), C.c_double(0.9), C.c_double(0.1),
+                                      C.c_double(0.0), C.c_double(stpmax), task.ctypes.data_as(C.c_void_p),
+                                      isv.ctypes.data_as(C.c_void_p), dsv.ctypes.data_as(C.c_void_p))
+            ref_steps.append((H.task_str(task)[:4], stp[0]))
+            if H.task_str(task)[:2] != "FG":
+                break
+            f[0], g[0] = phi(stp[0])
+        # device
+        code = np.zeros(1, np.int32)   # CS_START
+        isv = np.zeros(2, np.int32)
+        dsv = np.zeros(13)
+        stp = np.array([stp0])
+        fv, gv = phi(0.0)
+        got = []
+        for _ in range(40):
+            assert L.lbfgsb_test_dcsrch_f64(C.c_double(fv), C.c_double(gv), stp.ctypes.data_as(C.c_void_p),
+                                            C.c_double(stpmax), code.ctypes.data_as(C.c_void_p),
+                                            isv.ctypes.data_as(C.c_void_p), dsv.ctypes.data_as(C.c_void_p)) == 0
+            name = {1: "FG", 2: "CONV"}.get(int(code[0]), "WARN" if 3 <= code[0] <= 6 else "ERRO")
+            got.append((name[:4], stp[0]))
+            if code[0] != 1:
+                break
+            fv, gv = phi(stp[0])
+        assert len(got) == len(ref_steps)
+        for (a, sa), (b, sb) in zip(got, ref_steps):
+            assert a[:2] == b[:2] and sa == sb, (got, ref_steps)
