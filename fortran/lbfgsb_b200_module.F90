@@ -1,0 +1,164 @@
+!> Drop-in replacement for the reference's `lbfgsb_module` (src/lbfgsb.f90:46-58) that forwards
+!! `setulb` to the B200 engine through the C ABI of include/lbfgsb_b200.h.
+!!
+!! * `setulb`      -- same name, argument list and `task` protocol as src/lbfgsb.f90:88-89.
+!!                    Host arrays in / out; the engine stages them on the GPU.  `wa` / `iwa` are
+!!                    accepted and ignored (the workspace lives in HBM).
+!! * `setulb_dev`  -- x, l, u, nbd, g are CUDA device pointers (type(c_ptr), value); the caller's
+!!                    f/g evaluation and the whole iteration stay on the device.
+!! * `lbfgsp_wp`   -- the real kind, as exported by the reference (src/lbfgsb.f90:50).
+!!
+!! Build: compile with -DREAL32 for the single-precision engine (the analogue of
+!! src/lbfgsb_kinds_module.F90:29-37), default is real64; link with -llbfgsb_b200.
+!!
+!! NOTE: this image has no Fortran compiler, so this file is shipped as source only; the same C
+!! symbols are exercised with Fortran-shaped arguments (by-reference scalars, blank-padded
+!! character(60), 4-byte logicals) by tests/ through ctypes.  See INTEGRATION.md.
+module lbfgsb_module
+
+   use, intrinsic :: iso_c_binding
+   use, intrinsic :: iso_fortran_env, only: real32, real64
+
+   implicit none
+   private
+
+#ifdef REAL32
+   integer, parameter, public :: lbfgsp_wp = real32
+#else
+   integer, parameter, public :: lbfgsp_wp = real64
+#endif
+   integer, parameter :: wp = lbfgsp_wp
+
+   public :: setulb, setulb_dev
+   public :: lbfgsb_dev_create, lbfgsb_dev_destroy, lbfgsb_host_release
+
+   interface
+
+#ifdef REAL32
+      subroutine c_setulb(n, m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, iprint, csave, lsave, &
+                          isave, dsave, itfile, itfile_len) bind(C, name='lbfgsb_setulb_f32')
+#else
+      subroutine c_setulb(n, m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, iprint, csave, lsave, &
+                          isave, dsave, itfile, itfile_len) bind(C, name='lbfgsb_setulb_f64')
+#endif
+         import :: c_int32_t, c_char, c_ptr, wp
+         integer(c_int32_t), intent(in) :: n, m, iprint
+         real(wp), intent(inout) :: x(*), f, g(*), wa(*), dsave(29)
+         real(wp), intent(in) :: l(*), u(*), factr, pgtol
+         integer(c_int32_t), intent(in) :: nbd(*)
+         integer(c_int32_t), intent(inout) :: iwa(*), lsave(4), isave(44)
+         character(kind=c_char), intent(inout) :: task(60), csave(60)
+         type(c_ptr), value :: itfile
+         integer(c_int32_t), value :: itfile_len
+      end subroutine c_setulb
+
+#ifdef REAL32
+      subroutine c_setulb_dev(h, x, l, u, nbd, f, g, factr, pgtol, task, iprint, csave, lsave, isave, dsave) &
+         bind(C, name='lbfgsb_setulb_dev_f32')
+#else
+      subroutine c_setulb_dev(h, x, l, u, nbd, f, g, factr, pgtol, task, iprint, csave, lsave, isave, dsave) &
+         bind(C, name='lbfgsb_setulb_dev_f64')
+#endif
+         import :: c_int32_t, c_char, c_ptr, wp
+         type(c_ptr), value :: h, x, l, u, nbd, g      ! opaque handle and CUDA device pointers
+         real(wp), intent(inout) :: f, dsave(29)
+         real(wp), intent(in) :: factr, pgtol
+         integer(c_int32_t), intent(in) :: iprint
+         integer(c_int32_t), intent(inout) :: lsave(4), isave(44)
+         character(kind=c_char), intent(inout) :: task(60), csave(60)
+      end subroutine c_setulb_dev
+
+      function lbfgsb_dev_create(n, m, real_kind, cuda_stream) result(h) bind(C, name='lbfgsb_dev_create')
+         import :: c_int64_t, c_int32_t, c_ptr
+         integer(c_int64_t), value :: n
+         integer(c_int32_t), value :: m, real_kind
+         type(c_ptr), value :: cuda_stream
+         type(c_ptr) :: h
+      end function lbfgsb_dev_create
+
+      subroutine lbfgsb_dev_destroy(h) bind(C, name='lbfgsb_dev_destroy')
+         import :: c_ptr
+         type(c_ptr), value :: h
+      end subroutine lbfgsb_dev_destroy
+
+      subroutine lbfgsb_host_release(isave) bind(C, name='lbfgsb_host_release')
+         import :: c_int32_t
+         integer(c_int32_t), intent(inout) :: isave(44)
+      end subroutine lbfgsb_host_release
+
+   end interface
+
+contains
+
+   !> Same interface as the reference's setulb (src/lbfgsb.f90:88-89).
+   subroutine setulb(n, m, x, l, u, Nbd, f, g, Factr, Pgtol, Wa, Iwa, Task, Iprint, Csave, Lsave, Isave, Dsave, &
+                     iteration_file)
+      integer, intent(in) :: n, m
+      real(wp), intent(inout) :: x(n), f, g(n)
+      real(wp), intent(in) :: l(n), u(n), Factr, Pgtol
+      integer, intent(in) :: Nbd(n), Iprint
+      real(wp) :: Wa(*)
+      integer :: Iwa(*)
+      character(len=60) :: Task, Csave
+      logical :: Lsave(4)
+      integer :: Isave(44)
+      real(wp) :: Dsave(29)
+      character(len=*), intent(in), optional :: iteration_file
+
+      character(kind=c_char) :: ctask(60), ccsave(60)
+      integer(c_int32_t) :: clsave(4)
+      character(kind=c_char, len=:), allocatable, target :: fname
+      integer :: i
+
+      do i = 1, 60
+         ctask(i) = Task(i:i)
+         ccsave(i) = Csave(i:i)
+      end do
+      clsave = merge(1_c_int32_t, 0_c_int32_t, Lsave)
+      if (present(iteration_file)) then
+         fname = iteration_file
+         call c_setulb(int(n, c_int32_t), int(m, c_int32_t), x, l, u, Nbd, f, g, Factr, Pgtol, Wa, Iwa, ctask, &
+                       int(Iprint, c_int32_t), ccsave, clsave, Isave, Dsave, c_loc(fname), &
+                       int(len(fname), c_int32_t))
+      else
+         call c_setulb(int(n, c_int32_t), int(m, c_int32_t), x, l, u, Nbd, f, g, Factr, Pgtol, Wa, Iwa, ctask, &
+                       int(Iprint, c_int32_t), ccsave, clsave, Isave, Dsave, c_null_ptr, 0_c_int32_t)
+      end if
+      do i = 1, 60
+         Task(i:i) = ctask(i)
+         Csave(i:i) = ccsave(i)
+      end do
+      Lsave = clsave /= 0
+   end subroutine setulb
+
+   !> Device-pointer variant: `h` from lbfgsb_dev_create(n, m, kind, stream); x, l, u, nbd, g are
+   !! CUDA device addresses (e.g. c_devloc of CUDA Fortran arrays, or pointers obtained from C).
+   subroutine setulb_dev(h, x, l, u, nbd, f, g, Factr, Pgtol, Task, Iprint, Csave, Lsave, Isave, Dsave)
+      type(c_ptr), intent(in) :: h, x, l, u, nbd, g
+      real(wp), intent(inout) :: f
+      real(wp), intent(in) :: Factr, Pgtol
+      integer, intent(in) :: Iprint
+      character(len=60) :: Task, Csave
+      logical :: Lsave(4)
+      integer :: Isave(44)
+      real(wp) :: Dsave(29)
+
+      character(kind=c_char) :: ctask(60), ccsave(60)
+      integer(c_int32_t) :: clsave(4)
+      integer :: i
+
+      do i = 1, 60
+         ctask(i) = Task(i:i)
+         ccsave(i) = Csave(i:i)
+      end do
+      clsave = merge(1_c_int32_t, 0_c_int32_t, Lsave)
+      call c_setulb_dev(h, x, l, u, nbd, f, g, Factr, Pgtol, ctask, int(Iprint, c_int32_t), ccsave, clsave, &
+                        Isave, Dsave)
+      do i = 1, 60
+         Task(i:i) = ctask(i)
+         Csave(i:i) = ccsave(i)
+      end do
+      Lsave = clsave /= 0
+   end subroutine setulb_dev
+
+end module lbfgsb_module

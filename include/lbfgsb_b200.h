@@ -12,7 +12,7 @@
  * same meaning of isave(22:44), dsave(1:29), lsave(1:4)   (src/lbfgsb.f90:194-242, :904-947).
  * All arguments are passed by reference, strings are blank-padded character(60),
  * logicals are 4-byte, so a Fortran `bind(C)` interface forwards 1:1
- * (see fortran/lbfgsb_b200_module.f90 and INTEGRATION.md).
+ * (see fortran/lbfgsb_b200_module.F90 and INTEGRATION.md).
  *
  * There is no CPU fallback: every entry point needs a CUDA device and fails with
  * task = 'ERROR: ...' / a non-zero return code when there is none.
