@@ -19,6 +19,7 @@
 
 #include "../../include/lbfgsb_b200.h"
 #include "cauchy_walk.cuh"
+#include "kernels_tma.cuh"
 
 // ---------------------------------------------------------------------------
 // errors
@@ -139,6 +140,7 @@ struct Engine : EngineBase {
         n = n_; offset = off_; n_global = ng_; m = m_; R = world_; rank = rank_; comm = cm;
         real_kind = (int)sizeof(T);
         mt = (m <= 5) ? 5 : (m <= 10 ? 10 : 20);
+        if (!(mt == 5 ? set_smem_attrs<5>() : (mt == 10 ? set_smem_attrs<10>() : set_smem_attrs<20>()))) return false;
         for (int q = 0; q < F_COUNT; ++q) { fam_ms[q] = 0; fam_calls[q] = 0; }
         if (st) stream = st;
         else { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
@@ -238,12 +240,22 @@ struct Engine : EngineBase {
     }
 #define LG LBFGSB_GRID, LBFGSB_BLOCK, 0, stream
 #define LS 1, LB_SCALAR_THREADS, 0, stream
-#define MTCALL(kern, ...)                                                     \
-    do {                                                                      \
-        if (mt == 5) kern<T, 5><<<LG>>>(__VA_ARGS__);                         \
-        else if (mt == 10) kern<T, 10><<<LG>>>(__VA_ARGS__);                  \
-        else kern<T, 20><<<LG>>>(__VA_ARGS__);                                \
+#define MTCALL(kern, smemfn, ...)                                                                          \
+    do {                                                                                                   \
+        if (mt == 5) kern<T, 5><<<LBFGSB_GRID, LBFGSB_BLOCK, smemfn<T, 5>(), stream>>>(__VA_ARGS__);        \
+        else if (mt == 10) kern<T, 10><<<LBFGSB_GRID, LBFGSB_BLOCK, smemfn<T, 10>(), stream>>>(__VA_ARGS__); \
+        else kern<T, 20><<<LBFGSB_GRID, LBFGSB_BLOCK, smemfn<T, 20>(), stream>>>(__VA_ARGS__);              \
     } while (0)
+
+    // the TMA-staged kernels need more than the default 48 KB of dynamic shared memory
+    template <int MT> bool set_smem_attrs() {
+        CK(cudaFuncSetAttribute(k_update<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_update<T, MT>()));
+        CK(cudaFuncSetAttribute(k_cauchy_classify<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_classify<T, MT>()));
+        CK(cudaFuncSetAttribute(k_formk_gram<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk<T, MT>()));
+        CK(cudaFuncSetAttribute(k_cmprlb_wv<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cmprlb<T, MT>()));
+        CK(cudaFuncSetAttribute(k_subsm_step<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_subsm<T, MT>()));
+        return true;
+    }
 
     // ---- the breakpoint walk ------------------------------------------------
     bool enqueue_walk(i64 nbreak) {
@@ -288,7 +300,7 @@ struct Engine : EngineBase {
     // ---- prelims + first lnsrlb (:601-773) ----------------------------------
     bool enqueue_body() {
         for (;;) {
-            begin(F_CLASSIFY); MTCALL(k_cauchy_classify, w); end(F_CLASSIFY);
+            begin(F_CLASSIFY); MTCALL(k_cauchy_classify, smem_classify, w); end(F_CLASSIFY);
             if (!site(site_cauchy(mt))) return false;
             begin(F_SCALAR); s_cauchy<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);
             if (s_host->cnstnd) {
@@ -301,7 +313,7 @@ struct Engine : EngineBase {
             begin(F_GCP_FREEV); k_gcp_freev<T><<<LG>>>(w); end(F_GCP_FREEV);
             if (!site(site_freev())) return false;
             begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global); end(F_SCALAR);
-            begin(F_FORMK_GRAM); MTCALL(k_formk_gram, w); end(F_FORMK_GRAM);
+            begin(F_FORMK_GRAM); MTCALL(k_formk_gram, smem_formk, w); end(F_FORMK_GRAM);
             begin(F_FORMK_DELTA);
             k_flag_count<T, 1><<<LG>>>(w, tile_counts);
             k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 1, tile_counts, tile_offsets, ntiles, ctl_el);
@@ -311,10 +323,10 @@ struct Engine : EngineBase {
             end(F_FORMK_DELTA, 5);
             if (!site(site_formk(mt))) return false;
             begin(F_SCALAR); s_formk_dense<T><<<LS>>>(w, dist(), mt, delta); end(F_SCALAR);
-            begin(F_CMPRLB_WV); MTCALL(k_cmprlb_wv, w); end(F_CMPRLB_WV);
+            begin(F_CMPRLB_WV); MTCALL(k_cmprlb_wv, smem_cmprlb, w); end(F_CMPRLB_WV);
             if (!site(site_wv(mt))) return false;
             begin(F_SCALAR); s_subsm_dense<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);
-            begin(F_SUBSM_STEP); MTCALL(k_subsm_step, w); end(F_SUBSM_STEP);
+            begin(F_SUBSM_STEP); MTCALL(k_subsm_step, smem_subsm, w); end(F_SUBSM_STEP);
             if (!site(site_subsm())) return false;
             begin(F_SCALAR); s_subsm_post<T><<<LS>>>(w, dist()); end(F_SCALAR);
             begin(F_BACKTRACK);
@@ -398,7 +410,7 @@ struct Engine : EngineBase {
             }
         } else {   // NEW_X
             begin(F_SCALAR); s_newx_tests<T><<<1, 32, 0, stream>>>(w); end(F_SCALAR);
-            begin(F_UPDATE); MTCALL(k_update, w); end(F_UPDATE);
+            begin(F_UPDATE); MTCALL(k_update, smem_update, w); end(F_UPDATE);
             if (!site(site_update(mt))) return false;
             begin(F_SCALAR); s_update_dense<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);
             if (!enqueue_body()) return false;

@@ -141,111 +141,6 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_projgr(Wk<T> w) {
 }
 
 // ---------------------------------------------------------------------------
-// cauchy, per-variable pass (:1270-1341): classify iwhere, Cauchy direction d,
-// f1 = -sum d^2, p = W'd, smallest breakpoint; xcp = x.
-// part: [0,MT) sum Wy(:,j) d ; [MT,2MT) sum Ws(:,j) d ; 2MT: sum d^2 ; 2MT+1: bkmin
-// ipart: 0 argmin variable ; 1 nbreak ; 2 count of moving variables without breakpoint ;
-//        3 bnded (min over blocks)
-// ---------------------------------------------------------------------------
-template <typename T, int MT>
-__global__ void __launch_bounds__(LBFGSB_BLOCK) k_cauchy_classify(Wk<T> w) {
-    constexpr int VEC = Real<T>::VEC;
-    const DevState<T>* s = w.s;
-    if (!s->go || !s->in_body) return;
-    const int mode = s->cauchy_mode;
-    const i64 n = w.n;
-    if (mode != 0) {  // xcp = x only (:609 or :1247)
-        LB_FOR_TILES(T, n, base) {
-            T x[VEC];
-            ldv<T>(w.x, base, n, x);
-            stv<T>(w.z, base, n, x);
-        }
-        return;
-    }
-    const int col = s->col, m = s->m, head0 = s->head - 1;
-    __shared__ T sm[(2 * MT + 1) * (LBFGSB_BLOCK / 32)];
-    __shared__ T smv[LBFGSB_BLOCK / 32];
-    __shared__ i64 smi[LBFGSB_BLOCK / 32];
-    T acc[2 * MT + 1];
-#pragma unroll
-    for (int k = 0; k < 2 * MT + 1; ++k) acc[k] = (T)0;
-    T bk = LB_INF(T);
-    i64 ibk = LB_I64MAX, nbr = 0, nfc = 0, bnd = 1;
-    LB_FOR_TILES_NU(T, n, base) {
-        T x[VEC], l[VEC], u[VEC], g[VEC], d[VEC]; int nb[VEC], iw[VEC];
-        ldv<T>(w.x, base, n, x); ldv<T>(w.g, base, n, g); ldv<T>(w.l, base, n, l);
-        ldv<T>(w.u, base, n, u); ldvi<T>(w.nbd, base, n, nb); ldvi<T>(w.iwhere, base, n, iw);
-        bool anymv = false;
-        bool mv[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            mv[v] = false; d[v] = (T)0;
-            if (base + v < n) {
-                const T neggi = -g[v];
-                T tl = (T)0, tu = (T)0;
-                if (iw[v] != 3 && iw[v] != -1) {
-                    if (nb[v] <= 2) tl = x[v] - l[v];
-                    if (nb[v] >= 2) tu = u[v] - x[v];
-                    const bool xlower = nb[v] <= 2 && tl <= (T)0;
-                    const bool xupper = nb[v] >= 2 && tu <= (T)0;
-                    iw[v] = 0;
-                    if (xlower) { if (neggi <= (T)0) iw[v] = 1; }
-                    else if (xupper) { if (neggi >= (T)0) iw[v] = 2; }
-                    else { if (fabs(neggi) <= (T)0) iw[v] = -3; }
-                }
-                if (iw[v] == 0 || iw[v] == -1) {
-                    mv[v] = true; anymv = true;
-                    d[v] = neggi;
-                    acc[2 * MT] = acc[2 * MT] + neggi * neggi;
-                    T tb; bool hasb = false;
-                    if (nb[v] <= 2 && nb[v] != 0 && neggi < (T)0) { tb = tl / (-neggi); hasb = true; }
-                    else if (nb[v] >= 2 && neggi > (T)0) { tb = tu / neggi; hasb = true; }
-                    if (hasb) {
-                        nbr++;
-                        if (tb < bk) { bk = tb; ibk = base + v; }   // strict <: lowest index among ties (:1310)
-                    } else {
-                        nfc++;
-                        if (fabs(neggi) > (T)0) bnd = 0;
-                    }
-                }
-            }
-        }
-        stvi<T>(w.iwhere, base, n, iw);
-        stv<T>(w.d, base, n, d);
-        stv<T>(w.z, base, n, x);
-        if (col > 0 && anymv) {
-            int pj = head0;
-#pragma unroll
-            for (int j = 0; j < MT; ++j) {
-                if (j < col) {
-                    T wy[VEC], wsv[VEC];
-                    ldv<T>(w.wy + (i64)pj * w.ldw, base, n, wy);
-                    ldv<T>(w.ws + (i64)pj * w.ldw, base, n, wsv);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v)
-                        if (mv[v]) {
-                            acc[j] = acc[j] + wy[v] * d[v];
-                            acc[MT + j] = acc[MT + j] + wsv[v] * d[v];
-                        }
-                    pj = (pj + 1 == m) ? 0 : pj + 1;
-                }
-            }
-        }
-    }
-    block_sum_store<T, 2 * MT + 1>(acc, 2 * MT + 1, sm, w.part);
-    block_argmin<T>(bk, ibk, smv, smi);
-    i64 r1 = block_isum(nbr, smi), r2 = block_isum(nfc, smi);
-    i64 r3 = -block_isum(bnd ? 0 : 1, smi);  // <0 if any thread saw an unbounded moving variable
-    if (threadIdx.x == 0) {
-        LB_SLOT(w.part, 2 * MT + 1)[blockIdx.x] = bk;
-        LB_SLOT(w.ipart, 0)[blockIdx.x] = ibk;
-        LB_SLOT(w.ipart, 1)[blockIdx.x] = r1;
-        LB_SLOT(w.ipart, 2)[blockIdx.x] = r2;
-        LB_SLOT(w.ipart, 3)[blockIdx.x] = (r3 < 0) ? 0 : 1;
-    }
-}
-
-// ---------------------------------------------------------------------------
 // cauchy tail (:1515) fused with freev (:1980-2059): xcp += tsum*d, then count
 // free / entering / leaving variables and refresh the per-variable state byte.
 // The reference's index lists are not materialised: every later "over the free
@@ -290,196 +185,6 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_gcp_freev(Wk<T> w) {
         LB_SLOT(w.ipart, 0)[blockIdx.x] = r0; LB_SLOT(w.ipart, 1)[blockIdx.x] = r1;
         LB_SLOT(w.ipart, 2)[blockIdx.x] = r2;
     }
-}
-
-// ---------------------------------------------------------------------------
-// formk, new row/column of WN1 (:1756-1793): one pass over all rows of S,Y.
-// part: [0,MT) A_j = sum_free Wy_last*Wy_j ; [MT,2MT) B_j = sum_act Ws_last*Ws_j ;
-//       [2MT,3MT) C_j = sum_act Ws_last*Wy_j ; [3MT,4MT) D_j = sum_free Ws_j*Wy_last
-// ---------------------------------------------------------------------------
-template <typename T, int MT>
-__global__ void __launch_bounds__(LBFGSB_BLOCK) k_formk_gram(Wk<T> w) {
-    constexpr int VEC = Real<T>::VEC;
-    const DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || !s->do_formk || !s->updatd) return;
-    const i64 n = w.n;
-    const int col = s->col, m = s->m, head0 = s->head - 1;
-    const int lastp = (head0 + col - 1) % m;
-    __shared__ T sm[4 * MT * (LBFGSB_BLOCK / 32)];
-    T acc[4 * MT];
-#pragma unroll
-    for (int k = 0; k < 4 * MT; ++k) acc[k] = (T)0;
-    LB_FOR_TILES_NU(T, n, base) {
-        int st[VEC];
-        ldvb<T>(w.state, base, n, st);
-        T wyl[VEC], wsl[VEC];
-        ldv<T>(w.wy + (i64)lastp * w.ldw, base, n, wyl);
-        ldv<T>(w.ws + (i64)lastp * w.ldw, base, n, wsl);
-        int pj = head0;
-#pragma unroll
-        for (int j = 0; j < MT; ++j) {
-            if (j < col) {
-                T wy[VEC], wsv[VEC];
-                ldv<T>(w.wy + (i64)pj * w.ldw, base, n, wy);
-                ldv<T>(w.ws + (i64)pj * w.ldw, base, n, wsv);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    if (base + v < n) {
-                        if (st[v] & 1) {
-                            acc[j] = acc[j] + wyl[v] * wy[v];
-                            acc[3 * MT + j] = acc[3 * MT + j] + wsv[v] * wyl[v];
-                        } else {
-                            acc[MT + j] = acc[MT + j] + wsl[v] * wsv[v];
-                            acc[2 * MT + j] = acc[2 * MT + j] + wsl[v] * wy[v];
-                        }
-                    }
-                }
-                pj = (pj + 1 == m) ? 0 : pj + 1;
-            }
-        }
-    }
-    block_sum_store<T, 4 * MT>(acc, 4 * MT, sm, w.part);
-}
-
-// ---------------------------------------------------------------------------
-// cmprlb (:1565-1583) fused with the first half of subsm (:2742-2754):
-//   r_k = -theta (z_k - x_k) - g_k + sum_j Wy(k,j) a1_j + Ws(k,j) a2_j   (free k)
-//   wv  = W' Z r
-// r is kept by variable (the reference keeps it compact over the free list).
-// part: [0,MT) sum Wy(:,j) r ; [MT,2MT) sum Ws(:,j) r
-// ---------------------------------------------------------------------------
-template <typename T, int MT>
-__global__ void __launch_bounds__(LBFGSB_BLOCK) k_cmprlb_wv(Wk<T> w) {
-    constexpr int VEC = Real<T>::VEC;
-    const DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || !s->do_subspace) return;
-    const i64 n = w.n;
-    const int col = s->col, m = s->m, head0 = s->head - 1;
-    const T theta = s->theta;
-    const bool uc = (!s->cnstnd && col > 0);   // :1560-1563
-    __shared__ T sm[2 * MT * (LBFGSB_BLOCK / 32)];
-    T a1[MT], a2[MT], acc[2 * MT];
-#pragma unroll
-    for (int j = 0; j < MT; ++j) {
-        a1[j] = (j < col) ? s->a[j] : (T)0;
-        a2[j] = (j < col) ? theta * s->a[col + j] : (T)0;
-        acc[j] = (T)0; acc[MT + j] = (T)0;
-    }
-    LB_FOR_TILES_NU(T, n, base) {
-        int st[VEC];
-        ldvb<T>(w.state, base, n, st);
-        bool fr[VEC]; bool any = false;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) { fr[v] = (base + v < n) && (st[v] & 1); any |= fr[v]; }
-        if (!any) continue;
-        T z[VEC], x[VEC], g[VEC], r[VEC];
-        ldv<T>(w.g, base, n, g);
-        if (!uc) { ldv<T>(w.z, base, n, z); ldv<T>(w.x, base, n, x); }
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) r[v] = uc ? -g[v] : (-theta * (z[v] - x[v]) - g[v]);
-        T wyv[MT][VEC], wsv[MT][VEC];
-        int pj = head0;
-#pragma unroll
-        for (int j = 0; j < MT; ++j) {
-            if (j < col) {
-                ldv<T>(w.wy + (i64)pj * w.ldw, base, n, wyv[j]);
-                ldv<T>(w.ws + (i64)pj * w.ldw, base, n, wsv[j]);
-                if (!uc) {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) r[v] = r[v] + wyv[j][v] * a1[j] + wsv[j][v] * a2[j];
-                }
-                pj = (pj + 1 == m) ? 0 : pj + 1;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < MT; ++j) {
-            if (j < col) {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v)
-                    if (fr[v]) {
-                        acc[j] = acc[j] + wyv[j][v] * r[v];
-                        acc[MT + j] = acc[MT + j] + wsv[j][v] * r[v];
-                    }
-            }
-        }
-        // r of a non-free variable is never read (every later pass masks on the free set),
-        // so the whole vector is stored: no partial-sector writes.
-        stv<T>(w.r, base, n, r);
-    }
-    block_sum_store<T, 2 * MT>(acc, 2 * MT, sm, w.part);
-}
-
-// ---------------------------------------------------------------------------
-// subsm second half (:2770-2827): Newton direction on the free set, projected
-// step, xp = xcp backup, and the directional derivative dd_p over all variables.
-// part: 0 dd_p.  ipart: 0 iword (sum>0)
-// ---------------------------------------------------------------------------
-template <typename T, int MT>
-__global__ void __launch_bounds__(LBFGSB_BLOCK) k_subsm_step(Wk<T> w) {
-    constexpr int VEC = Real<T>::VEC;
-    const DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || !s->do_subspace) return;
-    const i64 n = w.n;
-    const int col = s->col, m = s->m, head0 = s->head - 1;
-    const T theta = s->theta, rtheta = (T)1 / theta;
-    __shared__ T sm[LBFGSB_BLOCK / 32];
-    __shared__ i64 smi[LBFGSB_BLOCK / 32];
-    T wv1[MT], wv2[MT];
-#pragma unroll
-    for (int j = 0; j < MT; ++j) { wv1[j] = (j < col) ? s->wv[j] : (T)0; wv2[j] = (j < col) ? s->wv[col + j] : (T)0; }
-    T acc[1]; acc[0] = (T)0;
-    i64 iwd = 0;
-    LB_FOR_TILES_NU(T, n, base) {
-        int st[VEC];
-        ldvb<T>(w.state, base, n, st);
-        bool fr[VEC]; bool any = false;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) { fr[v] = (base + v < n) && (st[v] & 1); any |= fr[v]; }
-        T z[VEC], x[VEC], g[VEC];
-        ldv<T>(w.z, base, n, z); ldv<T>(w.x, base, n, x); ldv<T>(w.g, base, n, g);
-        stv<T>(w.xp, base, n, z);   // :2787
-        if (any) {
-            T dk[VEC], l[VEC], u[VEC]; int nb[VEC];
-            ldv<T>(w.r, base, n, dk); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
-            ldvi<T>(w.nbd, base, n, nb);
-            int pj = head0;
-#pragma unroll
-            for (int j = 0; j < MT; ++j) {
-                if (j < col) {
-                    T wy[VEC], wsv[VEC];
-                    ldv<T>(w.wy + (i64)pj * w.ldw, base, n, wy);
-                    ldv<T>(w.ws + (i64)pj * w.ldw, base, n, wsv);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) dk[v] = dk[v] + wy[v] * wv1[j] / theta + wsv[v] * wv2[j];
-                    pj = (pj + 1 == m) ? 0 : pj + 1;
-                }
-            }
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                dk[v] = rtheta * dk[v];   // dscal(nsub, one/theta, d) :2780
-                if (fr[v]) {
-                    T xk = z[v];
-                    if (nb[v] != 0) {
-                        if (nb[v] == 1) { z[v] = dense::tmax(l[v], xk + dk[v]); if (z[v] == l[v]) iwd = 1; }
-                        else if (nb[v] == 2) {
-                            xk = dense::tmax(l[v], xk + dk[v]);
-                            z[v] = dense::tmin(u[v], xk);
-                            if (z[v] == l[v] || z[v] == u[v]) iwd = 1;
-                        } else if (nb[v] == 3) { z[v] = dense::tmin(u[v], xk + dk[v]); if (z[v] == u[v]) iwd = 1; }
-                    } else z[v] = xk + dk[v];
-                }
-            }
-            // direction (don't-care on non-free variables) and new point (unchanged there)
-            stv<T>(w.r, base, n, dk);
-            stv<T>(w.z, base, n, z);
-        }
-#pragma unroll
-        for (int v = 0; v < VEC; ++v)
-            if (base + v < n) acc[0] = acc[0] + (z[v] - x[v]) * g[v];   // :2825-2827
-    }
-    block_sum_store<T, 1>(acc, 1, sm, w.part);
-    i64 r0 = block_isum(iwd, smi);
-    if (threadIdx.x == 0) LB_SLOT(w.ipart, 0)[blockIdx.x] = r0;
 }
 
 // ---------------------------------------------------------------------------
@@ -662,57 +367,6 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_ls_trial(Wk<T> w) {
     block_sum_store<T, 1>(acc, 1, sm, w.part);
     T r = block_max<T>(pg, smm);
     if (threadIdx.x == 0) LB_SLOT(w.part, 1)[blockIdx.x] = r;
-}
-
-// ---------------------------------------------------------------------------
-// y/s preparation (:813-824) fused with matupd (:2313-2338): y = g - r,
-// s = stp*d written straight into the ring columns, rr = y.y, and the new row of
-// S'Y / column of S'S against the col-1 older pairs -- one pass.
-// part: 0 rr ; [1,1+MT) sum s*Wy(:,j) ; [1+MT,1+2MT) sum Ws(:,j)*s   (j = ring position, < col-1)
-// ---------------------------------------------------------------------------
-template <typename T, int MT>
-__global__ void __launch_bounds__(LBFGSB_BLOCK) k_update(Wk<T> w) {
-    constexpr int VEC = Real<T>::VEC;
-    const DevState<T>* s = w.s;
-    if (!s->go || !s->do_update) return;
-    const i64 n = w.n;
-    const int col = s->col, m = s->m, head0 = s->head - 1, itail0 = s->itail - 1;
-    const T stp = s->stp;
-    __shared__ T sm[(2 * MT + 1) * (LBFGSB_BLOCK / 32)];
-    T acc[2 * MT + 1];
-#pragma unroll
-    for (int k = 0; k < 2 * MT + 1; ++k) acc[k] = (T)0;
-    T* wsn = w.ws + (i64)itail0 * w.ldw;
-    T* wyn = w.wy + (i64)itail0 * w.ldw;
-    LB_FOR_TILES_NU(T, n, base) {
-        T g[VEC], r[VEC], d[VEC];
-        ldv<T>(w.g, base, n, g); ldv<T>(w.r, base, n, r); ldv<T>(w.d, base, n, d);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            r[v] = g[v] - r[v];
-            if (stp != (T)1) d[v] = stp * d[v];
-            if (base + v < n) acc[0] = acc[0] + r[v] * r[v];
-        }
-        int pj = head0;
-#pragma unroll
-        for (int j = 0; j < MT; ++j) {
-            if (j < col - 1) {
-                T wy[VEC], wsv[VEC];
-                ldv<T>(w.wy + (i64)pj * w.ldw, base, n, wy);
-                ldv<T>(w.ws + (i64)pj * w.ldw, base, n, wsv);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v)
-                    if (base + v < n) {
-                        acc[1 + j] = acc[1 + j] + d[v] * wy[v];
-                        acc[1 + MT + j] = acc[1 + MT + j] + wsv[v] * d[v];
-                    }
-                pj = (pj + 1 == m) ? 0 : pj + 1;
-            }
-        }
-        stv<T>(wsn, base, n, d);
-        stv<T>(wyn, base, n, r);
-    }
-    block_sum_store<T, 2 * MT + 1>(acc, 2 * MT + 1, sm, w.part);
 }
 
 // ---------------------------------------------------------------------------
