@@ -123,7 +123,8 @@ template <typename T> __device__ __forceinline__ T warp_min(T v) {
 }
 
 // Block-level sum of K per-thread accumulators -> part[k*GRID + blockIdx.x].
-// smem must hold K * (BLOCK/32) values.  All threads must call.
+// smem must hold K * (BLOCK/32) values.  All threads must call.  Only the first LBFGSB_BLOCK
+// threads contribute (the TMA-staged kernels carry an extra producer warp).
 template <typename T, int K>
 __device__ __forceinline__ void block_sum_store(const T (&acc)[K], int kcount, T* smem, T* part) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -132,7 +133,7 @@ __device__ __forceinline__ void block_sum_store(const T (&acc)[K], int kcount, T
     for (int k = 0; k < K; ++k) {
         if (k < kcount) {
             T v = warp_sum<T>(acc[k]);
-            if (lane == 0) smem[k * NW + w] = v;
+            if (lane == 0 && w < NW) smem[k * NW + w] = v;
         }
     }
     __syncthreads();
@@ -150,7 +151,7 @@ __device__ __forceinline__ T block_max(T v, T* smem) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr int NW = LBFGSB_BLOCK / 32;
     v = warp_max<T>(v);
-    if (lane == 0) smem[w] = v;
+    if (lane == 0 && w < NW) smem[w] = v;
     __syncthreads();
     T s = smem[0];
 #pragma unroll
@@ -163,7 +164,7 @@ __device__ __forceinline__ T block_min(T v, T* smem) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr int NW = LBFGSB_BLOCK / 32;
     v = warp_min<T>(v);
-    if (lane == 0) smem[w] = v;
+    if (lane == 0 && w < NW) smem[w] = v;
     __syncthreads();
     T s = smem[0];
 #pragma unroll
@@ -175,7 +176,7 @@ __device__ __forceinline__ i64 block_isum(i64 v, i64* smem) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr int NW = LBFGSB_BLOCK / 32;
     v = warp_sum<i64>(v);
-    if (lane == 0) smem[w] = v;
+    if (lane == 0 && w < NW) smem[w] = v;
     __syncthreads();
     i64 s = 0;
 #pragma unroll
@@ -194,7 +195,7 @@ __device__ __forceinline__ void block_argmin(T& v, i64& idx, T* smv, i64* smi) {
         i64 oi = shfl_xor_t<i64>(idx, off);
         if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
     }
-    if (lane == 0) { smv[w] = v; smi[w] = idx; }
+    if (lane == 0 && w < NW) { smv[w] = v; smi[w] = idx; }
     __syncthreads();
     v = smv[0]; idx = smi[0];
 #pragma unroll

@@ -242,9 +242,9 @@ struct Engine : EngineBase {
 #define LS 1, LB_SCALAR_THREADS, 0, stream
 #define MTCALL(kern, smemfn, ...)                                                                          \
     do {                                                                                                   \
-        if (mt == 5) kern<T, 5><<<LBFGSB_GRID, LBFGSB_BLOCK, smemfn<T, 5>(), stream>>>(__VA_ARGS__);        \
-        else if (mt == 10) kern<T, 10><<<LBFGSB_GRID, LBFGSB_BLOCK, smemfn<T, 10>(), stream>>>(__VA_ARGS__); \
-        else kern<T, 20><<<LBFGSB_GRID, LBFGSB_BLOCK, smemfn<T, 20>(), stream>>>(__VA_ARGS__);              \
+        if (mt == 5) kern<T, 5><<<LBFGSB_GRID, LB_TMA_THREADS, smemfn<T, 5>(), stream>>>(__VA_ARGS__);        \
+        else if (mt == 10) kern<T, 10><<<LBFGSB_GRID, LB_TMA_THREADS, smemfn<T, 10>(), stream>>>(__VA_ARGS__); \
+        else kern<T, 20><<<LBFGSB_GRID, LB_TMA_THREADS, smemfn<T, 20>(), stream>>>(__VA_ARGS__);              \
     } while (0)
 
     // the TMA-staged kernels need more than the default 48 KB of dynamic shared memory

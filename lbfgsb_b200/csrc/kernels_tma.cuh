@@ -2,7 +2,8 @@
 // history, as TMA-staged kernels (tma_pipe.cuh): bulk copies land every input stream of a
 // sub-tile in a two-stage shared-memory ring, the CTA computes from shared memory, outputs go
 // straight to global memory with 128-bit stores.  One CTA per SM (the ring takes ~200 KB);
-// LBFGSB_GRID = 4 x 148 CTAs run as four equal waves.
+// LBFGSB_GRID = 4 x 148 CTAs run as four equal waves.  A CTA is 8 consumer warps (the 256
+// threads of the fixed reduction shape) plus one producer warp (tma_pipe.cuh).
 //
 // Same reductions, same thread -> element mapping and same accumulation order as the plain
 // streaming kernels (include/lbfgsb_b200_shape.h), so the oracle's device-order mode replays
@@ -33,12 +34,12 @@ __device__ __forceinline__ void pipe_add_w(PipeSrc* ps, const Wk<T>& w, int head
 // part: 0 rr ; [1,1+MT) sum s*Wy(:,j) ; [1+MT,1+2MT) sum Ws(:,j)*s   (j = ring position, < col-1)
 // ---------------------------------------------------------------------------
 template <typename T, int MT>
-__global__ void __launch_bounds__(LBFGSB_BLOCK, 1) k_update(Wk<T> w) {
+__global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ char dyn[];
-    __shared__ unsigned long long full[LB_PIPE_STAGES];
+    __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
     __shared__ PipeSrc ps;
     __shared__ T sm[(2 * MT + 1) * (LBFGSB_BLOCK / 32)];
     const DevState<T>* s = w.s;
@@ -100,12 +101,12 @@ template <typename T, int MT> constexpr unsigned smem_update() { return pipe_sme
 //        3 bnded (min over blocks)
 // ---------------------------------------------------------------------------
 template <typename T, int MT>
-__global__ void __launch_bounds__(LBFGSB_BLOCK, 1) k_cauchy_classify(Wk<T> w) {
+__global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cauchy_classify(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ char dyn[];
-    __shared__ unsigned long long full[LB_PIPE_STAGES];
+    __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
     __shared__ PipeSrc ps;
     __shared__ T sm[(2 * MT + 1) * (LBFGSB_BLOCK / 32)];
     __shared__ T smv[LBFGSB_BLOCK / 32];
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK, 1) k_cauchy_classify(Wk<T> w) {
     const int mode = s->cauchy_mode;
     const i64 n = w.n;
     if (mode != 0) {  // xcp = x only (:609 or :1247)
+        if (threadIdx.x >= LBFGSB_BLOCK) return;
         LB_FOR_TILES(T, n, base) {
             T x[VEC];
             ldv<T>(w.x, base, n, x);
@@ -218,12 +220,12 @@ template <typename T, int MT> constexpr unsigned smem_classify() { return pipe_s
 //       [2MT,3MT) C_j = sum_act Ws_last*Wy_j ; [3MT,4MT) D_j = sum_free Ws_j*Wy_last
 // ---------------------------------------------------------------------------
 template <typename T, int MT>
-__global__ void __launch_bounds__(LBFGSB_BLOCK, 1) k_formk_gram(Wk<T> w) {
+__global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_gram(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ char dyn[];
-    __shared__ unsigned long long full[LB_PIPE_STAGES];
+    __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
     __shared__ PipeSrc ps;
     __shared__ T sm[4 * MT * (LBFGSB_BLOCK / 32)];
     const DevState<T>* s = w.s;
@@ -280,12 +282,12 @@ template <typename T, int MT> constexpr unsigned smem_formk() { return pipe_smem
 // part: [0,MT) sum Wy(:,j) r ; [MT,2MT) sum Ws(:,j) r
 // ---------------------------------------------------------------------------
 template <typename T, int MT>
-__global__ void __launch_bounds__(LBFGSB_BLOCK, 1) k_cmprlb_wv(Wk<T> w) {
+__global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cmprlb_wv(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ char dyn[];
-    __shared__ unsigned long long full[LB_PIPE_STAGES];
+    __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
     __shared__ PipeSrc ps;
     __shared__ T sm[2 * MT * (LBFGSB_BLOCK / 32)];
     const DevState<T>* s = w.s;
@@ -363,12 +365,12 @@ template <typename T, int MT> constexpr unsigned smem_cmprlb() { return pipe_sme
 // part: 0 dd_p.  ipart: 0 iword (sum>0)
 // ---------------------------------------------------------------------------
 template <typename T, int MT>
-__global__ void __launch_bounds__(LBFGSB_BLOCK, 1) k_subsm_step(Wk<T> w) {
+__global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_step(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ char dyn[];
-    __shared__ unsigned long long full[LB_PIPE_STAGES];
+    __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
     __shared__ PipeSrc ps;
     __shared__ T sm[LBFGSB_BLOCK / 32];
     __shared__ i64 smi[LBFGSB_BLOCK / 32];

@@ -2,11 +2,12 @@
 //
 // A pass over the variables touches up to 2*col + 8 input streams (the ring columns of
 // Wy/Ws are n apart in memory).  Issuing those as per-thread global loads costs two registers
-// per stream per thread and serialises the load latency behind every use.  Here one elected
-// thread per CTA issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP) of one sub-tile of every
-// stream into a two-stage shared-memory ring and the CTA consumes the other stage; completion
-// is tracked by one mbarrier per stage (expect_tx / complete_tx).  Registers hold only the
-// accumulators, and 100 KB per SM is in flight regardless of occupancy.
+// per stream per thread and serialises the load latency behind every use.  Here a producer
+// warp issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP) of one sub-tile of every stream
+// into a two-stage shared-memory ring while eight consumer warps compute from the other
+// stage; a full[] / empty[] mbarrier pair per stage (expect_tx / complete_tx, consumer release)
+// is the only synchronisation.  Registers hold only the accumulators, and 100 KB per SM is in
+// flight regardless of occupancy.
 //
 // The thread -> element mapping and the order in which a thread meets its elements are
 // exactly those of LB_FOR_TILES (include/lbfgsb_b200_shape.h): a stage is one k-sub-tile
@@ -123,13 +124,24 @@ __device__ __forceinline__ void lds_byte(const char* sm, unsigned off, int lt, i
 
 // The pass.  body(base, sm, lt): `base` = first variable of this thread in the stage, `sm` = stage
 // buffer, `lt` = thread index inside the stage.  Elements at or beyond n read as zero.
-// `stages` must be 128-byte aligned; `full` are LB_PIPE_STAGES mbarriers in shared memory.
-// All threads of the block must call; contains __syncthreads().
+// `stages` must be 128-byte aligned; `bars` are 2*LB_PIPE_STAGES mbarriers in shared memory
+// (full[], then empty[]).
+//
+// The CTA has LB_TMA_THREADS = LBFGSB_BLOCK + 32 threads: warps 0..7 are the consumers (the
+// LBFGSB_BLOCK threads of the fixed reduction shape), warp 8 is the producer -- its lanes issue
+// the bulk copies of a stage in parallel (one stream per lane) as soon as all consumer warps
+// have released the buffer (empty[] barrier).  Consumer warps never wait for one another.
+// All threads of the block must call.
+#define LB_TMA_THREADS (LBFGSB_BLOCK + 32)
+
 template <typename T, int SUBT, typename Body>
-__device__ __forceinline__ void tma_pass(i64 n, const PipeSrc* ps, char* stages, unsigned long long* full, Body body) {
+__device__ __forceinline__ void tma_pass(i64 n, const PipeSrc* ps, char* stages, unsigned long long* bars, Body body) {
     typedef PipeGeom<T, SUBT> G;
     constexpr int VEC = G::VEC;
-    const int tid = threadIdx.x;
+    constexpr int NCW = LBFGSB_BLOCK / 32;   // consumer warps
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    unsigned long long* full = bars;
+    unsigned long long* empty = bars + LB_PIPE_STAGES;
     const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
     const i64 ntiles = (n + tile - 1) / tile;
     const i64 b = blockIdx.x;
@@ -143,7 +155,7 @@ __device__ __forceinline__ void tma_pass(i64 n, const PipeSrc* ps, char* stages,
         nitems = (ntl - 1) * G::IPT + last;
     }
     if (tid == 0) {
-        for (int s = 0; s < LB_PIPE_STAGES; ++s) tma::mbar_init(&full[s], 1);
+        for (int s = 0; s < LB_PIPE_STAGES; ++s) { tma::mbar_init(&full[s], 1); tma::mbar_init(&empty[s], NCW); }
         tma::fence_barrier_init();
     }
     __syncthreads();
@@ -154,23 +166,30 @@ __device__ __forceinline__ void tma_pass(i64 n, const PipeSrc* ps, char* stages,
         const int r = (int)(q % G::IPT);
         return tl * tile + (i64)r * G::ELEMS;        // k*(BLOCK*VEC) + h*(SUBT*VEC) == r*ELEMS
     };
-    auto issue = [&](i64 q) {
-        const i64 sb = stage_base(q);
-        const int st = (int)(q % LB_PIPE_STAGES);
-        if (sb + G::ELEMS <= n) {
-            tma::mbar_expect_tx(&full[st], ps->stage_tx);
-            char* dst = stages + (size_t)st * stage_bytes;
-            for (int s = 0; s < nsrc; ++s) {
-                const unsigned e = ps->esz[s];
-                tma::bulk_g2s(dst + ps->off[s], ps->p[s] + sb * e, (unsigned)G::ELEMS * e, &full[st]);
+    if (wid == NCW) {
+        // ---- producer warp ----
+        const unsigned stage_tx = ps->stage_tx;
+        for (i64 q = 0; q < nitems; ++q) {
+            const int st = (int)(q % LB_PIPE_STAGES);
+            if (q >= LB_PIPE_STAGES) tma::mbar_wait(&empty[st], (unsigned)(((q / LB_PIPE_STAGES) - 1) & 1));
+            const i64 sb = stage_base(q);
+            if (sb + G::ELEMS <= n) {
+                if (lane == 0) tma::mbar_expect_tx(&full[st], stage_tx);
+                __syncwarp();
+                char* dst = stages + (size_t)st * stage_bytes;
+                for (int s = lane; s < nsrc; s += 32) {
+                    const unsigned e = ps->esz[s];
+                    tma::bulk_g2s(dst + ps->off[s], ps->p[s] + sb * e, (unsigned)G::ELEMS * e, &full[st]);
+                }
+            } else if (lane == 0) {
+                tma::mbar_arrive(&full[st]);   // ragged stage: filled by the consumers themselves
             }
-        } else {
-            tma::mbar_arrive(&full[st]);   // ragged stage: filled by the consumers themselves
+            __syncwarp();
         }
-    };
-    if (tid == 0 && nitems > 0) issue(0);
+        return;
+    }
+    // ---- consumer warps ----
     for (i64 q = 0; q < nitems; ++q) {
-        if (tid == 0 && q + 1 < nitems) issue(q + 1);
         const int st = (int)(q % LB_PIPE_STAGES);
         tma::mbar_wait(&full[st], (unsigned)((q / LB_PIPE_STAGES) & 1));
         const i64 sb = stage_base(q);
@@ -191,6 +210,7 @@ __device__ __forceinline__ void tma_pass(i64 n, const PipeSrc* ps, char* stages,
             }
             if (base < n) body(base, (const char*)sm, lt);
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(&empty[st]);
     }
 }
