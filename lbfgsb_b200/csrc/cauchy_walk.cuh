@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(LB_WB) k_walk_f2(Wk<T> w, WalkBuf<T> b, i64 st
     if (ok) {
         const typename Real<T>::key_t* keys = cur_keys<T>(b);
         const T tj = KeyBits<T>::from(keys[start + j]);
-        const T tp = (start + j > 0) ? KeyBits<T>::from(keys[start + j - 1]) : (T)0;
+        const T tp = (start + j > 0) ? KeyBits<T>::from(keys[start + j - 1]) : s->walk_tlast;   // 0, or the last key of the lower ranks
         const T dt = tj - tp;
         h = dt * f2j + b.g1[j];
         b.f2a[j] = f2j;

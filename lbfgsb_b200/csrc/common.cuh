@@ -80,7 +80,7 @@ struct DevState {
     T ls[13];                     // dcsrch dsave(1:13)
     T f1, f2, f2_org, dtm, tsum, bkmin;
     T dd_p, alpha;
-    T walk_f1, walk_f2, walk_tlast;   // carries across walk chunks
+    T walk_f1, walk_f2, walk_tlast, walk_tprev2;   // carries across walk chunks (and ranks)
     // ---- small matrices (column-major, leading dimension m or 2m as in the reference) ----
     T sy[LB_MMAX * LB_MMAX], ss[LB_MMAX * LB_MMAX], wt[LB_MMAX * LB_MMAX];
     T wn[4 * LB_MMAX * LB_MMAX], wn1[4 * LB_MMAX * LB_MMAX];

@@ -20,6 +20,8 @@
 #include "../../include/lbfgsb_b200.h"
 #include "cauchy_walk.cuh"
 #include "kernels_tma.cuh"
+#include "cauchy_walk_dist.cuh"
+#include <algorithm>
 
 // ---------------------------------------------------------------------------
 // errors
@@ -52,6 +54,10 @@ struct NcclApi {
     int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
     int (*CommDestroy)(ncclComm_t);
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*GroupStart)();
+    int (*GroupEnd)();
     const char* (*GetErrorString)(int);
     bool ok;
 };
@@ -69,7 +75,12 @@ static NcclApi* nccl_api() {
             api.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
             api.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
             api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
-            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather;
+            api.Send = (int (*)(const void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclSend");
+            api.Recv = (int (*)(void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclRecv");
+            api.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+            api.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Send && api.Recv &&
+                     api.GroupStart && api.GroupEnd;
         }
     }
     return &api;
@@ -109,12 +120,18 @@ struct Engine : EngineBase {
     SortCtl* ctl_el = nullptr;
     SortCtl* ctl_host = nullptr;     // pinned
     T* tmpAB = nullptr; T* tmpF = nullptr; unsigned long long* jmin = nullptr;
-    T* fd_parts = nullptr; T* delta = nullptr;
+    T* fd_parts = nullptr; T* delta = nullptr; T* delta_all = nullptr; T* delta_sum = nullptr;
     std::vector<void*> allocs;
     // sharding
     int R = 1, rank = 0;
     ncclComm_t comm = nullptr;
     Red<T>* rec_local = nullptr; Red<T>* rec_all = nullptr;
+    // sharded breakpoint walk (cauchy_walk_dist.cuh)
+    unsigned long long* samp_local = nullptr; unsigned long long* samp_all = nullptr; unsigned long long* spl_dev = nullptr;
+    DwCtl* dctl = nullptr; i64* pos_all = nullptr; SortCtl* ctl_d = nullptr;
+    WalkCarry<T>* carry_local = nullptr; WalkCarry<T>* carry_all = nullptr;
+    struct DynBuf { void* p = nullptr; size_t cap = 0; };
+    DynBuf dw_send, dw_recv, dw_k0, dw_k1, dw_v0, dw_v1;
     // accounting
     i64 launches = 0, syncs = 0;
     bool profile = false;
@@ -145,7 +162,7 @@ struct Engine : EngineBase {
         if (st) stream = st;
         else { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
         memset(&w, 0, sizeof w);
-        w.n = n; w.m = m;
+        w.n = n; w.m = m; w.off = offset;
         w.ldw = (n + 31) / 32 * 32;
         const size_t vb = (size_t)w.ldw * sizeof(T);
         if (!dalloc(&w.ws, vb * m) || !dalloc(&w.wy, vb * m)) return false;
@@ -185,7 +202,13 @@ struct Engine : EngineBase {
         if (!dalloc(&fd_parts, sizeof(T) * (size_t)LB_FD_GRID * 6 * LB_MMAX * LB_MMAX) || !dalloc(&delta, sizeof(T) * 6 * LB_MMAX * LB_MMAX)) return false;
         CK(cudaMemsetAsync(delta, 0, sizeof(T) * 6 * LB_MMAX * LB_MMAX, stream));
         if (R > 1) {
+            if (R > LB_MAXR) { set_error("at most %d ranks", LB_MAXR); return false; }
             if (!dalloc(&rec_local, sizeof(Red<T>)) || !dalloc(&rec_all, sizeof(Red<T>) * R)) return false;
+            const size_t sb = sizeof(unsigned long long) * (2 * LB_DW_SAMPLES + 1);
+            if (!dalloc(&samp_local, sb) || !dalloc(&samp_all, sb * R) || !dalloc(&spl_dev, 16 * LB_MAXR)) return false;
+            if (!dalloc(&dctl, sizeof(DwCtl)) || !dalloc(&pos_all, sizeof(i64) * (LB_MAXR + 1) * R) || !dalloc(&ctl_d, sizeof(SortCtl))) return false;
+            if (!dalloc(&carry_local, sizeof(WalkCarry<T>)) || !dalloc(&carry_all, sizeof(WalkCarry<T>) * R)) return false;
+            if (!dalloc(&delta_all, sizeof(T) * 6 * LB_MMAX * LB_MMAX * R) || !dalloc(&delta_sum, sizeof(T) * 6 * LB_MMAX * LB_MMAX)) return false;
         }
         CK(cudaStreamSynchronize(stream));
         return true;
@@ -193,6 +216,7 @@ struct Engine : EngineBase {
 
     ~Engine() {
         for (void* p : allocs) cudaFree(p);
+        for (DynBuf* d : {&dw_send, &dw_recv, &dw_k0, &dw_k1, &dw_v0, &dw_v1}) if (d->p) cudaFree(d->p);
         if (s_host) cudaFreeHost(s_host);
         if (ctl_host) cudaFreeHost(ctl_host);
         for (auto e : pool) cudaEventDestroy(e);
@@ -297,6 +321,139 @@ struct Engine : EngineBase {
         return true;
     }
 
+    // ---- the breakpoint walk on a sharded problem (cauchy_walk_dist.cuh) -----
+    bool ensure(DynBuf& d, size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        if (d.cap >= bytes) return true;
+        if (d.p) cudaFree(d.p);
+        d.p = nullptr; d.cap = 0;
+        const size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&d.p, want);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed in the sharded breakpoint walk: %s", want, cudaGetErrorString(e)); return false; }
+        d.cap = want;
+        return true;
+    }
+    bool allgather(const void* src, void* dst, size_t bytes) {
+        int rc = nccl_api()->AllGather(src, dst, bytes, 0 /*ncclChar*/, comm, stream);
+        if (rc != 0) { set_error("ncclAllGather failed: %d", rc); return false; }
+        return true;
+    }
+    void enqueue_sort(typename Real<T>::key_t* k0, typename Real<T>::key_t* k1, int* v0, int* v1, SortCtl* ctl) {
+        typedef typename Real<T>::key_t K;
+        for (int pass = 0; pass < (int)sizeof(K); ++pass) {
+            k_rs_hist<K><<<LB_RS_GRID, 256, 0, stream>>>(k0, k1, ctl, pass * 8, rs_counts);
+            k_rs_scan<<<1, 1024, 0, stream>>>(rs_counts, ctl);
+            k_rs_scatter<K><<<LB_RS_GRID, 256, 0, stream>>>(k0, k1, v0, v1, ctl, pass * 8, rs_counts);
+            k_rs_flip<<<1, 32, 0, stream>>>(ctl);
+            launches += 4;
+        }
+    }
+    bool enqueue_walk_sharded() {
+        typedef typename Real<T>::key_t K;
+        const int S = LB_DW_SAMPLES;
+        // 1. local breakpoints, sorted
+        begin(F_WALK_COMPACT);
+        k_flag_count<T, 0><<<LG>>>(w, tile_counts);
+        k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 0, tile_counts, tile_offsets, ntiles, wb.ctl);
+        k_flag_write<T, 0><<<LG>>>(w, tile_offsets, wb.k0, wb.v0);
+        end(F_WALK_COMPACT, 3);
+        begin(F_WALK_SORT);
+        enqueue_sort(wb.k0, wb.k1, wb.v0, wb.v1, wb.ctl);
+        end(F_WALK_SORT, 0);
+        // 2. splitters from regular samples
+        begin(F_WALK_SCAN);
+        k_dw_sample<T><<<1, 64, 0, stream>>>(w, wb, samp_local); launches++;
+        const size_t sbytes = sizeof(unsigned long long) * (2 * S + 1);
+        if (!allgather(samp_local, samp_all, sbytes)) return false;
+        std::vector<unsigned long long> hs((size_t)(2 * S + 1) * R);
+        CK(cudaMemcpyAsync(hs.data(), samp_all, sbytes * R, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream)); syncs++;
+        std::vector<std::pair<unsigned long long, i64>> smp;
+        for (int q = 0; q < R; ++q)
+            for (int i = 0; i < S; ++i) smp.push_back({hs[(size_t)q * (2 * S + 1) + i], (i64)hs[(size_t)q * (2 * S + 1) + S + i]});
+        std::sort(smp.begin(), smp.end());
+        std::vector<unsigned long long> spl(2 * (R - 1));
+        for (int q = 1; q < R; ++q) { spl[q - 1] = smp[(size_t)q * S].first; spl[(R - 1) + (q - 1)] = (unsigned long long)smp[(size_t)q * S].second; }
+        CK(cudaMemcpyAsync(spl_dev, spl.data(), sizeof(unsigned long long) * 2 * (R - 1), cudaMemcpyHostToDevice, stream));
+        k_dw_partition<T><<<1, 32, 0, stream>>>(w, wb, R, spl_dev, dctl); launches++;
+        if (!allgather(dctl->pos, pos_all, sizeof(i64) * (LB_MAXR + 1))) return false;
+        std::vector<i64> hp((size_t)(LB_MAXR + 1) * R);
+        CK(cudaMemcpyAsync(hp.data(), pos_all, sizeof(i64) * (LB_MAXR + 1) * R, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream)); syncs++;
+        // 3. exchange plan: cnt(q -> r) = pos_q[r+1] - pos_q[r]
+        auto cnt = [&](int q, int r) { return hp[(size_t)q * (LB_MAXR + 1) + r + 1] - hp[(size_t)q * (LB_MAXR + 1) + r]; };
+        DwCtl hc; memset(&hc, 0, sizeof hc);
+        for (int r = 0; r <= R; ++r) hc.pos[r] = hp[(size_t)rank * (LB_MAXR + 1) + r];
+        i64 nrecv = 0;
+        for (int q = 0; q < R; ++q) { hc.roff[q] = nrecv; nrecv += cnt(q, rank); }
+        hc.roff[R] = nrecv;
+        i64 nb_glob = 0, goff = 0;
+        for (int r = 0; r < R; ++r) {
+            i64 t = 0;
+            for (int q = 0; q < R; ++q) t += cnt(q, r);
+            if (r < rank) goff += t;
+            nb_glob += t;
+        }
+        hc.goff = goff; hc.nb_glob = nb_glob;
+        if (nrecv > 2147483647LL) { set_error("a rank would receive more than 2^31 breakpoints"); return false; }
+        const i64 nb_loc = hc.pos[R];
+        const int col = s_host->col;
+        const int rs = 3 + 2 * col;
+        if (!ensure(dw_send, sizeof(T) * (size_t)nb_loc * rs) || !ensure(dw_recv, sizeof(T) * (size_t)nrecv * rs)) return false;
+        if (!ensure(dw_k0, sizeof(K) * (size_t)nrecv) || !ensure(dw_k1, sizeof(K) * (size_t)nrecv) ||
+            !ensure(dw_v0, 4 * (size_t)nrecv) || !ensure(dw_v1, 4 * (size_t)nrecv)) return false;
+        CK(cudaMemcpyAsync(dctl, &hc, sizeof hc, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));   // hc is a stack object
+        T* send = (T*)dw_send.p; T* recv = (T*)dw_recv.p;
+        k_dw_pack<T><<<LBFGSB_GRID, 256, 0, stream>>>(w, wb, send, rs); launches++;
+        nccl_api()->GroupStart();
+        for (int q = 0; q < R; ++q) {
+            const i64 sc = cnt(rank, q), rc = cnt(q, rank);
+            if (q == rank) {
+                if (sc > 0) CK(cudaMemcpyAsync(recv + hc.roff[q] * rs, send + hc.pos[q] * rs, sizeof(T) * (size_t)sc * rs, cudaMemcpyDeviceToDevice, stream));
+                continue;
+            }
+            if (sc > 0) nccl_api()->Send(send + hc.pos[q] * rs, sizeof(T) * (size_t)sc * rs, 0, q, comm, stream);
+            if (rc > 0) nccl_api()->Recv(recv + hc.roff[q] * rs, sizeof(T) * (size_t)rc * rs, 0, q, comm, stream);
+        }
+        int grc = nccl_api()->GroupEnd();
+        if (grc != 0) { set_error("nccl send/recv group failed: %d", grc); return false; }
+        // 4. this rank's key range in global order
+        WalkBuf<T> wd = wb;
+        wd.k0 = (K*)dw_k0.p; wd.k1 = (K*)dw_k1.p; wd.v0 = (int*)dw_v0.p; wd.v1 = (int*)dw_v1.p; wd.ctl = ctl_d;
+        k_dw_keys<T><<<LBFGSB_GRID, 256, 0, stream>>>(recv, rs, nrecv, wd.k0, wd.v0, ctl_d); launches++;
+        enqueue_sort(wd.k0, wd.k1, wd.v0, wd.v1, ctl_d);
+        // 5. scans in rank order, carries handed from rank to rank
+        for (int turn = 0; turn < R; ++turn) {
+            if (turn == rank) {
+                for (i64 start = 0; start < nrecv; start += wd.cap) {
+                    const i64 len = (nrecv - start < wd.cap) ? (nrecv - start) : wd.cap;
+                    const i64 nblk = (len + LB_WB - 1) / LB_WB;
+                    CK(cudaMemsetAsync(jmin, 0xff, 8, stream));
+                    k_dw_gather<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wd, recv, rs, start, len);
+                    k_walk_scan_vec<T><<<1, 1024, 0, stream>>>(w, wd, nblk, tmpAB);
+                    k_walk_dots<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wd, start, len);
+                    k_walk_scan_f2<T><<<1, 32, 0, stream>>>(w, wd, nblk, tmpF);
+                    k_walk_f2<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wd, start, len);
+                    k_walk_scan_f1<T><<<1, 32, 0, stream>>>(w, wd, nblk, tmpF);
+                    k_walk_test<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wd, start, len, jmin);
+                    k_walk_chunk_end<T><<<1, 32, 0, stream>>>(w, wd, start, len, tmpAB, tmpF, jmin);
+                    launches += 8;
+                }
+                k_dw_fixcount<T><<<LBFGSB_GRID, 256, 0, stream>>>(w, wd, R, dctl); launches++;
+            }
+            k_dw_turn_end<T><<<1, LB_WB, 0, stream>>>(w, wd, dctl, wd.cap, turn == rank ? 1 : 0, R, carry_local); launches++;
+            if (!allgather(carry_local, carry_all, sizeof(WalkCarry<T>))) return false;
+            k_dw_adopt<T><<<1, 32, 0, stream>>>(w, carry_all, turn, R, rank, dctl, n_global); launches++;
+        }
+        end(F_WALK_SCAN, 0);
+        // 6. fix the local variables that precede the exit
+        begin(F_WALK_FIX);
+        k_dw_fix<T><<<LBFGSB_GRID, 256, 0, stream>>>(w, wb, dctl);
+        end(F_WALK_FIX);
+        return true;
+    }
+
     // ---- prelims + first lnsrlb (:601-773) ----------------------------------
     bool enqueue_body() {
         for (;;) {
@@ -306,8 +463,8 @@ struct Engine : EngineBase {
             if (s_host->cnstnd) {
                 if (!sync_state()) return false;
                 if (s_host->go && s_host->in_body && s_host->need_walk) {
-                    if (R > 1) { set_error("breakpoint walk on a sharded problem is not implemented yet"); return false; }
-                    if (!enqueue_walk(s_host->nbreak)) return false;
+                    if (R > 1) { if (!enqueue_walk_sharded()) return false; }
+                    else if (!enqueue_walk(s_host->nbreak)) return false;
                 }
             }
             begin(F_GCP_FREEV); k_gcp_freev<T><<<LG>>>(w); end(F_GCP_FREEV);
@@ -322,7 +479,8 @@ struct Engine : EngineBase {
             k_formk_delta_final<T><<<(6 * LB_MMAX * LB_MMAX + 255) / 256, 256, 0, stream>>>(w, fd_parts, LB_FD_GRID, delta);
             end(F_FORMK_DELTA, 5);
             if (!site(site_formk(mt))) return false;
-            begin(F_SCALAR); s_formk_dense<T><<<LS>>>(w, dist(), mt, delta); end(F_SCALAR);
+            if (R > 1 && !allgather(delta, delta_all, sizeof(T) * 6 * LB_MMAX * LB_MMAX)) return false;
+            begin(F_SCALAR); s_formk_dense<T><<<LS>>>(w, dist(), mt, R > 1 ? delta_all : delta, delta_sum); end(F_SCALAR);
             begin(F_CMPRLB_WV); MTCALL(k_cmprlb_wv, smem_cmprlb, w); end(F_CMPRLB_WV);
             if (!site(site_wv(mt))) return false;
             begin(F_SCALAR); s_subsm_dense<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);

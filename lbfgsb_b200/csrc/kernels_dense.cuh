@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
         // the first breakpoint is reached: the sorted walk takes over
         s->need_walk = 1;
         for (int j = 0; j < col2; ++j) { s->p0[j] = s->p[j]; s->walkA[j] = zero; s->walkB[j] = zero; }
-        s->walk_f1 = s->f1; s->walk_f2 = s->f2; s->walk_tlast = zero;
+        s->walk_f1 = s->f1; s->walk_f2 = s->f2; s->walk_tlast = zero; s->walk_tprev2 = zero;
         s->walk_J = -1; s->walk_done = 0;
         return;
     }
@@ -357,12 +357,22 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_freev(Wk<T> w, Dist<T> di
 //        (dE - dL kept separately: delta[0..2] enter, delta[3..5] leave)
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist<T> dist, int mt, const T* delta) {
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist<T> dist, int mt, const T* delta, T* delta_sum) {
     __shared__ Red<T> red;
     DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->do_subspace) return;
     const bool newrow = s->do_formk && s->updatd;
     if (newrow) site_reduce<T>(w, dist, site_formk(mt), &red);
+    if (dist.R > 1 && s->do_delta) {
+        // sharded: `delta` holds the all-gathered per-rank corrections [R][6*MMAX*MMAX]; add them in rank order
+        for (int e = threadIdx.x; e < 6 * LB_MMAX * LB_MMAX; e += blockDim.x) {
+            T acc = delta[e];
+            for (int q = 1; q < dist.R; ++q) acc = acc + delta[(i64)q * (6 * LB_MMAX * LB_MMAX) + e];
+            delta_sum[e] = acc;
+        }
+        __syncthreads();
+        delta = delta_sum;
+    }
     if (threadIdx.x != 0) return;
     const int m = s->m, col = s->col, m2 = 2 * m;
     T* wn = s->wn; T* wn1 = s->wn1;
@@ -499,7 +509,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_bt(Wk<T> w, Dist<T> dist,
     T alpha = (T)1; i64 ibd = -1;
     if (red.rv[0] < alpha) { alpha = red.rv[0]; ibd = red.iv[0]; }
     s->alpha = alpha;
-    s->ibd = ibd;   // global index when sharded (the kernel globalises), local otherwise
+    s->ibd = ibd;   // global variable index (k_bt_alpha adds the shard offset)
     (void)index_offset;
 }
 

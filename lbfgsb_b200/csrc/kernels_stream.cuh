@@ -11,6 +11,7 @@
 template <typename T>
 struct Wk {               // workspace + user vectors of one problem (device pointers)
     i64 n, ldw;           // variables; leading dimension of ws/wy (multiple of 32)
+    i64 off;              // global index of this shard's first variable (0 on a single GPU)
     int m;
     T *ws, *wy;           // S, Y histories, column-major [m][ldw]        (:390-391)
     T *z, *r, *d, *t, *xp;  // n-vectors of mainlb                         (:382-388)
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_bt_alpha(Wk<T> w) {
                     T t2 = u[v] - xk[v];
                     cand = (t2 <= (T)0) ? (T)0 : t2 / dk[v];
                 }
-                if (cand < best) { best = cand; ib = base + v; }
+                if (cand < best) { best = cand; ib = base + v + w.off; }   // global index: ties resolve identically on every rank
             }
         }
     }
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_bt_apply(Wk<T> w) {
         for (int v = 0; v < VEC; ++v) {
             if (base + v < n) {
                 if (st[v] & 1) {
-                    if (alpha < (T)1 && base + v == ibd) {
+                    if (alpha < (T)1 && base + v + w.off == ibd) {
                         if (dk[v] > (T)0) { xk[v] = u[v]; dk[v] = (T)0; }
                         else if (dk[v] < (T)0) { xk[v] = l[v]; dk[v] = (T)0; }
                     }

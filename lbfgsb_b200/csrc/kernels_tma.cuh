@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cauchy_classify(Wk<T> w) 
                     else if (nb[v] >= 2 && neggi > (T)0) { tb = tu / neggi; hasb = true; }
                     if (hasb) {
                         nbr++;
-                        if (tb < bk) { bk = tb; ibk = base + v; }   // strict <: lowest index among ties (:1310)
+                        if (tb < bk) { bk = tb; ibk = base + v + w.off; }   // strict <: lowest index among ties (:1310)
                     } else {
                         nfc++;
                         if (fabs(neggi) > (T)0) bnd = 0;

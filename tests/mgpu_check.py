@@ -1,0 +1,106 @@
+"""Multi-GPU parity check, launched under torchrun (one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tests/mgpu_check.py [n_global] [m] [l_odd] [iterations]
+
+Runs the sample problem sharded over the N ranks through lbfgsb_setulb_dev_f64 and, on rank 0,
+the same problem on one GPU; the per-iterate discrete trace (iter, nfgv, nseg, nfree, nact, iword,
+iback, active-set hash) must be equal and f, |proj g| agree to rounding.  Prints one line
+`MGPU_CHECK OK ...` or `MGPU_CHECK FAIL ...`; exit code 0 / 1.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+
+import lbfgsb_b200  # noqa: E402
+from lbfgsb_b200 import sharded  # noqa: E402
+
+
+def solve(n_local, off, n_global, m, l_odd, iters, shard, fg_factory, dev, rank, world):
+    x = torch.full((n_local,), 3.0, dtype=torch.float64, device=dev)
+    l = torch.full((n_local,), -100.0, dtype=torch.float64, device=dev)
+    l[(off % 2)::2] = l_odd
+    u = torch.full((n_local,), 100.0, dtype=torch.float64, device=dev)
+    nbd = torch.full((n_local,), 2, dtype=torch.int32, device=dev)
+    g = torch.zeros_like(x)
+    prob = lbfgsb_b200.DeviceProblem(n_local, m, np.float64, shard=shard)
+    fg = fg_factory()
+    rows = []
+    while True:
+        prob.setulb_dev(x, l, u, nbd, g, 0.0, 0.0)
+        t = prob.task_str()
+        if t[:2] == "FG":
+            prob.f[0] = fg(x, g)
+        elif t[:5] == "NEW_X":
+            h, c = prob.active_set_hash()
+            if world > 1 and shard is not None:
+                ht = torch.tensor([np.int64(np.uint64(h).astype(np.int64)), c], dtype=torch.int64, device=dev)
+                dist.all_reduce(ht)
+                h, c = int(ht[0]) & 0xFFFFFFFFFFFFFFFF, int(ht[1])
+            rows.append(dict(iter=int(prob.isave[29]), nfgv=int(prob.isave[33]), nseg=int(prob.isave[32]),
+                             nfree=int(prob.isave[37]), nact=int(prob.isave[38]), iword=int(prob.isave[36]),
+                             iback=int(prob.isave[24]), nenter=int(prob.isave[40]), col=int(prob.isave[27]),
+                             hash=h, hcount=c, f=float(prob.f[0]), sbgnrm=float(prob.dsave[12]),
+                             stp=float(prob.dsave[13]), theta=float(prob.dsave[0])))
+            if prob.isave[29] >= iters:
+                break
+        else:
+            break
+    task = prob.task_str()
+    prob.close()
+    return rows, task, x
+
+
+def main():
+    n_global = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+    m = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    l_odd = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+    iters = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    lo, hi = sharded.shard_bounds(n_global, rank, world)
+    comm = sharded.nccl_comm_for_engine(rank, world, dist, dev)
+    kern = lbfgsb_b200.RosenbrockDevice(np.float64)
+    rows, task, x = solve(hi - lo, lo, n_global, m, l_odd, iters, (lo, n_global, comm, rank, world),
+                          lambda: sharded.ShardedRosenbrockDevice(kern, rank, world, dist, dev), dev, rank, world)
+    ok = True
+    msg = ""
+    if rank == 0:
+        ref, rtask, xr = solve(n_global, 0, n_global, m, l_odd, iters, None, lambda: kern, dev, 0, 1)
+        if task != rtask or len(rows) != len(ref):
+            ok, msg = False, "task/len %r %r %d %d" % (task, rtask, len(rows), len(ref))
+        worst = 0.0
+        for a, b in zip(rows, ref):
+            for k in ("iter", "nfgv", "nseg", "nfree", "nact", "iword", "iback", "nenter", "col", "hash", "hcount"):
+                if a[k] != b[k]:
+                    ok, msg = False, msg + " | it %d %s: %r != %r" % (b["iter"], k, a[k], b[k])
+            rel = abs(a["f"] - b["f"]) / max(abs(b["f"]), 1e-300)
+            worst = max(worst, rel)
+            tol = 1e-10 if b["iter"] <= 10 else 1e-6
+            if rel > tol:
+                ok, msg = False, msg + " | it %d f rel %.2e" % (b["iter"], rel)
+            if not ok:
+                break
+        walks = [r["nseg"] for r in ref if r["nseg"] > 1]
+        print("MGPU_CHECK %s world=%d n=%d m=%d l_odd=%g iterations=%d walks(nseg>1)=%s worst_rel_f=%.2e %s" % (
+            "OK" if ok else "FAIL", world, n_global, m, l_odd, len(ref), walks[:6], worst, msg[:600]), flush=True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    lbfgsb_b200.lib().lbfgsb_dev_nccl_destroy(comm)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) else 1)
+
+
+if __name__ == "__main__":
+    main()
