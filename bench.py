@@ -208,6 +208,10 @@ def main():
     if a.impl == "reference":
         reference_arm(a)
         return
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import harness as H
@@ -244,38 +248,19 @@ def main():
     shard = None
     comm = None
     if world > 1:
-        idbuf = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            import ctypes as C
-            raw = (C.c_char * 128)()
-            if lbfgsb_b200.lib().lbfgsb_dev_nccl_unique_id(raw) != 0:
-                raise SystemExit("nccl unique id: " + lbfgsb_b200.last_error())
-            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
-        idd = idbuf.to(dev)
-        dist.broadcast(idd, 0)
-        idb = idd.cpu().numpy().tobytes()
-        comm = lbfgsb_b200.lib().lbfgsb_dev_nccl_init(idb, rank, world)
-        if not comm:
-            raise SystemExit("nccl init: " + lbfgsb_b200.last_error())
+        from lbfgsb_b200 import sharded
+        comm = sharded.nccl_comm_for_engine(rank, world, dist, dev)
         shard = (off, n_global, comm, rank, world)
     prob = lbfgsb_b200.DeviceProblem(n, m, np.float64, stream=stream, shard=shard)
     fgk = lbfgsb_b200.RosenbrockDevice(np.float64, stream=stream)
     nfg = [0]
 
+    if world > 1:
+        fg_sharded = sharded.ShardedRosenbrockDevice(fgk, rank, world, dist, dev)
+
     def fg():
         nfg[0] += 1
-        if world == 1:
-            return fgk(xd, gd)
-        # halo: the neighbours' boundary values
-        edge = torch.stack([xd[0], xd[-1]])
-        allv = [torch.empty_like(edge) for _ in range(world)]
-        dist.all_gather(allv, edge)
-        xl = float(allv[rank - 1][1]) if rank > 0 else 0.0
-        xr = float(allv[rank + 1][0]) if rank < world - 1 else 0.0
-        fl = fgk(xd, gd, first=1 if rank == 0 else 0, last=1 if rank == world - 1 else 0, xl=xl, xr=xr)
-        ft = torch.tensor([fl], dtype=torch.float64, device=dev)
-        dist.all_reduce(ft)
-        return float(ft)
+        return fgk(xd, gd) if world == 1 else fg_sharded(xd, gd)
 
     def run_until(target_iter):
         while True:
@@ -326,9 +311,7 @@ def main():
     okp = run_until(W + K + PK)
     prof = prob.profile_read()
     prob.profile(False)
-    nfree_t = torch.tensor([nfree], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(nfree_t)
+    nfree_t = nfree            # isave(38) is the global count on every rank
     roof = None
     fam_table = {}
     peaks = {}
@@ -415,10 +398,12 @@ def main():
                           "linearly to n=%d; host has %d cores" % (a.cpu_n, k, W, n, os.cpu_count())}
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "failed: %s" % e}
-    if rank == 0:
-        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
 
 
 def e2e_host_twin(n, m, W, K, dev):

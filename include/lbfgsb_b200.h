@@ -89,6 +89,8 @@ void lbfgsb_dev_nccl_destroy(void* comm);
 int lbfgsb_dev_active_set_hash(lbfgsb_dev_t* h, uint64_t* hash, int64_t* count);
 /* device pointer of a work vector: 0 z, 1 r, 2 d, 3 t, 4 xp, 5 ws, 6 wy, 7 iwhere */
 void* lbfgsb_dev_vector(lbfgsb_dev_t* h, int32_t which);
+/* device-to-device copy of `bytes` bytes of that work vector into dst_dev (after the engine's stream drained) */
+int lbfgsb_dev_vector_copy(lbfgsb_dev_t* h, int32_t which, void* dst_dev, int64_t bytes);
 /* counters since creation: kernels launched, host syncs, device ms per kernel family */
 int lbfgsb_dev_counters(lbfgsb_dev_t* h, int64_t* launches, int64_t* syncs);
 /* per-kernel timing: when enabled every streaming kernel is bracketed by CUDA events on the

@@ -79,6 +79,7 @@ def lib():
         L.lbfgsb_host_engine.argtypes = [C.c_void_p]
         L.lbfgsb_dev_vector.restype = C.c_void_p
         L.lbfgsb_dev_vector.argtypes = [C.c_void_p, C.c_int32]
+        L.lbfgsb_dev_vector_copy.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
         L.lbfgsb_dev_active_set_hash.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lbfgsb_dev_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lbfgsb_dev_profile.argtypes = [C.c_void_p, C.c_int32]
@@ -107,7 +108,7 @@ def _p(a):
 
 def _check_task(task):
     s = bytes(task[:60]).decode(errors="replace")
-    if s.startswith("ERROR: CUDA") or s.startswith("ERROR: NO CUDA") or s.startswith("ERROR: INVALID LBFGSB"):
+    if s.startswith(("ERROR: CUDA", "ERROR: NO CUDA", "ERROR: INVALID LBFGSB", "ERROR: DEVICE POINTERS", "ERROR: SETULB CALLED")):
         raise LbfgsbB200Error(s.rstrip() + " -- " + last_error())
 
 
@@ -243,18 +244,15 @@ class DeviceProblem:
 
     def vector(self, which, count=None, dtype=None):
         """Copy of a work vector: 0 z, 1 r, 2 d, 3 t, 4 xp, 7 iwhere (diagnostics)."""
-        import ctypes
-        ptr = lib().lbfgsb_dev_vector(C.c_void_p(self.h), which)
         torch = self.torch
         n = self.n if count is None else count
         tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}[self.dtype]
         if which == 7:
             tdt = torch.int32
         out = torch.empty(n, dtype=tdt, device="cuda")
-        cudart = torch.cuda.cudart()
-        torch.cuda.synchronize()
-        rc = cudart.cudaMemcpy(out.data_ptr(), ptr, out.numel() * out.element_size(), 3)  # D2D
-        torch.cuda.synchronize()
+        if lib().lbfgsb_dev_vector_copy(C.c_void_p(self.h), which, C.c_void_p(out.data_ptr()),
+                                        C.c_int64(out.numel() * out.element_size())) != 0:
+            raise LbfgsbB200Error("lbfgsb_dev_vector_copy failed")
         return out
 
     def close(self):

@@ -692,6 +692,11 @@ static void setulb_dev_impl(lbfgsb_dev_t* hh, T* x, const T* l, const T* u, cons
         for (int q = 0; q < 16; ++q) isave[q] = (v[q] <= 2147483647LL) ? (int32_t)v[q] : -1;
     }
     if (entry == 4 && !aux) { return; }   // finish(): nothing changes on this path
+    if ((((uintptr_t)x) | ((uintptr_t)l) | ((uintptr_t)u) | ((uintptr_t)nbd) | ((uintptr_t)g)) & 15) {
+        set_error("x, l, u, nbd, g must be 16-byte aligned device pointers");
+        put60(task, "ERROR: DEVICE POINTERS MUST BE 16-BYTE ALIGNED");
+        return;
+    }
     bool ok = e->call(entry, aux, x, l, u, nbd, f, g, *factr, *pgtol);
     if (!ok) {
         char buf[61];
@@ -1005,6 +1010,12 @@ void* lbfgsb_dev_vector(lbfgsb_dev_t* h, int32_t which) {
                      case 4: return E->w.xp; case 5: return E->w.ws; case 6: return E->w.wy; case 7: return E->w.iwhere; default: return nullptr; }
     if (b->real_kind == 8) { Engine<double>* e = (Engine<double>*)b; VSEL(e) }
     else { Engine<float>* e = (Engine<float>*)b; VSEL(e) }
+}
+int lbfgsb_dev_vector_copy(lbfgsb_dev_t* h, int32_t which, void* dst_dev, int64_t bytes) {
+    void* src = lbfgsb_dev_vector(h, which);
+    if (!src || !dst_dev || bytes < 0) return 1;
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    return cudaMemcpy(dst_dev, src, (size_t)bytes, cudaMemcpyDeviceToDevice) != cudaSuccess;
 }
 int lbfgsb_dev_counters(lbfgsb_dev_t* h, int64_t* launches, int64_t* syncs) {
     EngineBase* b = (EngineBase*)h;

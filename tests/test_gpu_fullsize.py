@@ -1,0 +1,94 @@
+"""BASELINE.json's full sizes, checked through size-independent properties (the oracle would need
+minutes per iterate at n = 1e8): monotone f, feasibility, an order-free recomputation of |proj g|
+(bit-exact: it is a max), counter identities, sortedness / permutation of the breakpoint sort,
+and the fixed-shape sum against a float64 torch dot."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N_FULL = 100_000_000
+
+
+def _need(gb):
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < gb * (1 << 30):
+        pytest.skip("needs %d GB of free HBM" % gb)
+
+
+def test_config3_full_size_iteration_properties():
+    import torch
+    import lbfgsb_b200
+    _need(60)
+    n, m = N_FULL, 10
+    dev = torch.device("cuda")
+    x = torch.full((n,), 3.0, dtype=torch.float64, device=dev)
+    l = torch.full((n,), -100.0, dtype=torch.float64, device=dev)
+    l[0::2] = 1.1
+    u = torch.full((n,), 100.0, dtype=torch.float64, device=dev)
+    nbd = torch.full((n,), 2, dtype=torch.int32, device=dev)
+    g = torch.zeros_like(x)
+    prob = lbfgsb_b200.DeviceProblem(n, m, np.float64)
+    fg = lbfgsb_b200.RosenbrockDevice(np.float64)
+    fs, nacts = [], []
+    while True:
+        prob.setulb_dev(x, l, u, nbd, g, 0.0, 0.0)
+        t = prob.task_str()
+        if t[:2] == "FG":
+            prob.f[0] = fg(x, g)
+        elif t[:5] == "NEW_X":
+            it = int(prob.isave[29])
+            fs.append(float(prob.f[0]))
+            assert bool(((x >= l) & (x <= u)).all()), "iterate left the box at iteration %d" % it
+            pg = torch.where(g < 0, torch.maximum(x - u, g), torch.minimum(x - l, g)).abs().max().item()
+            assert pg == float(prob.dsave[12]), (it, pg, float(prob.dsave[12]))       # projgr :2594-2622, exact
+            h, c = prob.active_set_hash()
+            nfree, nact = int(prob.isave[37]), int(prob.isave[38])
+            assert nfree + nact == n and c == nact
+            nacts.append(nact)
+            if it == 1:
+                assert int(prob.isave[32]) == n     # every breakpoint is walked at iteration 1 (col = 0)
+            if it >= 16:
+                break
+        else:
+            raise AssertionError("unexpected task " + t)
+    assert all(b <= a for a, b in zip(fs, fs[1:])), fs
+    assert abs(nacts[-1] - n // 2) < 100, nacts        # about half of the variables sit on their lower bound
+    assert int(prob.isave[27]) == m                    # col = m
+    prob.close()
+
+
+def test_full_size_fixed_shape_sum_and_sort():
+    import torch
+    import lbfgsb_b200
+    _need(12)
+    L = lbfgsb_b200.lib()
+    n = N_FULL
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    b = torch.rand(n, dtype=torch.float64, device="cuda", generator=gen)
+    out = np.zeros(1)
+    assert L.lbfgsb_test_sum_f64(C.c_int64(n), C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), out.ctypes.data_as(C.c_void_p)) == 0
+    ref = torch.dot(a, b).item()
+    scale = torch.dot(a.abs(), b).item()
+    assert abs(out[0] - ref) <= 1e-13 * scale
+    # linearity: sum(a * (2b)) == 2 * sum(a * b) exactly (scaling by 2 is exact in binary floating point)
+    b2 = b * 2
+    out2 = np.zeros(1)
+    L.lbfgsb_test_sum_f64(C.c_int64(n), C.c_void_p(a.data_ptr()), C.c_void_p(b2.data_ptr()), out2.ctypes.data_as(C.c_void_p))
+    assert out2[0] == 2 * out[0]
+    del b2
+    # the breakpoint sort at full size: ascending, a permutation, stable on the tie group
+    t = b
+    t[: n // 4] = 0.25                       # 2.5e7 exact ties
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    srt = torch.empty(n, dtype=torch.float64, device="cuda")
+    assert L.lbfgsb_test_sort_f64(C.c_int64(n), C.c_void_p(t.data_ptr()), C.c_void_p(order.data_ptr()), C.c_void_p(srt.data_ptr())) == 0
+    assert bool((srt[1:] >= srt[:-1]).all())
+    assert bool((t[order.long()] == srt).all())
+    assert int(order.long().sum()) == n * (n - 1) // 2
+    tie = order[srt == 0.25].long()
+    assert bool((tie[1:] > tie[:-1]).all())  # ties stay in index order

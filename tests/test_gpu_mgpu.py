@@ -1,0 +1,33 @@
+"""Sharded (N > 1 GPUs) vs single-GPU parity; skipped on a box with one GPU.
+Run on a multi-GPU box:  gpurun --gpus 2 -- python -m pytest tests/test_gpu_mgpu.py -m gpu"""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("args", [("200000", "5", "1.0", "30"), ("100001", "10", "1.1", "25"), ("4099", "7", "1.5", "20")])
+def test_sharded_matches_single_gpu(args):
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if ng < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "mgpu_check.py")] + list(args)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0 and "MGPU_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
