@@ -182,7 +182,15 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 def family_bytes(n, col, nfree, nmv, w=8):
     na = n - nfree
+    upd = n * (3 * w + 2 * w) + 2 * (col - 1) * w * n
+    cls = n * (4 * w + 8) + n * (2 * w + 4) + 2 * col * w * nmv
+    fgram = n * 1 + 2 * col * w * n
+    cwv = n + nfree * 4 * w + 2 * col * w * nfree
     return {
+        # fused passes: the algorithmic bytes of the two routines they replace (each routine's own inputs
+        # and outputs once); the fusion reads the shared streams only once
+        "update_classify": upd + cls,
+        "formk_cmprlb": fgram + cwv,
         "ls_trial": n * (5 * w + 4),                                   # gd (2w) + projgr (4w+4) sharing g
         "update": n * (3 * w + 2 * w) + 2 * (col - 1) * w * n,         # g,r,d in; s,y out; col-1 older pairs
         "cauchy_classify": n * (4 * w + 8) + n * (2 * w + 4) + 2 * col * w * nmv,

@@ -63,6 +63,8 @@ struct DevState {
     int need_walk;     // cauchy: the breakpoint walk (sort + scans) is required
     int cauchy_mode;   // 0: full classify pass; 1: xcp = x only (:607-611 or :1245-1249)
     int do_subspace, do_formk, do_delta, do_backtrack, do_update, do_step, do_restore;
+    int fuse_uc;       // NEW_X entry: the S/Y update and cauchy's per-variable pass run as one fused kernel
+    int classify_done; // cauchy's per-variable pass of this body was already done by that fused kernel
     int task, csave, info;
     // ---- mainlb locals (:416-424) ----
     int col, head, itail, iupdat, iter, nfgv, nskip, ifun, iback, iword;

@@ -92,12 +92,12 @@ static NcclApi* nccl_api() {
 enum Fam {
     F_ERRCLB, F_ACTIVE, F_PROJGR, F_CLASSIFY, F_GCP_FREEV, F_FORMK_GRAM, F_FORMK_DELTA, F_CMPRLB_WV,
     F_SUBSM_STEP, F_BACKTRACK, F_LS_INIT, F_LS_STEP, F_LS_TRIAL, F_UPDATE, F_RESTORE, F_WALK_COMPACT,
-    F_WALK_SORT, F_WALK_SCAN, F_WALK_FIX, F_SCALAR, F_HASH, F_COUNT
+    F_WALK_SORT, F_WALK_SCAN, F_WALK_FIX, F_SCALAR, F_HASH, F_UPDATE_CLASSIFY, F_FORMK_CMPRLB, F_COUNT
 };
 static const char* fam_name[F_COUNT] = {
     "errclb", "active", "projgr", "cauchy_classify", "gcp_freev", "formk_gram", "formk_delta", "cmprlb_wv",
     "subsm_step", "backtrack", "ls_init", "ls_step", "ls_trial", "update", "restore", "walk_compact",
-    "walk_sort", "walk_scan", "walk_fix", "scalar", "hash"};
+    "walk_sort", "walk_scan", "walk_fix", "scalar", "hash", "update_classify", "formk_cmprlb"};
 
 struct EngineBase {
     virtual ~EngineBase() {}
@@ -108,6 +108,7 @@ template <typename T>
 struct Engine : EngineBase {
     i64 n = 0, n_global = 0, offset = 0;
     int m = 0, mt = 0;
+    bool fused = false;              // the cross-routine fused passes are in use (kernels_tma.cuh: fused_passes_ok)
     cudaStream_t stream = 0;
     bool own_stream = false;
     Wk<T> w;
@@ -157,6 +158,8 @@ struct Engine : EngineBase {
         n = n_; offset = off_; n_global = ng_; m = m_; R = world_; rank = rank_; comm = cm;
         real_kind = (int)sizeof(T);
         mt = (m <= 5) ? 5 : (m <= 10 ? 10 : 20);
+        fused = (mt == 5 ? fused_passes_ok<T, 5>() : (mt == 10 ? fused_passes_ok<T, 10>() : fused_passes_ok<T, 20>()));
+        if (const char* e = getenv("LBFGSB_B200_NO_FUSION")) { if (e[0] == '1') fused = false; }
         if (!(mt == 5 ? set_smem_attrs<5>() : (mt == 10 ? set_smem_attrs<10>() : set_smem_attrs<20>()))) return false;
         for (int q = 0; q < F_COUNT; ++q) { fam_ms[q] = 0; fam_calls[q] = 0; }
         if (st) stream = st;
@@ -169,6 +172,7 @@ struct Engine : EngineBase {
         if (!dalloc(&w.z, vb) || !dalloc(&w.r, vb) || !dalloc(&w.d, vb) || !dalloc(&w.t, vb) || !dalloc(&w.xp, vb)) return false;
         if (!dalloc(&w.iwhere, (size_t)w.ldw * 4) || !dalloc(&w.state, (size_t)w.ldw)) return false;
         if (!dalloc(&w.part, sizeof(T) * LB_KMAX * LBFGSB_GRID) || !dalloc(&w.ipart, sizeof(i64) * LB_IMAX * LBFGSB_GRID)) return false;
+        if (!dalloc(&w.part2, sizeof(T) * LB_KMAX * LBFGSB_GRID) || !dalloc(&w.ipart2, sizeof(i64) * LB_IMAX * LBFGSB_GRID)) return false;
         if (!dalloc(&s_dev, sizeof(DevState<T>))) return false;
         CK(cudaMemsetAsync(s_dev, 0, sizeof(DevState<T>), stream));
         CK(cudaMemsetAsync(w.ws, 0, vb * m, stream));
@@ -271,6 +275,15 @@ struct Engine : EngineBase {
         else kern<T, 20><<<LBFGSB_GRID, LB_TMA_THREADS, smemfn<T, 20>(), stream>>>(__VA_ARGS__);              \
     } while (0)
 
+    // fused passes exist only for the (T, MT) pairs whose accumulators fit in registers
+    template <int MT> void launch_update_classify() {
+        if constexpr (fused_passes_ok<T, MT>()) k_update_classify<T, MT><<<LBFGSB_GRID, LB_TMA_THREADS, smem_update_classify<T, MT>(), stream>>>(w);
+    }
+    template <int MT> void launch_formk_cmprlb() {
+        if constexpr (fused_passes_ok<T, MT>()) k_formk_cmprlb<T, MT><<<LBFGSB_GRID, LB_TMA_THREADS, smem_formk_cmprlb<T, MT>(), stream>>>(w);
+    }
+#define MTFUSED(fn) do { if (mt == 5) fn<5>(); else if (mt == 10) fn<10>(); else fn<20>(); } while (0)
+
     // the TMA-staged kernels need more than the default 48 KB of dynamic shared memory
     template <int MT> bool set_smem_attrs() {
         CK(cudaFuncSetAttribute(k_update<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_update<T, MT>()));
@@ -278,6 +291,10 @@ struct Engine : EngineBase {
         CK(cudaFuncSetAttribute(k_formk_gram<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk<T, MT>()));
         CK(cudaFuncSetAttribute(k_cmprlb_wv<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cmprlb<T, MT>()));
         CK(cudaFuncSetAttribute(k_subsm_step<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_subsm<T, MT>()));
+        if constexpr (fused_passes_ok<T, MT>()) {
+            CK(cudaFuncSetAttribute(k_update_classify<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_update_classify<T, MT>()));
+            CK(cudaFuncSetAttribute(k_formk_cmprlb<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk_cmprlb<T, MT>()));
+        }
         return true;
     }
 
@@ -470,7 +487,8 @@ struct Engine : EngineBase {
             begin(F_GCP_FREEV); k_gcp_freev<T><<<LG>>>(w); end(F_GCP_FREEV);
             if (!site(site_freev())) return false;
             begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global); end(F_SCALAR);
-            begin(F_FORMK_GRAM); MTCALL(k_formk_gram, smem_formk, w); end(F_FORMK_GRAM);
+            if (fused) { begin(F_FORMK_CMPRLB); MTFUSED(launch_formk_cmprlb); end(F_FORMK_CMPRLB); }
+            else { begin(F_FORMK_GRAM); MTCALL(k_formk_gram, smem_formk, w); end(F_FORMK_GRAM); }
             begin(F_FORMK_DELTA);
             k_flag_count<T, 1><<<LG>>>(w, tile_counts);
             k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 1, tile_counts, tile_offsets, ntiles, ctl_el);
@@ -481,7 +499,7 @@ struct Engine : EngineBase {
             if (!site(site_formk(mt))) return false;
             if (R > 1 && !allgather(delta, delta_all, sizeof(T) * 6 * LB_MMAX * LB_MMAX)) return false;
             begin(F_SCALAR); s_formk_dense<T><<<LS>>>(w, dist(), mt, R > 1 ? delta_all : delta, delta_sum); end(F_SCALAR);
-            begin(F_CMPRLB_WV); MTCALL(k_cmprlb_wv, smem_cmprlb, w); end(F_CMPRLB_WV);
+            if (!fused) { begin(F_CMPRLB_WV); MTCALL(k_cmprlb_wv, smem_cmprlb, w); end(F_CMPRLB_WV); }
             if (!site(site_wv(mt))) return false;
             begin(F_SCALAR); s_subsm_dense<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);
             begin(F_SUBSM_STEP); MTCALL(k_subsm_step, smem_subsm, w); end(F_SUBSM_STEP);
@@ -567,7 +585,8 @@ struct Engine : EngineBase {
                 if (!enqueue_body()) return false;
             }
         } else {   // NEW_X
-            begin(F_SCALAR); s_newx_tests<T><<<1, 32, 0, stream>>>(w); end(F_SCALAR);
+            begin(F_SCALAR); s_newx_tests<T><<<1, 32, 0, stream>>>(w, fused ? 1 : 0); end(F_SCALAR);
+            if (fused) { begin(F_UPDATE_CLASSIFY); MTFUSED(launch_update_classify); end(F_UPDATE_CLASSIFY); }
             begin(F_UPDATE); MTCALL(k_update, smem_update, w); end(F_UPDATE);
             if (!site(site_update(mt))) return false;
             begin(F_SCALAR); s_update_dense<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);

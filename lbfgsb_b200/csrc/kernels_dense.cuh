@@ -30,18 +30,21 @@ struct SiteSpec {
     int min_from, min_to; // real slots [min_from, min_to) are OP_MIN (excluding argmin_slot)
     int imin_from, imin_to;  // integer slots that are minima; others are sums; iv[0] is the argmin index if argmin_slot>=0
     int imax_from, imax_to;  // integer slots that are maxima
+    int buf;              // 0: partials in w.part / w.ipart ; 1: in w.part2 / w.ipart2
 };
 
 // Finish the local block partials of a site into red (shared memory), using all warps.
 template <typename T>
 __device__ void site_finish_local(const Wk<T>& w, const SiteSpec sp, Red<T>* red) {
     const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const T* part = sp.buf ? w.part2 : w.part;
+    const i64* ipart = sp.buf ? w.ipart2 : w.ipart;
     for (int k = wid; k < sp.nreal; k += nw) {
-        const T* p = LB_SLOT(w.part, k);
+        const T* p = LB_SLOT(part, k);
         T r;
         if (k == sp.argmin_slot) {
             i64 idx;
-            final_argmin_warp<T>(p, LB_SLOT(w.ipart, 0), r, idx);
+            final_argmin_warp<T>(p, LB_SLOT(ipart, 0), r, idx);
             if (lane == 0) red->iv[0] = idx;
         } else if (k >= sp.max_from && k < sp.max_to) r = final_max_warp<T>(p);
         else if (k >= sp.min_from && k < sp.min_to) r = final_min_warp<T>(p);
@@ -50,7 +53,7 @@ __device__ void site_finish_local(const Wk<T>& w, const SiteSpec sp, Red<T>* red
     }
     for (int k = wid; k < sp.nint; k += nw) {
         if (k == 0 && sp.argmin_slot >= 0) continue;
-        const i64* p = LB_SLOT(w.ipart, k);
+        const i64* p = LB_SLOT(ipart, k);
         i64 r;
         if (k >= sp.imin_from && k < sp.imin_to) r = final_imin_warp(p);
         else if (k >= sp.imax_from && k < sp.imax_to) r = final_imax_warp(p);
@@ -119,6 +122,7 @@ __host__ __device__ inline SiteSpec make_site(int nreal, int nint) {
     sp.nreal = nreal; sp.nint = nint; sp.argmin_slot = -1;
     sp.max_from = sp.max_to = sp.min_from = sp.min_to = 0;
     sp.imin_from = sp.imin_to = sp.imax_from = sp.imax_to = 0;
+    sp.buf = 0;
     return sp;
 }
 // the sites
@@ -126,11 +130,11 @@ __host__ __device__ inline SiteSpec site_errclb() { SiteSpec s = make_site(0, 2)
 __host__ __device__ inline SiteSpec site_active() { return make_site(0, 4); }
 __host__ __device__ inline SiteSpec site_projgr() { SiteSpec s = make_site(1, 0); s.max_from = 0; s.max_to = 1; return s; }
 __host__ __device__ inline SiteSpec site_cauchy(int mt) {
-    SiteSpec s = make_site(2 * mt + 2, 4); s.argmin_slot = 2 * mt + 1; s.imin_from = 3; s.imin_to = 4; return s;
+    SiteSpec s = make_site(2 * mt + 2, 4); s.argmin_slot = 2 * mt + 1; s.imin_from = 3; s.imin_to = 4; s.buf = 1; return s;
 }
 __host__ __device__ inline SiteSpec site_freev() { return make_site(0, 3); }
 __host__ __device__ inline SiteSpec site_formk(int mt) { return make_site(4 * mt, 0); }
-__host__ __device__ inline SiteSpec site_wv(int mt) { return make_site(2 * mt, 0); }
+__host__ __device__ inline SiteSpec site_wv(int mt) { SiteSpec s = make_site(2 * mt, 0); s.buf = 1; return s; }
 __host__ __device__ inline SiteSpec site_subsm() { return make_site(1, 1); }
 __host__ __device__ inline SiteSpec site_bt() { SiteSpec s = make_site(1, 1); s.argmin_slot = 0; return s; }
 __host__ __device__ inline SiteSpec site_lsinit() { SiteSpec s = make_site(3, 0); s.min_from = 2; s.min_to = 3; return s; }
@@ -209,10 +213,11 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_fg_start(Wk<T> w, Dist<T>
 // tests, skip rule, ring pointers.
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void s_newx_tests(Wk<T> w) {
+__global__ void s_newx_tests(Wk<T> w, int fused_supported) {
     if (threadIdx.x != 0) return;
     DevState<T>* s = w.s;
     const T one = (T)1;
+    s->fuse_uc = 0; s->classify_done = 0;
     if (s->sbgnrm <= s->pgtol) { s->task = TK_CONV_PG; s->go = 0; return; }
     T ddum = dense::tmax(dense::tmax(fabs(s->fold), fabs(s->f)), one);
     if ((s->fold - s->f) <= s->tol * ddum) {
@@ -230,6 +235,9 @@ __global__ void s_newx_tests(Wk<T> w) {
         const int m = s->m;
         if (s->iupdat <= m) { s->col = s->iupdat; s->itail = (s->head + s->iupdat - 2) % m + 1; }
         else { s->itail = s->itail % m + 1; s->head = s->head % m + 1; }
+        // begin_body will choose the full per-variable pass of cauchy (cauchy_mode 0) exactly when
+        // bounds are present and sbgnrm > 0: that pass is then fused with the update (k_update_classify)
+        if (fused_supported && s->cnstnd && s->sbgnrm > (T)0) { s->fuse_uc = 1; s->classify_done = 1; }
     }
 }
 
@@ -272,6 +280,7 @@ __global__ void s_restart_body(Wk<T> w) {
     if (threadIdx.x != 0) return;
     DevState<T>* s = w.s;
     s->go = 1;
+    s->classify_done = 0;
     begin_body<T>(s);
 }
 
@@ -286,6 +295,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
     if (!s->go || !s->in_body || s->cauchy_mode != 0) return;
     site_reduce<T>(w, dist, site_cauchy(mt), &red);
     if (threadIdx.x != 0) return;
+    s->classify_done = 0;
     const int col = s->col, col2 = 2 * col, m = s->m;
     const T zero = (T)0, one = (T)1;
     for (int j = 0; j < col; ++j) { s->p[j] = red.rv[j]; s->p[col + j] = red.rv[mt + j]; }
@@ -347,6 +357,16 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_freev(Wk<T> w, Dist<T> di
     s->do_subspace = !(s->nfree == 0 || s->col == 0);
     s->do_formk = s->do_subspace && s->wrk;
     s->do_delta = s->do_formk && (s->nenter + s->nleave > 0);
+    // cmprlb's a = M c (:1569; not needed on the unconstrained shortcut :1560-1563).  It depends only on
+    // sy, wt and c, which are final here, and is hoisted in front of formk so that formk's Gram pass and
+    // cmprlb's pass over S/Y can run as one kernel.  A failure of either ends in the same memory reset.
+    if (s->do_subspace && !(!s->cnstnd && s->col > 0)) {
+        int info = dense::bmv<T>(s->m, s->sy, s->wt, s->col, s->c, s->a);
+        if (info != 0) {   // info = -8 -> :694-710
+            reset_memory<T>(s);
+            s->restart = 1; s->in_body = 0; s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -452,14 +472,6 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist
     }
 #undef WN
 #undef WN1
-    // cmprlb :1569 (not needed on the unconstrained shortcut :1560-1563)
-    if (!(!s->cnstnd && col > 0)) {
-        int info = dense::bmv<T>(m, s->sy, s->wt, col, s->c, s->a);
-        if (info != 0) {   // info = -8 -> :694-710
-            reset_memory<T>(s);
-            s->restart = 1; s->in_body = 0;
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -613,6 +625,7 @@ __global__ void s_call_begin(Wk<T> w, T f, int entry_task) {
     s->go = 1; s->in_body = 0; s->restart = 0; s->need_walk = 0;
     s->do_step = 0; s->do_restore = 0; s->do_update = 0;
     s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0;
+    s->fuse_uc = 0; s->classify_done = 0;
     s->f = f;
     (void)entry_task;
 }
@@ -625,6 +638,7 @@ __global__ void s_start(Wk<T> w, T factr, T pgtol, int host_err_task) {
     const T zero = (T)0;
     s->go = 1; s->in_body = 0; s->restart = 0; s->need_walk = 0; s->cauchy_mode = 0;
     s->do_subspace = s->do_formk = s->do_delta = s->do_backtrack = s->do_update = s->do_step = s->do_restore = 0;
+    s->fuse_uc = 0; s->classify_done = 0;
     s->task = TK_START; s->csave = CS_BLANK; s->info = 0;
     s->col = 0; s->head = 1; s->theta = (T)1; s->iupdat = 0; s->updatd = 0;
     s->iback = 0; s->itail = 0; s->iword = 0; s->nact = 0; s->nleave = 0; s->nenter = 0;

@@ -19,6 +19,8 @@ struct Wk {               // workspace + user vectors of one problem (device poi
     unsigned char* state; // bit0: free at the GCP (freev :2047); bit1: free at the previous freev
     T* part;              // [LB_KMAX][GRID] block partials
     i64* ipart;           // [LB_IMAX][GRID]
+    T* part2;             // second set of partials: a fused pass feeds two reduction sites
+    i64* ipart2;          //   (cauchy's site and the W'Zr site always live here)
     DevState<T>* s;
     T* x; const T* l; const T* u; const int* nbd; T* g;   // caller's vectors
 };

@@ -14,7 +14,10 @@
 
 template <int MT> struct SubT { static constexpr int v = (MT <= 10) ? 256 : 128; };
 
-#define LB_DYN_STAGES(dyn) reinterpret_cast<char*>((reinterpret_cast<unsigned long long>(dyn) + 127ULL) & ~127ULL)
+// The stage ring starts at the (128-byte aligned) base of the dynamic shared memory.  It must stay a pointer
+// derived from `dyn` (no integer round trip): the compiler then knows the address space and reads the
+// stages with LDS instead of generic loads.
+#define LB_DYN_STAGES(dyn) (dyn)
 
 // add the ring columns head, head+1, ... (count pairs) as (Wy_j, Ws_j) stream pairs
 template <typename T>
@@ -38,12 +41,12 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<MT>::v;
     typedef PipeGeom<T, SUBT> G;
-    extern __shared__ char dyn[];
+    extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
     __shared__ PipeSrc ps;
     __shared__ T sm[(2 * MT + 1) * (LBFGSB_BLOCK / 32)];
     const DevState<T>* s = w.s;
-    if (!s->go || !s->do_update) return;
+    if (!s->go || !s->do_update || s->fuse_uc) return;
     const i64 n = w.n;
     const int col = s->col, m = s->m, head0 = s->head - 1, itail0 = s->itail - 1;
     const T stp = s->stp;
@@ -94,10 +97,66 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update(Wk<T> w) {
 template <typename T, int MT> constexpr unsigned smem_update() { return pipe_smem_bytes<T, SubT<MT>::v>(3 + 2 * (MT - 1), 0, 0); }
 
 // ---------------------------------------------------------------------------
+// cauchy, one variable of the per-variable pass (:1270-1327): new iwhere, Cauchy direction,
+// the term of f1, breakpoint bookkeeping.  Shared by the standalone pass and by the pass fused
+// with the S/Y update, so that both produce the same bits.
+// ---------------------------------------------------------------------------
+template <typename T>
+struct CauchyScan {
+    T bk; i64 ibk, nbr, nfc, bnd;
+    __device__ __forceinline__ void init() { bk = LB_INF(T); ibk = LB_I64MAX; nbr = 0; nfc = 0; bnd = 1; }
+};
+template <typename T>
+__device__ __forceinline__ void cauchy_classify_one(T x, T l, T u, T g, int nb, int& iw, T& d, bool& mv, T& d2acc,
+                                                    CauchyScan<T>& cs, i64 gidx) {
+    const T neggi = -g;
+    T tl = (T)0, tu = (T)0;
+    if (iw != 3 && iw != -1) {
+        if (nb <= 2) tl = x - l;
+        if (nb >= 2) tu = u - x;
+        const bool xlower = nb <= 2 && tl <= (T)0;
+        const bool xupper = nb >= 2 && tu <= (T)0;
+        iw = 0;
+        if (xlower) { if (neggi <= (T)0) iw = 1; }
+        else if (xupper) { if (neggi >= (T)0) iw = 2; }
+        else { if (fabs(neggi) <= (T)0) iw = -3; }
+    }
+    if (iw == 0 || iw == -1) {
+        mv = true;
+        d = neggi;
+        d2acc = d2acc + neggi * neggi;
+        T tb; bool hasb = false;
+        if (nb <= 2 && nb != 0 && neggi < (T)0) { tb = tl / (-neggi); hasb = true; }
+        else if (nb >= 2 && neggi > (T)0) { tb = tu / neggi; hasb = true; }
+        if (hasb) {
+            cs.nbr++;
+            if (tb < cs.bk) { cs.bk = tb; cs.ibk = gidx; }   // strict <: lowest index among ties (:1310)
+        } else {
+            cs.nfc++;
+            if (fabs(neggi) > (T)0) cs.bnd = 0;
+        }
+    }
+}
+// block partials of the scan quantities -> part2 slot 2MT+1 (bkmin), ipart2 0..3
+template <typename T, int MT>
+__device__ __forceinline__ void cauchy_scan_store(const Wk<T>& w, CauchyScan<T>& cs, T* smv, i64* smi) {
+    block_argmin<T>(cs.bk, cs.ibk, smv, smi);
+    i64 r1 = block_isum(cs.nbr, smi), r2 = block_isum(cs.nfc, smi);
+    i64 r3 = -block_isum(cs.bnd ? 0 : 1, smi);  // <0 if any thread saw an unbounded moving variable
+    if (threadIdx.x == 0) {
+        LB_SLOT(w.part2, 2 * MT + 1)[blockIdx.x] = cs.bk;
+        LB_SLOT(w.ipart2, 0)[blockIdx.x] = cs.ibk;
+        LB_SLOT(w.ipart2, 1)[blockIdx.x] = r1;
+        LB_SLOT(w.ipart2, 2)[blockIdx.x] = r2;
+        LB_SLOT(w.ipart2, 3)[blockIdx.x] = (r3 < 0) ? 0 : 1;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // cauchy, per-variable pass (:1270-1341): classify iwhere, Cauchy direction d,
 // f1 = -sum d^2, p = W'd, smallest breakpoint; xcp = x.
-// part: [0,MT) sum Wy(:,j) d ; [MT,2MT) sum Ws(:,j) d ; 2MT: sum d^2 ; 2MT+1: bkmin
-// ipart: 0 argmin variable ; 1 nbreak ; 2 count of moving variables without breakpoint ;
+// part2: [0,MT) sum Wy(:,j) d ; [MT,2MT) sum Ws(:,j) d ; 2MT: sum d^2 ; 2MT+1: bkmin
+// ipart2: 0 argmin variable ; 1 nbreak ; 2 count of moving variables without breakpoint ;
 //        3 bnded (min over blocks)
 // ---------------------------------------------------------------------------
 template <typename T, int MT>
@@ -105,14 +164,14 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cauchy_classify(Wk<T> w) 
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<MT>::v;
     typedef PipeGeom<T, SUBT> G;
-    extern __shared__ char dyn[];
+    extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
     __shared__ PipeSrc ps;
     __shared__ T sm[(2 * MT + 1) * (LBFGSB_BLOCK / 32)];
     __shared__ T smv[LBFGSB_BLOCK / 32];
     __shared__ i64 smi[LBFGSB_BLOCK / 32];
     const DevState<T>* s = w.s;
-    if (!s->go || !s->in_body) return;
+    if (!s->go || !s->in_body || s->classify_done) return;
     const int mode = s->cauchy_mode;
     const i64 n = w.n;
     if (mode != 0) {  // xcp = x only (:609 or :1247)
@@ -141,8 +200,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cauchy_classify(Wk<T> w) 
     T acc[2 * MT + 1];
 #pragma unroll
     for (int k = 0; k < 2 * MT + 1; ++k) acc[k] = (T)0;
-    T bk = LB_INF(T);
-    i64 ibk = LB_I64MAX, nbr = 0, nfc = 0, bnd = 1;
+    CauchyScan<T> cs; cs.init();
     tma_pass<T, SUBT>(n, &ps, LB_DYN_STAGES(dyn), full, [&](i64 base, const char* sb, int lt) {
         T x[VEC], l[VEC], u[VEC], g[VEC], d[VEC];
         int nb[VEC], iw[VEC];
@@ -152,35 +210,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cauchy_classify(Wk<T> w) 
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             mv[v] = false; d[v] = (T)0;
-            if (base + v < n) {
-                const T neggi = -g[v];
-                T tl = (T)0, tu = (T)0;
-                if (iw[v] != 3 && iw[v] != -1) {
-                    if (nb[v] <= 2) tl = x[v] - l[v];
-                    if (nb[v] >= 2) tu = u[v] - x[v];
-                    const bool xlower = nb[v] <= 2 && tl <= (T)0;
-                    const bool xupper = nb[v] >= 2 && tu <= (T)0;
-                    iw[v] = 0;
-                    if (xlower) { if (neggi <= (T)0) iw[v] = 1; }
-                    else if (xupper) { if (neggi >= (T)0) iw[v] = 2; }
-                    else { if (fabs(neggi) <= (T)0) iw[v] = -3; }
-                }
-                if (iw[v] == 0 || iw[v] == -1) {
-                    mv[v] = true;
-                    d[v] = neggi;
-                    acc[2 * MT] = acc[2 * MT] + neggi * neggi;
-                    T tb; bool hasb = false;
-                    if (nb[v] <= 2 && nb[v] != 0 && neggi < (T)0) { tb = tl / (-neggi); hasb = true; }
-                    else if (nb[v] >= 2 && neggi > (T)0) { tb = tu / neggi; hasb = true; }
-                    if (hasb) {
-                        nbr++;
-                        if (tb < bk) { bk = tb; ibk = base + v + w.off; }   // strict <: lowest index among ties (:1310)
-                    } else {
-                        nfc++;
-                        if (fabs(neggi) > (T)0) bnd = 0;
-                    }
-                }
-            }
+            if (base + v < n) cauchy_classify_one<T>(x[v], l[v], u[v], g[v], nb[v], iw[v], d[v], mv[v], acc[2 * MT], cs, base + v + w.off);
         }
         stvi<T>(w.iwhere, base, n, iw);
         stv<T>(w.d, base, n, d);
@@ -200,17 +230,8 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cauchy_classify(Wk<T> w) 
             }
         }
     });
-    block_sum_store<T, 2 * MT + 1>(acc, 2 * MT + 1, sm, w.part);
-    block_argmin<T>(bk, ibk, smv, smi);
-    i64 r1 = block_isum(nbr, smi), r2 = block_isum(nfc, smi);
-    i64 r3 = -block_isum(bnd ? 0 : 1, smi);  // <0 if any thread saw an unbounded moving variable
-    if (threadIdx.x == 0) {
-        LB_SLOT(w.part, 2 * MT + 1)[blockIdx.x] = bk;
-        LB_SLOT(w.ipart, 0)[blockIdx.x] = ibk;
-        LB_SLOT(w.ipart, 1)[blockIdx.x] = r1;
-        LB_SLOT(w.ipart, 2)[blockIdx.x] = r2;
-        LB_SLOT(w.ipart, 3)[blockIdx.x] = (r3 < 0) ? 0 : 1;
-    }
+    block_sum_store<T, 2 * MT + 1>(acc, 2 * MT + 1, sm, w.part2);
+    cauchy_scan_store<T, MT>(w, cs, smv, smi);
 }
 template <typename T, int MT> constexpr unsigned smem_classify() { return pipe_smem_bytes<T, SubT<MT>::v>(4 + 2 * MT, 2, 0); }
 
@@ -224,7 +245,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_gram(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<MT>::v;
     typedef PipeGeom<T, SUBT> G;
-    extern __shared__ char dyn[];
+    extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
     __shared__ PipeSrc ps;
     __shared__ T sm[4 * MT * (LBFGSB_BLOCK / 32)];
@@ -279,14 +300,14 @@ template <typename T, int MT> constexpr unsigned smem_formk() { return pipe_smem
 //   r_k = -theta (z_k - x_k) - g_k + sum_j Wy(k,j) a1_j + Ws(k,j) a2_j   (free k)
 //   wv  = W' Z r
 // r is kept by variable (the reference keeps it compact over the free list).
-// part: [0,MT) sum Wy(:,j) r ; [MT,2MT) sum Ws(:,j) r
+// part2: [0,MT) sum Wy(:,j) r ; [MT,2MT) sum Ws(:,j) r
 // ---------------------------------------------------------------------------
 template <typename T, int MT>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cmprlb_wv(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<MT>::v;
     typedef PipeGeom<T, SUBT> G;
-    extern __shared__ char dyn[];
+    extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
     __shared__ PipeSrc ps;
     __shared__ T sm[2 * MT * (LBFGSB_BLOCK / 32)];
@@ -355,7 +376,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cmprlb_wv(Wk<T> w) {
         // so the whole vector is stored: no partial-sector writes.
         stv<T>(w.r, base, n, r);
     });
-    block_sum_store<T, 2 * MT>(acc, 2 * MT, sm, w.part);
+    block_sum_store<T, 2 * MT>(acc, 2 * MT, sm, w.part2);
 }
 template <typename T, int MT> constexpr unsigned smem_cmprlb() { return pipe_smem_bytes<T, SubT<MT>::v>(3 + 2 * MT, 0, 1); }
 
@@ -369,7 +390,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_step(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<MT>::v;
     typedef PipeGeom<T, SUBT> G;
-    extern __shared__ char dyn[];
+    extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
     __shared__ PipeSrc ps;
     __shared__ T sm[LBFGSB_BLOCK / 32];
@@ -451,3 +472,232 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_step(Wk<T> w) {
     if (threadIdx.x == 0) LB_SLOT(w.ipart, 0)[blockIdx.x] = r0;
 }
 template <typename T, int MT> constexpr unsigned smem_subsm() { return pipe_smem_bytes<T, SubT<MT>::v>(6 + 2 * MT, 1, 1); }
+
+// ===========================================================================
+// Cross-routine fusions.  The iteration streams the 2*col S/Y columns once per routine in the
+// reference (matupd, cauchy, formk, cmprlb, subsm); two pairs of those passes have no global
+// reduction between them and are merged here, so the history is read three times per iteration
+// instead of five.  Thread -> element mapping, accumulation order and every arithmetic expression
+// are those of the separate kernels above: the results are bit-identical.
+// Used when the accumulators fit in registers (fused_passes_ok): double m <= 10, float m <= 20.
+// ===========================================================================
+template <typename T, int MT> constexpr bool fused_passes_ok() { return sizeof(T) * MT <= 80; }
+
+// ---------------------------------------------------------------------------
+// k_update (y/s preparation + matupd) fused with the per-variable pass of the NEXT cauchy
+// (k_cauchy_classify).  Both run inside the same setulb call (NEW_X entry, :813-839 then :617)
+// with only formt's 2m x 2m algebra between them, and everything cauchy's pass needs (x, g, l, u,
+// nbd, iwhere, the ring after the update) is known here: the newest pair is taken from registers.
+// Runs when s_newx_tests set fuse_uc (update not skipped, bounds present, sbgnrm > 0).
+// part : as k_update            part2 / ipart2 : as k_cauchy_classify
+// ---------------------------------------------------------------------------
+template <typename T, int MT>
+__global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update_classify(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    constexpr int SUBT = SubT<MT>::v;
+    typedef PipeGeom<T, SUBT> G;
+    extern __shared__ __align__(128) char dyn[];
+    __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
+    __shared__ PipeSrc ps;
+    __shared__ T sm[(2 * MT + 1) * (LBFGSB_BLOCK / 32)];
+    __shared__ T smv[LBFGSB_BLOCK / 32];
+    __shared__ i64 smi[LBFGSB_BLOCK / 32];
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->do_update || !s->fuse_uc) return;
+    const i64 n = w.n;
+    const int col = s->col, head0 = s->head - 1, itail0 = s->itail - 1;
+    const T stp = s->stp;
+    constexpr unsigned OG = 0, OR = G::REAL_SLOT, OD = 2 * G::REAL_SLOT, OX = 3 * G::REAL_SLOT, OL = 4 * G::REAL_SLOT,
+                       OU = 5 * G::REAL_SLOT, ONB = 6 * G::REAL_SLOT, OIW = ONB + G::INT_SLOT, OW = OIW + G::INT_SLOT;
+    if (threadIdx.x == 0) {
+        pipe_begin(&ps);
+        pipe_add(&ps, w.g, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.r, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.d, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.x, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.l, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.u, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.nbd, 4, G::INT_SLOT);
+        pipe_add(&ps, w.iwhere, 4, G::INT_SLOT);
+        pipe_add_w<T>(&ps, w, head0, col - 1, G::REAL_SLOT);
+        pipe_end(&ps);
+    }
+    T au[2 * MT + 1], ac[2 * MT + 1];
+#pragma unroll
+    for (int k = 0; k < 2 * MT + 1; ++k) { au[k] = (T)0; ac[k] = (T)0; }
+    CauchyScan<T> cs; cs.init();
+    T* wsn = w.ws + (i64)itail0 * w.ldw;
+    T* wyn = w.wy + (i64)itail0 * w.ldw;
+    tma_pass<T, SUBT>(n, &ps, LB_DYN_STAGES(dyn), full, [&](i64 base, const char* sb, int lt) {
+        T g[VEC], y[VEC], sn[VEC];
+        lds_real<T>(sb, OG, lt, g);
+        lds_real<T>(sb, OR, lt, y);
+        lds_real<T>(sb, OD, lt, sn);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            y[v] = g[v] - y[v];
+            if (stp != (T)1) sn[v] = stp * sn[v];
+            if (base + v < n) au[0] = au[0] + y[v] * y[v];
+        }
+        stv<T>(wsn, base, n, sn);
+        stv<T>(wyn, base, n, y);
+        T x[VEC], l[VEC], u[VEC], dc[VEC];
+        int nb[VEC], iw[VEC];
+        lds_real<T>(sb, OX, lt, x); lds_real<T>(sb, OL, lt, l); lds_real<T>(sb, OU, lt, u);
+        lds_int<T>(sb, ONB, lt, nb); lds_int<T>(sb, OIW, lt, iw);
+        bool mv[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            mv[v] = false; dc[v] = (T)0;
+            if (base + v < n) cauchy_classify_one<T>(x[v], l[v], u[v], g[v], nb[v], iw[v], dc[v], mv[v], ac[2 * MT], cs, base + v + w.off);
+        }
+        stvi<T>(w.iwhere, base, n, iw);
+        stv<T>(w.d, base, n, dc);
+        stv<T>(w.z, base, n, x);
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+            if (j < col - 1) {
+                T wy[VEC], wsv[VEC];
+                lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
+                lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    if (base + v < n) {
+                        au[1 + j] = au[1 + j] + sn[v] * wy[v];
+                        au[1 + MT + j] = au[1 + MT + j] + wsv[v] * sn[v];
+                    }
+                    if (mv[v]) {
+                        ac[j] = ac[j] + wy[v] * dc[v];
+                        ac[MT + j] = ac[MT + j] + wsv[v] * dc[v];
+                    }
+                }
+            } else if (j == col - 1) {   // the pair being written: ring position col-1
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (mv[v]) {
+                        ac[j] = ac[j] + y[v] * dc[v];
+                        ac[MT + j] = ac[MT + j] + sn[v] * dc[v];
+                    }
+            }
+        }
+    });
+    block_sum_store<T, 2 * MT + 1>(au, 2 * MT + 1, sm, w.part);
+    block_sum_store<T, 2 * MT + 1>(ac, 2 * MT + 1, sm, w.part2);
+    cauchy_scan_store<T, MT>(w, cs, smv, smi);
+}
+template <typename T, int MT> constexpr unsigned smem_update_classify() { return pipe_smem_bytes<T, SubT<MT>::v>(6 + 2 * (MT - 1), 2, 0); }
+
+// ---------------------------------------------------------------------------
+// k_formk_gram fused with k_cmprlb_wv: the new row/column of WN1 over all rows of S,Y, the reduced
+// gradient r on the free set and wv = W'Zr in one pass.  a = M c (cmprlb's bmv, :1569) depends only
+// on sy, wt and c and is therefore computed before this pass (s_freev).
+// part : as k_formk_gram (written when the Gram row is needed)     part2 : as k_cmprlb_wv
+// ---------------------------------------------------------------------------
+template <typename T, int MT>
+__global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    constexpr int SUBT = SubT<MT>::v;
+    typedef PipeGeom<T, SUBT> G;
+    extern __shared__ __align__(128) char dyn[];
+    __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
+    __shared__ PipeSrc ps;
+    __shared__ T sm[4 * MT * (LBFGSB_BLOCK / 32)];
+    __shared__ T coef[2 * MT];
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_subspace) return;
+    const bool gram = s->do_formk && s->updatd;
+    const i64 n = w.n;
+    const int col = s->col, head0 = s->head - 1;
+    const T theta = s->theta;
+    const bool uc = (!s->cnstnd && col > 0);   // :1560-1563
+    constexpr unsigned OG = 0, OZ = G::REAL_SLOT, OX = 2 * G::REAL_SLOT, OW = 3 * G::REAL_SLOT;
+    if (threadIdx.x == 0) {
+        pipe_begin(&ps);
+        pipe_add(&ps, w.g, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.z, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.x, sizeof(T), G::REAL_SLOT);
+        pipe_add_w<T>(&ps, w, head0, col, G::REAL_SLOT);
+        pipe_add(&ps, w.state, 1, G::BYTE_SLOT);
+        pipe_end(&ps);
+    }
+    if (threadIdx.x < 2 * MT) {
+        const int j = threadIdx.x % MT;
+        coef[threadIdx.x] = (j < col) ? ((threadIdx.x < MT) ? s->a[j] : theta * s->a[col + j]) : (T)0;
+    }
+    const unsigned ost = OW + 2u * (unsigned)col * G::REAL_SLOT;
+    const unsigned olast = OW + 2u * (unsigned)(col - 1) * G::REAL_SLOT;   // the newest pair sits at ring position col-1
+    T af[4 * MT], aw[2 * MT];
+#pragma unroll
+    for (int k = 0; k < 4 * MT; ++k) af[k] = (T)0;
+#pragma unroll
+    for (int k = 0; k < 2 * MT; ++k) aw[k] = (T)0;
+    // (tma_pass starts with a __syncthreads: coef is visible to every consumer)
+    tma_pass<T, SUBT>(n, &ps, LB_DYN_STAGES(dyn), full, [&](i64 base, const char* sb, int lt) {
+        int st[VEC];
+        lds_byte<T>(sb, ost, lt, st);
+        bool fr[VEC]; bool any = false;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { fr[v] = (base + v < n) && (st[v] & 1); any |= fr[v]; }
+        if (!any && !gram) return;
+        T r[VEC];
+        if (any) {
+            T z[VEC], x[VEC], g[VEC];
+            lds_real<T>(sb, OG, lt, g); lds_real<T>(sb, OZ, lt, z); lds_real<T>(sb, OX, lt, x);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) r[v] = uc ? -g[v] : (-theta * (z[v] - x[v]) - g[v]);
+        }
+        T wyl[VEC], wsl[VEC];
+        if (gram) {
+            lds_real<T>(sb, olast, lt, wyl);
+            lds_real<T>(sb, olast + G::REAL_SLOT, lt, wsl);
+        }
+        if (gram || (any && !uc)) {
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                if (j < col) {
+                    T wy[VEC], wsv[VEC];
+                    lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
+                    lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
+                    if (gram) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            if (base + v < n) {
+                                if (st[v] & 1) {
+                                    af[j] = af[j] + wyl[v] * wy[v];
+                                    af[3 * MT + j] = af[3 * MT + j] + wsv[v] * wyl[v];
+                                } else {
+                                    af[MT + j] = af[MT + j] + wsl[v] * wsv[v];
+                                    af[2 * MT + j] = af[2 * MT + j] + wsl[v] * wy[v];
+                                }
+                            }
+                        }
+                    }
+                    if (any && !uc) {
+                        const T a1 = coef[j], a2 = coef[MT + j];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) r[v] = r[v] + wy[v] * a1 + wsv[v] * a2;
+                    }
+                }
+            }
+        }
+        if (!any) return;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+            if (j < col) {
+                T wy[VEC], wsv[VEC];
+                lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
+                lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (fr[v]) {
+                        aw[j] = aw[j] + wy[v] * r[v];
+                        aw[MT + j] = aw[MT + j] + wsv[v] * r[v];
+                    }
+            }
+        }
+        stv<T>(w.r, base, n, r);
+    });
+    if (gram) block_sum_store<T, 4 * MT>(af, 4 * MT, sm, w.part);
+    block_sum_store<T, 2 * MT>(aw, 2 * MT, sm, w.part2);
+}
+template <typename T, int MT> constexpr unsigned smem_formk_cmprlb() { return pipe_smem_bytes<T, SubT<MT>::v>(3 + 2 * MT, 0, 1); }

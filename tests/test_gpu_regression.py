@@ -1,0 +1,37 @@
+"""Bit-level regression of the engine's per-iterate traces (tools/trace_digest.py).
+
+The reductions have a fixed shape (include/lbfgsb_b200_shape.h), so every iterate of a given problem
+is bit-reproducible: across runs, across GPUs, and across re-organisations of the kernels that keep the
+shape -- the fused passes (k_update_classify, k_formk_cmprlb) must give exactly the bits of the
+separate passes they replace.  tests/golden/gpu_trace_digest.json was recorded on a B200 with the
+unfused kernels; it is compared here with a fresh run, with the fused passes on and off.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "gpu_trace_digest.json")
+
+
+def _run(env_extra, tmp_path, tag):
+    out = os.path.join(str(tmp_path), "digest_%s.json" % tag)
+    env = dict(os.environ)
+    env.update(env_extra)
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "trace_digest.py"), out], env=env,
+                          stdout=subprocess.DEVNULL)
+    return json.load(open(out))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fusion", ["fused", "unfused"])
+def test_trace_bits_match_recorded(fusion, tmp_path):
+    gold = json.load(open(GOLD))
+    got = _run({"LBFGSB_B200_NO_FUSION": "0" if fusion == "fused" else "1"}, tmp_path, fusion)
+    assert set(got) == set(gold)
+    for name in sorted(gold):
+        for key in ("iterations", "task", "sha256"):
+            assert got[name][key] == gold[name][key], (fusion, name, key, got[name], gold[name])
