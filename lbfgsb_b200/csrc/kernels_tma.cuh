@@ -632,26 +632,32 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
 #pragma unroll
     for (int k = 0; k < 2 * MT; ++k) aw[k] = (T)0;
     // (tma_pass starts with a __syncthreads: coef is visible to every consumer)
+    // Elements at or beyond n read as zero from the stage (state 0, W = 0): their terms are +0 and leave
+    // every accumulator unchanged, so the loops below carry no range checks.  The conditionals are kept
+    // to a couple of instructions so that they compile to predication, not branches.
     tma_pass<T, SUBT>(n, &ps, LB_DYN_STAGES(dyn), full, [&](i64 base, const char* sb, int lt) {
         int st[VEC];
         lds_byte<T>(sb, ost, lt, st);
         bool fr[VEC]; bool any = false;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { fr[v] = (base + v < n) && (st[v] & 1); any |= fr[v]; }
+        for (int v = 0; v < VEC; ++v) { fr[v] = (st[v] & 1) != 0; any |= fr[v]; }
         if (!any && !gram) return;
         T r[VEC];
-        if (any) {
+        {
             T z[VEC], x[VEC], g[VEC];
             lds_real<T>(sb, OG, lt, g); lds_real<T>(sb, OZ, lt, z); lds_real<T>(sb, OX, lt, x);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) r[v] = uc ? -g[v] : (-theta * (z[v] - x[v]) - g[v]);
         }
-        T wyl[VEC], wsl[VEC];
+        T wl[VEC];   // the newest pair's Wy on a free row, its Ws on an active row
         if (gram) {
+            T wyl[VEC], wsl[VEC];
             lds_real<T>(sb, olast, lt, wyl);
             lds_real<T>(sb, olast + G::REAL_SLOT, lt, wsl);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) wl[v] = fr[v] ? wyl[v] : wsl[v];
         }
-        if (gram || (any && !uc)) {
+        if (gram || !uc) {
 #pragma unroll
             for (int j = 0; j < MT; ++j) {
                 if (j < col) {
@@ -661,18 +667,12 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
                     if (gram) {
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
-                            if (base + v < n) {
-                                if (st[v] & 1) {
-                                    af[j] = af[j] + wyl[v] * wy[v];
-                                    af[3 * MT + j] = af[3 * MT + j] + wsv[v] * wyl[v];
-                                } else {
-                                    af[MT + j] = af[MT + j] + wsl[v] * wsv[v];
-                                    af[2 * MT + j] = af[2 * MT + j] + wsl[v] * wy[v];
-                                }
-                            }
+                            const T py = wl[v] * wy[v], psv = wl[v] * wsv[v];
+                            if (fr[v]) { af[j] = af[j] + py; af[3 * MT + j] = af[3 * MT + j] + psv; }
+                            else { af[2 * MT + j] = af[2 * MT + j] + py; af[MT + j] = af[MT + j] + psv; }
                         }
                     }
-                    if (any && !uc) {
+                    if (!uc) {
                         const T a1 = coef[j], a2 = coef[MT + j];
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) r[v] = r[v] + wy[v] * a1 + wsv[v] * a2;
@@ -688,11 +688,10 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
                 lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
                 lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
 #pragma unroll
-                for (int v = 0; v < VEC; ++v)
-                    if (fr[v]) {
-                        aw[j] = aw[j] + wy[v] * r[v];
-                        aw[MT + j] = aw[MT + j] + wsv[v] * r[v];
-                    }
+                for (int v = 0; v < VEC; ++v) {
+                    const T py = wy[v] * r[v], psv = wsv[v] * r[v];
+                    if (fr[v]) { aw[j] = aw[j] + py; aw[MT + j] = aw[MT + j] + psv; }
+                }
             }
         }
         stv<T>(w.r, base, n, r);
