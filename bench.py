@@ -43,28 +43,57 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=14)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--n", type=int, default=100_000_000, help="variables per GPU")
+    ap.add_argument("--workload", default="rosenbrock", choices=["rosenbrock", "quadratic"],
+                    help="rosenbrock = BASELINE.json configs[2] (the headline); quadratic = configs[3] (weak scaling to n=1e9)")
+    ap.add_argument("--n", type=int, default=None, help="variables per GPU (default 1e8; 1.25e8 for the quadratic)")
     ap.add_argument("--m", type=int, default=10)
     ap.add_argument("--cpu-n", type=int, default=2_000_000, help="sample size of the CPU baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-family table here (JSON)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.n is None:
+        a.n = 100_000_000 if a.workload == "rosenbrock" else 125_000_000
+    return a
 
 
-def workload_name(n, m, world):
-    return "bounded extended Rosenbrock (driver1 bounds, odd lower bound %.1f), n=%d%s, m=%d, real64" % (
-        L_ODD, n * world, (" (%d per GPU)" % n) if world > 1 else "", m)
+QUAD_SEED = 0
+QUAD_SCALE = 0.5
+
+
+def workload_name(n, m, world, kind="rosenbrock"):
+    tail = "n=%d%s, m=%d, real64" % (n * world, (" (%d per GPU)" % n) if world > 1 else "", m)
+    if kind == "quadratic":
+        return ("bound-constrained convex quadratic (A = tridiag(-1, 2+delta_i, -1), hashed delta and b, box [0, %.1f]), "
+                % QUAD_SCALE) + tail
+    return "bounded extended Rosenbrock (driver1 bounds, odd lower bound %.1f), " % L_ODD + tail
+
+
+def host_problem(kind, n):
+    """(x, l, u, nbd, fg) on the host for the CPU arm."""
+    import harness as H
+    from oracle import oracle_py as O
+    if kind == "quadratic":
+        from lbfgsb_b200 import sharded
+        x, l, u, nbd = sharded.quadratic_problem(n, np.float64, QUAD_SCALE)
+
+        def fg(xx, gg):
+            f, g2 = sharded.quadratic_shard_numpy(xx, 0, QUAD_SEED, 0.0, 0.0)
+            gg[:] = g2
+            return f
+        return x, l, u, nbd, fg
+    x, l, u, nbd = H.rosenbrock_problem(n, l_odd=L_ODD)
+    return x, l, u, nbd, O.rosenbrock_fg
 
 
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (test infrastructure used here only as the measured baseline)
 # ---------------------------------------------------------------------------------------------
-def cpu_run(n, m, warmup, steps):
+def cpu_run(n, m, warmup, steps, kind="rosenbrock"):
     """Returns (seconds per iteration inside setulb, iterations timed)."""
     import harness as H
     from oracle import oracle_py as O
-    x, l, u, nbd = H.rosenbrock_problem(n, l_odd=L_ODD)
+    x, l, u, nbd, fg = host_problem(kind, n)
     s = O.OracleSetulb()
     g = np.zeros(n)
     f = np.zeros(1)
@@ -86,7 +115,7 @@ def cpu_run(n, m, warmup, steps):
         t_in += time.perf_counter() - a
         ts = H.task_str(task)
         if ts[:2] == "FG":
-            f[0] = O.rosenbrock_fg(x, g)
+            f[0] = fg(x, g)
         elif ts[:5] == "NEW_X":
             it = int(isave[29])
             if it == warmup:
@@ -104,7 +133,7 @@ def reference_arm(a):
     if rank != 0:
         return
     n = a.cpu_n
-    spi, k = cpu_run(n, a.m, a.warmup, a.steps)
+    spi, k = cpu_run(n, a.m, a.warmup, a.steps, a.workload)
     world = max(1, a.gpus)
     full_n = a.n * world
     v = 1.0 / (spi * full_n / n)
@@ -115,7 +144,7 @@ def reference_arm(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": k,
         "warmup": a.warmup, "ms_per_step": spi * full_n / n * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a.n, a.m, world), "sample_n": n},
+        "config": {"workload": workload_name(a.n, a.m, world, a.workload), "sample_n": n},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -245,11 +274,17 @@ def main():
         torch.cuda.synchronize()
 
     # ---- problem data on the device (synthetic, generated in place) ----
-    xd = torch.full((n,), 3.0, dtype=torch.float64, device=dev)
-    ld = torch.full((n,), -100.0, dtype=torch.float64, device=dev)
-    first_odd = off % 2            # global index parity: odd (1-based) variables are the even 0-based ones
-    ld[first_odd::2] = L_ODD
-    ud = torch.full((n,), 100.0, dtype=torch.float64, device=dev)
+    quad = a.workload == "quadratic"
+    if quad:
+        xd = torch.full((n,), 0.5 * QUAD_SCALE, dtype=torch.float64, device=dev)
+        ld = torch.zeros(n, dtype=torch.float64, device=dev)
+        ud = torch.full((n,), QUAD_SCALE, dtype=torch.float64, device=dev)
+    else:
+        xd = torch.full((n,), 3.0, dtype=torch.float64, device=dev)
+        ld = torch.full((n,), -100.0, dtype=torch.float64, device=dev)
+        first_odd = off % 2            # global index parity: odd (1-based) variables are the even 0-based ones
+        ld[first_odd::2] = L_ODD
+        ud = torch.full((n,), 100.0, dtype=torch.float64, device=dev)
     nd = torch.full((n,), 2, dtype=torch.int32, device=dev)
     gd = torch.zeros_like(xd)
 
@@ -260,15 +295,21 @@ def main():
         comm = sharded.nccl_comm_for_engine(rank, world, dist, dev)
         shard = (off, n_global, comm, rank, world)
     prob = lbfgsb_b200.DeviceProblem(n, m, np.float64, stream=stream, shard=shard)
-    fgk = lbfgsb_b200.RosenbrockDevice(np.float64, stream=stream)
     nfg = [0]
-
-    if world > 1:
-        fg_sharded = sharded.ShardedRosenbrockDevice(fgk, rank, world, dist, dev)
+    if quad:
+        fgk = lbfgsb_b200.QuadraticDevice(np.float64, seed=QUAD_SEED, stream=stream)
+        fg_one = (lambda: fgk(xd, gd, offset=0))
+        if world > 1:
+            fg_sh = sharded.ShardedQuadraticDevice(fgk, off, rank, world, dist, dev)
+    else:
+        fgk = lbfgsb_b200.RosenbrockDevice(np.float64, stream=stream)
+        fg_one = (lambda: fgk(xd, gd))
+        if world > 1:
+            fg_sh = sharded.ShardedRosenbrockDevice(fgk, rank, world, dist, dev)
 
     def fg():
         nfg[0] += 1
-        return fgk(xd, gd) if world == 1 else fg_sharded(xd, gd)
+        return fg_one() if world == 1 else fg_sh(xd, gd)
 
     def run_until(target_iter):
         while True:
@@ -329,7 +370,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    if okp:
+    if okp or any(v["calls"] for v in prof.values()):
         # local counts for the byte formulas (this rank's shard)
         st_free = nfree if world == 1 else None
         if st_free is None:
@@ -368,12 +409,13 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(n, m, world), "n_per_gpu": n, "m": m, "col_in_timed_region": col,
+        "config": {"workload": workload_name(n, m, world, a.workload), "n_per_gpu": n, "m": m, "col_in_timed_region": col,
                    "nfree": int(nfree_t), "fg_evals_per_step": fg_per_iter,
                    "l2": "working set (%.1f GB per GPU) is far larger than the 126 MB L2; no flush needed" % (
                        (2 * m + 9) * n * 8 / 1e9),
                    "fg": "device kernel, inside the timed region"},
         "gpu_launches": int(launches),
+        "task_after_profile_pass": prob.task_str(),
         "clocks": clocks.summary(),
         "iteration_roofline": {"canonical_bytes_per_iteration_per_gpu": canon, "achieved_gbs_per_gpu": iter_gbs,
                                "frac_of_peak": iter_gbs / peak, "peak": peak, "peak_source": peak_src},
@@ -394,10 +436,10 @@ def main():
 
     # ---- e2e: host twin with HOST buffers (rank 0's own shard size; N = 1 only) ----
     if world == 1 and not a.no_e2e:
-        out["e2e"] = e2e_host_twin(n, m, W, K, dev)
+        out["e2e"] = e2e_host_twin(n, m, W, K, dev, a.workload)
     if rank == 0 and world == 1 and not a.no_cpu:
         try:
-            spi, k = cpu_run(a.cpu_n, m, W, min(K, 8))
+            spi, k = cpu_run(a.cpu_n, m, W, min(K, 8), a.workload)
             v = 1.0 / (spi * n / a.cpu_n)
             out["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": 1, "kind": "port",
@@ -414,23 +456,33 @@ def main():
         print(json.dumps(out), flush=True)
 
 
-def e2e_host_twin(n, m, W, K, dev):
+def e2e_host_twin(n, m, W, K, dev, kind="rosenbrock"):
     """The same iterations through lbfgsb_setulb_f64 (host arrays).  Timed: the setulb calls only
     (they contain the H2D copy of g and the D2H copy of x); the caller's f/g runs on the device from
     a staged copy of x outside the timed region, as the metric excludes the user's f/g."""
     import torch
     import harness as H
     import lbfgsb_b200
-    xh = torch.full((n,), 3.0, dtype=torch.float64).pin_memory()
+    quad = kind == "quadratic"
+    xh = torch.full((n,), 0.5 * QUAD_SCALE if quad else 3.0, dtype=torch.float64).pin_memory()
     gh = torch.zeros(n, dtype=torch.float64).pin_memory()
     x, g = xh.numpy(), gh.numpy()
-    l = np.full(n, -100.0)
-    l[0::2] = L_ODD
-    u = np.full(n, 100.0)
+    if quad:
+        l = np.zeros(n)
+        u = np.full(n, QUAD_SCALE)
+    else:
+        l = np.full(n, -100.0)
+        l[0::2] = L_ODD
+        u = np.full(n, 100.0)
     nbd = np.full(n, 2, np.int32)
     xs = torch.empty(n, dtype=torch.float64, device=dev)
     gs = torch.empty(n, dtype=torch.float64, device=dev)
-    fgk = lbfgsb_b200.RosenbrockDevice(np.float64, stream=torch.cuda.current_stream().cuda_stream)
+    st = torch.cuda.current_stream().cuda_stream
+    if quad:
+        qk = lbfgsb_b200.QuadraticDevice(np.float64, seed=QUAD_SEED, stream=st)
+        fgk = (lambda xx, gg: qk(xx, gg, offset=0))
+    else:
+        fgk = lbfgsb_b200.RosenbrockDevice(np.float64, stream=st)
     task = H.make_task("START")
     csave = H.make_task("")
     lsave = np.zeros(4, np.int32)

@@ -109,6 +109,18 @@ int lbfgsb_problem_rosenbrock_f32(int64_t n, const float* x_dev, float* g_dev, f
                                   int32_t first, int32_t last, float xl, float xr, void* scratch_dev);
 int64_t lbfgsb_problem_scratch_bytes(void);
 
+/* ---- bound-constrained convex quadratic (BASELINE.json configs[3]; SURVEY.md section 8(d) "Config 4") ----
+ * f = 1/2 x'Ax - b'x,  A = tridiag(-1, 2 + delta_i, -1),
+ * delta_i = 0.1 + hi32(splitmix64(2 i + 2 seed'))/2^32,  b_i = 2 hi32(splitmix64(2 i + 1 + 2 seed'))/2^32 - 1,
+ * seed' = seed * 0x9E3779B97F4A7C15 (mod 2^64), i = global 0-based index = index_offset + local index.
+ * g = Ax - b.  On a shard the caller passes the neighbours' boundary values xl / xr (0 at the ends of
+ * the chain) and adds the partial f over the ranks.  There is no reference file for this objective: the
+ * reference ships only the Rosenbrock drivers; this is the weak-scaling workload the north star names. */
+int lbfgsb_problem_quadratic_f64(int64_t n, const double* x_dev, double* g_dev, double* f_out, void* cuda_stream,
+                                 int64_t index_offset, uint64_t seed, double xl, double xr, void* scratch_dev);
+int lbfgsb_problem_quadratic_f32(int64_t n, const float* x_dev, float* g_dev, float* f_out, void* cuda_stream,
+                                 int64_t index_offset, uint64_t seed, float xl, float xr, void* scratch_dev);
+
 /* ---- single-kernel entry points for the per-routine parity tests (device pointers) ---------- */
 int lbfgsb_test_projgr_f64(int64_t n, const double* l, const double* u, const int32_t* nbd, const double* x,
                            const double* g, double* sbgnrm_out);

@@ -94,6 +94,8 @@ def lib():
             getattr(L, "lbfgsb_setulb_dev_" + sfx).restype = None
             getattr(L, "lbfgsb_problem_rosenbrock_" + sfx).argtypes = [
                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, cr, cr, C.c_void_p]
+            getattr(L, "lbfgsb_problem_quadratic_" + sfx).argtypes = [
+                C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, cr, cr, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -284,4 +286,27 @@ class RosenbrockDevice:
                       self.stream, first, last, self._cr(xl), self._cr(xr), C.c_void_p(self.scratch.data_ptr()))
         if rc != 0:
             raise LbfgsbB200Error("rosenbrock kernel failed: " + last_error())
+        return self._f[0]
+
+
+class QuadraticDevice:
+    """f/g of the bound-constrained convex quadratic of BASELINE.json configs[3] on the device
+    (include/lbfgsb_b200.h: lbfgsb_problem_quadratic_*).  `offset` is the global index of x[0]."""
+
+    def __init__(self, dtype, seed=0, stream=None):
+        import torch
+        self.dtype = np.dtype(dtype)
+        self.seed = int(seed)
+        self.scratch = torch.empty(int(lib().lbfgsb_problem_scratch_bytes()), dtype=torch.uint8, device="cuda")
+        sfx, self._cr = _REAL[self.dtype]
+        self._fn = getattr(lib(), "lbfgsb_problem_quadratic_" + sfx)
+        self._f = np.zeros(1, dtype=self.dtype)
+        self.stream = stream
+
+    def __call__(self, x, g, offset=0, xl=0.0, xr=0.0):
+        rc = self._fn(C.c_int64(x.numel()), C.c_void_p(x.data_ptr()), C.c_void_p(g.data_ptr()), _p(self._f),
+                      self.stream, C.c_int64(offset), C.c_uint64(self.seed), self._cr(xl), self._cr(xr),
+                      C.c_void_p(self.scratch.data_ptr()))
+        if rc != 0:
+            raise LbfgsbB200Error("quadratic kernel failed: " + last_error())
         return self._f[0]

@@ -12,6 +12,15 @@
 //      exit at the first j with -f1_j/f2_j < dt_j  (:1416)
 //   4. scatter of the fixed variables (xcp = bound, iwhere = 1/2, d = 0)  (k_walk_fix)
 //
+// Rounds.  The search usually ends after a small fraction of the breakpoints (the reference pops them one
+// by one for the same reason), so steps 1-4 run in rounds over increasing ranges of t -- (0, 2 dtm0],
+// (2 dtm0, 16 dtm0], (16 dtm0, inf) with dtm0 the minimiser of the first segment -- and stop as soon as
+// the exit is known.  The count pass of a round also returns the smallest breakpoint not yet passed,
+// which is all the exit test of the reference needs ("pop the next t, compare dt with dtm"), so a round
+// whose predecessors already contain the exit is never compacted or sorted.  The running state
+// (prefix sums, f1, f2, the last two t) is carried from round to round in the state block, exactly as
+// it is carried from chunk to chunk and, on a sharded problem, from rank to rank.
+//
 // Decisions are the reference's decisions up to the rounding of the re-associated
 // sums; see DESIGN.md "Cauchy walk" for the tie-order caveat.
 #pragma once
@@ -182,7 +191,8 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_write(Wk<T> w, const i64*
 }
 
 // ---------------------------------------------------------------------------
-// Stable LSD radix sort, 8-bit digits.  LB_RS_GRID blocks, each owning one
+// Stable LSD radix sort, 8-bit digits.  gridDim.x <= LB_RS_GRID blocks (the host sizes the grid by the
+// item count: a short list is sorted by a few blocks and a short scan), each owning one
 // contiguous chunk of the input; counts are laid out [digit][block] so that one
 // exclusive scan of the flattened array gives every (digit, block) its output base.
 // ---------------------------------------------------------------------------
@@ -190,7 +200,8 @@ template <typename K>
 __global__ void __launch_bounds__(256) k_rs_hist(const K* k0, const K* k1, const SortCtl* ctl, int shift, int* counts) {
     const i64 nitems = ctl->count;
     const K* keys = ctl->cur ? k1 : k0;
-    const i64 chunk = ((nitems + LB_RS_GRID - 1) / LB_RS_GRID + LB_RS_TILE - 1) / LB_RS_TILE * LB_RS_TILE;
+    const int nblk = (int)gridDim.x;
+    const i64 chunk = ((nitems + nblk - 1) / nblk + LB_RS_TILE - 1) / LB_RS_TILE * LB_RS_TILE;
     const i64 beg = (i64)blockIdx.x * chunk;
     i64 end = beg + chunk; if (end > nitems) end = nitems;
     __shared__ int h[256];
@@ -198,20 +209,20 @@ __global__ void __launch_bounds__(256) k_rs_hist(const K* k0, const K* k1, const
     __syncthreads();
     for (i64 i = beg + threadIdx.x; i < end; i += 256) atomicAdd(&h[(int)((keys[i] >> shift) & 0xff)], 1);
     __syncthreads();
-    counts[threadIdx.x * LB_RS_GRID + blockIdx.x] = h[threadIdx.x];
+    counts[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
 // exclusive scan of counts[256*GRID] in place; sets ctl->skip if one digit holds everything
-__global__ void __launch_bounds__(1024) k_rs_scan(int* counts, SortCtl* ctl) {
+__global__ void __launch_bounds__(1024) k_rs_scan(int* counts, SortCtl* ctl, int nblk) {
     __shared__ i64 sm[33];
     __shared__ int allsame;
-    const i64 total = 256 * LB_RS_GRID;
+    const i64 total = 256 * (i64)nblk;
     if (threadIdx.x == 0) allsame = 0;
     __syncthreads();
     // digit totals: thread d < 256 sums its row
     if (threadIdx.x < 256) {
         i64 t = 0;
-        for (int b = 0; b < LB_RS_GRID; ++b) t += counts[threadIdx.x * LB_RS_GRID + b];
+        for (int b = 0; b < nblk; ++b) t += counts[threadIdx.x * nblk + b];
         if (t == ctl->count) allsame = 1;
     }
     __syncthreads();
@@ -235,14 +246,15 @@ __global__ void __launch_bounds__(256) k_rs_scatter(K* k0, K* k1, int* v0, int* 
     const i64 nitems = ctl->count;
     const K* kin = ctl->cur ? k1 : k0; K* kout = ctl->cur ? k0 : k1;
     const int* vin = ctl->cur ? v1 : v0; int* vout = ctl->cur ? v0 : v1;
-    const i64 chunk = ((nitems + LB_RS_GRID - 1) / LB_RS_GRID + LB_RS_TILE - 1) / LB_RS_TILE * LB_RS_TILE;
+    const int nblk = (int)gridDim.x;
+    const i64 chunk = ((nitems + nblk - 1) / nblk + LB_RS_TILE - 1) / LB_RS_TILE * LB_RS_TILE;
     const i64 beg = (i64)blockIdx.x * chunk;
     i64 end = beg + chunk; if (end > nitems) end = nitems;
     __shared__ int cnt[8][257];
     __shared__ int dig_off[256];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    dig_off[threadIdx.x] = offsets[threadIdx.x * LB_RS_GRID + blockIdx.x];
+    dig_off[threadIdx.x] = offsets[threadIdx.x * nblk + blockIdx.x];
     __syncthreads();
     for (i64 t0 = beg; t0 < end; t0 += LB_RS_TILE) {
         for (int q = threadIdx.x; q < 8 * 257; q += 256) (&cnt[0][0])[q] = 0;
@@ -572,28 +584,212 @@ __global__ void k_walk_chunk_end(Wk<T> w, WalkBuf<T> b, i64 start, i64 len, cons
     DevState<T>* s = w.s;
     if (threadIdx.x != 0) return;
     if (!s->go || !s->in_body || !s->need_walk || s->walk_J >= 0) return;
-    if (*jmin != 0xffffffffffffffffULL) { s->walk_J = (i64)*jmin; return; }
+    if (*jmin != 0xffffffffffffffffULL) { s->walk_J = (i64)*jmin; s->walk_cstart = start; return; }
     const int col2 = 2 * s->col;
     for (int c = 0; c < col2; ++c) { s->walkA[c] = tmpAB[c]; s->walkB[c] = tmpAB[2 * LB_MMAX + c]; }
     s->walk_f1 = tmpF[0]; s->walk_f2 = tmpF[1];
     s->walk_done = start + len;
 }
 
-// After all chunks: state at the exit, GCP scalars (:1436-1442, :1484-1495, :1509-1526).
-// One block; if the exit is inside a chunk, re-derives A_J, B_J from that chunk's scratch.
+// ---------------------------------------------------------------------------
+// Rounds: range-filtered compaction, the "next breakpoint" peek, and the closing of the search.
+// ---------------------------------------------------------------------------
+struct BpRange { unsigned long long lo, hi; int lo_valid; };   // keys in (lo, hi]; no lower limit when !lo_valid
+__device__ __forceinline__ bool bp_rem(const BpRange& r, unsigned long long k) { return !r.lo_valid || k > r.lo; }
+__device__ __forceinline__ bool bp_in(const BpRange& r, unsigned long long k) { return bp_rem(r, k) && k <= r.hi; }
+struct RoundRec { i64 count, rem; unsigned long long kmin; i64 pad; };   // of one rank
+
+// count pass of a round: per tile the breakpoints in range; per block the number of breakpoints not yet
+// passed (key > lo) and the smallest of them.  ipart slot 0: rem, slot 1: kmin (keys of t >= 0 fit in i64).
 template <typename T>
-__global__ void __launch_bounds__(LB_WB) k_walk_final(Wk<T> w, WalkBuf<T> b, i64 chunk_cap, i64 n_global) {
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_bp_count(Wk<T> w, BpRange rg, int* tile_counts) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_closed) return;
+    const i64 n = w.n;
+    const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
+    const i64 ntiles = (n + tile - 1) / tile;
+    __shared__ i64 smi[LBFGSB_BLOCK / 32];
+    i64 rem = 0, kmin = LB_I64MAX;
+    for (i64 tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        i64 c = 0;
+#pragma unroll
+        for (int k = 0; k < LBFGSB_UNROLL; ++k) {
+            const i64 base = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC) + (i64)threadIdx.x * VEC;
+            if (base >= n) continue;
+            T d[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC];
+            ldv<T>(w.d, base, n, d); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
+            ldvi<T>(w.nbd, base, n, nb);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                T t;
+                if (base + v < n && bp_of<T>(d[v], x[v], l[v], u[v], nb[v], t)) {
+                    const unsigned long long key = (unsigned long long)KeyBits<T>::to(t);
+                    if (bp_rem(rg, key)) { rem++; if ((i64)key < kmin) kmin = (i64)key; }
+                    if (bp_in(rg, key)) c++;
+                }
+            }
+        }
+        i64 r = block_isum(c, smi);
+        if (threadIdx.x == 0) tile_counts[tl] = (int)r;
+    }
+    const i64 r0 = block_isum(rem, smi);
+    i64 km = warp_min<i64>(kmin);
+    if ((threadIdx.x & 31) == 0) smi[threadIdx.x >> 5] = km;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < LBFGSB_BLOCK / 32; ++q) km = smi[q] < km ? smi[q] : km;
+        LB_SLOT(w.ipart, 0)[blockIdx.x] = r0;
+        LB_SLOT(w.ipart, 1)[blockIdx.x] = km;
+    }
+}
+
+// ordered compaction of the breakpoints in range -> (key, local variable)
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_bp_write(Wk<T> w, BpRange rg, const i64* tile_offsets,
+                                                          typename Real<T>::key_t* keys, int* vals) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_closed) return;
+    const i64 n = w.n;
+    const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
+    const i64 ntiles = (n + tile - 1) / tile;
+    __shared__ i64 sm[33];
+    for (i64 tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        i64 run = tile_offsets[tl];
+#pragma unroll 1
+        for (int k = 0; k < LBFGSB_UNROLL; ++k) {
+            const i64 base = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC) + (i64)threadIdx.x * VEC;
+            bool fl[VEC]; T tv[VEC];
+            i64 c = 0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { fl[v] = false; tv[v] = (T)0; }
+            if (base < n) {
+                T d[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC];
+                ldv<T>(w.d, base, n, d); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
+                ldvi<T>(w.nbd, base, n, nb);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (base + v < n && bp_of<T>(d[v], x[v], l[v], u[v], nb[v], tv[v]) &&
+                        bp_in(rg, (unsigned long long)KeyBits<T>::to(tv[v]))) { fl[v] = true; c++; }
+            }
+            i64 tot;
+            i64 pos = run + block_excl_scan<i64>(c, sm, tot);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (fl[v]) { keys[pos] = KeyBits<T>::to(tv[v]); vals[pos] = (int)(base + v); pos++; }
+            run += tot;
+        }
+    }
+}
+
+// this rank's part of a round: tile offsets, ctl->count, and the record (count, rem, kmin).  One block of 1024.
+template <typename T>
+__global__ void __launch_bounds__(1024) k_walk_round_local(Wk<T> w, const int* counts, i64* offsets, i64 ntiles, SortCtl* ctl,
+                                                          RoundRec* out) {
     DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || !s->need_walk) return;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_closed) return;
+    __shared__ i64 sm[33];
+    i64 carry = 0;
+    for (i64 b0 = 0; b0 < ntiles; b0 += 1024) {
+        const i64 i = b0 + threadIdx.x;
+        i64 v = (i < ntiles) ? (i64)counts[i] : 0;
+        i64 tot;
+        i64 ex = block_excl_scan<i64>(v, sm, tot);
+        if (i < ntiles) offsets[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x < 32) {
+        const i64 rem = final_isum_warp(LB_SLOT(w.ipart, 0));
+        const i64 km = final_imin_warp(LB_SLOT(w.ipart, 1));
+        if (threadIdx.x == 0) {
+            ctl->count = carry; ctl->cur = 0; ctl->skip = 0;
+            s->walk_lcount = carry;
+            out->count = carry; out->rem = rem; out->kmin = (unsigned long long)km; out->pad = 0;
+        }
+    }
+}
+
+// every breakpoint was passed (:1436-1442, :1484-1495): close from the carried state
+template <typename T>
+__device__ inline void walk_close_all_passed(DevState<T>* s, i64 n_global) {
+    const int col2 = 2 * s->col;
+    const i64 nb = s->nbreak;
+    const T tlast = s->walk_tlast;
+    T dtm;
+    if (nb == n_global) {   // all n variables fixed (:1436-1442)
+        dtm = tlast - ((nb > 1) ? s->walk_tprev2 : (T)0);
+        s->nseg = nb;
+        s->tsum = tlast;
+        for (int c = 0; c < col2; ++c) { const T pJ = s->p0[c] - s->walkA[c]; s->p[c] = pJ; s->c[c] = tlast * pJ + s->walkB[c]; }
+        s->dtm = dtm;
+    } else {
+        s->nseg = nb + 1;
+        T f1 = s->walk_f1, f2 = s->walk_f2;
+        if (s->bnded) { f1 = (T)0; f2 = (T)0; dtm = (T)0; }
+        else dtm = -f1 / f2;
+        if (dtm <= (T)0) dtm = (T)0;
+        s->f1 = f1; s->f2 = f2; s->dtm = dtm;
+        s->tsum = tlast + dtm;
+        for (int c = 0; c < col2; ++c) {
+            const T pJ = s->p0[c] - s->walkA[c];
+            s->p[c] = pJ;
+            s->c[c] = (tlast * pJ + s->walkB[c]) + dtm * pJ;
+        }
+    }
+    s->walk_closed = 1;
+}
+// the exit lies in the segment that starts at tprev, with prefix sums AJ, BJ (:1416, :1509-1526)
+template <typename T>
+__device__ inline void walk_close_at(DevState<T>* s, T f1, T f2, T tprev, const T* AJ, const T* BJ, i64 nseg) {
+    const int col2 = 2 * s->col;
+    T dtm = -f1 / f2;
+    if (dtm <= (T)0) dtm = (T)0;
+    s->f1 = f1; s->f2 = f2; s->dtm = dtm;
+    s->tsum = tprev + dtm;
+    s->nseg = nseg;
+    for (int c = 0; c < col2; ++c) {
+        const T pJ = s->p0[c] - AJ[c];
+        s->p[c] = pJ;
+        s->c[c] = (tprev * pJ + BJ[c]) + dtm * pJ;
+    }
+    s->walk_closed = 1;
+}
+
+// Start of a round (every rank, identical inputs): totals over the ranks, and the test the reference makes
+// when it pops the next breakpoint (:1416) against the smallest breakpoint not yet passed -- exactly what
+// k_walk_test would compute for the first entry of this or a later round.
+template <typename T>
+__global__ void k_walk_round_begin(Wk<T> w, const RoundRec* all, int R, i64 n_global) {
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_closed) return;
+    i64 cnt = 0, rem = 0; unsigned long long kmin = 0xffffffffffffffffULL;
+    for (int q = 0; q < R; ++q) { cnt += all[q].count; rem += all[q].rem; if (all[q].rem > 0 && all[q].kmin < kmin) kmin = all[q].kmin; }
+    s->walk_rcount = cnt; s->walk_rem = rem; s->walk_J = -1; s->walk_done = 0; s->walk_fixn = 0;
+    if (rem == 0) { walk_close_all_passed<T>(s, n_global); return; }
+    if (s->walk_base > 0) {
+        const T tnext = KeyBits<T>::from((typename Real<T>::key_t)kmin);
+        const T dt = tnext - s->walk_tlast;
+        const T dtm = -s->walk_f1 / s->walk_f2;
+        if (dtm < dt) walk_close_at<T>(s, s->walk_f1, s->walk_f2, s->walk_tlast, s->walkA, s->walkB, 1 + s->walk_base);
+    }
+}
+
+// End of a round on a single GPU, after its chunks.  One block of LB_WB threads.
+template <typename T>
+__global__ void __launch_bounds__(LB_WB) k_walk_round_end(Wk<T> w, WalkBuf<T> b, i64 n_global) {
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_closed) return;
     __shared__ T AJ[2 * LB_MMAX], BJ[2 * LB_MMAX];
     __shared__ T sm[33];
-    const int col = s->col, col2 = 2 * col;
-    const i64 nb = b.ctl->count;
+    const int col2 = 2 * s->col;
+    const i64 cnt = b.ctl->count;
     const i64 J = s->walk_J;
     const typename Real<T>::key_t* keys = cur_keys<T>(b);
     if (J >= 0) {
         // prefix sums at J: block prefix + in-block partial sums of the chunk that holds J
-        const i64 start = (J / chunk_cap) * chunk_cap;
+        const i64 start = s->walk_cstart;
         const i64 jl = J - start;
         const i64 blk = jl / LB_WB;
         const i64 j = blk * LB_WB + threadIdx.x;
@@ -608,54 +804,26 @@ __global__ void __launch_bounds__(LB_WB) k_walk_final(Wk<T> w, WalkBuf<T> b, i64
         }
         __syncthreads();
         if (threadIdx.x != 0) return;
-        const T f1 = b.f1a[jl], f2 = b.f2a[jl];
-        const T tprev = KeyBits<T>::from(keys[J - 1]);   // J >= 1: the first test is done by s_cauchy
-        T dtm = -f1 / f2;
-        if (dtm <= (T)0) dtm = (T)0;
-        s->f1 = f1; s->f2 = f2; s->dtm = dtm;
-        s->tsum = tprev + dtm;
-        s->nseg = 1 + J;
-        for (int c = 0; c < col2; ++c) {
-            const T pJ = s->p0[c] - AJ[c];
-            s->p[c] = pJ;
-            s->c[c] = (tprev * pJ + BJ[c]) + dtm * pJ;
-        }
-    } else {
-        if (threadIdx.x != 0) return;
-        // every breakpoint was passed
-        const T tlast = KeyBits<T>::from(keys[nb - 1]);
-        T dtm;
-        if (nb == n_global) {   // all n variables fixed (:1436-1442)
-            const T tprev = (nb > 1) ? KeyBits<T>::from(keys[nb - 2]) : (T)0;
-            dtm = tlast - tprev;
-            s->nseg = nb;
-            s->tsum = tlast;
-            for (int c = 0; c < col2; ++c) { const T pJ = s->p0[c] - s->walkA[c]; s->p[c] = pJ; s->c[c] = tlast * pJ + s->walkB[c]; }
-            s->dtm = dtm;
-        } else {
-            s->nseg = nb + 1;
-            T f1 = s->walk_f1, f2 = s->walk_f2;
-            if (s->bnded) { f1 = (T)0; f2 = (T)0; dtm = (T)0; }
-            else dtm = -f1 / f2;
-            if (dtm <= (T)0) dtm = (T)0;
-            s->f1 = f1; s->f2 = f2; s->dtm = dtm;
-            s->tsum = tlast + dtm;
-            for (int c = 0; c < col2; ++c) {
-                const T pJ = s->p0[c] - s->walkA[c];
-                s->p[c] = pJ;
-                s->c[c] = (tlast * pJ + s->walkB[c]) + dtm * pJ;
-            }
-        }
-        s->walk_J = nb;
+        const T tprev = (J > 0) ? KeyBits<T>::from(keys[J - 1]) : s->walk_tlast;
+        walk_close_at<T>(s, b.f1a[jl], b.f2a[jl], tprev, AJ, BJ, 1 + s->walk_base + J);
+        s->walk_fixn = J;
+        return;
     }
+    if (threadIdx.x != 0) return;
+    // every breakpoint of the round was passed
+    if (cnt >= 2) { s->walk_tprev2 = KeyBits<T>::from(keys[cnt - 2]); s->walk_tlast = KeyBits<T>::from(keys[cnt - 1]); }
+    else if (cnt == 1) { s->walk_tprev2 = s->walk_tlast; s->walk_tlast = KeyBits<T>::from(keys[0]); }
+    s->walk_base += cnt;
+    s->walk_fixn = cnt;
+    if (cnt == s->walk_rem) walk_close_all_passed<T>(s, n_global);
 }
 
-// fix the variables whose breakpoints were passed (:1424-1434)
+// fix the variables whose breakpoints were passed in this round (:1424-1434)
 template <typename T>
 __global__ void __launch_bounds__(256) k_walk_fix(Wk<T> w, WalkBuf<T> b) {
     const DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->need_walk) return;
-    const i64 J = s->walk_J;
+    const i64 J = s->walk_fixn;
     const int* vals = cur_vals<T>(b);
     for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < J; j += (i64)gridDim.x * blockDim.x) {
         const int var = vals[j];

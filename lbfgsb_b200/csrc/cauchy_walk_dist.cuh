@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(LB_WB) k_dw_turn_end(Wk<T> w, WalkBuf<T> b, co
         if (dtm <= (T)0) dtm = (T)0;
         out->found = 1;
         out->fin_f1 = f1; out->fin_f2 = f2; out->dtm = dtm; out->tsum = tprev + dtm;
-        out->nseg = 1 + dc->goff + J;
+        out->nseg = 1 + s->walk_base + dc->goff + J;
         for (int c = 0; c < col2; ++c) {
             const T pJ = s->p0[c] - AJ[c];
             out->p[c] = pJ;
@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(LB_WB) k_dw_turn_end(Wk<T> w, WalkBuf<T> b, co
     else { out->tlast = s->walk_tlast; out->tprev2 = s->walk_tprev2; }
 }
 
-// Every rank adopts the carry of rank `turn`; after the last turn the search is closed
-// (all-passed exits :1436-1442, :1484-1495 as in k_walk_final).
+// Every rank adopts the carry of rank `turn`; after the last turn of the last round the search is
+// closed (all-passed exits :1436-1442, :1484-1495, walk_close_all_passed).
 template <typename T>
 __global__ void k_dw_adopt(Wk<T> w, const WalkCarry<T>* all, int turn, int R, int rank, DwCtl* dc, i64 n_global) {
     if (threadIdx.x != 0) return;
@@ -262,38 +262,17 @@ __global__ void k_dw_adopt(Wk<T> w, const WalkCarry<T>* all, int turn, int R, in
         // my entries before the exit: everything I sent to lower ranks + my records before J on rank `turn`
         dc->jloc = dc->pos[turn] + cr->fixcnt[rank];
         s->walk_J = LB_I64MAX;
+        s->walk_closed = 1;
         return;
     }
     for (int c = 0; c < col2; ++c) { s->walkA[c] = cr->A[c]; s->walkB[c] = cr->B[c]; }
     s->walk_f1 = cr->f1; s->walk_f2 = cr->f2; s->walk_tlast = cr->tlast; s->walk_tprev2 = cr->tprev2;
     s->walk_J = -1;
     if (turn != R - 1) return;
-    // all breakpoints passed
-    const i64 nb = dc->nb_glob;
-    const T tlast = s->walk_tlast;
-    T dtm;
-    if (nb == n_global) {
-        dtm = tlast - ((nb > 1) ? s->walk_tprev2 : (T)0);
-        s->nseg = nb;
-        s->tsum = tlast;
-        for (int c = 0; c < col2; ++c) { const T pJ = s->p0[c] - s->walkA[c]; s->p[c] = pJ; s->c[c] = tlast * pJ + s->walkB[c]; }
-        s->dtm = dtm;
-    } else {
-        s->nseg = nb + 1;
-        T f1 = s->walk_f1, f2 = s->walk_f2;
-        if (s->bnded) { f1 = (T)0; f2 = (T)0; dtm = (T)0; }
-        else dtm = -f1 / f2;
-        if (dtm <= (T)0) dtm = (T)0;
-        s->f1 = f1; s->f2 = f2; s->dtm = dtm;
-        s->tsum = tlast + dtm;
-        for (int c = 0; c < col2; ++c) {
-            const T pJ = s->p0[c] - s->walkA[c];
-            s->p[c] = pJ;
-            s->c[c] = (tlast * pJ + s->walkB[c]) + dtm * pJ;
-        }
-    }
+    // every breakpoint of this round was passed
+    s->walk_base += dc->nb_glob;
     dc->jloc = dc->pos[R];
-    s->walk_J = LB_I64MAX;
+    if (dc->nb_glob == s->walk_rem) { walk_close_all_passed<T>(s, n_global); s->walk_J = LB_I64MAX; }
 }
 
 // fix the first dc->jloc entries of the LOCAL sorted list (:1424-1434)

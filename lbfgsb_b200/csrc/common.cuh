@@ -74,8 +74,16 @@ struct DevState {
     i64 n, nintol, nseg, nfree, nact, nenter, nleave, nbreak, nfreec, nbdd, errk;
     i64 ibkmin;                   // variable index (0-based) of the smallest breakpoint
     i64 ibd;                      // subsm backtrack: variable index of the binding bound
-    i64 walk_J;                   // exit position in the sorted breakpoint list
-    i64 walk_done;                // number of sorted breakpoints already processed
+    i64 walk_J;                   // exit position in the sorted breakpoint list of the current round (-1: none yet)
+    i64 walk_done;                // number of sorted breakpoints of the current round already processed
+    // the walk proceeds in rounds over increasing ranges of t (cauchy_walk.cuh "rounds")
+    i64 walk_base;                // breakpoints passed in the earlier rounds (all ranks)
+    i64 walk_rcount;              // breakpoints of the current round (all ranks)
+    i64 walk_lcount;              // ... of which on this rank (rank-local field)
+    i64 walk_rem;                 // breakpoints not yet passed when the current round began (all ranks)
+    i64 walk_cstart;              // start of the chunk that holds walk_J
+    i64 walk_fixn;                // how many entries of this rank's current sorted list are fixed at the end of the round
+    int walk_closed, pad1;        // the search is finished (exit found or every breakpoint passed)
     i64 n_el;                     // entering + leaving rows compacted for formk
     T theta, fold, tol, dnorm, epsmch, gd, gdold, stp, stpmx, sbgnrm, dtd, xstep, f, rr, dr, ddum;
     T pgtol, factr, sbg_spec;

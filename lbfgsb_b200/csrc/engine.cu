@@ -130,6 +130,7 @@ struct Engine : EngineBase {
     // sharded breakpoint walk (cauchy_walk_dist.cuh)
     unsigned long long* samp_local = nullptr; unsigned long long* samp_all = nullptr; unsigned long long* spl_dev = nullptr;
     DwCtl* dctl = nullptr; i64* pos_all = nullptr; SortCtl* ctl_d = nullptr;
+    RoundRec* rr_local = nullptr; RoundRec* rr_all = nullptr;
     WalkCarry<T>* carry_local = nullptr; WalkCarry<T>* carry_all = nullptr;
     struct DynBuf { void* p = nullptr; size_t cap = 0; };
     DynBuf dw_send, dw_recv, dw_k0, dw_k1, dw_v0, dw_v1;
@@ -205,6 +206,7 @@ struct Engine : EngineBase {
         if (!dalloc(&tmpAB, sizeof(T) * 4 * LB_MMAX) || !dalloc(&tmpF, sizeof(T) * 2) || !dalloc(&jmin, 8)) return false;
         if (!dalloc(&fd_parts, sizeof(T) * (size_t)LB_FD_GRID * 6 * LB_MMAX * LB_MMAX) || !dalloc(&delta, sizeof(T) * 6 * LB_MMAX * LB_MMAX)) return false;
         CK(cudaMemsetAsync(delta, 0, sizeof(T) * 6 * LB_MMAX * LB_MMAX, stream));
+        if (!dalloc(&rr_local, sizeof(RoundRec)) || !dalloc(&rr_all, sizeof(RoundRec) * (R > 1 ? R : 1))) return false;
         if (R > 1) {
             if (R > LB_MAXR) { set_error("at most %d ranks", LB_MAXR); return false; }
             if (!dalloc(&rec_local, sizeof(Red<T>)) || !dalloc(&rec_all, sizeof(Red<T>) * R)) return false;
@@ -298,26 +300,51 @@ struct Engine : EngineBase {
         return true;
     }
 
-    // ---- the breakpoint walk ------------------------------------------------
-    bool enqueue_walk(i64 nbreak) {
-        typedef typename Real<T>::key_t K;
-        begin(F_WALK_COMPACT);
-        k_flag_count<T, 0><<<LG>>>(w, tile_counts);
-        k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 0, tile_counts, tile_offsets, ntiles, wb.ctl);
-        k_flag_write<T, 0><<<LG>>>(w, tile_offsets, wb.k0, wb.v0);
-        end(F_WALK_COMPACT, 3);
-        begin(F_WALK_SORT);
-        for (int pass = 0; pass < (int)sizeof(K); ++pass) {
-            k_rs_hist<K><<<LB_RS_GRID, 256, 0, stream>>>(wb.k0, wb.k1, wb.ctl, pass * 8, rs_counts);
-            k_rs_scan<<<1, 1024, 0, stream>>>(rs_counts, wb.ctl);
-            k_rs_scatter<K><<<LB_RS_GRID, 256, 0, stream>>>(wb.k0, wb.k1, wb.v0, wb.v1, wb.ctl, pass * 8, rs_counts);
-            k_rs_flip<<<1, 32, 0, stream>>>(wb.ctl);
-            launches += 4;
+    // ---- the breakpoint walk, in rounds over increasing ranges of t (cauchy_walk.cuh) -------
+    static unsigned long long key_of(T t) {
+        typename Real<T>::key_t k;
+        memcpy(&k, &t, sizeof k);
+        return (unsigned long long)k;
+    }
+    bool enqueue_walk_rounds() {
+        const T dtm0 = s_host->dtm;          // minimiser of the first segment (s_cauchy); dtm0 >= bkmin here
+        unsigned long long his[3];
+        int nr = 0;
+        if (dtm0 > (T)0 && dtm0 < (T)INFINITY) {
+            const T t1 = (T)2 * dtm0, t2 = (T)16 * dtm0;
+            if (t1 < (T)INFINITY) his[nr++] = key_of(t1);
+            if (t2 < (T)INFINITY) his[nr++] = key_of(t2);
         }
-        end(F_WALK_SORT, 0);
+        his[nr++] = 0xffffffffffffffffULL;
+        BpRange rg; rg.lo = 0; rg.lo_valid = 0; rg.hi = 0;
+        for (int r = 0; r < nr; ++r) {
+            rg.hi = his[r];
+            begin(F_WALK_COMPACT);
+            k_bp_count<T><<<LG>>>(w, rg, tile_counts);
+            k_walk_round_local<T><<<1, 1024, 0, stream>>>(w, tile_counts, tile_offsets, ntiles, wb.ctl, rr_local);
+            end(F_WALK_COMPACT, 2);
+            if (R > 1 && !allgather(rr_local, rr_all, sizeof(RoundRec))) return false;
+            k_walk_round_begin<T><<<1, 32, 0, stream>>>(w, R > 1 ? rr_all : rr_local, R, n_global); launches++;
+            if (!sync_state()) return false;
+            if (s_host->walk_closed) break;
+            if (s_host->walk_rcount > 0) {
+                begin(F_WALK_COMPACT); k_bp_write<T><<<LG>>>(w, rg, tile_offsets, wb.k0, wb.v0); end(F_WALK_COMPACT);
+                begin(F_WALK_SORT); enqueue_sort(wb.k0, wb.k1, wb.v0, wb.v1, wb.ctl, s_host->walk_lcount); end(F_WALK_SORT, 0);
+                if (R > 1) { if (!round_scan_sharded()) return false; }
+                else if (!round_scan_single(s_host->walk_lcount)) return false;
+                if (!sync_state()) return false;
+                if (s_host->walk_closed) break;
+            }
+            rg.lo = rg.hi; rg.lo_valid = 1;
+        }
+        if (!s_host->walk_closed) { set_error("the breakpoint walk did not close (internal error)"); return false; }
+        return true;
+    }
+    // scans of one round's sorted list on a single GPU
+    bool round_scan_single(i64 count) {
         begin(F_WALK_SCAN);
-        for (i64 start = 0; start < nbreak; start += wb.cap) {
-            const i64 len = (nbreak - start < wb.cap) ? (nbreak - start) : wb.cap;
+        for (i64 start = 0; start < count; start += wb.cap) {
+            const i64 len = (count - start < wb.cap) ? (count - start) : wb.cap;
             const i64 nblk = (len + LB_WB - 1) / LB_WB;
             CK(cudaMemsetAsync(jmin, 0xff, 8, stream));
             k_walk_gather<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wb, start, len);
@@ -330,7 +357,7 @@ struct Engine : EngineBase {
             k_walk_chunk_end<T><<<1, 32, 0, stream>>>(w, wb, start, len, tmpAB, tmpF, jmin);
             launches += 8;
         }
-        k_walk_final<T><<<1, LB_WB, 0, stream>>>(w, wb, wb.cap, n_global);
+        k_walk_round_end<T><<<1, LB_WB, 0, stream>>>(w, wb, n_global);
         end(F_WALK_SCAN, 1);
         begin(F_WALK_FIX);
         k_walk_fix<T><<<LBFGSB_GRID, 256, 0, stream>>>(w, wb);
@@ -355,28 +382,26 @@ struct Engine : EngineBase {
         if (rc != 0) { set_error("ncclAllGather failed: %d", rc); return false; }
         return true;
     }
-    void enqueue_sort(typename Real<T>::key_t* k0, typename Real<T>::key_t* k1, int* v0, int* v1, SortCtl* ctl) {
+    // `count` = number of items (what ctl->count holds on the device): sizes the grid
+    static int sort_blocks(i64 count) {
+        i64 nb = (count + 2 * LB_RS_TILE - 1) / (2 * LB_RS_TILE);
+        return (int)(nb < 1 ? 1 : (nb > LB_RS_GRID ? LB_RS_GRID : nb));
+    }
+    void enqueue_sort(typename Real<T>::key_t* k0, typename Real<T>::key_t* k1, int* v0, int* v1, SortCtl* ctl, i64 count) {
         typedef typename Real<T>::key_t K;
+        const int nblk = sort_blocks(count);
         for (int pass = 0; pass < (int)sizeof(K); ++pass) {
-            k_rs_hist<K><<<LB_RS_GRID, 256, 0, stream>>>(k0, k1, ctl, pass * 8, rs_counts);
-            k_rs_scan<<<1, 1024, 0, stream>>>(rs_counts, ctl);
-            k_rs_scatter<K><<<LB_RS_GRID, 256, 0, stream>>>(k0, k1, v0, v1, ctl, pass * 8, rs_counts);
+            k_rs_hist<K><<<nblk, 256, 0, stream>>>(k0, k1, ctl, pass * 8, rs_counts);
+            k_rs_scan<<<1, 1024, 0, stream>>>(rs_counts, ctl, nblk);
+            k_rs_scatter<K><<<nblk, 256, 0, stream>>>(k0, k1, v0, v1, ctl, pass * 8, rs_counts);
             k_rs_flip<<<1, 32, 0, stream>>>(ctl);
             launches += 4;
         }
     }
-    bool enqueue_walk_sharded() {
+    // one round on a sharded problem: this rank's breakpoints of the round are sorted in wb
+    bool round_scan_sharded() {
         typedef typename Real<T>::key_t K;
         const int S = LB_DW_SAMPLES;
-        // 1. local breakpoints, sorted
-        begin(F_WALK_COMPACT);
-        k_flag_count<T, 0><<<LG>>>(w, tile_counts);
-        k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 0, tile_counts, tile_offsets, ntiles, wb.ctl);
-        k_flag_write<T, 0><<<LG>>>(w, tile_offsets, wb.k0, wb.v0);
-        end(F_WALK_COMPACT, 3);
-        begin(F_WALK_SORT);
-        enqueue_sort(wb.k0, wb.k1, wb.v0, wb.v1, wb.ctl);
-        end(F_WALK_SORT, 0);
         // 2. splitters from regular samples
         begin(F_WALK_SCAN);
         k_dw_sample<T><<<1, 64, 0, stream>>>(w, wb, samp_local); launches++;
@@ -439,7 +464,7 @@ struct Engine : EngineBase {
         WalkBuf<T> wd = wb;
         wd.k0 = (K*)dw_k0.p; wd.k1 = (K*)dw_k1.p; wd.v0 = (int*)dw_v0.p; wd.v1 = (int*)dw_v1.p; wd.ctl = ctl_d;
         k_dw_keys<T><<<LBFGSB_GRID, 256, 0, stream>>>(recv, rs, nrecv, wd.k0, wd.v0, ctl_d); launches++;
-        enqueue_sort(wd.k0, wd.k1, wd.v0, wd.v1, ctl_d);
+        enqueue_sort(wd.k0, wd.k1, wd.v0, wd.v1, ctl_d, nrecv);
         // 5. scans in rank order, carries handed from rank to rank
         for (int turn = 0; turn < R; ++turn) {
             if (turn == rank) {
@@ -480,8 +505,7 @@ struct Engine : EngineBase {
             if (s_host->cnstnd) {
                 if (!sync_state()) return false;
                 if (s_host->go && s_host->in_body && s_host->need_walk) {
-                    if (R > 1) { if (!enqueue_walk_sharded()) return false; }
-                    else if (!enqueue_walk(s_host->nbreak)) return false;
+                    if (!enqueue_walk_rounds()) return false;
                 }
             }
             begin(F_GCP_FREEV); k_gcp_freev<T><<<LG>>>(w); end(F_GCP_FREEV);
@@ -871,6 +895,71 @@ static int rosenbrock_impl(i64 n, const T* x, T* g, T* f_out, void* st, int firs
 }
 
 // ---------------------------------------------------------------------------
+// bound-constrained convex quadratic (include/lbfgsb_b200.h): f = 1/2 x'Ax - b'x, g = Ax - b,
+// A = tridiag(-1, 2 + delta_i, -1); delta, b from a counter-based hash of the global index.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline unsigned long long lb_mix64(unsigned long long v) {
+    v += 0x9E3779B97F4A7C15ULL;
+    v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    v = (v ^ (v >> 27)) * 0x94D049BB133111EBULL;
+    return v ^ (v >> 31);
+}
+template <typename T>
+__device__ __forceinline__ void quad_coeff(unsigned long long gi, unsigned long long seedp, T& diag, T& b) {
+    const double u1 = (double)(lb_mix64(2ULL * gi + 2ULL * seedp) >> 32) * (1.0 / 4294967296.0);
+    const double u2 = (double)(lb_mix64(2ULL * gi + 1ULL + 2ULL * seedp) >> 32) * (1.0 / 4294967296.0);
+    diag = (T)(2.0 + (0.1 + u1));
+    b = (T)(2.0 * u2 - 1.0);
+}
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_quadratic(i64 n, const T* __restrict__ x, T* __restrict__ g, T* part,
+                                                           i64 off, unsigned long long seedp, T xl, T xr) {
+    constexpr int VEC = Real<T>::VEC;
+    __shared__ T sm[LBFGSB_BLOCK / 32];
+    T acc[1]; acc[0] = (T)0;
+    LB_FOR_TILES(T, n, base) {
+        T xv[VEC], gv[VEC];
+        ldv<T>(x, base, n, xv);
+        const T xm = (base > 0) ? x[base - 1] : xl;
+        const T xp = (base + VEC < n) ? x[base + VEC] : xr;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const i64 i = base + v;
+            gv[v] = (T)0;
+            if (i < n) {
+                const T xi = xv[v];
+                const T xprev = (v == 0) ? xm : xv[v - 1];
+                const T xnext = (i + 1 >= n) ? xr : ((v == VEC - 1) ? xp : xv[v + 1]);
+                T diag, b;
+                quad_coeff<T>((unsigned long long)(i + off), seedp, diag, b);
+                const T ax = diag * xi - xprev - xnext;
+                gv[v] = ax - b;
+                acc[0] = acc[0] + ((T)0.5 * ax - b) * xi;
+            }
+        }
+        stv<T>(g, base, n, gv);
+    }
+    block_sum_store<T, 1>(acc, 1, sm, part);
+}
+template <typename T>
+__global__ void k_sum_final(const T* part, T* out) {
+    T s = final_sum_warp<T>(part);
+    if (threadIdx.x == 0) out[0] = s;
+}
+template <typename T>
+static int quadratic_impl(i64 n, const T* x, T* g, T* f_out, void* st, i64 off, unsigned long long seed, T xl, T xr, void* scratch) {
+    cudaStream_t s = (cudaStream_t)st;
+    T* part = (T*)scratch;
+    T* out = part + LBFGSB_GRID;
+    const unsigned long long seedp = seed * 0x9E3779B97F4A7C15ULL;
+    k_quadratic<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, off, seedp, xl, xr);
+    k_sum_final<T><<<1, 32, 0, s>>>(part, out);
+    if (cudaMemcpyAsync(f_out, out, sizeof(T), cudaMemcpyDeviceToHost, s) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("quadratic kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // test-only single kernels
 // ---------------------------------------------------------------------------
 template <typename T>
@@ -1079,6 +1168,15 @@ int lbfgsb_problem_rosenbrock_f32(int64_t n, const float* x, float* g, float* f_
     return rosenbrock_impl<float>(n, x, g, f_out, st, first, last, xl, xr, scratch);
 }
 
+int lbfgsb_problem_quadratic_f64(int64_t n, const double* x, double* g, double* f_out, void* st, int64_t off, uint64_t seed,
+                                 double xl, double xr, void* scratch) {
+    return quadratic_impl<double>(n, x, g, f_out, st, off, seed, xl, xr, scratch);
+}
+int lbfgsb_problem_quadratic_f32(int64_t n, const float* x, float* g, float* f_out, void* st, int64_t off, uint64_t seed,
+                                 float xl, float xr, void* scratch) {
+    return quadratic_impl<float>(n, x, g, f_out, st, off, seed, xl, xr, scratch);
+}
+
 int lbfgsb_test_projgr_f64(int64_t n, const double* l, const double* u, const int32_t* nbd, const double* x, const double* g,
                            double* out) {
     Wk<double> w; memset(&w, 0, sizeof w);
@@ -1108,7 +1206,7 @@ int lbfgsb_test_sort_f64(int64_t n, const double* t, int32_t* order_out, double*
     k_test_setctl<<<1, 32>>>(ctl, n);
     for (int pass = 0; pass < 8; ++pass) {
         k_rs_hist<K><<<LB_RS_GRID, 256>>>(k0, k1, ctl, pass * 8, cnt);
-        k_rs_scan<<<1, 1024>>>(cnt, ctl);
+        k_rs_scan<<<1, 1024>>>(cnt, ctl, LB_RS_GRID);
         k_rs_scatter<K><<<LB_RS_GRID, 256>>>(k0, k1, v0, v1, ctl, pass * 8, cnt);
         k_rs_flip<<<1, 32>>>(ctl);
     }

@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
         s->need_walk = 1;
         for (int j = 0; j < col2; ++j) { s->p0[j] = s->p[j]; s->walkA[j] = zero; s->walkB[j] = zero; }
         s->walk_f1 = s->f1; s->walk_f2 = s->f2; s->walk_tlast = zero; s->walk_tprev2 = zero;
-        s->walk_J = -1; s->walk_done = 0;
+        s->walk_J = -1; s->walk_done = 0; s->walk_base = 0; s->walk_rcount = 0; s->walk_lcount = 0; s->walk_rem = 0;
+        s->walk_cstart = 0; s->walk_fixn = 0; s->walk_closed = 0;
         return;
     }
     if (s->dtm <= zero) s->dtm = zero;   // :1509

@@ -61,6 +61,81 @@ def rosenbrock_shard_numpy(x, first, last, xl, xr):
     return 4.0 * float(terms.sum()), g
 
 
+_MASK = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix64(v):
+    """splitmix64 finaliser on uint64 arrays (wrapping arithmetic), as lb_mix64 in csrc/engine.cu."""
+    with np.errstate(over="ignore"):
+        v = v + np.uint64(0x9E3779B97F4A7C15)
+        v = (v ^ (v >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        v = (v ^ (v >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return v ^ (v >> np.uint64(31))
+
+
+def quadratic_coefficients(lo, hi, seed=0, dtype=np.float64):
+    """diag (2 + delta_i) and b_i of the convex quadratic of BASELINE.json configs[3] for the global
+    indices [lo, hi) (numpy reference of quad_coeff in csrc/engine.cu)."""
+    with np.errstate(over="ignore"):
+        i = np.arange(lo, hi, dtype=np.uint64)
+        sp = np.uint64((int(seed) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
+        u1 = (_mix64(np.uint64(2) * i + np.uint64(2) * sp) >> np.uint64(32)).astype(np.float64) * (1.0 / 4294967296.0)
+        u2 = (_mix64(np.uint64(2) * i + np.uint64(1) + np.uint64(2) * sp) >> np.uint64(32)).astype(np.float64) * (1.0 / 4294967296.0)
+    return (2.0 + (0.1 + u1)).astype(dtype), (2.0 * u2 - 1.0).astype(dtype)
+
+
+def quadratic_shard_numpy(x, lo, seed, xl, xr):
+    """f contribution and gradient of one shard of f = 1/2 x'Ax - b'x, A = tridiag(-1, 2+delta, -1)
+    (numpy reference of lbfgsb_problem_quadratic_*; same operation order per element).
+    Returns (this shard's part of f, g)."""
+    n = x.shape[0]
+    diag, b = quadratic_coefficients(lo, lo + n, seed, x.dtype)
+    xprev = np.empty_like(x)
+    xprev[1:] = x[:-1]
+    xprev[0] = xl
+    xnext = np.empty_like(x)
+    xnext[:-1] = x[1:]
+    xnext[-1] = xr
+    ax = diag * x - xprev - xnext
+    g = ax - b
+    half = x.dtype.type(0.5)
+    return float(((half * ax - b) * x).sum(dtype=np.float64)), g
+
+
+def quadratic_problem(n_local, dtype=np.float64, scale=0.5):
+    """Box [0, scale] on every variable (nbd = 2), start in the middle of the box.  With scale = 0.5 about
+    half of the variables end on a bound (measured with the oracle at n = 2e4: 36.5% on l = 0, 13.7% on
+    u = 0.5; the unconstrained minimiser has |x| up to 2.3 and half of its components negative)."""
+    l = np.zeros(n_local, dtype=dtype)
+    u = np.full(n_local, scale, dtype=dtype)
+    nbd = np.full(n_local, 2, dtype=np.int32)
+    x = np.full(n_local, 0.5 * scale, dtype=dtype)
+    return x, l, u, nbd
+
+
+class ShardedQuadraticDevice:
+    """Device f/g of the convex quadratic on a shard: halo exchange + partial-f all-reduce around
+    lbfgsb_problem_quadratic_* (lbfgsb_b200.QuadraticDevice)."""
+
+    def __init__(self, kernel, lo, rank, world, dist, device):
+        self.k, self.lo, self.rank, self.world, self.dist, self.device = kernel, lo, rank, world, dist, device
+
+    def __call__(self, x, g):
+        import torch
+        if self.world == 1:
+            return self.k(x, g, offset=self.lo)
+        edge = torch.stack([x[0], x[-1]])
+        allv = [torch.empty_like(edge) for _ in range(self.world)]
+        self.dist.all_gather(allv, edge)
+        r = self.rank
+        xl = float(allv[r - 1][1]) if r > 0 else 0.0
+        xr = float(allv[r + 1][0]) if r < self.world - 1 else 0.0
+        fl = self.k(x, g, offset=self.lo, xl=xl, xr=xr)
+        ft = torch.tensor([fl], dtype=torch.float64, device=self.device)
+        self.dist.all_reduce(ft)
+        return float(ft)
+
+
 class ShardedRosenbrockDevice:
     """Device f/g of the sample problem on a shard: halo exchange + partial-f all-reduce around
     lbfgsb_problem_rosenbrock_* (lbfgsb_b200.RosenbrockDevice)."""

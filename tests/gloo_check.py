@@ -2,7 +2,8 @@
 gloo backend by tests/test_sharded_cpu.py:
   - shard_bounds partitions [0, n) into contiguous blocks,
   - halo exchange + partial-f all-reduce reproduce the global f and g of the sample problem
-    (test/driver1.f90:274-289) exactly as the unsharded routine computes them.
+    (test/driver1.f90:274-289) and of the convex quadratic of BASELINE.json configs[3] exactly as
+    the unsharded routines compute them.
 """
 import os
 import sys
@@ -36,6 +37,12 @@ def main():
         fref, gref = sharded.rosenbrock_shard_numpy(xg, True, True, 0.0, 0.0)
         ok &= abs(f - fref) <= 1e-12 * abs(fref)
         ok &= np.array_equal(g, gref[lo:hi])
+        # the convex quadratic of BASELINE.json configs[3]: hashed coefficients by global index
+        qpart, qg = sharded.quadratic_shard_numpy(x, lo, 11, xl, xr)
+        qf = sharded.allreduce_sum(qpart, dist)
+        qfref, qgref = sharded.quadratic_shard_numpy(xg, 0, 11, 0.0, 0.0)
+        ok &= abs(qf - qfref) <= 1e-12 * max(1.0, abs(qfref))
+        ok &= np.array_equal(qg, qgref[lo:hi])
         if rank > 0:
             ok &= xl == xg[lo - 1]
         if rank < world - 1:

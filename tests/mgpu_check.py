@@ -1,7 +1,7 @@
 """Multi-GPU parity check, launched under torchrun (one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        tests/mgpu_check.py [n_global] [m] [l_odd] [iterations]
+        tests/mgpu_check.py [n_global] [m] [l_odd] [iterations] [rosenbrock|quadratic]
 
 Runs the sample problem sharded over the N ranks through lbfgsb_setulb_dev_f64 and, on rank 0,
 the same problem on one GPU; the per-iterate discrete trace (iter, nfgv, nseg, nfree, nact, iword,
@@ -23,11 +23,16 @@ import lbfgsb_b200  # noqa: E402
 from lbfgsb_b200 import sharded  # noqa: E402
 
 
-def solve(n_local, off, n_global, m, l_odd, iters, shard, fg_factory, dev, rank, world):
-    x = torch.full((n_local,), 3.0, dtype=torch.float64, device=dev)
-    l = torch.full((n_local,), -100.0, dtype=torch.float64, device=dev)
-    l[(off % 2)::2] = l_odd
-    u = torch.full((n_local,), 100.0, dtype=torch.float64, device=dev)
+def solve(n_local, off, n_global, m, l_odd, iters, shard, fg_factory, dev, rank, world, kind="rosenbrock"):
+    if kind == "quadratic":      # BASELINE.json configs[3]: box [0, 0.5], start in the middle
+        x = torch.full((n_local,), 0.25, dtype=torch.float64, device=dev)
+        l = torch.zeros(n_local, dtype=torch.float64, device=dev)
+        u = torch.full((n_local,), 0.5, dtype=torch.float64, device=dev)
+    else:
+        x = torch.full((n_local,), 3.0, dtype=torch.float64, device=dev)
+        l = torch.full((n_local,), -100.0, dtype=torch.float64, device=dev)
+        l[(off % 2)::2] = l_odd
+        u = torch.full((n_local,), 100.0, dtype=torch.float64, device=dev)
     nbd = torch.full((n_local,), 2, dtype=torch.int32, device=dev)
     g = torch.zeros_like(x)
     prob = lbfgsb_b200.DeviceProblem(n_local, m, np.float64, shard=shard)
@@ -63,6 +68,7 @@ def main():
     m = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     l_odd = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
     iters = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+    kind = sys.argv[5] if len(sys.argv) > 5 else "rosenbrock"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -71,13 +77,20 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     lo, hi = sharded.shard_bounds(n_global, rank, world)
     comm = sharded.nccl_comm_for_engine(rank, world, dist, dev)
-    kern = lbfgsb_b200.RosenbrockDevice(np.float64)
+    if kind == "quadratic":
+        kern = lbfgsb_b200.QuadraticDevice(np.float64, seed=0)
+        mk_sharded = lambda: sharded.ShardedQuadraticDevice(kern, lo, rank, world, dist, dev)   # noqa: E731
+        mk_single = lambda: (lambda xx, gg: kern(xx, gg, offset=0))                             # noqa: E731
+    else:
+        kern = lbfgsb_b200.RosenbrockDevice(np.float64)
+        mk_sharded = lambda: sharded.ShardedRosenbrockDevice(kern, rank, world, dist, dev)      # noqa: E731
+        mk_single = lambda: kern                                                                # noqa: E731
     rows, task, x = solve(hi - lo, lo, n_global, m, l_odd, iters, (lo, n_global, comm, rank, world),
-                          lambda: sharded.ShardedRosenbrockDevice(kern, rank, world, dist, dev), dev, rank, world)
+                          mk_sharded, dev, rank, world, kind)
     ok = True
     msg = ""
     if rank == 0:
-        ref, rtask, xr = solve(n_global, 0, n_global, m, l_odd, iters, None, lambda: kern, dev, 0, 1)
+        ref, rtask, xr = solve(n_global, 0, n_global, m, l_odd, iters, None, mk_single, dev, 0, 1, kind)
         if task != rtask or len(rows) != len(ref):
             ok, msg = False, "task/len %r %r %d %d" % (task, rtask, len(rows), len(ref))
         worst = 0.0
@@ -93,8 +106,8 @@ def main():
             if not ok:
                 break
         walks = [r["nseg"] for r in ref if r["nseg"] > 1]
-        print("MGPU_CHECK %s world=%d n=%d m=%d l_odd=%g iterations=%d walks(nseg>1)=%s worst_rel_f=%.2e %s" % (
-            "OK" if ok else "FAIL", world, n_global, m, l_odd, len(ref), walks[:6], worst, msg[:600]), flush=True)
+        print("MGPU_CHECK %s %s world=%d n=%d m=%d l_odd=%g iterations=%d walks(nseg>1)=%s worst_rel_f=%.2e %s" % (
+            "OK" if ok else "FAIL", kind, world, n_global, m, l_odd, len(ref), walks[:6], worst, msg[:600]), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     lbfgsb_b200.lib().lbfgsb_dev_nccl_destroy(comm)

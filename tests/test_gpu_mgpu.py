@@ -19,7 +19,8 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("args", [("200000", "5", "1.0", "30"), ("100001", "10", "1.1", "25"), ("4099", "7", "1.5", "20")])
+@pytest.mark.parametrize("args", [("200000", "5", "1.0", "30"), ("100001", "10", "1.1", "25"), ("4099", "7", "1.5", "20"),
+                                  ("150001", "10", "0", "25", "quadratic")])
 def test_sharded_matches_single_gpu(args):
     import torch
     ng = torch.cuda.device_count()

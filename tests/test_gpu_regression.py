@@ -3,8 +3,10 @@
 The reductions have a fixed shape (include/lbfgsb_b200_shape.h), so every iterate of a given problem
 is bit-reproducible: across runs, across GPUs, and across re-organisations of the kernels that keep the
 shape -- the fused passes (k_update_classify, k_formk_cmprlb) must give exactly the bits of the
-separate passes they replace.  tests/golden/gpu_trace_digest.json was recorded on a B200 with the
-unfused kernels; it is compared here with a fresh run, with the fused passes on and off.
+separate passes they replace.  tests/golden/gpu_trace_digest.json was recorded on a B200 (first with the
+unfused kernels; re-recorded for the two cases whose Cauchy search crosses a round boundary when the
+breakpoint walk was split into rounds, which re-associates the prefix sums there -- every case still
+passes the oracle parity tests); it is compared here with a fresh run, with the fused passes on and off.
 """
 import json
 import os

@@ -40,6 +40,35 @@ def test_shard_numpy_matches_oracle_fg():
     assert np.allclose(g, g2, rtol=1e-13, atol=0)
 
 
+def test_quadratic_problem_oracle_half_active():
+    """BASELINE.json configs[3] at a size the oracle solves in a second: the quadratic is convex, the oracle
+    converges, about half of the variables end on the lower bound, and the result is the box-constrained
+    minimiser (projected gradient zero to pgtol)."""
+    import harness as H
+    from lbfgsb_b200 import sharded
+    from oracle import oracle_py as O
+    n, m = 4000, 10
+
+    def fg(x, g):
+        f, gg = sharded.quadratic_shard_numpy(x, 0, 0, 0.0, 0.0)
+        g[:] = gg
+        return f
+    x, l, u, nbd = sharded.quadratic_problem(n)
+    tr, task, x, f, isave, dsave = H.run_driver(O.OracleSetulb(), fg, n, m, x, l, u, nbd, 1.0e1, 1.0e-8)
+    assert task.startswith("CONVERGENCE"), task
+    assert 0.4 * n < tr[-1]["nact"] < 0.6 * n
+    fs = [r["f"] for r in tr]
+    assert all(b <= a for a, b in zip(fs, fs[1:]))
+    _, g = sharded.quadratic_shard_numpy(x, 0, 0, 0.0, 0.0)
+    pg = np.where(g < 0, np.maximum(x - u, g), np.minimum(x - l, g))
+    assert np.abs(pg).max() <= 1e-6
+    # coefficients are a pure function of the global index: a shard sees the same numbers
+    d0, b0 = sharded.quadratic_coefficients(0, n, 0)
+    d1, b1 = sharded.quadratic_coefficients(1234, 2000, 0)
+    assert np.array_equal(d0[1234:2000], d1) and np.array_equal(b0[1234:2000], b1)
+    assert 2.1 <= d0.min() and d0.max() < 3.1 and -1.0 <= b0.min() and b0.max() < 1.0
+
+
 def test_library_exports_every_declared_symbol():
     """No compute calls: only that the in-tree .so loads and exports include/lbfgsb_b200.h."""
     import lbfgsb_b200
