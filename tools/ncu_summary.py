@@ -16,7 +16,8 @@ from collections import defaultdict
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FAM = {"k_update": "update", "k_cauchy_classify": "cauchy_classify", "k_formk_gram": "formk_gram",
        "k_cmprlb_wv": "cmprlb_wv", "k_subsm_step": "subsm_step", "k_ls_init": "ls_init", "k_ls_trial": "ls_trial",
-       "k_ls_step": "ls_step", "k_gcp_freev": "gcp_freev", "k_iter_head": "iter_head"}
+       "k_ls_step": "ls_step", "k_gcp_freev": "gcp_freev", "k_iter_head": "iter_head",
+       "k_update_classify": "update_classify", "k_formk_cmprlb": "formk_cmprlb", "k_subsm_lsinit": "subsm_lsinit"}
 
 
 def short(name):
