@@ -70,6 +70,9 @@ lbfgsb_dev_t* lbfgsb_dev_create_sharded(int64_t n_local, int64_t offset, int64_t
                                         int32_t real_kind, void* cuda_stream, void* nccl_comm,
                                         int32_t rank, int32_t world);
 void lbfgsb_dev_destroy(lbfgsb_dev_t* h);
+/* name of the summary file written when iprint >= 1 (the optional `iteration_file` argument of setulb,
+ * src/lbfgsb.f90:243; default 'iterate.dat').  Call before the START entry.                      */
+void lbfgsb_dev_set_iteration_file(lbfgsb_dev_t* h, const char* name);
 void lbfgsb_setulb_dev_f64(lbfgsb_dev_t* h, double* x_dev, const double* l_dev, const double* u_dev,
                            const int32_t* nbd_dev, double* f, double* g_dev, const double* factr,
                            const double* pgtol, char* task, const int32_t* iprint, char* csave,

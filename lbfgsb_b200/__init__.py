@@ -75,6 +75,7 @@ def lib():
         L.lbfgsb_dev_create_sharded.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.lbfgsb_dev_destroy.argtypes = [C.c_void_p]
+        L.lbfgsb_dev_set_iteration_file.argtypes = [C.c_void_p, C.c_char_p]
         L.lbfgsb_host_engine.restype = C.c_void_p
         L.lbfgsb_host_engine.argtypes = [C.c_void_p]
         L.lbfgsb_dev_vector.restype = C.c_void_p
@@ -135,9 +136,10 @@ def setulb(n, m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, iprint, csave,
 class HostSetulb:
     """Callable with the calling convention of tests/harness.py (same as oracle_py.OracleSetulb)."""
 
-    def __init__(self, dtype=np.float64):
+    def __init__(self, dtype=np.float64, iteration_file=None):
         self.dtype = np.dtype(dtype)
         self._isave = None
+        self.iteration_file = iteration_file    # setulb's optional argument (src/lbfgsb.f90:243)
 
     def workspace(self, n, m):
         # the reference's sizes (src/lbfgsb.f90:146-148) are not needed: the state is on the device
@@ -145,7 +147,8 @@ class HostSetulb:
 
     def __call__(self, n, m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, iprint, csave, lsave, isave, dsave):
         self._isave = isave
-        setulb(n, m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, iprint, csave, lsave, isave, dsave)
+        setulb(n, m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, iprint, csave, lsave, isave, dsave,
+               iteration_file=self.iteration_file)
 
     def engine(self):
         return lib().lbfgsb_host_engine(_p(self._isave))
@@ -175,7 +178,7 @@ class DeviceProblem:
     tensors; f/g evaluation and the whole iteration stay on the GPU.  `stream` is a raw cudaStream_t
     (int) or None for the engine's private stream."""
 
-    def __init__(self, n, m, dtype, stream=None, shard=None):
+    def __init__(self, n, m, dtype, stream=None, shard=None, iprint=-1, iteration_file=None):
         import torch
         self.torch = torch
         self.n, self.m = int(n), int(m)
@@ -197,7 +200,9 @@ class DeviceProblem:
         self.f = np.zeros(1, dtype=self.dtype)
         sfx, self._cr = _REAL[self.dtype]
         self._fn = getattr(lib(), "lbfgsb_setulb_dev_" + sfx)
-        self._ip = C.c_int32(-1)
+        self._ip = C.c_int32(iprint)
+        if iteration_file:
+            lib().lbfgsb_dev_set_iteration_file(C.c_void_p(self.h), iteration_file.encode())
 
     def task_str(self):
         return bytes(self.task).decode().rstrip()

@@ -34,6 +34,22 @@ enum {
 __host__ __device__ inline bool cs_is_warn(int c) { return c >= CS_WARN_ROUND && c <= CS_WARN_STPMIN; }
 __host__ __device__ inline bool cs_is_err(int c) { return c >= CS_ERR_STP_LT_MIN && c <= CS_ERR_STPMAX; }
 
+// messages of mainlb / cauchy / subsm / lnsrlb that the host prints (iprint >= 0), logged in order by the
+// scalar kernels during one setulb call (host_print.h)
+enum {
+    EV_ITER_BEGIN = 1,      // :603   'ITERATION n' (iprint >= 99); a = n
+    EV_SUBGNORM0 = 2,       // :1246  'Subgnorm = 0.  GCP = X.'
+    EV_CAUCHY_SINGULAR = 3, // :622   singular triangular system in cauchy's bmv
+    EV_FORMK_FAIL = 4,      // :669
+    EV_SUBSM_SINGULAR = 5,  // :697   cmprlb / subsm
+    EV_BACKTRACK = 6,       // :2831-2832
+    EV_ASCENT = 7,          // :2250  a = gd
+    EV_LNSRCH_RESTART = 8,  // :754
+    EV_SKIP = 9,            // :830   a = dr, b = ddum
+    EV_FORMT_FAIL = 10      // :854
+};
+#define LB_EVMAX 24
+
 template <typename T> struct Real;
 template <> struct Real<double> {
     static constexpr int VEC = 2;
@@ -84,6 +100,9 @@ struct DevState {
     i64 walk_cstart;              // start of the chunk that holds walk_J
     i64 walk_fixn;                // how many entries of this rank's current sorted list are fixed at the end of the round
     int walk_closed, pad1;        // the search is finished (exit found or every breakpoint passed)
+    // message log of this setulb call (printed by the host in order)
+    int ev_n, ev_code[LB_EVMAX];
+    T ev_a[LB_EVMAX], ev_b[LB_EVMAX];
     i64 n_el;                     // entering + leaving rows compacted for formk
     T theta, fold, tol, dnorm, epsmch, gd, gdold, stp, stpmx, sbgnrm, dtd, xstep, f, rr, dr, ddum;
     T pgtol, factr, sbg_spec;
@@ -98,6 +117,11 @@ struct DevState {
     T p0[2 * LB_MMAX];            // p at the start of the walk
     T walkA[2 * LB_MMAX], walkB[2 * LB_MMAX];  // carries of the 2col-vector prefix sums
 };
+
+template <typename T> __device__ inline void ev_push(DevState<T>* s, int code, T a = (T)0, T b = (T)0) {
+    const int k = s->ev_n;
+    if (k < LB_EVMAX) { s->ev_code[k] = code; s->ev_a[k] = a; s->ev_b[k] = b; s->ev_n = k + 1; }
+}
 
 // ---------------------------------------------------------------------------
 // Fixed-shape reductions (include/lbfgsb_b200_shape.h).

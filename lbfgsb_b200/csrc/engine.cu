@@ -21,6 +21,7 @@
 #include "cauchy_walk.cuh"
 #include "kernels_tma.cuh"
 #include "cauchy_walk_dist.cuh"
+#include "host_print.h"
 #include <algorithm>
 
 // ---------------------------------------------------------------------------
@@ -102,6 +103,7 @@ static const char* fam_name[F_COUNT] = {
 struct EngineBase {
     virtual ~EngineBase() {}
     int real_kind;
+    lbprint::Ctx pr;     // the reference's text output (host_print.h)
 };
 
 template <typename T>
@@ -711,13 +713,53 @@ static void export_state(const Engine<T>* e, char* task, char* csave, int32_t* l
     if (s->csave != CS_BLANK) put60(csave, csave_text(s->csave));
 }
 
+// Text output of one setulb call (host_print.h), in the reference's order: the iterate-0 lines, the logged
+// messages, then prn2lb on NEW_X or prn3lb on termination.
+template <typename T>
+static void print_after_call(Engine<T>* e, int entry, const T* x, const T* l, const T* u, const T* g, T f, const char* task) {
+    lbprint::Ctx& c = e->pr;
+    const DevState<T>* s = e->s_host;
+    if (c.iprint < 0 && s->ev_n == 0) return;
+    const i64 n = e->n;
+    std::vector<T> hx, hg, hl, hu;
+    auto fetch = [&](const T* dv, std::vector<T>& hv) -> const T* {
+        hv.resize((size_t)n);
+        if (cudaMemcpy(hv.data(), dv, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) return nullptr;
+        return hv.data();
+    };
+    const bool term = pre60(task, "CONV") || pre60(task, "ABNO") || pre60(task, "ERROR") || pre60(task, "STOP");
+    if (entry == 0) {
+        if (!pre60(task, "ERROR")) {
+            const bool vec = c.iprint > 100 && e->R == 1;
+            lbprint::prn1lb<T>(c, e->n_global, e->m, (double)s->epsmch, s->prjctd != 0, s->cnstnd != 0, s->nbdd,
+                               vec ? fetch(l, hl) : nullptr, vec ? fetch(u, hu) : nullptr, vec ? fetch(x, hx) : nullptr);
+        }
+    } else if (entry != 4) {
+        if (entry == 1) lbprint::iterate0(c, 0, 1, (double)f, (double)s->sbgnrm);
+        for (int k = 0; k < s->ev_n && k < LB_EVMAX; ++k) lbprint::event(c, s->ev_code[k], (double)s->ev_a[k], (double)s->ev_b[k]);
+        if (s->task == TK_NEW_X) {
+            const bool vec = c.iprint > 100 && e->R == 1;
+            lbprint::prn2lb<T>(c, n, vec ? fetch(x, hx) : nullptr, vec ? fetch(g, hg) : nullptr, (double)s->f, s->iter, s->nfgv,
+                               s->nact, (double)s->sbgnrm, s->nseg, s->iword, s->iback, (double)s->stp, (double)s->xstep);
+        }
+    }
+    if (term && c.iprint >= 0) {
+        const bool vec = c.iprint >= 100 && e->R == 1 && !pre60(task, "ERROR");
+        lbprint::prn3lb<T>(c, e->n_global, vec ? fetch(x, hx) : nullptr, (double)f, task, s->info, s->iter, s->nfgv, s->nintol,
+                           s->nskip, s->nact, (double)s->sbgnrm, c.elapsed(), s->nseg, s->iback, (double)s->stp, (double)s->xstep,
+                           s->errk);
+    }
+    fflush(stdout);
+    if (c.itf) fflush(c.itf);
+}
+
 template <typename T>
 static void setulb_dev_impl(lbfgsb_dev_t* hh, T* x, const T* l, const T* u, const int32_t* nbd, T* f, T* g,
                             const T* factr, const T* pgtol, char* task, const int32_t* iprint, char* csave,
                             int32_t* lsave, int32_t* isave, T* dsave) {
-    (void)iprint;
     Engine<T>* e = (Engine<T>*)hh;
     if (!e || e->real_kind != (int)sizeof(T)) { put60(task, "ERROR: INVALID LBFGSB_B200 HANDLE"); set_error("invalid handle"); return; }
+    e->pr.iprint = (iprint && e->rank == 0) ? *iprint : -1;   // on a sharded problem rank 0 prints
     int entry, aux = 0;
     if (eq60(task, "START")) entry = 0;
     else if (pre60(task, "FG_LN")) entry = 2;
@@ -733,8 +775,11 @@ static void setulb_dev_impl(lbfgsb_dev_t* hh, T* x, const T* l, const T* u, cons
         v[7] = v[6] + m2; v[8] = v[7] + m2; v[9] = v[8] + m24; v[10] = v[9] + m24; v[11] = v[10] + n; v[12] = v[11] + n;
         v[13] = v[12] + n; v[14] = v[13] + n; v[15] = v[14] + n;
         for (int q = 0; q < 16; ++q) isave[q] = (v[q] <= 2147483647LL) ? (int32_t)v[q] : -1;
+        e->pr.t0 = std::chrono::steady_clock::now();
+        e->pr.word[0] = e->pr.word[1] = e->pr.word[2] = '-';
+        e->pr.open_file();
     }
-    if (entry == 4 && !aux) { return; }   // finish(): nothing changes on this path
+    if (entry == 4 && !aux) { print_after_call<T>(e, 4, x, l, u, g, *f, task); return; }   // finish(): only prn3lb
     if ((((uintptr_t)x) | ((uintptr_t)l) | ((uintptr_t)u) | ((uintptr_t)nbd) | ((uintptr_t)g)) & 15) {
         set_error("x, l, u, nbd, g must be 16-byte aligned device pointers");
         put60(task, "ERROR: DEVICE POINTERS MUST BE 16-BYTE ALIGNED");
@@ -747,10 +792,11 @@ static void setulb_dev_impl(lbfgsb_dev_t* hh, T* x, const T* l, const T* u, cons
         put60(task, buf);
         return;
     }
-    if (entry == 4) return;               // the caller's STOP text stays in task
+    if (entry == 4) { print_after_call<T>(e, 4, x, l, u, g, *f, task); return; }   // the caller's STOP text stays in task
     if (entry == 5) { put60(task, "FG_START"); return; }
     export_state<T>(e, task, csave, lsave, isave, dsave);
     if (entry == 0 && pre60(task, "ERROR")) { isave[34] = e->s_host->info; isave[41] = (int32_t)e->s_host->errk; }
+    print_after_call<T>(e, entry, x, l, u, g, *f, task);
 }
 
 // ---------------------------------------------------------------------------
@@ -785,7 +831,7 @@ static void hp_free(HostProblem* p) {
 template <typename T>
 static void setulb_host_impl(const int32_t* n, const int32_t* m, T* x, const T* l, const T* u, const int32_t* nbd, T* f,
                              T* g, const T* factr, const T* pgtol, char* task, const int32_t* iprint, char* csave,
-                             int32_t* lsave, int32_t* isave, T* dsave) {
+                             int32_t* lsave, int32_t* isave, T* dsave, const char* itfile, int32_t itfile_len) {
     HostProblem* p = nullptr;
     if (eq60(task, "START")) {
         HostProblem* old = hp_from_isave(isave);
@@ -803,6 +849,7 @@ static void setulb_host_impl(const int32_t* n, const int32_t* m, T* x, const T* 
         }
         Engine<T>* e = new Engine<T>();
         if (!e->init(*n, 0, *n, *m, nullptr, nullptr, 0, 1)) { delete e; put60(task, "ERROR: CUDA FAILURE (see lbfgsb_b200_last_error)"); return; }
+        if (itfile && itfile_len > 0) e->pr.itname = std::string(itfile, (size_t)itfile_len);   // iteration_file (:243)
         p = new HostProblem();
         p->eng = e; p->n = *n; p->kind = (int)sizeof(T);
         const size_t vb = (size_t)(*n) * sizeof(T);
@@ -1039,6 +1086,10 @@ lbfgsb_dev_t* lbfgsb_dev_create(int64_t n, int32_t m, int32_t real_kind, void* c
     return lbfgsb_dev_create_sharded(n, 0, n, m, real_kind, cuda_stream, nullptr, 0, 1);
 }
 void lbfgsb_dev_destroy(lbfgsb_dev_t* h) { delete (EngineBase*)h; }
+void lbfgsb_dev_set_iteration_file(lbfgsb_dev_t* h, const char* name) {
+    EngineBase* b = (EngineBase*)h;
+    if (b && name && name[0]) b->pr.itname = name;
+}
 
 void lbfgsb_setulb_dev_f64(lbfgsb_dev_t* h, double* x, const double* l, const double* u, const int32_t* nbd, double* f,
                            double* g, const double* factr, const double* pgtol, char* task, const int32_t* iprint,
@@ -1055,15 +1106,15 @@ void lbfgsb_setulb_f64(const int32_t* n, const int32_t* m, double* x, const doub
                        double* f, double* g, const double* factr, const double* pgtol, double* wa, int32_t* iwa, char* task,
                        const int32_t* iprint, char* csave, int32_t* lsave, int32_t* isave, double* dsave,
                        const char* itfile, int32_t itfile_len) {
-    (void)wa; (void)iwa; (void)itfile; (void)itfile_len;
-    setulb_host_impl<double>(n, m, x, l, u, nbd, f, g, factr, pgtol, task, iprint, csave, lsave, isave, dsave);
+    (void)wa; (void)iwa;
+    setulb_host_impl<double>(n, m, x, l, u, nbd, f, g, factr, pgtol, task, iprint, csave, lsave, isave, dsave, itfile, itfile_len);
 }
 void lbfgsb_setulb_f32(const int32_t* n, const int32_t* m, float* x, const float* l, const float* u, const int32_t* nbd,
                        float* f, float* g, const float* factr, const float* pgtol, float* wa, int32_t* iwa, char* task,
                        const int32_t* iprint, char* csave, int32_t* lsave, int32_t* isave, float* dsave,
                        const char* itfile, int32_t itfile_len) {
-    (void)wa; (void)iwa; (void)itfile; (void)itfile_len;
-    setulb_host_impl<float>(n, m, x, l, u, nbd, f, g, factr, pgtol, task, iprint, csave, lsave, isave, dsave);
+    (void)wa; (void)iwa;
+    setulb_host_impl<float>(n, m, x, l, u, nbd, f, g, factr, pgtol, task, iprint, csave, lsave, isave, dsave, itfile, itfile_len);
 }
 void lbfgsb_host_release(int32_t* isave) {
     HostProblem* p = hp_from_isave(isave);

@@ -151,10 +151,12 @@ template <typename T> __device__ inline void begin_body(DevState<T>* s) {
     s->in_body = 1; s->restart = 0; s->need_walk = 0;
     s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0; s->do_step = 0;
     s->iword = -1;
+    ev_push<T>(s, EV_ITER_BEGIN, (T)(s->iter + 1));
     if (!s->cnstnd && s->col > 0) {  // :607-611
         s->cauchy_mode = 1; s->wrk = s->updatd; s->nseg = 0;
     } else if (s->sbgnrm <= (T)0) {  // :1245-1249
         s->cauchy_mode = 2;
+        ev_push<T>(s, EV_SUBGNORM0);
     } else s->cauchy_mode = 0;
     s->tsum = (T)0;
 }
@@ -230,6 +232,7 @@ __global__ void s_newx_tests(Wk<T> w, int fused_supported) {
     else { s->dr = (s->gd - s->gdold) * s->stp; s->ddum = -s->gdold * s->stp; }
     if (s->dr <= s->epsmch * s->ddum) {
         s->nskip = s->nskip + 1; s->updatd = 0; s->do_update = 0;
+        ev_push<T>(s, EV_SKIP, s->dr, s->ddum);
     } else {
         s->updatd = 1; s->iupdat = s->iupdat + 1; s->do_update = 1;
         const int m = s->m;
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_update_dense(Wk<T> w, Dis
         ss[(col - 1) + (col - 1) * m] = (s->stp == (T)1) ? s->dtd : s->stp * s->stp * s->dtd;
         sy[(col - 1) + (col - 1) * m] = s->dr;
         int info = dense::formt<T>(m, s->wt, sy, ss, col, s->theta);
-        if (info != 0) reset_memory<T>(s);   // :851-863
+        if (info != 0) { ev_push<T>(s, EV_FORMT_FAIL); reset_memory<T>(s); }   // :851-863
     }
     begin_body<T>(s);
 }
@@ -314,6 +317,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
     if (col > 0) {
         int info = dense::bmv<T>(m, s->sy, s->wt, col, s->p, s->v);
         if (info != 0) {   // :620-635
+            ev_push<T>(s, EV_CAUCHY_SINGULAR);
             reset_memory<T>(s);
             s->restart = 1; s->in_body = 0;
             return;
@@ -364,6 +368,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_freev(Wk<T> w, Dist<T> di
     if (s->do_subspace && !(!s->cnstnd && s->col > 0)) {
         int info = dense::bmv<T>(s->m, s->sy, s->wt, s->col, s->c, s->a);
         if (info != 0) {   // info = -8 -> :694-710
+            ev_push<T>(s, EV_SUBSM_SINGULAR);
             reset_memory<T>(s);
             s->restart = 1; s->in_body = 0; s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0;
         }
@@ -466,6 +471,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist
             if (info != 0) info = -2;
         }
         if (info != 0) {   // :666-682
+            ev_push<T>(s, EV_FORMK_FAIL);
             reset_memory<T>(s);
             s->restart = 1; s->in_body = 0;
             return;
@@ -493,6 +499,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_dense(Wk<T> w, Dist
         info = dense::dtrsl<T>(s->wn, m2, col2, s->wv, 1);
     }
     if (info != 0) {   // :694-710
+        ev_push<T>(s, EV_SUBSM_SINGULAR);
         reset_memory<T>(s);
         s->restart = 1; s->in_body = 0; s->do_subspace = 0;
     }
@@ -509,6 +516,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_post(Wk<T> w, Dist<
     s->iword = red.iv[0] > 0 ? 1 : 0;
     s->dd_p = red.rv[0];
     s->do_backtrack = (s->iword == 1 && s->dd_p > (T)0);
+    if (s->do_backtrack) ev_push<T>(s, EV_BACKTRACK);
 }
 
 // subsm: backtrack step length (:2836-2863)
@@ -541,6 +549,7 @@ __device__ inline void ls_failure(DevState<T>* s, bool at_first_entry) {
         s->iter += 1;
         s->go = 0; s->in_body = 0;
     } else {
+        ev_push<T>(s, EV_LNSRCH_RESTART);
         if (s->info == 0) s->nfgv -= 1;
         reset_memory<T>(s);
         s->task = TK_RESTART;
@@ -570,6 +579,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_init(Wk<T> w, Dist<T> 
     s->gd = red.rv[1];
     s->gdold = s->gd;
     if (s->gd >= zero) {   // :2247-2253
+        ev_push<T>(s, EV_ASCENT, s->gd);
         s->info = -4;
         ls_failure<T>(s, true);
         return;
@@ -598,7 +608,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_trial(Wk<T> w, Dist<T>
     s->gd = red.rv[0];
     if (s->ifun == 0) {   // only after a dcsrch input error on the first entry; kept for fidelity
         s->gdold = s->gd;
-        if (s->gd >= zero) { s->info = -4; ls_failure<T>(s, false); return; }
+        if (s->gd >= zero) { ev_push<T>(s, EV_ASCENT, s->gd); s->info = -4; ls_failure<T>(s, false); return; }
     }
     dense::dcsrch<T>(s->f, s->gd, s->stp, ftol, gtol, xtol, zero, s->stpmx, s->csave, s->brackt, s->stage, s->ls);
     s->xstep = s->stp * s->dnorm;
@@ -627,6 +637,7 @@ __global__ void s_call_begin(Wk<T> w, T f, int entry_task) {
     s->do_step = 0; s->do_restore = 0; s->do_update = 0;
     s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0;
     s->fuse_uc = 0; s->classify_done = 0;
+    s->ev_n = 0;
     s->f = f;
     (void)entry_task;
 }
@@ -639,7 +650,7 @@ __global__ void s_start(Wk<T> w, T factr, T pgtol, int host_err_task) {
     const T zero = (T)0;
     s->go = 1; s->in_body = 0; s->restart = 0; s->need_walk = 0; s->cauchy_mode = 0;
     s->do_subspace = s->do_formk = s->do_delta = s->do_backtrack = s->do_update = s->do_step = s->do_restore = 0;
-    s->fuse_uc = 0; s->classify_done = 0;
+    s->fuse_uc = 0; s->classify_done = 0; s->ev_n = 0;
     s->task = TK_START; s->csave = CS_BLANK; s->info = 0;
     s->col = 0; s->head = 1; s->theta = (T)1; s->iupdat = 0; s->updatd = 0;
     s->iback = 0; s->itail = 0; s->iword = 0; s->nact = 0; s->nleave = 0; s->nenter = 0;

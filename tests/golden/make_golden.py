@@ -77,6 +77,9 @@ def main():
         "driver3_90": parse_driver23(os.path.join(REF, "output_90_3")),
         "driver3_77": parse_driver23(os.path.join(REF, "output_77_3")),
         "iterate_dat": parse_iterate_dat(os.path.join(REF, "iterate.dat")),
+        # the raw text (lines without the trailing newline) for the end-to-end diff of the iprint output
+        "driver1_90_text": [ln.rstrip("\n") for ln in open(os.path.join(REF, "output_90_1"))],
+        "iterate_dat_text": [ln.rstrip("\n") for ln in open(os.path.join(REF, "iterate.dat"))],
     }
     with open(os.path.join(HERE, "reference_outputs.json"), "w") as fh:
         json.dump(g, fh, indent=1)
