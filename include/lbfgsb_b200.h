@@ -82,6 +82,34 @@ void lbfgsb_setulb_dev_f32(lbfgsb_dev_t* h, float* x_dev, const float* l_dev, co
                            const float* pgtol, char* task, const int32_t* iprint, char* csave,
                            int32_t* lsave, int32_t* isave, float* dsave);
 
+/* ---- (3) driver that owns the task loop (the reference's own @todo, src/lbfgsb.f90:36-37) -----------
+ * The loop of test/driver1.f90:263-292 / driver2.f90:112-190 in C: calls fg whenever task(1:2) == 'FG',
+ * stops like driver2 (:174-181) when the number of iterations reaches max_iter or the number of f/g
+ * evaluations reaches max_fg (task = 'STOP: ...'; a limit <= 0 is no limit).  fg evaluates f and g at
+ * x_dev on the given stream, stores f in *f_out (host) and returns 0 (non-zero aborts with
+ * task = 'STOP: THE OBJECTIVE CALLBACK FAILED').  Returns 0 when the loop ended on CONVERGENCE or a STOP
+ * limit, 1 on ABNORMAL_TERMINATION, 2 on ERROR.  task/csave/lsave/isave/dsave as in setulb. */
+typedef int (*lbfgsb_fg_dev_f64)(void* user, int64_t n, const double* x_dev, double* g_dev, double* f_out, void* cuda_stream);
+typedef int (*lbfgsb_fg_dev_f32)(void* user, int64_t n, const float* x_dev, float* g_dev, float* f_out, void* cuda_stream);
+int lbfgsb_minimize_dev_f64(lbfgsb_dev_t* h, double* x_dev, const double* l_dev, const double* u_dev, const int32_t* nbd_dev,
+                            lbfgsb_fg_dev_f64 fg, void* user, double factr, double pgtol, int32_t max_iter, int32_t max_fg,
+                            int32_t iprint, double* f, double* g_dev, char* task, char* csave, int32_t* lsave, int32_t* isave,
+                            double* dsave);
+int lbfgsb_minimize_dev_f32(lbfgsb_dev_t* h, float* x_dev, const float* l_dev, const float* u_dev, const int32_t* nbd_dev,
+                            lbfgsb_fg_dev_f32 fg, void* user, float factr, float pgtol, int32_t max_iter, int32_t max_fg,
+                            int32_t iprint, float* f, float* g_dev, char* task, char* csave, int32_t* lsave, int32_t* isave,
+                            float* dsave);
+
+/* ---- (4) checkpoint / resume of the device workspace ----------------------------------------------
+ * The reference keeps its whole state in the caller's wa/iwa/isave/dsave/lsave/task/csave, so a caller can
+ * checkpoint by saving those arrays (and test/driver3.f90:152-182 reads `t` out of wa).  Here wa/iwa live on
+ * the device: these two calls write / read them (S, Y, the five work vectors, iwhere, the free-set flags
+ * and the state block) to / from a file, in chunks through pinned memory.  To resume: create a workspace of
+ * the same n, m, real_kind (and shard), read the file, restore your own x, g, f, task, csave, lsave, isave,
+ * dsave, and continue calling setulb_dev.  Call them between two setulb calls.  Return 0 on success.   */
+int lbfgsb_dev_checkpoint_write(lbfgsb_dev_t* h, const char* path);
+int lbfgsb_dev_checkpoint_read(lbfgsb_dev_t* h, const char* path);
+
 /* NCCL plumbing for the sharded variant (128-byte unique id made on rank 0, broadcast by the caller) */
 int lbfgsb_dev_nccl_unique_id(void* id128);
 void* lbfgsb_dev_nccl_init(const void* id128, int32_t rank, int32_t world);

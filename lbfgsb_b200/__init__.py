@@ -76,6 +76,8 @@ def lib():
                                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.lbfgsb_dev_destroy.argtypes = [C.c_void_p]
         L.lbfgsb_dev_set_iteration_file.argtypes = [C.c_void_p, C.c_char_p]
+        L.lbfgsb_dev_checkpoint_write.argtypes = [C.c_void_p, C.c_char_p]
+        L.lbfgsb_dev_checkpoint_read.argtypes = [C.c_void_p, C.c_char_p]
         L.lbfgsb_host_engine.restype = C.c_void_p
         L.lbfgsb_host_engine.argtypes = [C.c_void_p]
         L.lbfgsb_dev_vector.restype = C.c_void_p
@@ -218,6 +220,38 @@ class DeviceProblem:
                  C.c_void_p(nbd.data_ptr()), _p(self.f), C.c_void_p(g.data_ptr()), C.byref(fa), C.byref(pg),
                  _p(self.task), C.byref(self._ip), _p(self.csave), _p(self.lsave), _p(self.isave), _p(self.dsave))
         _check_task(self.task)
+
+    def minimize(self, x, l, u, nbd, g, fg, factr, pgtol, max_iter=0, max_fg=0):
+        """lbfgsb_minimize_dev_*: the library owns the task loop (include/lbfgsb_b200.h section 3).
+        fg(x, g) -> f evaluates the objective at the tensor x into the tensor g.  Returns the C return code;
+        self.task / self.f / self.isave / self.dsave hold the final state."""
+        sfx, cr = _REAL[self.dtype]
+        CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(cr), C.c_void_p)
+
+        def _cb(user, n, xp, gp, fout, stream):
+            try:
+                fout[0] = fg(x, g)
+                return 0
+            except Exception:  # noqa: BLE001
+                return 1
+        cb = CB(_cb)
+        fn = getattr(lib(), "lbfgsb_minimize_dev_" + sfx)
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p] * 5 + [CB, C.c_void_p, cr, cr, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7
+        rc = fn(C.c_void_p(self.h), C.c_void_p(x.data_ptr()), C.c_void_p(l.data_ptr()), C.c_void_p(u.data_ptr()),
+                C.c_void_p(nbd.data_ptr()), cb, None, cr(factr), cr(pgtol), int(max_iter), int(max_fg), self._ip.value,
+                _p(self.f), C.c_void_p(g.data_ptr()), _p(self.task), _p(self.csave), _p(self.lsave), _p(self.isave),
+                _p(self.dsave))
+        _check_task(self.task)
+        return rc
+
+    def checkpoint_write(self, path):
+        if lib().lbfgsb_dev_checkpoint_write(C.c_void_p(self.h), path.encode()) != 0:
+            raise LbfgsbB200Error("checkpoint write failed: " + last_error())
+
+    def checkpoint_read(self, path):
+        if lib().lbfgsb_dev_checkpoint_read(C.c_void_p(self.h), path.encode()) != 0:
+            raise LbfgsbB200Error("checkpoint read failed: " + last_error())
 
     def active_set_hash(self):
         h, c = C.c_uint64(0), C.c_int64(0)

@@ -622,6 +622,50 @@ struct Engine : EngineBase {
         return check_launch();
     }
 
+    // ---- checkpoint / resume (include/lbfgsb_b200.h section 4) --------------------------------
+    struct CkHeader { char magic[8]; i64 n, ldw, n_global, offset; int m, real_kind, R, rank; i64 state_bytes; };
+    bool checkpoint_io(const char* path, bool write) {
+        FILE* fp = fopen(path, write ? "wb" : "rb");
+        if (!fp) { set_error("cannot open checkpoint file %s", path); return false; }
+        CK(cudaStreamSynchronize(stream));
+        CkHeader hd; memset(&hd, 0, sizeof hd);
+        memcpy(hd.magic, "LBB2CKP1", 8);
+        hd.n = n; hd.ldw = w.ldw; hd.n_global = n_global; hd.offset = offset; hd.m = m; hd.real_kind = (int)sizeof(T); hd.R = R; hd.rank = rank;
+        hd.state_bytes = (i64)sizeof(DevState<T>);
+        bool ok = true;
+        if (write) ok = fwrite(&hd, sizeof hd, 1, fp) == 1;
+        else {
+            CkHeader in;
+            ok = fread(&in, sizeof in, 1, fp) == 1 && memcmp(in.magic, hd.magic, 8) == 0 && in.n == hd.n && in.ldw == hd.ldw &&
+                 in.n_global == hd.n_global && in.offset == hd.offset && in.m == hd.m && in.real_kind == hd.real_kind &&
+                 in.R == hd.R && in.rank == hd.rank && in.state_bytes == hd.state_bytes;
+            if (!ok) set_error("checkpoint %s does not match this workspace (n, m, real kind or shard differ)", path);
+        }
+        const size_t CH = (size_t)64 << 20;
+        void* stage = nullptr;
+        if (ok && cudaMallocHost(&stage, CH) != cudaSuccess) { set_error("cudaMallocHost failed"); ok = false; }
+        auto xfer = [&](void* dptr, size_t bytes) {
+            for (size_t o = 0; ok && o < bytes; o += CH) {
+                const size_t c = bytes - o < CH ? bytes - o : CH;
+                if (write) {
+                    ok = cudaMemcpy(stage, (char*)dptr + o, c, cudaMemcpyDeviceToHost) == cudaSuccess && fwrite(stage, 1, c, fp) == c;
+                } else {
+                    ok = fread(stage, 1, c, fp) == c && cudaMemcpy((char*)dptr + o, stage, c, cudaMemcpyHostToDevice) == cudaSuccess;
+                }
+            }
+        };
+        const size_t vb = (size_t)w.ldw * sizeof(T);
+        xfer(s_dev, sizeof(DevState<T>));
+        xfer(w.ws, vb * m); xfer(w.wy, vb * m);
+        xfer(w.z, vb); xfer(w.r, vb); xfer(w.d, vb); xfer(w.t, vb); xfer(w.xp, vb);
+        xfer(w.iwhere, (size_t)w.ldw * 4); xfer(w.state, (size_t)w.ldw);
+        if (stage) cudaFreeHost(stage);
+        if (ok && !write) ok = cudaMemcpy(s_host, s_dev, header_bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (fclose(fp) != 0) ok = false;
+        if (!ok && g_last_error.empty()) set_error("checkpoint %s failed on %s", write ? "write" : "read", path);
+        return ok;
+    }
+
     bool active_hash(uint64_t* hash, i64* count) {
         begin(F_HASH); k_active_hash<T><<<LG>>>(w, offset); end(F_HASH);
         // finish on the host: 2 x GRID integers
@@ -797,6 +841,41 @@ static void setulb_dev_impl(lbfgsb_dev_t* hh, T* x, const T* l, const T* u, cons
     export_state<T>(e, task, csave, lsave, isave, dsave);
     if (entry == 0 && pre60(task, "ERROR")) { isave[34] = e->s_host->info; isave[41] = (int32_t)e->s_host->errk; }
     print_after_call<T>(e, entry, x, l, u, g, *f, task);
+}
+
+// ---------------------------------------------------------------------------
+// The task loop of the reference's sample programs (test/driver1.f90:263-292, driver2.f90:112-190) as a
+// library call (the reference's own @todo, src/lbfgsb.f90:36-37).
+// ---------------------------------------------------------------------------
+template <typename T, typename FG>
+static int minimize_impl(lbfgsb_dev_t* h, T* x, const T* l, const T* u, const int32_t* nbd, FG fg, void* user, T factr, T pgtol,
+                         int32_t max_iter, int32_t max_fg, int32_t iprint, T* f, T* g, char* task, char* csave, int32_t* lsave,
+                         int32_t* isave, T* dsave) {
+    Engine<T>* e = (Engine<T>*)h;
+    if (!e || e->real_kind != (int)sizeof(T) || !fg) { put60(task, "ERROR: INVALID LBFGSB_B200 HANDLE"); return 2; }
+    put60(task, "START");
+    for (;;) {
+        setulb_dev_impl<T>(h, x, l, u, nbd, f, g, &factr, &pgtol, task, &iprint, csave, lsave, isave, dsave);
+        if (pre60(task, "FG")) {
+            if (fg(user, e->n, x, g, f, (void*)e->stream) != 0) {
+                put60(task, "STOP: THE OBJECTIVE CALLBACK FAILED");
+                setulb_dev_impl<T>(h, x, l, u, nbd, f, g, &factr, &pgtol, task, &iprint, csave, lsave, isave, dsave);
+                return 2;
+            }
+        } else if (pre60(task, "NEW_X")) {
+            const char* stop = nullptr;
+            if (max_fg > 0 && isave[33] >= max_fg) stop = "STOP: TOTAL NO. of f AND g EVALUATIONS EXCEEDS LIMIT";   // driver2.f90:176
+            if (max_iter > 0 && isave[29] >= max_iter) stop = "STOP: TOTAL NO. of ITERATIONS REACHED LIMIT";
+            if (stop) {
+                put60(task, stop);
+                setulb_dev_impl<T>(h, x, l, u, nbd, f, g, &factr, &pgtol, task, &iprint, csave, lsave, isave, dsave);
+                return 0;
+            }
+        } else break;
+    }
+    if (pre60(task, "CONV")) return 0;
+    if (pre60(task, "ABNO")) return 1;
+    return 2;
 }
 
 // ---------------------------------------------------------------------------
@@ -1136,6 +1215,30 @@ int lbfgsb_host_previous_x_f32(const int32_t* isave, float* t_out) {
 lbfgsb_dev_t* lbfgsb_host_engine(const int32_t* isave) {
     HostProblem* p = hp_from_isave(isave);
     return p ? (lbfgsb_dev_t*)p->eng : nullptr;
+}
+
+int lbfgsb_dev_checkpoint_write(lbfgsb_dev_t* h, const char* path) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b || !path) return 1;
+    g_last_error.clear();
+    return ((b->real_kind == 8) ? ((Engine<double>*)b)->checkpoint_io(path, true) : ((Engine<float>*)b)->checkpoint_io(path, true)) ? 0 : 1;
+}
+int lbfgsb_dev_checkpoint_read(lbfgsb_dev_t* h, const char* path) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b || !path) return 1;
+    g_last_error.clear();
+    return ((b->real_kind == 8) ? ((Engine<double>*)b)->checkpoint_io(path, false) : ((Engine<float>*)b)->checkpoint_io(path, false)) ? 0 : 1;
+}
+
+int lbfgsb_minimize_dev_f64(lbfgsb_dev_t* h, double* x, const double* l, const double* u, const int32_t* nbd, lbfgsb_fg_dev_f64 fg,
+                            void* user, double factr, double pgtol, int32_t max_iter, int32_t max_fg, int32_t iprint, double* f,
+                            double* g, char* task, char* csave, int32_t* lsave, int32_t* isave, double* dsave) {
+    return minimize_impl<double>(h, x, l, u, nbd, fg, user, factr, pgtol, max_iter, max_fg, iprint, f, g, task, csave, lsave, isave, dsave);
+}
+int lbfgsb_minimize_dev_f32(lbfgsb_dev_t* h, float* x, const float* l, const float* u, const int32_t* nbd, lbfgsb_fg_dev_f32 fg,
+                            void* user, float factr, float pgtol, int32_t max_iter, int32_t max_fg, int32_t iprint, float* f,
+                            float* g, char* task, char* csave, int32_t* lsave, int32_t* isave, float* dsave) {
+    return minimize_impl<float>(h, x, l, u, nbd, fg, user, factr, pgtol, max_iter, max_fg, iprint, f, g, task, csave, lsave, isave, dsave);
 }
 
 int lbfgsb_dev_nccl_unique_id(void* id128) {
