@@ -219,6 +219,7 @@ def family_bytes(n, col, nfree, nmv, w=8):
         # fused passes: the algorithmic bytes of the two routines they replace (each routine's own inputs
         # and outputs once); the fusion reads the shared streams only once
         "update_classify": upd + cls,
+        "subsm_lsinit": n * (1 + 3 * w + w) + nfree * (4 * w + 4 + w) + 2 * col * w * nfree + n * (3 * w + 3 * w + 2 * w + 4),
         "formk_cmprlb": fgram + cwv,
         "ls_trial": n * (5 * w + 4),                                   # gd (2w) + projgr (4w+4) sharing g
         "update": n * (3 * w + 2 * w) + 2 * (col - 1) * w * n,         # g,r,d in; s,y out; col-1 older pairs

@@ -118,7 +118,7 @@ void lbfgsb_dev_nccl_destroy(void* comm);
 /* ---- diagnostics used by the parity tests and the benchmark -------------------------------- */
 /* 64-bit identity of the active set {i : iwhere(i) > 0} (freev, src/lbfgsb.f90:2047) and its size */
 int lbfgsb_dev_active_set_hash(lbfgsb_dev_t* h, uint64_t* hash, int64_t* count);
-/* device pointer of a work vector: 0 z, 1 r, 2 d, 3 t, 4 xp, 5 ws, 6 wy, 7 iwhere */
+/* device pointer of a work vector: 0 z, 1 r, 2 d, 3 t, 4 xp, 5 ws, 6 wy, 7 iwhere, 8 previous gradient */
 void* lbfgsb_dev_vector(lbfgsb_dev_t* h, int32_t which);
 /* device-to-device copy of `bytes` bytes of that work vector into dst_dev (after the engine's stream drained) */
 int lbfgsb_dev_vector_copy(lbfgsb_dev_t* h, int32_t which, void* dst_dev, int64_t bytes);

@@ -81,6 +81,7 @@ struct DevState {
     int do_subspace, do_formk, do_delta, do_backtrack, do_update, do_step, do_restore;
     int fuse_uc;       // NEW_X entry: the S/Y update and cauchy's per-variable pass run as one fused kernel
     int classify_done; // cauchy's per-variable pass of this body was already done by that fused kernel
+    int lsinit_done;   // d = z - x and lnsrlb's first-entry sums were already formed by k_subsm_lsinit
     int task, csave, info;
     // ---- mainlb locals (:416-424) ----
     int col, head, itail, iupdat, iter, nfgv, nskip, ifun, iback, iword;

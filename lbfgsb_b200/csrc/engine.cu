@@ -93,12 +93,12 @@ static NcclApi* nccl_api() {
 enum Fam {
     F_ERRCLB, F_ACTIVE, F_PROJGR, F_CLASSIFY, F_GCP_FREEV, F_FORMK_GRAM, F_FORMK_DELTA, F_CMPRLB_WV,
     F_SUBSM_STEP, F_BACKTRACK, F_LS_INIT, F_LS_STEP, F_LS_TRIAL, F_UPDATE, F_RESTORE, F_WALK_COMPACT,
-    F_WALK_SORT, F_WALK_SCAN, F_WALK_FIX, F_SCALAR, F_HASH, F_UPDATE_CLASSIFY, F_FORMK_CMPRLB, F_COUNT
+    F_WALK_SORT, F_WALK_SCAN, F_WALK_FIX, F_SCALAR, F_HASH, F_UPDATE_CLASSIFY, F_FORMK_CMPRLB, F_SUBSM_LSINIT, F_COUNT
 };
 static const char* fam_name[F_COUNT] = {
     "errclb", "active", "projgr", "cauchy_classify", "gcp_freev", "formk_gram", "formk_delta", "cmprlb_wv",
     "subsm_step", "backtrack", "ls_init", "ls_step", "ls_trial", "update", "restore", "walk_compact",
-    "walk_sort", "walk_scan", "walk_fix", "scalar", "hash", "update_classify", "formk_cmprlb"};
+    "walk_sort", "walk_scan", "walk_fix", "scalar", "hash", "update_classify", "formk_cmprlb", "subsm_lsinit"};
 
 struct EngineBase {
     virtual ~EngineBase() {}
@@ -172,7 +172,7 @@ struct Engine : EngineBase {
         w.ldw = (n + 31) / 32 * 32;
         const size_t vb = (size_t)w.ldw * sizeof(T);
         if (!dalloc(&w.ws, vb * m) || !dalloc(&w.wy, vb * m)) return false;
-        if (!dalloc(&w.z, vb) || !dalloc(&w.r, vb) || !dalloc(&w.d, vb) || !dalloc(&w.t, vb) || !dalloc(&w.xp, vb)) return false;
+        if (!dalloc(&w.z, vb) || !dalloc(&w.r, vb) || !dalloc(&w.d, vb) || !dalloc(&w.t, vb) || !dalloc(&w.xp, vb) || !dalloc(&w.gold, vb)) return false;
         if (!dalloc(&w.iwhere, (size_t)w.ldw * 4) || !dalloc(&w.state, (size_t)w.ldw)) return false;
         if (!dalloc(&w.part, sizeof(T) * LB_KMAX * LBFGSB_GRID) || !dalloc(&w.ipart, sizeof(i64) * LB_IMAX * LBFGSB_GRID)) return false;
         if (!dalloc(&w.part2, sizeof(T) * LB_KMAX * LBFGSB_GRID) || !dalloc(&w.ipart2, sizeof(i64) * LB_IMAX * LBFGSB_GRID)) return false;
@@ -286,6 +286,9 @@ struct Engine : EngineBase {
     template <int MT> void launch_formk_cmprlb() {
         if constexpr (fused_passes_ok<T, MT>()) k_formk_cmprlb<T, MT><<<LBFGSB_GRID, LB_TMA_THREADS, smem_formk_cmprlb<T, MT>(), stream>>>(w);
     }
+    template <int MT> void launch_subsm_lsinit() {
+        if constexpr (fused_passes_ok<T, MT>()) k_subsm_lsinit<T, MT><<<LBFGSB_GRID, LB_TMA_THREADS, smem_subsm<T, MT>(), stream>>>(w);
+    }
 #define MTFUSED(fn) do { if (mt == 5) fn<5>(); else if (mt == 10) fn<10>(); else fn<20>(); } while (0)
 
     // the TMA-staged kernels need more than the default 48 KB of dynamic shared memory
@@ -298,6 +301,7 @@ struct Engine : EngineBase {
         if constexpr (fused_passes_ok<T, MT>()) {
             CK(cudaFuncSetAttribute(k_update_classify<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_update_classify<T, MT>()));
             CK(cudaFuncSetAttribute(k_formk_cmprlb<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk_cmprlb<T, MT>()));
+            CK(cudaFuncSetAttribute(k_subsm_lsinit<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_subsm<T, MT>()));
         }
         return true;
     }
@@ -528,9 +532,10 @@ struct Engine : EngineBase {
             if (!fused) { begin(F_CMPRLB_WV); MTCALL(k_cmprlb_wv, smem_cmprlb, w); end(F_CMPRLB_WV); }
             if (!site(site_wv(mt))) return false;
             begin(F_SCALAR); s_subsm_dense<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);
-            begin(F_SUBSM_STEP); MTCALL(k_subsm_step, smem_subsm, w); end(F_SUBSM_STEP);
+            if (fused) { begin(F_SUBSM_LSINIT); MTFUSED(launch_subsm_lsinit); end(F_SUBSM_LSINIT); }
+            else { begin(F_SUBSM_STEP); MTCALL(k_subsm_step, smem_subsm, w); end(F_SUBSM_STEP); }
             if (!site(site_subsm())) return false;
-            begin(F_SCALAR); s_subsm_post<T><<<LS>>>(w, dist()); end(F_SCALAR);
+            begin(F_SCALAR); s_subsm_post<T><<<LS>>>(w, dist(), fused ? 1 : 0); end(F_SCALAR);
             begin(F_BACKTRACK);
             k_bt_alpha<T><<<LG>>>(w);
             if (!site(site_bt())) return false;
@@ -578,7 +583,7 @@ struct Engine : EngineBase {
         if (entry == 4) {   // user STOP (:565-572)
             if (aux) {
                 CK(cudaMemcpyAsync(x, w.t, sizeof(T) * n, cudaMemcpyDeviceToDevice, stream));
-                CK(cudaMemcpyAsync(g, w.r, sizeof(T) * n, cudaMemcpyDeviceToDevice, stream));
+                CK(cudaMemcpyAsync(g, w.gold, sizeof(T) * n, cudaMemcpyDeviceToDevice, stream));
                 CK(cudaStreamSynchronize(stream));
                 *f = s_host->fold;
                 s_host->f = s_host->fold;
@@ -657,7 +662,7 @@ struct Engine : EngineBase {
         const size_t vb = (size_t)w.ldw * sizeof(T);
         xfer(s_dev, sizeof(DevState<T>));
         xfer(w.ws, vb * m); xfer(w.wy, vb * m);
-        xfer(w.z, vb); xfer(w.r, vb); xfer(w.d, vb); xfer(w.t, vb); xfer(w.xp, vb);
+        xfer(w.z, vb); xfer(w.r, vb); xfer(w.d, vb); xfer(w.t, vb); xfer(w.xp, vb); xfer(w.gold, vb);
         xfer(w.iwhere, (size_t)w.ldw * 4); xfer(w.state, (size_t)w.ldw);
         if (stage) cudaFreeHost(stage);
         if (ok && !write) ok = cudaMemcpy(s_host, s_dev, header_bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
@@ -1269,7 +1274,7 @@ void* lbfgsb_dev_vector(lbfgsb_dev_t* h, int32_t which) {
     if (!b) return nullptr;
 #define VSEL(E)                                                                                          \
     switch (which) { case 0: return E->w.z; case 1: return E->w.r; case 2: return E->w.d; case 3: return E->w.t; \
-                     case 4: return E->w.xp; case 5: return E->w.ws; case 6: return E->w.wy; case 7: return E->w.iwhere; default: return nullptr; }
+                     case 4: return E->w.xp; case 5: return E->w.ws; case 6: return E->w.wy; case 7: return E->w.iwhere; case 8: return E->w.gold; default: return nullptr; }
     if (b->real_kind == 8) { Engine<double>* e = (Engine<double>*)b; VSEL(e) }
     else { Engine<float>* e = (Engine<float>*)b; VSEL(e) }
 }

@@ -137,7 +137,7 @@ __host__ __device__ inline SiteSpec site_formk(int mt) { return make_site(4 * mt
 __host__ __device__ inline SiteSpec site_wv(int mt) { SiteSpec s = make_site(2 * mt, 0); s.buf = 1; return s; }
 __host__ __device__ inline SiteSpec site_subsm() { return make_site(1, 1); }
 __host__ __device__ inline SiteSpec site_bt() { SiteSpec s = make_site(1, 1); s.argmin_slot = 0; return s; }
-__host__ __device__ inline SiteSpec site_lsinit() { SiteSpec s = make_site(3, 0); s.min_from = 2; s.min_to = 3; return s; }
+__host__ __device__ inline SiteSpec site_lsinit() { SiteSpec s = make_site(3, 0); s.min_from = 2; s.min_to = 3; s.buf = 1; return s; }
 __host__ __device__ inline SiteSpec site_lstrial() { SiteSpec s = make_site(2, 0); s.max_from = 1; s.max_to = 2; return s; }
 __host__ __device__ inline SiteSpec site_update(int mt) { return make_site(2 * mt + 1, 0); }
 __host__ __device__ inline SiteSpec site_hash() { return make_site(0, 2); }
@@ -148,7 +148,7 @@ template <typename T> __device__ inline void reset_memory(DevState<T>* s) {
 }
 // prepare the flags for the prelims block (:601-612)
 template <typename T> __device__ inline void begin_body(DevState<T>* s) {
-    s->in_body = 1; s->restart = 0; s->need_walk = 0;
+    s->in_body = 1; s->restart = 0; s->need_walk = 0; s->lsinit_done = 0;
     s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0; s->do_step = 0;
     s->iword = -1;
     ev_push<T>(s, EV_ITER_BEGIN, (T)(s->iter + 1));
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_dense(Wk<T> w, Dist
 
 // subsm: projection outcome (:2820-2828)
 template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_post(Wk<T> w, Dist<T> dist) {
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_post(Wk<T> w, Dist<T> dist, int fused_lsinit) {
     __shared__ Red<T> red;
     DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->do_subspace) return;
@@ -517,6 +517,8 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_post(Wk<T> w, Dist<
     s->dd_p = red.rv[0];
     s->do_backtrack = (s->iword == 1 && s->dd_p > (T)0);
     if (s->do_backtrack) ev_push<T>(s, EV_BACKTRACK);
+    // the subspace pass also formed d = z - x and lnsrlb's sums; they stand unless the backtrack moves z
+    s->lsinit_done = (fused_lsinit && !s->do_backtrack) ? 1 : 0;
 }
 
 // subsm: backtrack step length (:2836-2863)
@@ -636,7 +638,7 @@ __global__ void s_call_begin(Wk<T> w, T f, int entry_task) {
     s->go = 1; s->in_body = 0; s->restart = 0; s->need_walk = 0;
     s->do_step = 0; s->do_restore = 0; s->do_update = 0;
     s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0;
-    s->fuse_uc = 0; s->classify_done = 0;
+    s->fuse_uc = 0; s->classify_done = 0; s->lsinit_done = 0;
     s->ev_n = 0;
     s->f = f;
     (void)entry_task;
@@ -650,7 +652,7 @@ __global__ void s_start(Wk<T> w, T factr, T pgtol, int host_err_task) {
     const T zero = (T)0;
     s->go = 1; s->in_body = 0; s->restart = 0; s->need_walk = 0; s->cauchy_mode = 0;
     s->do_subspace = s->do_formk = s->do_delta = s->do_backtrack = s->do_update = s->do_step = s->do_restore = 0;
-    s->fuse_uc = 0; s->classify_done = 0; s->ev_n = 0;
+    s->fuse_uc = 0; s->classify_done = 0; s->lsinit_done = 0; s->ev_n = 0;
     s->task = TK_START; s->csave = CS_BLANK; s->info = 0;
     s->col = 0; s->head = 1; s->theta = (T)1; s->iupdat = 0; s->updatd = 0;
     s->iback = 0; s->itail = 0; s->iword = 0; s->nact = 0; s->nleave = 0; s->nenter = 0;

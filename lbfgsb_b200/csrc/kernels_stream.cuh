@@ -15,6 +15,8 @@ struct Wk {               // workspace + user vectors of one problem (device poi
     int m;
     T *ws, *wy;           // S, Y histories, column-major [m][ldw]        (:390-391)
     T *z, *r, *d, *t, *xp;  // n-vectors of mainlb                         (:382-388)
+    T* gold;              // previous gradient (the reference keeps it in r between lnsrlb :2236 and :814; here r stays
+                          // the reduced gradient / Newton direction of subsm so that the two can live in one pass)
     int* iwhere;          // (:348-355)
     unsigned char* state; // bit0: free at the GCP (freev :2047); bit1: free at the previous freev
     T* part;              // [LB_KMAX][GRID] block partials
@@ -258,14 +260,15 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_bt_apply(Wk<T> w) {
 
 // ---------------------------------------------------------------------------
 // d = z - x (:720-722) fused with the first entry of lnsrlb (:2196-2244):
-// dtd, stpmx candidates, t = x, r = g, gd = g.d
-// part: 0 dtd ; 1 gd ; 2 stpmx candidate (min)
+// dtd, stpmx candidates, t = x, gold = g, gd = g.d
+// part2: 0 dtd ; 1 gd ; 2 stpmx candidate (min)
+// Skipped when k_subsm_lsinit already did this work in the subspace pass (lsinit_done).
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(LBFGSB_BLOCK) k_ls_init(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     const DevState<T>* s = w.s;
-    if (!s->go || !s->in_body) return;
+    if (!s->go || !s->in_body || s->lsinit_done) return;
     const i64 n = w.n;
     const bool bounds = (s->cnstnd && s->iter != 0);
     __shared__ T sm[2 * (LBFGSB_BLOCK / 32)];
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_ls_init(Wk<T> w) {
             d[v] = z[v] - x[v];
             if (base + v < n) { acc[0] = acc[0] + d[v] * d[v]; acc[1] = acc[1] + g[v] * d[v]; }
         }
-        stv<T>(w.d, base, n, d); stv<T>(w.t, base, n, x); stv<T>(w.r, base, n, g);
+        stv<T>(w.d, base, n, d); stv<T>(w.t, base, n, x); stv<T>(w.gold, base, n, g);
         if (bounds) {
             T l[VEC], u[VEC]; int nb[VEC];
             ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u); ldvi<T>(w.nbd, base, n, nb);
@@ -301,9 +304,9 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_ls_init(Wk<T> w) {
             }
         }
     }
-    block_sum_store<T, 2>(acc, 2, sm, w.part);
+    block_sum_store<T, 2>(acc, 2, sm, w.part2);
     T r = block_min<T>(smx, smm);
-    if (threadIdx.x == 0) LB_SLOT(w.part, 2)[blockIdx.x] = r;
+    if (threadIdx.x == 0) LB_SLOT(w.part2, 2)[blockIdx.x] = r;
 }
 
 // ---------------------------------------------------------------------------
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_restore(Wk<T> w) {
     const i64 n = w.n;
     LB_FOR_TILES(T, n, base) {
         T t[VEC], r[VEC];
-        ldv<T>(w.t, base, n, t); ldv<T>(w.r, base, n, r);
+        ldv<T>(w.t, base, n, t); ldv<T>(w.gold, base, n, r);
         stv<T>(w.x, base, n, t); stv<T>(w.g, base, n, r);
     }
 }

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update(Wk<T> w) {
     if (threadIdx.x == 0) {
         pipe_begin(&ps);
         pipe_add(&ps, w.g, sizeof(T), G::REAL_SLOT);
-        pipe_add(&ps, w.r, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.gold, sizeof(T), G::REAL_SLOT);
         pipe_add(&ps, w.d, sizeof(T), G::REAL_SLOT);
         pipe_add_w<T>(&ps, w, head0, col - 1, G::REAL_SLOT);
         pipe_end(&ps);
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update_classify(Wk<T> w) 
     if (threadIdx.x == 0) {
         pipe_begin(&ps);
         pipe_add(&ps, w.g, sizeof(T), G::REAL_SLOT);
-        pipe_add(&ps, w.r, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.gold, sizeof(T), G::REAL_SLOT);
         pipe_add(&ps, w.d, sizeof(T), G::REAL_SLOT);
         pipe_add(&ps, w.x, sizeof(T), G::REAL_SLOT);
         pipe_add(&ps, w.l, sizeof(T), G::REAL_SLOT);
@@ -700,3 +700,129 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
     block_sum_store<T, 2 * MT>(aw, 2 * MT, sm, w.part2);
 }
 template <typename T, int MT> constexpr unsigned smem_formk_cmprlb() { return pipe_smem_bytes<T, SubT<MT>::v>(3 + 2 * MT, 0, 1); }
+
+// ---------------------------------------------------------------------------
+// k_subsm_step fused with k_ls_init: the subspace pass has z (the Newton point), x, g, l, u, nbd of every
+// variable in hand, which is all that d = z - x (:720-722) and the first entry of lnsrlb (:2196-2244) need.
+// gd = g.d is the same sum as subsm's dd_p (same products, same order).  The results stand unless the
+// backtrack (:2830-2879, rare) moves z afterwards; then k_ls_init runs as a separate pass (lsinit_done = 0).
+// part: 0 dd_p ; ipart: 0 iword        part2: 0 dtd ; 1 gd ; 2 stpmx candidate (min)
+// ---------------------------------------------------------------------------
+template <typename T, int MT>
+__global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    constexpr int SUBT = SubT<MT>::v;
+    typedef PipeGeom<T, SUBT> G;
+    extern __shared__ __align__(128) char dyn[];
+    __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
+    __shared__ PipeSrc ps;
+    __shared__ T sm[2 * (LBFGSB_BLOCK / 32)];
+    __shared__ T smm[LBFGSB_BLOCK / 32];
+    __shared__ i64 smi[LBFGSB_BLOCK / 32];
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_subspace) return;
+    const i64 n = w.n;
+    const int col = s->col, head0 = s->head - 1;
+    const T theta = s->theta, rtheta = (T)1 / theta;
+    const bool bounds = (s->cnstnd && s->iter != 0);
+    constexpr unsigned OZ = 0, OX = G::REAL_SLOT, OG = 2 * G::REAL_SLOT, OR = 3 * G::REAL_SLOT, OL = 4 * G::REAL_SLOT,
+                       OU = 5 * G::REAL_SLOT, OW = 6 * G::REAL_SLOT;
+    if (threadIdx.x == 0) {
+        pipe_begin(&ps);
+        pipe_add(&ps, w.z, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.x, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.g, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.r, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.l, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.u, sizeof(T), G::REAL_SLOT);
+        pipe_add_w<T>(&ps, w, head0, col, G::REAL_SLOT);
+        pipe_add(&ps, w.nbd, 4, G::INT_SLOT);
+        pipe_add(&ps, w.state, 1, G::BYTE_SLOT);
+        pipe_end(&ps);
+    }
+    const unsigned onb = OW + 2u * (unsigned)col * G::REAL_SLOT, ost = onb + G::INT_SLOT;
+    T wv1[MT], wv2[MT];
+#pragma unroll
+    for (int j = 0; j < MT; ++j) { wv1[j] = (j < col) ? s->wv[j] : (T)0; wv2[j] = (j < col) ? s->wv[col + j] : (T)0; }
+    T acc[2]; acc[0] = (T)0; acc[1] = (T)0;   // dtd, dd_p (= gd)
+    T smx = LB_INF(T);
+    i64 iwd = 0;
+    tma_pass<T, SUBT>(n, &ps, LB_DYN_STAGES(dyn), full, [&](i64 base, const char* sb, int lt) {
+        int st[VEC];
+        lds_byte<T>(sb, ost, lt, st);
+        bool fr[VEC]; bool any = false;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { fr[v] = (base + v < n) && (st[v] & 1); any |= fr[v]; }
+        T z[VEC], x[VEC], g[VEC], l[VEC], u[VEC]; int nb[VEC];
+        lds_real<T>(sb, OZ, lt, z); lds_real<T>(sb, OX, lt, x); lds_real<T>(sb, OG, lt, g);
+        lds_real<T>(sb, OL, lt, l); lds_real<T>(sb, OU, lt, u);
+        lds_int<T>(sb, onb, lt, nb);
+        stv<T>(w.xp, base, n, z);   // :2787
+        if (any) {
+            T dk[VEC];
+            lds_real<T>(sb, OR, lt, dk);
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                if (j < col) {
+                    T wy[VEC], wsv[VEC];
+                    lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
+                    lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) dk[v] = dk[v] + wy[v] * wv1[j] / theta + wsv[v] * wv2[j];
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                dk[v] = rtheta * dk[v];   // dscal(nsub, one/theta, d) :2780
+                if (fr[v]) {
+                    T xk = z[v];
+                    if (nb[v] != 0) {
+                        if (nb[v] == 1) { z[v] = dense::tmax(l[v], xk + dk[v]); if (z[v] == l[v]) iwd = 1; }
+                        else if (nb[v] == 2) {
+                            xk = dense::tmax(l[v], xk + dk[v]);
+                            z[v] = dense::tmin(u[v], xk);
+                            if (z[v] == l[v] || z[v] == u[v]) iwd = 1;
+                        } else if (nb[v] == 3) { z[v] = dense::tmin(u[v], xk + dk[v]); if (z[v] == u[v]) iwd = 1; }
+                    } else z[v] = xk + dk[v];
+                }
+            }
+            // direction (don't-care on non-free variables) and new point (unchanged there)
+            stv<T>(w.r, base, n, dk);
+            stv<T>(w.z, base, n, z);
+        }
+        // d = z - x, dtd, gd (= dd_p :2825-2827), stpmx candidates (:2201-2227), t = x, gold = g
+        T d[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            d[v] = z[v] - x[v];
+            if (base + v < n) { acc[0] = acc[0] + d[v] * d[v]; acc[1] = acc[1] + d[v] * g[v]; }
+        }
+        stv<T>(w.d, base, n, d); stv<T>(w.t, base, n, x); stv<T>(w.gold, base, n, g);
+        if (bounds) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if (base + v < n && nb[v] != 0) {
+                    const T a1 = d[v];
+                    if (a1 < (T)0 && nb[v] <= 2) {
+                        const T a2 = l[v] - x[v];
+                        const T cand = (a2 >= (T)0) ? (T)0 : a2 / a1;
+                        smx = dense::tmin(smx, cand);
+                    } else if (a1 > (T)0 && nb[v] >= 2) {
+                        const T a2 = u[v] - x[v];
+                        const T cand = (a2 <= (T)0) ? (T)0 : a2 / a1;
+                        smx = dense::tmin(smx, cand);
+                    }
+                }
+            }
+        }
+    });
+    // site subsm: dd_p in part slot 0, iword in ipart slot 0
+    T ddp[1]; ddp[0] = acc[1];
+    block_sum_store<T, 1>(ddp, 1, sm, w.part);
+    i64 r0 = block_isum(iwd, smi);
+    if (threadIdx.x == 0) LB_SLOT(w.ipart, 0)[blockIdx.x] = r0;
+    // site lsinit: dtd, gd, stpmx in part2
+    block_sum_store<T, 2>(acc, 2, sm, w.part2);
+    T rm = block_min<T>(smx, smm);
+    if (threadIdx.x == 0) LB_SLOT(w.part2, 2)[blockIdx.x] = rm;
+}
