@@ -378,6 +378,12 @@ def main():
             iw = prob.vector(7)
             st_free = int((iw <= 0).sum())
         fb = family_bytes(n, col, st_free, st_free)
+        # passes that the engine folded into a neighbour in this run (their own launches did not happen or
+        # returned at once): the neighbour is credited with the routine's algorithmic bytes
+        if prof.get("gcp_freev", {"calls": 0})["calls"] == 0:
+            fb["formk_cmprlb"] += fb["gcp_freev"]          # cauchy's tail + freev inside k_formk_cmprlb (fuse_gf)
+        fb["subsm_lsinit"] += fb["ls_step"]                # the stp = 1 trial point x = z is written by the subspace pass
+        fb.pop("ls_step")
         total_ms = sum(v["ms"] for v in prof.values())
         for name, v in prof.items():
             if v["calls"] == 0 or v["ms"] <= 0:

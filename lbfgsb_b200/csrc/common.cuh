@@ -82,6 +82,12 @@ struct DevState {
     int fuse_uc;       // NEW_X entry: the S/Y update and cauchy's per-variable pass run as one fused kernel
     int classify_done; // cauchy's per-variable pass of this body was already done by that fused kernel
     int lsinit_done;   // d = z - x and lnsrlb's first-entry sums were already formed by k_subsm_lsinit
+    int spec_step;     // k_subsm_lsinit wrote the stp = 1 trial point straight into x (z, xp, r left untouched)
+    int step_done;     // ... and lnsrlb's first trial is that point: k_ls_step has nothing to do
+    int do_unstep;     // ... but the line search failed at its first entry: k_ls_step puts x = t back
+    int lazy_gcp;      // cauchy's d and xcp are not materialised: xcp = x + tsum*d, d = -g or 0 by iwhere
+    int fuse_gf;       // the cauchy tail (:1515) and freev (:1980-2059) run inside k_formk_cmprlb
+    int pad_ctl;
     int task, csave, info;
     // ---- mainlb locals (:416-424) ----
     int col, head, itail, iupdat, iter, nfgv, nskip, ifun, iback, iword;

@@ -139,6 +139,7 @@ struct Engine : EngineBase {
     // accounting
     i64 launches = 0, syncs = 0;
     bool profile = false;
+    bool debug_launch = (getenv("LBFGSB_B200_DEBUG_LAUNCH") != nullptr);
     struct Ev { int fam; cudaEvent_t a, b; };
     std::vector<Ev> pending;
     std::vector<cudaEvent_t> pool;
@@ -242,6 +243,10 @@ struct Engine : EngineBase {
     }
     void end(int fam, int nlaunch = 1) {
         launches += nlaunch;
+        if (debug_launch) {   // LBFGSB_B200_DEBUG_LAUNCH=1: name the kernel family whose launch failed
+            cudaError_t e = cudaPeekAtLastError();
+            if (e != cudaSuccess) fprintf(stderr, "lbfgsb_b200: launch of family '%s' failed: %s\n", fam_name[fam], cudaGetErrorString(e));
+        }
         if (profile) cudaEventRecord(pending.back().b, stream);
         else fam_calls[fam] += 1;
     }
@@ -287,7 +292,10 @@ struct Engine : EngineBase {
         if constexpr (fused_passes_ok<T, MT>()) k_formk_cmprlb<T, MT><<<LBFGSB_GRID, LB_TMA_THREADS, smem_formk_cmprlb<T, MT>(), stream>>>(w);
     }
     template <int MT> void launch_subsm_lsinit() {
-        if constexpr (fused_passes_ok<T, MT>()) k_subsm_lsinit<T, MT><<<LBFGSB_GRID, LB_TMA_THREADS, smem_subsm<T, MT>(), stream>>>(w);
+        if constexpr (fused_passes_ok<T, MT>()) k_subsm_lsinit<T, MT, 0><<<LBFGSB_GRID, LB_TMA_THREADS, smem_subsm<T, MT>(), stream>>>(w);
+    }
+    template <int MT> void launch_subsm_dir() {
+        if constexpr (fused_passes_ok<T, MT>()) k_subsm_lsinit<T, MT, 1><<<LBFGSB_GRID, LB_TMA_THREADS, smem_subsm<T, MT>(), stream>>>(w);
     }
 #define MTFUSED(fn) do { if (mt == 5) fn<5>(); else if (mt == 10) fn<10>(); else fn<20>(); } while (0)
 
@@ -301,7 +309,8 @@ struct Engine : EngineBase {
         if constexpr (fused_passes_ok<T, MT>()) {
             CK(cudaFuncSetAttribute(k_update_classify<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_update_classify<T, MT>()));
             CK(cudaFuncSetAttribute(k_formk_cmprlb<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk_cmprlb<T, MT>()));
-            CK(cudaFuncSetAttribute(k_subsm_lsinit<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_subsm<T, MT>()));
+            CK(cudaFuncSetAttribute(k_subsm_lsinit<T, MT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_subsm<T, MT>()));
+            CK(cudaFuncSetAttribute(k_subsm_lsinit<T, MT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_subsm<T, MT>()));
         }
         return true;
     }
@@ -507,18 +516,27 @@ struct Engine : EngineBase {
         for (;;) {
             begin(F_CLASSIFY); MTCALL(k_cauchy_classify, smem_classify, w); end(F_CLASSIFY);
             if (!site(site_cauchy(mt))) return false;
-            begin(F_SCALAR); s_cauchy<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);
+            begin(F_SCALAR); s_cauchy<T><<<LS>>>(w, dist(), mt, fused ? 1 : 0); end(F_SCALAR);
+            bool gf = false;   // cauchy's tail and freev run inside k_formk_cmprlb (decided by s_cauchy)
             if (s_host->cnstnd) {
                 if (!sync_state()) return false;
                 if (s_host->go && s_host->in_body && s_host->need_walk) {
+                    begin(F_WALK_COMPACT); k_materialize<T><<<LG>>>(w); end(F_WALK_COMPACT);
                     if (!enqueue_walk_rounds()) return false;
                 }
+                gf = fused && s_host->go && s_host->in_body && s_host->fuse_gf;
             }
-            begin(F_GCP_FREEV); k_gcp_freev<T><<<LG>>>(w); end(F_GCP_FREEV);
-            if (!site(site_freev())) return false;
-            begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global); end(F_SCALAR);
+            if (!gf) {
+                begin(F_GCP_FREEV); k_gcp_freev<T><<<LG>>>(w); end(F_GCP_FREEV);
+                if (!site(site_freev())) return false;
+            }
+            begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global, 0); end(F_SCALAR);
             if (fused) { begin(F_FORMK_CMPRLB); MTFUSED(launch_formk_cmprlb); end(F_FORMK_CMPRLB); }
             else { begin(F_FORMK_GRAM); MTCALL(k_formk_gram, smem_formk, w); end(F_FORMK_GRAM); }
+            if (gf) {
+                if (!site(site_freev())) return false;
+                begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global, 1); end(F_SCALAR);
+            }
             begin(F_FORMK_DELTA);
             k_flag_count<T, 1><<<LG>>>(w, tile_counts);
             k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 1, tile_counts, tile_offsets, ntiles, ctl_el);
@@ -531,12 +549,13 @@ struct Engine : EngineBase {
             begin(F_SCALAR); s_formk_dense<T><<<LS>>>(w, dist(), mt, R > 1 ? delta_all : delta, delta_sum); end(F_SCALAR);
             if (!fused) { begin(F_CMPRLB_WV); MTCALL(k_cmprlb_wv, smem_cmprlb, w); end(F_CMPRLB_WV); }
             if (!site(site_wv(mt))) return false;
-            begin(F_SCALAR); s_subsm_dense<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);
+            begin(F_SCALAR); s_subsm_dense<T><<<LS>>>(w, dist(), mt, fused ? 1 : 0); end(F_SCALAR);
             if (fused) { begin(F_SUBSM_LSINIT); MTFUSED(launch_subsm_lsinit); end(F_SUBSM_LSINIT); }
             else { begin(F_SUBSM_STEP); MTCALL(k_subsm_step, smem_subsm, w); end(F_SUBSM_STEP); }
             if (!site(site_subsm())) return false;
             begin(F_SCALAR); s_subsm_post<T><<<LS>>>(w, dist(), fused ? 1 : 0); end(F_SCALAR);
             begin(F_BACKTRACK);
+            if (fused) { MTFUSED(launch_subsm_dir); launches++; }   // direction for the backtrack after a speculative step
             k_bt_alpha<T><<<LG>>>(w);
             if (!site(site_bt())) return false;
             s_bt<T><<<LS>>>(w, dist(), offset);

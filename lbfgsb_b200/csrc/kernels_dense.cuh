@@ -149,6 +149,7 @@ template <typename T> __device__ inline void reset_memory(DevState<T>* s) {
 // prepare the flags for the prelims block (:601-612)
 template <typename T> __device__ inline void begin_body(DevState<T>* s) {
     s->in_body = 1; s->restart = 0; s->need_walk = 0; s->lsinit_done = 0;
+    s->spec_step = 0; s->step_done = 0; s->do_unstep = 0; s->lazy_gcp = 0; s->fuse_gf = 0;
     s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0; s->do_step = 0;
     s->iword = -1;
     ev_push<T>(s, EV_ITER_BEGIN, (T)(s->iter + 1));
@@ -292,7 +293,7 @@ __global__ void s_restart_body(Wk<T> w) {
 // test (:1384-1416 with iter == 1).
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> dist, int mt) {
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> dist, int mt, int fused_supported) {
     __shared__ Red<T> red;
     DevState<T>* s = w.s;
     if (!s->go || !s->in_body || s->cauchy_mode != 0) return;
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
     s->bnded = red.iv[3] > 0;
     if (s->theta != one) for (int j = 0; j < col; ++j) s->p[col + j] = s->theta * s->p[col + j];  // :1337
     s->tsum = zero;
+    s->lazy_gcp = 1;   // the per-variable pass did not write d and xcp = x (k_gcp_freev / k_formk_cmprlb form xcp)
     if (s->nbreak == 0 && s->nfreec == 0) return;   // d is the zero vector (:1343-1347); nseg untouched
     for (int j = 0; j < col2; ++j) s->c[j] = zero;
     s->f2 = -s->theta * s->f1;
@@ -327,8 +329,8 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
     s->dtm = -s->f1 / s->f2;
     s->nseg = 1;
     if (s->nbreak != 0 && !(s->dtm < s->bkmin)) {
-        // the first breakpoint is reached: the sorted walk takes over
-        s->need_walk = 1;
+        // the first breakpoint is reached: the sorted walk takes over (k_materialize writes d, xcp = x first)
+        s->need_walk = 1; s->lazy_gcp = 0;
         for (int j = 0; j < col2; ++j) { s->p0[j] = s->p[j]; s->walkA[j] = zero; s->walkB[j] = zero; }
         s->walk_f1 = s->f1; s->walk_f2 = s->f2; s->walk_tlast = zero; s->walk_tprev2 = zero;
         s->walk_J = -1; s->walk_done = 0; s->walk_base = 0; s->walk_rcount = 0; s->walk_lcount = 0; s->walk_rem = 0;
@@ -338,16 +340,32 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
     if (s->dtm <= zero) s->dtm = zero;   // :1509
     s->tsum = s->tsum + s->dtm;
     if (col > 0) dense::daxpy<T>(col2, s->dtm, s->p, s->c);  // :1526
+    // The generalized Cauchy point is known without a walk and c is final: cmprlb's a = M c (:1569) can be
+    // formed here, and then the tail of cauchy (:1515) and freev run inside k_formk_cmprlb (fuse_gf).  The
+    // counts of freev, and with them nfree == 0 / wrk, are evaluated after that pass (s_freev phase 1).  If
+    // the product fails, the separate passes run and s_freev reports the failure in the reference's order.
+    if (fused_supported && col > 0 && s->cnstnd) {
+        if (dense::bmv<T>(m, s->sy, s->wt, col, s->c, s->a) == 0) s->fuse_gf = 1;
+    }
 }
 
 // ---------------------------------------------------------------------------
 // after freev (:638-648): counters, wrk, what of the subspace phase runs.
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_freev(Wk<T> w, Dist<T> dist, i64 n_global) {
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_freev(Wk<T> w, Dist<T> dist, i64 n_global, int phase) {
     __shared__ Red<T> red;
     DevState<T>* s = w.s;
     if (!s->go || !s->in_body) return;
+    // phase 0: after k_gcp_freev (the separate pass).  With fuse_gf the counts do not exist yet: the subspace
+    // flags are set tentatively (col > 0 holds; the Gram row is wanted iff updatd) and phase 1, after
+    // k_formk_cmprlb, evaluates them.  phase 1 does nothing without fuse_gf.
+    const bool gf = s->fuse_gf != 0;
+    if (phase == 1 && !gf) return;
+    if (phase == 0 && gf) {
+        if (threadIdx.x == 0) { s->do_subspace = 1; s->do_formk = s->updatd; s->do_delta = 0; }
+        return;
+    }
     const int mode = s->cauchy_mode;
     if (mode != 1) site_reduce<T>(w, dist, site_freev(), &red);
     if (threadIdx.x != 0) return;
@@ -365,7 +383,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_freev(Wk<T> w, Dist<T> di
     // cmprlb's a = M c (:1569; not needed on the unconstrained shortcut :1560-1563).  It depends only on
     // sy, wt and c, which are final here, and is hoisted in front of formk so that formk's Gram pass and
     // cmprlb's pass over S/Y can run as one kernel.  A failure of either ends in the same memory reset.
-    if (s->do_subspace && !(!s->cnstnd && s->col > 0)) {
+    if (!gf && s->do_subspace && !(!s->cnstnd && s->col > 0)) {   // (with fuse_gf s_cauchy formed a)
         int info = dense::bmv<T>(s->m, s->sy, s->wt, s->col, s->c, s->a);
         if (info != 0) {   // info = -8 -> :694-710
             ev_push<T>(s, EV_SUBSM_SINGULAR);
@@ -485,7 +503,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist
 // subsm: wv = K^{-1} wv (:2751-2766)
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_dense(Wk<T> w, Dist<T> dist, int mt) {
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_dense(Wk<T> w, Dist<T> dist, int mt, int fused_lsinit) {
     __shared__ Red<T> red;
     DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->do_subspace) return;
@@ -502,7 +520,11 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_dense(Wk<T> w, Dist
         ev_push<T>(s, EV_SUBSM_SINGULAR);
         reset_memory<T>(s);
         s->restart = 1; s->in_body = 0; s->do_subspace = 0;
+        return;
     }
+    // lnsrlb starts at stp = 1 unless this is the first iteration of a problem that is not boxed (:2229-2233):
+    // the fused subspace pass then writes that trial point (x = z, :2265) itself
+    s->spec_step = (fused_lsinit && (s->iter != 0 || s->boxed)) ? 1 : 0;
 }
 
 // subsm: projection outcome (:2820-2828)
@@ -542,7 +564,8 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_bt(Wk<T> w, Dist<T> dist,
 template <typename T>
 __device__ inline void ls_failure(DevState<T>* s, bool at_first_entry) {
     // :734-769 ; x = t, g = r, f = fold
-    if (!at_first_entry) s->do_restore = 1;   // at the first entry x, g are still the old iterate
+    if (!at_first_entry) s->do_restore = 1;   // at the first entry x, g are still the old iterate ...
+    else if (s->spec_step) s->do_unstep = 1;  // ... unless the subspace pass already stepped: x = t again
     s->do_step = 0;
     s->f = s->fold;
     if (s->col == 0) {
@@ -592,6 +615,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_init(Wk<T> w, Dist<T> 
         s->task = TK_FG_LNSRCH;
         s->ifun += 1; s->nfgv += 1; s->iback = s->ifun - 1;
         s->do_step = 1;
+        s->step_done = (s->spec_step && s->lsinit_done && s->stp == one) ? 1 : 0;   // x already holds z
         s->go = 0; s->in_body = 0;   // return to the caller for f and g
     } else {
         // cannot happen on the first entry (dcsrch 'START' returns 'FG' or 'ERROR')
@@ -639,6 +663,7 @@ __global__ void s_call_begin(Wk<T> w, T f, int entry_task) {
     s->do_step = 0; s->do_restore = 0; s->do_update = 0;
     s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0;
     s->fuse_uc = 0; s->classify_done = 0; s->lsinit_done = 0;
+    s->spec_step = 0; s->step_done = 0; s->do_unstep = 0; s->lazy_gcp = 0; s->fuse_gf = 0;
     s->ev_n = 0;
     s->f = f;
     (void)entry_task;
@@ -653,6 +678,7 @@ __global__ void s_start(Wk<T> w, T factr, T pgtol, int host_err_task) {
     s->go = 1; s->in_body = 0; s->restart = 0; s->need_walk = 0; s->cauchy_mode = 0;
     s->do_subspace = s->do_formk = s->do_delta = s->do_backtrack = s->do_update = s->do_step = s->do_restore = 0;
     s->fuse_uc = 0; s->classify_done = 0; s->lsinit_done = 0; s->ev_n = 0;
+    s->spec_step = 0; s->step_done = 0; s->do_unstep = 0; s->lazy_gcp = 0; s->fuse_gf = 0;
     s->task = TK_START; s->csave = CS_BLANK; s->info = 0;
     s->col = 0; s->head = 1; s->theta = (T)1; s->iupdat = 0; s->updatd = 0;
     s->iback = 0; s->itail = 0; s->iword = 0; s->nact = 0; s->nleave = 0; s->nenter = 0;

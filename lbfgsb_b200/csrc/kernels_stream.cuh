@@ -152,21 +152,53 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_projgr(Wk<T> w) {
 // set" loop is a masked pass over the variables.
 // ipart: 0 nfree ; 1 nenter ; 2 nleave
 // ---------------------------------------------------------------------------
+// Cauchy direction of one variable from its class (cauchy :1294-1298): -g if the variable moves, else 0.
+template <typename T>
+__device__ __forceinline__ T cauchy_dir(int iw, T g) { return (iw == 0 || iw == -1) ? -g : (T)0; }
+
+// cauchy's d and xcp = x written out (they are otherwise implied by iwhere, g, x): the breakpoint walk
+// reads d and scatters into d, xcp.  Runs only in front of that walk.
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_materialize(Wk<T> w) {
+    constexpr int VEC = Real<T>::VEC;
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk) return;
+    const i64 n = w.n;
+    LB_FOR_TILES(T, n, base) {
+        int iw[VEC]; T g[VEC], x[VEC], d[VEC];
+        ldvi<T>(w.iwhere, base, n, iw); ldv<T>(w.g, base, n, g); ldv<T>(w.x, base, n, x);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) d[v] = cauchy_dir<T>(iw[v], g[v]);
+        stv<T>(w.d, base, n, d); stv<T>(w.z, base, n, x);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(LBFGSB_BLOCK) k_gcp_freev(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     const DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || s->cauchy_mode == 1) return;
+    if (!s->go || !s->in_body || s->cauchy_mode == 1 || s->fuse_gf) return;
     const i64 n = w.n;
     const T tsum = s->tsum;
     const bool axpy = (s->cauchy_mode == 0) && (tsum != (T)0);   // daxpy early-out (:49-50)
+    const bool lazy = (s->cauchy_mode == 0) && s->lazy_gcp;      // d, xcp not materialised: xcp = x + tsum*d
     const bool cnt = (s->iter > 0 && s->cnstnd);
     __shared__ i64 smi[LBFGSB_BLOCK / 32];
     i64 nfr = 0, nen = 0, nle = 0;
     LB_FOR_TILES(T, n, base) {
         int iw[VEC], st[VEC];
         ldvi<T>(w.iwhere, base, n, iw); ldvb<T>(w.state, base, n, st);
-        if (axpy) {
+        if (lazy) {
+            T z[VEC];
+            ldv<T>(w.x, base, n, z);
+            if (axpy) {
+                T g[VEC];
+                ldv<T>(w.g, base, n, g);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) z[v] = z[v] + tsum * cauchy_dir<T>(iw[v], g[v]);
+            }
+            stv<T>(w.z, base, n, z);
+        } else if (axpy) {
             T d[VEC], z[VEC];
             ldv<T>(w.d, base, n, d); ldv<T>(w.z, base, n, z);
 #pragma unroll
@@ -205,10 +237,11 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_bt_alpha(Wk<T> w) {
     __shared__ T smv[LBFGSB_BLOCK / 32];
     __shared__ i64 smi[LBFGSB_BLOCK / 32];
     T best = LB_INF(T); i64 ib = LB_I64MAX;
+    const T* xcp = s->spec_step ? w.z : w.xp;   // the speculative subspace pass leaves xcp in z
     LB_FOR_TILES(T, n, base) {
         int st[VEC], nb[VEC]; T dk[VEC], xk[VEC], l[VEC], u[VEC];
         ldvb<T>(w.state, base, n, st); ldvi<T>(w.nbd, base, n, nb);
-        ldv<T>(w.r, base, n, dk); ldv<T>(w.xp, base, n, xk); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
+        ldv<T>(w.r, base, n, dk); ldv<T>(xcp, base, n, xk); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             if (base + v < n && (st[v] & 1) && nb[v] != 0) {
@@ -238,10 +271,11 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_bt_apply(Wk<T> w) {
     const i64 n = w.n;
     const T alpha = s->alpha;
     const i64 ibd = s->ibd;
+    const T* xcp = s->spec_step ? w.z : w.xp;
     LB_FOR_TILES(T, n, base) {
         int st[VEC]; T dk[VEC], xk[VEC], l[VEC], u[VEC];
         ldvb<T>(w.state, base, n, st);
-        ldv<T>(w.r, base, n, dk); ldv<T>(w.xp, base, n, xk); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
+        ldv<T>(w.r, base, n, dk); ldv<T>(xcp, base, n, xk); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             if (base + v < n) {
@@ -275,9 +309,10 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_ls_init(Wk<T> w) {
     __shared__ T smm[LBFGSB_BLOCK / 32];
     T acc[2]; acc[0] = (T)0; acc[1] = (T)0;
     T smx = LB_INF(T);
+    const T* xs = s->spec_step ? w.t : w.x;   // after a speculative step the iterate is in t
     LB_FOR_TILES(T, n, base) {
         T z[VEC], x[VEC], g[VEC], d[VEC];
-        ldv<T>(w.z, base, n, z); ldv<T>(w.x, base, n, x); ldv<T>(w.g, base, n, g);
+        ldv<T>(w.z, base, n, z); ldv<T>(xs, base, n, x); ldv<T>(w.g, base, n, g);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             d[v] = z[v] - x[v];
@@ -316,8 +351,12 @@ template <typename T>
 __global__ void __launch_bounds__(LBFGSB_BLOCK) k_ls_step(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     const DevState<T>* s = w.s;
-    if (!s->do_step) return;
     const i64 n = w.n;
+    if (s->do_unstep) {   // the speculative step is withdrawn (line search failed at its first entry)
+        LB_FOR_TILES(T, n, base) { T t[VEC]; ldv<T>(w.t, base, n, t); stv<T>(w.x, base, n, t); }
+        return;
+    }
+    if (!s->do_step || s->step_done) return;
     const T stp = s->stp;
     if (stp == (T)1) {
         LB_FOR_TILES(T, n, base) { T z[VEC]; ldv<T>(w.z, base, n, z); stv<T>(w.x, base, n, z); }

@@ -154,7 +154,7 @@ __device__ __forceinline__ void cauchy_scan_store(const Wk<T>& w, CauchyScan<T>&
 
 // ---------------------------------------------------------------------------
 // cauchy, per-variable pass (:1270-1341): classify iwhere, Cauchy direction d,
-// f1 = -sum d^2, p = W'd, smallest breakpoint; xcp = x.
+// f1 = -sum d^2, p = W'd, smallest breakpoint.  (xcp = x and d are implied, see lazy_gcp.)
 // part2: [0,MT) sum Wy(:,j) d ; [MT,2MT) sum Ws(:,j) d ; 2MT: sum d^2 ; 2MT+1: bkmin
 // ipart2: 0 argmin variable ; 1 nbreak ; 2 count of moving variables without breakpoint ;
 //        3 bnded (min over blocks)
@@ -212,9 +212,9 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cauchy_classify(Wk<T> w) 
             mv[v] = false; d[v] = (T)0;
             if (base + v < n) cauchy_classify_one<T>(x[v], l[v], u[v], g[v], nb[v], iw[v], d[v], mv[v], acc[2 * MT], cs, base + v + w.off);
         }
+        // d and xcp = x are not written: they follow from iwhere, g and x (lazy_gcp; k_materialize writes them
+        // out in front of a breakpoint walk)
         stvi<T>(w.iwhere, base, n, iw);
-        stv<T>(w.d, base, n, d);
-        stv<T>(w.z, base, n, x);
 #pragma unroll
         for (int j = 0; j < MT; ++j) {
             if (j < col) {
@@ -551,9 +551,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update_classify(Wk<T> w) 
             mv[v] = false; dc[v] = (T)0;
             if (base + v < n) cauchy_classify_one<T>(x[v], l[v], u[v], g[v], nb[v], iw[v], dc[v], mv[v], ac[2 * MT], cs, base + v + w.off);
         }
-        stvi<T>(w.iwhere, base, n, iw);
-        stv<T>(w.d, base, n, dc);
-        stv<T>(w.z, base, n, x);
+        stvi<T>(w.iwhere, base, n, iw);   // d, xcp: see k_cauchy_classify
 #pragma unroll
         for (int j = 0; j < MT; ++j) {
             if (j < col - 1) {
@@ -603,21 +601,30 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
     __shared__ PipeSrc ps;
     __shared__ T sm[4 * MT * (LBFGSB_BLOCK / 32)];
     __shared__ T coef[2 * MT];
+    __shared__ i64 smi[LBFGSB_BLOCK / 32];
     const DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->do_subspace) return;
+    // gf: the tail of cauchy (xcp = x + tsum*d, :1515) and freev (:1980-2059) are part of this pass; the flags
+    // do_subspace / do_formk are then s_freev's tentative values (the counts are only known after this pass)
+    const bool gf = s->fuse_gf != 0;
     const bool gram = s->do_formk && s->updatd;
     const i64 n = w.n;
     const int col = s->col, head0 = s->head - 1;
     const T theta = s->theta;
     const bool uc = (!s->cnstnd && col > 0);   // :1560-1563
-    constexpr unsigned OG = 0, OZ = G::REAL_SLOT, OX = 2 * G::REAL_SLOT, OW = 3 * G::REAL_SLOT;
+    const T tsum = s->tsum;
+    const bool axpy = tsum != (T)0;            // daxpy early-out (:49-50)
+    const bool cnt = (s->iter > 0 && s->cnstnd);
+    constexpr unsigned OG = 0, OX = G::REAL_SLOT, OZ = 2 * G::REAL_SLOT;
+    const unsigned OW = (gf ? 2u : 3u) * G::REAL_SLOT;
     if (threadIdx.x == 0) {
         pipe_begin(&ps);
         pipe_add(&ps, w.g, sizeof(T), G::REAL_SLOT);
-        pipe_add(&ps, w.z, sizeof(T), G::REAL_SLOT);
         pipe_add(&ps, w.x, sizeof(T), G::REAL_SLOT);
+        if (!gf) pipe_add(&ps, w.z, sizeof(T), G::REAL_SLOT);
         pipe_add_w<T>(&ps, w, head0, col, G::REAL_SLOT);
         pipe_add(&ps, w.state, 1, G::BYTE_SLOT);
+        if (gf) pipe_add(&ps, w.iwhere, 4, G::INT_SLOT);
         pipe_end(&ps);
     }
     if (threadIdx.x < 2 * MT) {
@@ -625,12 +632,14 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
         coef[threadIdx.x] = (j < col) ? ((threadIdx.x < MT) ? s->a[j] : theta * s->a[col + j]) : (T)0;
     }
     const unsigned ost = OW + 2u * (unsigned)col * G::REAL_SLOT;
+    const unsigned oiw = ost + G::BYTE_SLOT;
     const unsigned olast = OW + 2u * (unsigned)(col - 1) * G::REAL_SLOT;   // the newest pair sits at ring position col-1
     T af[4 * MT], aw[2 * MT];
 #pragma unroll
     for (int k = 0; k < 4 * MT; ++k) af[k] = (T)0;
 #pragma unroll
     for (int k = 0; k < 2 * MT; ++k) aw[k] = (T)0;
+    int nfr = 0, nen = 0, nle = 0;   // per thread: at most n / (GRID*BLOCK) * VEC, far below 2^31
     // (tma_pass starts with a __syncthreads: coef is visible to every consumer)
     // Elements at or beyond n read as zero from the stage (state 0, W = 0): their terms are +0 and leave
     // every accumulator unchanged, so the loops below carry no range checks.  The conditionals are kept
@@ -639,11 +648,31 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
         int st[VEC];
         lds_byte<T>(sb, ost, lt, st);
         bool fr[VEC]; bool any = false;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) { fr[v] = (st[v] & 1) != 0; any |= fr[v]; }
-        if (!any && !gram) return;
         T r[VEC];
-        {
+        if (gf) {
+            int iw[VEC];
+            lds_int<T>(sb, oiw, lt, iw);
+            T z[VEC], x[VEC], g[VEC];
+            lds_real<T>(sb, OG, lt, g); lds_real<T>(sb, OX, lt, x);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const bool inr = base + v < n;
+                const bool f = inr && iw[v] <= 0;
+                const int old = st[v] & 1;
+                nfr += f ? 1 : 0;
+                if (cnt) { nen += (f && !old) ? 1 : 0; nle += (inr && !f && old) ? 1 : 0; }
+                st[v] = (f ? 1 : 0) | ((cnt ? old : (f ? 1 : 0)) << 1);
+                fr[v] = f; any |= f;
+                z[v] = axpy ? (x[v] + tsum * cauchy_dir<T>(iw[v], g[v])) : x[v];
+                r[v] = uc ? -g[v] : (-theta * (z[v] - x[v]) - g[v]);
+            }
+            stvb<T>(w.state, base, n, st);
+            stv<T>(w.z, base, n, z);
+            if (!any && !gram) return;
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { fr[v] = (st[v] & 1) != 0; any |= fr[v]; }
+            if (!any && !gram) return;
             T z[VEC], x[VEC], g[VEC];
             lds_real<T>(sb, OG, lt, g); lds_real<T>(sb, OZ, lt, z); lds_real<T>(sb, OX, lt, x);
 #pragma unroll
@@ -698,6 +727,13 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
     });
     if (gram) block_sum_store<T, 4 * MT>(af, 4 * MT, sm, w.part);
     block_sum_store<T, 2 * MT>(aw, 2 * MT, sm, w.part2);
+    if (gf) {   // site freev
+        i64 r0 = block_isum((i64)nfr, smi), r1 = block_isum((i64)nen, smi), r2 = block_isum((i64)nle, smi);
+        if (threadIdx.x == 0) {
+            LB_SLOT(w.ipart, 0)[blockIdx.x] = r0; LB_SLOT(w.ipart, 1)[blockIdx.x] = r1;
+            LB_SLOT(w.ipart, 2)[blockIdx.x] = r2;
+        }
+    }
 }
 template <typename T, int MT> constexpr unsigned smem_formk_cmprlb() { return pipe_smem_bytes<T, SubT<MT>::v>(3 + 2 * MT, 0, 1); }
 
@@ -707,8 +743,14 @@ template <typename T, int MT> constexpr unsigned smem_formk_cmprlb() { return pi
 // gd = g.d is the same sum as subsm's dd_p (same products, same order).  The results stand unless the
 // backtrack (:2830-2879, rare) moves z afterwards; then k_ls_init runs as a separate pass (lsinit_done = 0).
 // part: 0 dd_p ; ipart: 0 iword        part2: 0 dtd ; 1 gd ; 2 stpmx candidate (min)
+//
+// Speculative step (spec_step, set by s_subsm_dense when lnsrlb's first trial will be stp = 1, i.e. iter > 0
+// or a boxed problem): that trial point is the Newton point itself (x = z, :2265), so it is written straight
+// into x and neither z, nor the backup xp (:2787), nor the direction r (read only by the backtrack) are
+// stored.  If the backtrack is needed after all, xcp is still intact in z, the iterate is in t, and PASS 1
+// of this kernel (same arithmetic, no other effect) writes the direction into r.
 // ---------------------------------------------------------------------------
-template <typename T, int MT>
+template <typename T, int MT, int PASS>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<MT>::v;
@@ -721,6 +763,8 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
     __shared__ i64 smi[LBFGSB_BLOCK / 32];
     const DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->do_subspace) return;
+    const bool spec = s->spec_step != 0;
+    if (PASS == 1 && !(spec && s->do_backtrack)) return;
     const i64 n = w.n;
     const int col = s->col, head0 = s->head - 1;
     const T theta = s->theta, rtheta = (T)1 / theta;
@@ -753,11 +797,30 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
         bool fr[VEC]; bool any = false;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { fr[v] = (base + v < n) && (st[v] & 1); any |= fr[v]; }
+        if (PASS == 1) {   // the direction only (for the backtrack after a speculative step)
+            if (!any) return;
+            T dk[VEC];
+            lds_real<T>(sb, OR, lt, dk);
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                if (j < col) {
+                    T wy[VEC], wsv[VEC];
+                    lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
+                    lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) dk[v] = dk[v] + wy[v] * wv1[j] / theta + wsv[v] * wv2[j];
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) dk[v] = rtheta * dk[v];
+            stv<T>(w.r, base, n, dk);
+            return;
+        }
         T z[VEC], x[VEC], g[VEC], l[VEC], u[VEC]; int nb[VEC];
         lds_real<T>(sb, OZ, lt, z); lds_real<T>(sb, OX, lt, x); lds_real<T>(sb, OG, lt, g);
         lds_real<T>(sb, OL, lt, l); lds_real<T>(sb, OU, lt, u);
         lds_int<T>(sb, onb, lt, nb);
-        stv<T>(w.xp, base, n, z);   // :2787
+        if (!spec) stv<T>(w.xp, base, n, z);   // :2787
         if (any) {
             T dk[VEC];
             lds_real<T>(sb, OR, lt, dk);
@@ -786,9 +849,11 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
                     } else z[v] = xk + dk[v];
                 }
             }
-            // direction (don't-care on non-free variables) and new point (unchanged there)
-            stv<T>(w.r, base, n, dk);
-            stv<T>(w.z, base, n, z);
+            if (!spec) {
+                // direction (don't-care on non-free variables) and new point (unchanged there)
+                stv<T>(w.r, base, n, dk);
+                stv<T>(w.z, base, n, z);
+            }
         }
         // d = z - x, dtd, gd (= dd_p :2825-2827), stpmx candidates (:2201-2227), t = x, gold = g
         T d[VEC];
@@ -798,6 +863,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
             if (base + v < n) { acc[0] = acc[0] + d[v] * d[v]; acc[1] = acc[1] + d[v] * g[v]; }
         }
         stv<T>(w.d, base, n, d); stv<T>(w.t, base, n, x); stv<T>(w.gold, base, n, g);
+        if (spec) stv<T>(w.x, base, n, z);   // the stp = 1 trial point (:2265)
         if (bounds) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
@@ -816,6 +882,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
             }
         }
     });
+    if (PASS == 1) return;
     // site subsm: dd_p in part slot 0, iword in ipart slot 0
     T ddp[1]; ddp[0] = acc[1];
     block_sum_store<T, 1>(ddp, 1, sm, w.part);
