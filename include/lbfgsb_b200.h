@@ -130,6 +130,15 @@ void lbfgsb_dev_profile(lbfgsb_dev_t* h, int32_t enable);
 int lbfgsb_dev_profile_read(lbfgsb_dev_t* h, int32_t cap, char* names /* cap*32 */, double* ms, double* bytes,
                             int64_t* calls);
 void lbfgsb_dev_profile_reset(lbfgsb_dev_t* h);
+/* Equal breakpoints at the exit of the generalized-Cauchy-point search (src/lbfgsb.f90:1416 inside a group of
+ * equal t): which members of the group end up fixed depends on the order in which they are popped, and the
+ * reference pops them in the order of its heap (hpsolb, :2079-2157).  The engine then replays that heap on the
+ * device (one thread; single-GPU workspaces) if the call has at most `max_breakpoints` breakpoints (default
+ * 2^21, environment LBFGSB_B200_TIE_LIMIT; 0 switches the replay off).  Beyond the limit, and on sharded
+ * workspaces, such a group is taken in variable order and the event is counted.
+ * tie_stats: replays done, exits inside a tie group that were not replayed (since START).            */
+void lbfgsb_dev_set_tie_limit(lbfgsb_dev_t* h, int64_t max_breakpoints);
+int lbfgsb_dev_tie_stats(lbfgsb_dev_t* h, int64_t* replays, int64_t* not_replayed);
 
 /* ---- sample problem of the reference drivers, evaluated on the device -----------------------
  * test/driver1.f90:274-289: f = 4[ 1/4 (x1-1)^2 + sum_{i>=2} (x_i - x_{i-1}^2)^2 ] and its gradient.
@@ -158,6 +167,8 @@ int lbfgsb_test_projgr_f64(int64_t n, const double* l, const double* u, const in
 int lbfgsb_test_sum_f64(int64_t n, const double* a, const double* b, double* out);      /* fixed-shape sum of a*b */
 int lbfgsb_test_sum_f32(int64_t n, const float* a, const float* b, float* out);
 int lbfgsb_test_sort_f64(int64_t n, const double* t_dev, int32_t* order_out_dev, double* sorted_out_dev);
+/* hpsolb (:2079-2157) replayed on the device: heap built over t(1..n), popped n times; order_out = iorder of the pops */
+int lbfgsb_test_heap_order_f64(int64_t n, const double* t_dev, int32_t* order_out_dev);
 int lbfgsb_test_dense_f64(int32_t op, int32_t m, int32_t col, double theta, double* a, double* b, double* c,
                           int32_t* info);   /* op 0 dpofa(a,lda=m,n=col) 1 dtrsl job01 2 dtrsl job11 3 bmv 4 formt */
 int lbfgsb_test_dcsrch_f64(double f, double g, double* stp, double stpmax, int32_t* task, int32_t* isave2,

@@ -87,6 +87,9 @@ def lib():
         L.lbfgsb_dev_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lbfgsb_dev_profile.argtypes = [C.c_void_p, C.c_int32]
         L.lbfgsb_dev_profile_reset.argtypes = [C.c_void_p]
+        L.lbfgsb_dev_set_tie_limit.argtypes = [C.c_void_p, C.c_int64]
+        L.lbfgsb_dev_set_tie_limit.restype = None
+        L.lbfgsb_dev_tie_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lbfgsb_dev_profile_read.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.lbfgsb_dev_nccl_init.restype = C.c_void_p
         L.lbfgsb_dev_nccl_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
@@ -262,6 +265,16 @@ class DeviceProblem:
     def counters(self):
         a, b = C.c_int64(0), C.c_int64(0)
         lib().lbfgsb_dev_counters(C.c_void_p(self.h), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def set_tie_limit(self, max_breakpoints):
+        """Heap replay of equal breakpoints at the exit of the Cauchy search (include/lbfgsb_b200.h); 0 = off."""
+        lib().lbfgsb_dev_set_tie_limit(C.c_void_p(self.h), C.c_int64(int(max_breakpoints)))
+
+    def tie_stats(self):
+        """(heap replays done, exits inside a tie group that were not replayed)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        lib().lbfgsb_dev_tie_stats(C.c_void_p(self.h), C.byref(a), C.byref(b))
         return a.value, b.value
 
     def profile(self, on=True):

@@ -79,6 +79,17 @@ __device__ __forceinline__ bool bp_of(T d, T x, T l, T u, int nb, T& t) {
     return false;
 }
 __device__ __forceinline__ bool el_of(int st) { return ((st & 1) != 0) != ((st & 2) != 0); }
+// The breakpoint a variable had when cauchy's per-variable pass ran, also if the walk has fixed the variable
+// since (d = 0, iwhere = 1/2, xcp = bound): such a variable is recognised by sitting off the bound it was
+// sent to (the per-variable pass itself marks only variables that are ON the bound), and its d was -g.
+template <typename T>
+__device__ __forceinline__ bool bp_orig(T d, T g, T x, T l, T u, int nb, int iw, T& t) {
+    if (d == (T)0) {
+        if (iw == 1 && nb != 0 && nb <= 2 && x > l) d = -g;
+        else if (iw == 2 && nb >= 2 && x < u) d = -g;
+    }
+    return bp_of<T>(d, x, l, u, nb, t);
+}
 
 // ---------------------------------------------------------------------------
 // Ordered compaction.  MODE 0: breakpoints -> (key = bits of t, val = variable);
@@ -91,6 +102,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_count(Wk<T> w, int* tile_
     if (!s->go || !s->in_body) return;
     if (MODE == 0 && !s->need_walk) return;
     if (MODE == 1 && !s->do_delta) return;
+    if (MODE == 2 && !s->need_walk) return;
     const i64 n = w.n;
     const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
     const i64 ntiles = (n + tile - 1) / tile;
@@ -101,7 +113,13 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_count(Wk<T> w, int* tile_
         for (int k = 0; k < LBFGSB_UNROLL; ++k) {
             const i64 base = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC) + (i64)threadIdx.x * VEC;
             if (base >= n) continue;
-            if (MODE == 0) {
+            if (MODE == 2) {   // every breakpoint of this cauchy call, passed ones included (heap replay)
+                T d[VEC], g[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC], iw[VEC];
+                ldv<T>(w.d, base, n, d); ldv<T>(w.g, base, n, g); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l);
+                ldv<T>(w.u, base, n, u); ldvi<T>(w.nbd, base, n, nb); ldvi<T>(w.iwhere, base, n, iw);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { T t; if (base + v < n && bp_orig<T>(d[v], g[v], x[v], l[v], u[v], nb[v], iw[v], t)) c++; }
+            } else if (MODE == 0) {
                 T d[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC];
                 ldv<T>(w.d, base, n, d); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
                 ldvi<T>(w.nbd, base, n, nb);
@@ -125,7 +143,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(Wk<T> w, int mode, const int
                                                    SortCtl* ctl) {
     const DevState<T>* s = w.s;
     if (!s->go || !s->in_body) return;
-    if (mode == 0 && !s->need_walk) return;
+    if ((mode == 0 || mode == 2) && !s->need_walk) return;
     if (mode == 1 && !s->do_delta) return;
     __shared__ i64 sm[33];
     i64 carry = 0;
@@ -148,6 +166,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_write(Wk<T> w, const i64*
     if (!s->go || !s->in_body) return;
     if (MODE == 0 && !s->need_walk) return;
     if (MODE == 1 && !s->do_delta) return;
+    if (MODE == 2 && !s->need_walk) return;
     const i64 n = w.n;
     const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
     const i64 ntiles = (n + tile - 1) / tile;
@@ -162,7 +181,14 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_write(Wk<T> w, const i64*
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { fl[v] = false; tv[v] = (T)0; }
             if (base < n) {
-                if (MODE == 0) {
+                if (MODE == 2) {
+                    T d[VEC], g[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC], iw[VEC];
+                    ldv<T>(w.d, base, n, d); ldv<T>(w.g, base, n, g); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l);
+                    ldv<T>(w.u, base, n, u); ldvi<T>(w.nbd, base, n, nb); ldvi<T>(w.iwhere, base, n, iw);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+                        if (base + v < n && bp_orig<T>(d[v], g[v], x[v], l[v], u[v], nb[v], iw[v], tv[v])) { fl[v] = true; c++; }
+                } else if (MODE == 0) {
                     T d[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC];
                     ldv<T>(w.d, base, n, d); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
                     ldvi<T>(w.nbd, base, n, nb);
@@ -181,7 +207,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_write(Wk<T> w, const i64*
 #pragma unroll
             for (int v = 0; v < VEC; ++v)
                 if (fl[v]) {
-                    if (MODE == 0) keys[pos] = KeyBits<T>::to(tv[v]);
+                    if (MODE != 1) keys[pos] = KeyBits<T>::to(tv[v]);
                     vals[pos] = (int)(base + v);
                     pos++;
                 }
@@ -767,6 +793,13 @@ __global__ void k_walk_round_begin(Wk<T> w, const RoundRec* all, int R, i64 n_gl
     i64 cnt = 0, rem = 0; unsigned long long kmin = 0xffffffffffffffffULL;
     for (int q = 0; q < R; ++q) { cnt += all[q].count; rem += all[q].rem; if (all[q].rem > 0 && all[q].kmin < kmin) kmin = all[q].kmin; }
     s->walk_rcount = cnt; s->walk_rem = rem; s->walk_J = -1; s->walk_done = 0; s->walk_fixn = 0;
+    s->tie_round = 0; s->tie_redo = 0;
+    {   // the carried state at the start of the round (restored if the round is redone up to a group of ties)
+        const int col2 = 2 * s->col;
+        for (int c = 0; c < col2; ++c) { s->snapA[c] = s->walkA[c]; s->snapB[c] = s->walkB[c]; }
+        s->snap_f1 = s->walk_f1; s->snap_f2 = s->walk_f2; s->snap_tlast = s->walk_tlast; s->snap_tprev2 = s->walk_tprev2;
+        s->snap_base = s->walk_base;
+    }
     if (rem == 0) { walk_close_all_passed<T>(s, n_global); return; }
     if (s->walk_base > 0) {
         const T tnext = KeyBits<T>::from((typename Real<T>::key_t)kmin);
@@ -778,7 +811,7 @@ __global__ void k_walk_round_begin(Wk<T> w, const RoundRec* all, int R, i64 n_gl
 
 // End of a round on a single GPU, after its chunks.  One block of LB_WB threads.
 template <typename T>
-__global__ void __launch_bounds__(LB_WB) k_walk_round_end(Wk<T> w, WalkBuf<T> b, i64 n_global) {
+__global__ void __launch_bounds__(LB_WB) k_walk_round_end(Wk<T> w, WalkBuf<T> b, i64 n_global, int single_gpu) {
     DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->need_walk || s->walk_closed) return;
     __shared__ T AJ[2 * LB_MMAX], BJ[2 * LB_MMAX];
@@ -804,6 +837,17 @@ __global__ void __launch_bounds__(LB_WB) k_walk_round_end(Wk<T> w, WalkBuf<T> b,
         }
         __syncthreads();
         if (threadIdx.x != 0) return;
+        if (J > 0 && keys[J - 1] == keys[J] && !s->tie_round) {
+            // The exit lies inside a group of equal breakpoints: which members of the group were passed depends
+            // on the order in which they are taken.  The reference takes them in hpsolb's heap order; redo the
+            // round up to the group and then the group in that order (host: tie_replay), if the heap is small
+            // enough to be replayed.  Otherwise the variable order stands and the event is counted.
+            if (single_gpu && s->tie_limit > 0 && s->nbreak <= s->tie_limit) {
+                s->tie_redo = 1; s->tie_key = (unsigned long long)keys[J]; s->walk_J = -1; s->walk_fixn = 0;
+                return;
+            }
+            s->tie_events += 1;
+        }
         const T tprev = (J > 0) ? KeyBits<T>::from(keys[J - 1]) : s->walk_tlast;
         walk_close_at<T>(s, b.f1a[jl], b.f2a[jl], tprev, AJ, BJ, 1 + s->walk_base + J);
         s->walk_fixn = J;
@@ -832,6 +876,105 @@ __global__ void __launch_bounds__(256) k_walk_fix(Wk<T> w, WalkBuf<T> b) {
         else { w.z[var] = w.l[var]; w.iwhere[var] = 1; }
         w.d[var] = (T)0;
     }
+}
+
+// ---------------------------------------------------------------------------
+// Heap replay.  When the search ends inside a group of equal breakpoints, the members of the group that
+// were passed (fixed at their bounds, iwhere = 1/2) are the first ones in the order in which the reference
+// pops them from its heap (hpsolb :2079-2157) -- an order that depends on the whole history of the heap.
+// The replay rebuilds that history: the breakpoint array in variable order as cauchy's per-variable pass
+// leaves it (:1305-1322), the first minimum replaced by the last entry (:1391-1397), the heap built by
+// successive insertion and popped until the group is exhausted.  One thread does the heap operations (they
+// are a chain of dependent compares), which is why the replay is limited to tie_limit breakpoints.
+// The popped members of the group, in order, become the sorted list of the next round.
+// ---------------------------------------------------------------------------
+template <typename K>
+__device__ inline void heap_build(K* t, int* io, i64 n) {   // t, io: 1-based views; hpsolb :2096-2119
+    for (i64 k = 2; k <= n; ++k) {
+        const K ddum = t[k];
+        const int indxin = io[k];
+        i64 i = k;
+        while (i > 1) {
+            const i64 j = i / 2;
+            const K tj = t[j];
+            if (ddum < tj) { t[i] = tj; io[i] = io[j]; i = j; } else break;
+        }
+        t[i] = ddum; io[i] = indxin;
+    }
+}
+// least member out, the rest re-heaped as t(1..n-1); the reference leaves the least member in t(n)  (:2125-2155)
+template <typename K>
+__device__ inline void heap_pop(K* t, int* io, i64 n, K& out, int& indxou) {
+    out = t[1]; indxou = io[1];
+    if (n > 1) {
+        i64 i = 1;
+        const K ddum = t[n];
+        const int indxin = io[n];
+        for (;;) {
+            i64 j = i + i;
+            if (j <= n - 1) {
+                K tj = t[j];
+                const K tj1 = t[j + 1];   // j + 1 <= n: the last slot still holds ddum, as in the reference
+                if (tj1 < tj) { j = j + 1; tj = tj1; }
+                if (tj < ddum) { t[i] = tj; io[i] = io[j]; i = j; continue; }
+            }
+            break;
+        }
+        t[i] = ddum; io[i] = indxin;
+        t[n] = out; io[n] = indxou;
+    }
+}
+
+// carried state back to the start of the round
+template <typename T>
+__global__ void k_tie_restore(Wk<T> w) {
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || !s->tie_redo) return;
+    const int col2 = 2 * s->col;
+    for (int c = 0; c < col2; ++c) { s->walkA[c] = s->snapA[c]; s->walkB[c] = s->snapB[c]; }
+    s->walk_f1 = s->snap_f1; s->walk_f2 = s->snap_f2; s->walk_tlast = s->snap_tlast; s->walk_tprev2 = s->snap_tprev2;
+    s->walk_base = s->snap_base;
+    s->walk_J = -1; s->walk_done = 0; s->walk_fixn = 0; s->walk_closed = 0;
+    s->tie_redo = 0;
+}
+
+// b.k0 / b.v0: every breakpoint of this cauchy call in variable order (k_flag_write<T, 2>), b.ctl->count of them.
+// Out: the group with key == tie_key in heap order in b.k1 / b.v1, b.ctl->count = its size, b.ctl->cur = 1, and the
+// fields a round needs (what k_walk_round_begin sets).
+template <typename T>
+__global__ void __launch_bounds__(1024) k_heap_replay(Wk<T> w, WalkBuf<T> b) {
+    typedef typename Real<T>::key_t K;
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_closed) return;
+    __shared__ i64 spos;
+    const i64 nb = b.ctl->count;
+    const int vmin = (int)(s->ibkmin - w.off);
+    if (threadIdx.x == 0) spos = -1;
+    __syncthreads();
+    for (i64 i = threadIdx.x; i < nb; i += blockDim.x) if (b.v0[i] == vmin) spos = i;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    K* t = b.k0 - 1; int* io = b.v0 - 1;      // 1-based
+    const K tk = (K)s->tie_key;
+    const K kfirst = KeyBits<T>::to(s->bkmin);
+    i64 cnt = 0;
+    if (kfirst == tk) { b.k1[cnt] = tk; b.v1[cnt] = vmin; cnt++; }   // the first breakpoint is taken before the heap exists (:1384-1389)
+    const i64 ib = spos + 1;
+    if (ib >= 1 && ib != nb) { t[ib] = t[nb]; io[ib] = io[nb]; }   // :1394-1397
+    i64 nleft = nb - 1;
+    heap_build<K>(t, io, nleft);
+    while (nleft > 0) {
+        K out; int var;
+        heap_pop<K>(t, io, nleft, out, var);
+        nleft--;
+        if (out > tk) break;
+        if (out == tk) { b.k1[cnt] = out; b.v1[cnt] = var; cnt++; }
+    }
+    b.ctl->count = cnt; b.ctl->cur = 1; b.ctl->skip = 0;
+    s->walk_lcount = cnt; s->walk_rcount = cnt; s->walk_rem = s->nbreak - s->walk_base;
+    s->walk_J = -1; s->walk_done = 0; s->walk_fixn = 0;
+    s->tie_round = 1;
 }
 
 // ---------------------------------------------------------------------------

@@ -107,6 +107,13 @@ struct DevState {
     i64 walk_cstart;              // start of the chunk that holds walk_J
     i64 walk_fixn;                // how many entries of this rank's current sorted list are fixed at the end of the round
     int walk_closed, pad1;        // the search is finished (exit found or every breakpoint passed)
+    // equal breakpoints at the exit (cauchy_walk.cuh "heap replay"): the reference pops them in hpsolb's order
+    int tie_redo;                 // the round found its exit inside a group of equal breakpoints: redo it in heap order
+    int tie_round;                // the current round is such a group, listed in heap order
+    i64 tie_limit;                // replay the heap only for nbreak <= tie_limit (0: never; ties then stay in variable order)
+    i64 tie_events;               // how many exits fell inside a group of equal breakpoints but were not replayed
+    unsigned long long tie_key;   // bit pattern of that breakpoint value
+    i64 snap_base;                // walk_base at the start of the current round
     // message log of this setulb call (printed by the host in order)
     int ev_n, ev_code[LB_EVMAX];
     T ev_a[LB_EVMAX], ev_b[LB_EVMAX];
@@ -123,6 +130,8 @@ struct DevState {
     T p[2 * LB_MMAX], c[2 * LB_MMAX], v[2 * LB_MMAX], wv[2 * LB_MMAX], a[2 * LB_MMAX];
     T p0[2 * LB_MMAX];            // p at the start of the walk
     T walkA[2 * LB_MMAX], walkB[2 * LB_MMAX];  // carries of the 2col-vector prefix sums
+    T snapA[2 * LB_MMAX], snapB[2 * LB_MMAX];  // the carries as they were at the start of the current round
+    T snap_f1, snap_f2, snap_tlast, snap_tprev2;
 };
 
 template <typename T> __device__ inline void ev_push(DevState<T>* s, int code, T a = (T)0, T b = (T)0) {

@@ -137,7 +137,7 @@ struct Engine : EngineBase {
     struct DynBuf { void* p = nullptr; size_t cap = 0; };
     DynBuf dw_send, dw_recv, dw_k0, dw_k1, dw_v0, dw_v1;
     // accounting
-    i64 launches = 0, syncs = 0;
+    i64 launches = 0, syncs = 0, tie_replays = 0;
     bool profile = false;
     bool debug_launch = (getenv("LBFGSB_B200_DEBUG_LAUNCH") != nullptr);
     struct Ev { int fam; cudaEvent_t a, b; };
@@ -179,6 +179,11 @@ struct Engine : EngineBase {
         if (!dalloc(&w.part2, sizeof(T) * LB_KMAX * LBFGSB_GRID) || !dalloc(&w.ipart2, sizeof(i64) * LB_IMAX * LBFGSB_GRID)) return false;
         if (!dalloc(&s_dev, sizeof(DevState<T>))) return false;
         CK(cudaMemsetAsync(s_dev, 0, sizeof(DevState<T>), stream));
+        {
+            i64 lim = (i64)1 << 21;   // heap replay of tied breakpoints at the exit: up to 2M breakpoints by default
+            if (const char* e = getenv("LBFGSB_B200_TIE_LIMIT")) lim = atoll(e);
+            CK(cudaMemcpyAsync(&s_dev->tie_limit, &lim, sizeof lim, cudaMemcpyHostToDevice, stream));
+        }
         CK(cudaMemsetAsync(w.ws, 0, vb * m, stream));
         CK(cudaMemsetAsync(w.wy, 0, vb * m, stream));
         w.s = s_dev;
@@ -321,6 +326,57 @@ struct Engine : EngineBase {
         memcpy(&k, &t, sizeof k);
         return (unsigned long long)k;
     }
+    // One round over the breakpoints with keys in rg.  Returns 0: go on with the next range, 1: the search is
+    // closed, 2: the exit fell inside a group of equal breakpoints and the round must be redone in heap order,
+    // -1: error.
+    int run_round(const BpRange& rg) {
+        begin(F_WALK_COMPACT);
+        k_bp_count<T><<<LG>>>(w, rg, tile_counts);
+        k_walk_round_local<T><<<1, 1024, 0, stream>>>(w, tile_counts, tile_offsets, ntiles, wb.ctl, rr_local);
+        end(F_WALK_COMPACT, 2);
+        if (R > 1 && !allgather(rr_local, rr_all, sizeof(RoundRec))) return -1;
+        k_walk_round_begin<T><<<1, 32, 0, stream>>>(w, R > 1 ? rr_all : rr_local, R, n_global); launches++;
+        if (!sync_state()) return -1;
+        if (s_host->walk_closed) return 1;
+        if (s_host->walk_rcount > 0) {
+            begin(F_WALK_COMPACT); k_bp_write<T><<<LG>>>(w, rg, tile_offsets, wb.k0, wb.v0); end(F_WALK_COMPACT);
+            begin(F_WALK_SORT); enqueue_sort(wb.k0, wb.k1, wb.v0, wb.v1, wb.ctl, s_host->walk_lcount); end(F_WALK_SORT, 0);
+            if (R > 1) { if (!round_scan_sharded()) return -1; }
+            else if (!round_scan_single(s_host->walk_lcount)) return -1;
+            if (!sync_state()) return -1;
+            if (s_host->walk_closed) return 1;
+            if (s_host->tie_redo) return 2;
+        }
+        return 0;
+    }
+    // The exit fell inside the group of breakpoints equal to tie_key (single GPU): the round is redone up to
+    // that group, then the group runs as a round of its own in the reference's heap order (cauchy_walk.cuh
+    // "heap replay").  Returns like run_round.
+    int tie_replay(const BpRange& rg) {
+        const unsigned long long tk = s_host->tie_key;
+        k_tie_restore<T><<<1, 32, 0, stream>>>(w); launches++;
+        if (tk > 0) {
+            BpRange ra = rg; ra.hi = tk - 1;
+            if (!(ra.lo_valid && ra.hi <= ra.lo)) {
+                const int st = run_round(ra);
+                if (st < 0) return -1;
+                if (st != 0) { set_error("heap replay: the round below the tie group did not pass (internal error)"); return -1; }
+            }
+        }
+        begin(F_WALK_COMPACT);
+        k_flag_count<T, 2><<<LG>>>(w, tile_counts);
+        k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 2, tile_counts, tile_offsets, ntiles, wb.ctl);
+        k_flag_write<T, 2><<<LG>>>(w, tile_offsets, wb.k0, wb.v0);
+        end(F_WALK_COMPACT, 3);
+        begin(F_WALK_SORT); k_heap_replay<T><<<1, 1024, 0, stream>>>(w, wb); end(F_WALK_SORT);
+        if (!sync_state()) return -1;
+        tie_replays++;
+        if (s_host->walk_lcount <= 0) { set_error("heap replay: empty tie group (internal error)"); return -1; }
+        if (!round_scan_single(s_host->walk_lcount)) return -1;
+        if (!sync_state()) return -1;
+        return s_host->walk_closed ? 1 : 0;
+    }
+    // ---- the breakpoint walk, in rounds over increasing ranges of t (cauchy_walk.cuh) -------
     bool enqueue_walk_rounds() {
         const T dtm0 = s_host->dtm;          // minimiser of the first segment (s_cauchy); dtm0 >= bkmin here
         unsigned long long his[3];
@@ -332,25 +388,21 @@ struct Engine : EngineBase {
         }
         his[nr++] = 0xffffffffffffffffULL;
         BpRange rg; rg.lo = 0; rg.lo_valid = 0; rg.hi = 0;
-        for (int r = 0; r < nr; ++r) {
+        for (int r = 0; r < nr;) {
             rg.hi = his[r];
-            begin(F_WALK_COMPACT);
-            k_bp_count<T><<<LG>>>(w, rg, tile_counts);
-            k_walk_round_local<T><<<1, 1024, 0, stream>>>(w, tile_counts, tile_offsets, ntiles, wb.ctl, rr_local);
-            end(F_WALK_COMPACT, 2);
-            if (R > 1 && !allgather(rr_local, rr_all, sizeof(RoundRec))) return false;
-            k_walk_round_begin<T><<<1, 32, 0, stream>>>(w, R > 1 ? rr_all : rr_local, R, n_global); launches++;
-            if (!sync_state()) return false;
-            if (s_host->walk_closed) break;
-            if (s_host->walk_rcount > 0) {
-                begin(F_WALK_COMPACT); k_bp_write<T><<<LG>>>(w, rg, tile_offsets, wb.k0, wb.v0); end(F_WALK_COMPACT);
-                begin(F_WALK_SORT); enqueue_sort(wb.k0, wb.k1, wb.v0, wb.v1, wb.ctl, s_host->walk_lcount); end(F_WALK_SORT, 0);
-                if (R > 1) { if (!round_scan_sharded()) return false; }
-                else if (!round_scan_single(s_host->walk_lcount)) return false;
-                if (!sync_state()) return false;
-                if (s_host->walk_closed) break;
+            if (rg.lo_valid && rg.hi <= rg.lo) { ++r; continue; }
+            int st = run_round(rg);
+            if (st < 0) return false;
+            if (st == 1) break;
+            if (st == 2) {
+                const unsigned long long tk = s_host->tie_key;
+                st = tie_replay(rg);
+                if (st < 0) return false;
+                if (st == 1) break;
+                rg.lo = tk; rg.lo_valid = 1;   // the whole group was passed: the rest of this range follows
+                continue;
             }
-            rg.lo = rg.hi; rg.lo_valid = 1;
+            rg.lo = rg.hi; rg.lo_valid = 1; ++r;
         }
         if (!s_host->walk_closed) { set_error("the breakpoint walk did not close (internal error)"); return false; }
         return true;
@@ -372,7 +424,7 @@ struct Engine : EngineBase {
             k_walk_chunk_end<T><<<1, 32, 0, stream>>>(w, wb, start, len, tmpAB, tmpF, jmin);
             launches += 8;
         }
-        k_walk_round_end<T><<<1, LB_WB, 0, stream>>>(w, wb, n_global);
+        k_walk_round_end<T><<<1, LB_WB, 0, stream>>>(w, wb, n_global, R == 1 ? 1 : 0);
         end(F_WALK_SCAN, 1);
         begin(F_WALK_FIX);
         k_walk_fix<T><<<LBFGSB_GRID, 256, 0, stream>>>(w, wb);
@@ -1157,6 +1209,15 @@ template <typename K>
 __global__ void k_test_iota(int* v, i64 n) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) v[i] = (int)i;
 }
+__global__ void k_test_heap_order(unsigned long long* k, int* v, i64 n, int* order_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    heap_build<unsigned long long>(k - 1, v - 1, n);
+    for (i64 nleft = n; nleft > 0; --nleft) {
+        unsigned long long out; int var;
+        heap_pop<unsigned long long>(k - 1, v - 1, nleft, out, var);
+        order_out[n - nleft] = var;
+    }
+}
 __global__ void k_test_setctl(SortCtl* c, i64 n) { if (threadIdx.x == 0) { c->count = n; c->cur = 0; c->skip = 0; } }
 
 // ---------------------------------------------------------------------------
@@ -1315,6 +1376,23 @@ void lbfgsb_dev_profile(lbfgsb_dev_t* h, int32_t enable) {
     if (!b) return;
     if (b->real_kind == 8) ((Engine<double>*)b)->profile = enable != 0; else ((Engine<float>*)b)->profile = enable != 0;
 }
+void lbfgsb_dev_set_tie_limit(lbfgsb_dev_t* h, int64_t max_breakpoints) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b) return;
+    i64 lim = max_breakpoints < 0 ? 0 : max_breakpoints;
+    if (b->real_kind == 8) { Engine<double>* e = (Engine<double>*)b; cudaStreamSynchronize(e->stream); cudaMemcpy(&e->s_dev->tie_limit, &lim, sizeof lim, cudaMemcpyHostToDevice); }
+    else { Engine<float>* e = (Engine<float>*)b; cudaStreamSynchronize(e->stream); cudaMemcpy(&e->s_dev->tie_limit, &lim, sizeof lim, cudaMemcpyHostToDevice); }
+}
+int lbfgsb_dev_tie_stats(lbfgsb_dev_t* h, int64_t* replays, int64_t* not_replayed) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b) return 1;
+    i64 ev = 0;
+    cudaError_t e;
+    if (b->real_kind == 8) { Engine<double>* g = (Engine<double>*)b; cudaStreamSynchronize(g->stream); e = cudaMemcpy(&ev, &g->s_dev->tie_events, sizeof ev, cudaMemcpyDeviceToHost); *replays = g->tie_replays; }
+    else { Engine<float>* g = (Engine<float>*)b; cudaStreamSynchronize(g->stream); e = cudaMemcpy(&ev, &g->s_dev->tie_events, sizeof ev, cudaMemcpyDeviceToHost); *replays = g->tie_replays; }
+    *not_replayed = ev;
+    return e != cudaSuccess;
+}
 void lbfgsb_dev_profile_reset(lbfgsb_dev_t* h) {
     EngineBase* b = (EngineBase*)h;
     if (!b) return;
@@ -1393,6 +1471,17 @@ int lbfgsb_test_sort_f64(int64_t n, const double* t, int32_t* order_out, double*
     cudaMemcpy(order_out, hc.cur ? v1 : v0, 4 * n, cudaMemcpyDeviceToDevice);
     cudaError_t e = cudaMemcpy(sorted_out, hc.cur ? k1 : k0, 8 * n, cudaMemcpyDeviceToDevice);
     cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(cnt); cudaFree(ctl);
+    return e != cudaSuccess || cudaGetLastError() != cudaSuccess;
+}
+int lbfgsb_test_heap_order_f64(int64_t n, const double* t, int32_t* order_out) {
+    unsigned long long* k; int* v;
+    if (n <= 0) return 1;
+    if (cudaMalloc(&k, 8 * n) || cudaMalloc(&v, 4 * n)) return 1;
+    cudaMemcpy(k, t, 8 * n, cudaMemcpyDeviceToDevice);   // t >= 0: bit pattern order == value order
+    k_test_iota<unsigned long long><<<256, 256>>>(v, n);
+    k_test_heap_order<<<1, 32>>>(k, v, n, order_out);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(k); cudaFree(v);
     return e != cudaSuccess || cudaGetLastError() != cudaSuccess;
 }
 int lbfgsb_test_dense_f64(int32_t op, int32_t m, int32_t col, double theta, double* a, double* b, double* c, int32_t* info) {

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
         for (int j = 0; j < col2; ++j) { s->p0[j] = s->p[j]; s->walkA[j] = zero; s->walkB[j] = zero; }
         s->walk_f1 = s->f1; s->walk_f2 = s->f2; s->walk_tlast = zero; s->walk_tprev2 = zero;
         s->walk_J = -1; s->walk_done = 0; s->walk_base = 0; s->walk_rcount = 0; s->walk_lcount = 0; s->walk_rem = 0;
-        s->walk_cstart = 0; s->walk_fixn = 0; s->walk_closed = 0;
+        s->walk_cstart = 0; s->walk_fixn = 0; s->walk_closed = 0; s->tie_redo = 0; s->tie_round = 0;
         return;
     }
     if (s->dtm <= zero) s->dtm = zero;   // :1509
@@ -692,6 +692,7 @@ __global__ void s_start(Wk<T> w, T factr, T pgtol, int host_err_task) {
     s->prjctd = s->cnstnd = s->boxed = 0; s->wrk = 0; s->bnded = 0;
     s->errk = 0; s->nbdd = 0; s->n = w.n; s->m = w.m;
     s->nbreak = 0; s->nfreec = 0; s->ibkmin = 0; s->ibd = -1; s->walk_J = -1; s->walk_done = 0; s->n_el = 0;
+    s->tie_redo = 0; s->tie_round = 0; s->tie_events = 0;
     for (int q = 0; q < 13; ++q) s->ls[q] = zero;
     s->f = zero; s->rr = zero; s->dr = zero; s->ddum = zero; s->tsum = zero; s->dtm = zero;
     if (host_err_task != 0) { s->task = host_err_task; }   // n<=0 / m<=0 / factr<0 (:1618-1620); array errors overwrite

@@ -48,6 +48,12 @@ typedef int64_t i64;
 // Summation mode.  0 = reference order (default), 1 = device order.
 // ---------------------------------------------------------------------------
 static int g_sum_mode = 0;
+// 0: hpsolb's heap decides the order of equal breakpoints (the reference); 1: equal breakpoints are taken in
+// variable order (what a stable sort gives -- the CUDA engine's order when its heap replay is switched off)
+static int g_tie_mode = 0;
+// path counters for the tests (how often the rare branches ran): 0 subsm backtrack (:2830), 1 ascent direction (:2247),
+// 2 memory resets ("refresh the lbfgs memory"), 3 skipped updates (:826)
+static long long g_events[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 // Replays the CUDA reduction shape of include/lbfgsb_b200_shape.h on the CPU:
 // LBFGSB_GRID blocks of LBFGSB_BLOCK threads walk tiles b, b+G, b+2G, ...; in a
@@ -514,7 +520,18 @@ struct LB {
                             iorder[ibkmin] = iorder[nbreak];
                         }
                     }
-                    hpsolb(nleft, t0, iorder0, iter - 2);
+                    if (g_tie_mode == 1) {
+                        if (iter == 2) {   // descending (t, variable): reading from the end pops ascending
+                            std::vector<std::pair<T, int>> bp((size_t)nleft);
+                            for (i64 q = 1; q <= nleft; ++q) bp[(size_t)q - 1] = {t[q], iorder[q]};
+                            std::sort(bp.begin(), bp.end(), [](const std::pair<T, int>& a, const std::pair<T, int>& b) {
+                                return a.first > b.first || (a.first == b.first && a.second > b.second);
+                            });
+                            for (i64 q = 1; q <= nleft; ++q) { t[q] = bp[(size_t)q - 1].first; iorder[q] = bp[(size_t)q - 1].second; }
+                        }
+                    } else {
+                        hpsolb(nleft, t0, iorder0, iter - 2);
+                    }
                     tj = t[nleft];
                     ibp = iorder[nleft];
                 }
@@ -1160,6 +1177,7 @@ struct LB {
             if (gd >= zero) {
                 // the reference prints ' ascent direction in projection gd = ' here
                 // unconditionally (:2250); the oracle stays silent.
+                g_events[1]++;
                 info = -4;
                 return;
             }
@@ -1341,6 +1359,7 @@ struct LB {
             for (i = 1; i <= n; ++i) dd_p = dd_p + (x[i] - xx[i]) * gg[i];
         }
         if (dd_p <= zero) return;
+        g_events[0]++;
 
         dcopy(n, xp0, x0);
         alpha = one;
@@ -1800,6 +1819,10 @@ static uint64_t splitmix64(uint64_t v) {
 extern "C" {
 
 void oracle_set_sum_mode(int mode) { g_sum_mode = mode; }
+void oracle_set_tie_mode(int mode) { g_tie_mode = mode; }
+void oracle_event_counts(long long* out, int reset) {
+    for (int i = 0; i < 8; ++i) { out[i] = g_events[i]; if (reset) g_events[i] = 0; }
+}
 int oracle_get_sum_mode() { return g_sum_mode; }
 
 void oracle_setulb_f64(const int64_t* n, const int32_t* m, double* x, const double* l,

@@ -86,3 +86,15 @@ def rosenbrock_fg(x, g):
 
 def set_sum_mode(mode):
     lib().oracle_set_sum_mode(int(mode))
+
+
+def event_counts(reset=True):
+    """[subsm backtracks (:2830), ascent directions (:2247), ...] seen by the oracle since the last reset."""
+    out = (C.c_longlong * 8)()
+    lib().oracle_event_counts(out, C.c_int(1 if reset else 0))
+    return list(out)
+
+
+def set_tie_mode(mode):
+    """0: equal breakpoints in hpsolb's heap order (the reference); 1: in variable order (stable sort)."""
+    lib().oracle_set_tie_mode(int(mode))

@@ -95,6 +95,30 @@ def test_breakpoint_sort_is_stable(L, n, ties):
     assert np.array_equal(srt.cpu().numpy(), t[ref])
 
 
+@pytest.mark.parametrize("n,distinct", [(1, 1), (2, 1), (7, 2), (100, 1), (1000, 3), (4097, 17), (50000, 5), (50000, 50000)])
+def test_heap_replay_pops_in_hpsolb_order(L, n, distinct):
+    """hpsolb (src/lbfgsb.f90:2079-2157) replayed on the device pops equal keys in the reference's order
+    (bit-exact against the oracle's verbatim heap)."""
+    import torch
+    rng = np.random.default_rng(n + distinct)
+    vals = rng.uniform(0.1, 5.0, distinct)
+    t = vals[rng.integers(0, distinct, n)].astype(np.float64)
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    assert L.lbfgsb_test_heap_order_f64(C.c_int64(n), _vp(_dev(t)), _vp(order)) == 0
+    # the oracle: build on the first call (iheap = 0), then pop; the least member is left in t(nleft)
+    tt = t.copy()
+    io = np.arange(n, dtype=np.int32)
+    ref = np.empty(n, dtype=np.int32)
+    for k in range(n):
+        nleft = n - k
+        O.lib().oracle_hpsolb_f64(C.c_int64(nleft), tt.ctypes.data_as(C.c_void_p), io.ctypes.data_as(C.c_void_p),
+                                  C.c_int64(0 if k == 0 else 1))
+        ref[k] = io[nleft - 1]
+    got = order.cpu().numpy()
+    assert np.array_equal(got, ref)
+    assert np.all(np.diff(t[got]) >= 0)
+
+
 def _spd(rng, m, col):
     a = rng.standard_normal((col, col))
     s = a @ a.T + col * np.eye(col)
