@@ -148,6 +148,12 @@ int lbfgsb_problem_rosenbrock_f64(int64_t n, const double* x_dev, double* g_dev,
 int lbfgsb_problem_rosenbrock_f32(int64_t n, const float* x_dev, float* g_dev, float* f_out, void* cuda_stream,
                                   int32_t first, int32_t last, float xl, float xr, void* scratch_dev);
 int64_t lbfgsb_problem_scratch_bytes(void);
+/* shard variants without a host round trip: xl, xr are read from halo_dev[0..1], the shard's part of f is left
+ * in f_part_dev[0] (device), nothing is synchronised -- the caller all-reduces f_part_dev on the same stream */
+int lbfgsb_problem_rosenbrock_halo_f64(int64_t n, const double* x_dev, double* g_dev, double* f_part_dev, void* cuda_stream,
+                                       int32_t first, int32_t last, const double* halo_dev, void* scratch_dev);
+int lbfgsb_problem_quadratic_halo_f64(int64_t n, const double* x_dev, double* g_dev, double* f_part_dev, void* cuda_stream,
+                                      int64_t index_offset, uint64_t seed, const double* halo_dev, void* scratch_dev);
 
 /* ---- bound-constrained convex quadratic (BASELINE.json configs[3]; SURVEY.md section 8(d) "Config 4") ----
  * f = 1/2 x'Ax - b'x,  A = tridiag(-1, 2 + delta_i, -1),

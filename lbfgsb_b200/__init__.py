@@ -340,6 +340,14 @@ class RosenbrockDevice:
             raise LbfgsbB200Error("rosenbrock kernel failed: " + last_error())
         return self._f[0]
 
+    def shard_async(self, x, g, first, last, halo_dev, f_part_dev):
+        """Shard evaluation without a host round trip (float64): xl, xr from halo_dev[0..1], partial f -> f_part_dev."""
+        rc = lib().lbfgsb_problem_rosenbrock_halo_f64(
+            C.c_int64(x.numel()), C.c_void_p(x.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(f_part_dev.data_ptr()),
+            self.stream, C.c_int32(first), C.c_int32(last), C.c_void_p(halo_dev.data_ptr()), C.c_void_p(self.scratch.data_ptr()))
+        if rc != 0:
+            raise LbfgsbB200Error("rosenbrock kernel failed")
+
 
 class QuadraticDevice:
     """f/g of the bound-constrained convex quadratic of BASELINE.json configs[3] on the device
@@ -362,3 +370,11 @@ class QuadraticDevice:
         if rc != 0:
             raise LbfgsbB200Error("quadratic kernel failed: " + last_error())
         return self._f[0]
+
+    def shard_async(self, x, g, offset, halo_dev, f_part_dev):
+        rc = lib().lbfgsb_problem_quadratic_halo_f64(
+            C.c_int64(x.numel()), C.c_void_p(x.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(f_part_dev.data_ptr()),
+            self.stream, C.c_int64(offset), C.c_uint64(self.seed), C.c_void_p(halo_dev.data_ptr()),
+            C.c_void_p(self.scratch.data_ptr()))
+        if rc != 0:
+            raise LbfgsbB200Error("quadratic kernel failed")

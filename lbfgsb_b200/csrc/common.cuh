@@ -87,7 +87,9 @@ struct DevState {
     int do_unstep;     // ... but the line search failed at its first entry: k_ls_step puts x = t back
     int lazy_gcp;      // cauchy's d and xcp are not materialised: xcp = x + tsum*d, d = -g or 0 by iwhere
     int fuse_gf;       // the cauchy tail (:1515) and freev (:1980-2059) run inside k_formk_cmprlb
-    int pad_ctl;
+    int lazy_z;        // ... and xcp was not stored: xcp = x + tsum*d with d = -g where state bit 2 is set, else 0
+    int z_in_x;        // line search: the Newton point z exists only as the current x (speculative step); persists over calls
+    int save_z;        // this call's k_ls_step moves x away from it: copy it into z first (a later trial may ask for stp = 1 again)
     int task, csave, info;
     // ---- mainlb locals (:416-424) ----
     int col, head, itail, iupdat, iter, nfgv, nskip, ifun, iback, iword;

@@ -1047,9 +1047,10 @@ static void setulb_host_impl(const int32_t* n, const int32_t* m, T* x, const T* 
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(LBFGSB_BLOCK) k_rosenbrock(i64 n, const T* __restrict__ x, T* __restrict__ g,
-                                                            T* part, int first, int last, T xl, T xr) {
+                                                            T* part, int first, int last, T xl, T xr, const T* halo) {
     constexpr int VEC = Real<T>::VEC;
     __shared__ T sm[LBFGSB_BLOCK / 32];
+    if (halo) { xl = halo[0]; xr = halo[1]; }   // the neighbours' boundary values, still on the device
     T acc[1]; acc[0] = (T)0;
     LB_FOR_TILES(T, n, base) {
         T xv[VEC], gv[VEC];
@@ -1089,7 +1090,7 @@ static int rosenbrock_impl(i64 n, const T* x, T* g, T* f_out, void* st, int firs
     cudaStream_t s = (cudaStream_t)st;
     T* part = (T*)scratch;
     T* out = part + LBFGSB_GRID;
-    k_rosenbrock<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, first, last, xl, xr);
+    k_rosenbrock<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, first, last, xl, xr, nullptr);
     k_rosenbrock_final<T><<<1, 32, 0, s>>>(part, out);
     if (cudaMemcpyAsync(f_out, out, sizeof(T), cudaMemcpyDeviceToHost, s) != cudaSuccess) return 1;
     if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("rosenbrock kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
@@ -1115,9 +1116,10 @@ __device__ __forceinline__ void quad_coeff(unsigned long long gi, unsigned long 
 }
 template <typename T>
 __global__ void __launch_bounds__(LBFGSB_BLOCK) k_quadratic(i64 n, const T* __restrict__ x, T* __restrict__ g, T* part,
-                                                           i64 off, unsigned long long seedp, T xl, T xr) {
+                                                           i64 off, unsigned long long seedp, T xl, T xr, const T* halo) {
     constexpr int VEC = Real<T>::VEC;
     __shared__ T sm[LBFGSB_BLOCK / 32];
+    if (halo) { xl = halo[0]; xr = halo[1]; }
     T acc[1]; acc[0] = (T)0;
     LB_FOR_TILES(T, n, base) {
         T xv[VEC], gv[VEC];
@@ -1154,11 +1156,32 @@ static int quadratic_impl(i64 n, const T* x, T* g, T* f_out, void* st, i64 off, 
     T* part = (T*)scratch;
     T* out = part + LBFGSB_GRID;
     const unsigned long long seedp = seed * 0x9E3779B97F4A7C15ULL;
-    k_quadratic<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, off, seedp, xl, xr);
+    k_quadratic<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, off, seedp, xl, xr, nullptr);
     k_sum_final<T><<<1, 32, 0, s>>>(part, out);
     if (cudaMemcpyAsync(f_out, out, sizeof(T), cudaMemcpyDeviceToHost, s) != cudaSuccess) return 1;
     if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("quadratic kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
     return 0;
+}
+
+// Shard variants without a host round trip: the neighbours' boundary values are read from halo_dev[0..1] and the
+// shard's part of f is left in f_part_dev[0]; nothing is synchronised (the caller all-reduces f_part_dev on the
+// same stream and reads it once).
+template <typename T>
+static int rosenbrock_halo_impl(i64 n, const T* x, T* g, T* f_part_dev, void* st, int first, int last, const T* halo_dev, void* scratch) {
+    cudaStream_t s = (cudaStream_t)st;
+    T* part = (T*)scratch;
+    k_rosenbrock<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, first, last, (T)0, (T)0, halo_dev);
+    k_rosenbrock_final<T><<<1, 32, 0, s>>>(part, f_part_dev);
+    return cudaGetLastError() != cudaSuccess;
+}
+template <typename T>
+static int quadratic_halo_impl(i64 n, const T* x, T* g, T* f_part_dev, void* st, i64 off, unsigned long long seed, const T* halo_dev, void* scratch) {
+    cudaStream_t s = (cudaStream_t)st;
+    T* part = (T*)scratch;
+    const unsigned long long seedp = seed * 0x9E3779B97F4A7C15ULL;
+    k_quadratic<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, off, seedp, (T)0, (T)0, halo_dev);
+    k_sum_final<T><<<1, 32, 0, s>>>(part, f_part_dev);
+    return cudaGetLastError() != cudaSuccess;
 }
 
 // ---------------------------------------------------------------------------
@@ -1424,6 +1447,14 @@ int lbfgsb_problem_rosenbrock_f32(int64_t n, const float* x, float* g, float* f_
     return rosenbrock_impl<float>(n, x, g, f_out, st, first, last, xl, xr, scratch);
 }
 
+int lbfgsb_problem_rosenbrock_halo_f64(int64_t n, const double* x, double* g, double* f_part_dev, void* st, int32_t first,
+                                       int32_t last, const double* halo_dev, void* scratch) {
+    return rosenbrock_halo_impl<double>(n, x, g, f_part_dev, st, first, last, halo_dev, scratch);
+}
+int lbfgsb_problem_quadratic_halo_f64(int64_t n, const double* x, double* g, double* f_part_dev, void* st, int64_t off,
+                                      uint64_t seed, const double* halo_dev, void* scratch) {
+    return quadratic_halo_impl<double>(n, x, g, f_part_dev, st, off, seed, halo_dev, scratch);
+}
 int lbfgsb_problem_quadratic_f64(int64_t n, const double* x, double* g, double* f_out, void* st, int64_t off, uint64_t seed,
                                  double xl, double xr, void* scratch) {
     return quadratic_impl<double>(n, x, g, f_out, st, off, seed, xl, xr, scratch);

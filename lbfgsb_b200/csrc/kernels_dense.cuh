@@ -148,8 +148,8 @@ template <typename T> __device__ inline void reset_memory(DevState<T>* s) {
 }
 // prepare the flags for the prelims block (:601-612)
 template <typename T> __device__ inline void begin_body(DevState<T>* s) {
-    s->in_body = 1; s->restart = 0; s->need_walk = 0; s->lsinit_done = 0;
-    s->spec_step = 0; s->step_done = 0; s->do_unstep = 0; s->lazy_gcp = 0; s->fuse_gf = 0;
+    s->in_body = 1; s->restart = 0; s->need_walk = 0; s->lsinit_done = 0; s->z_in_x = 0; s->save_z = 0;
+    s->spec_step = 0; s->step_done = 0; s->do_unstep = 0; s->lazy_gcp = 0; s->fuse_gf = 0; s->lazy_z = 0;
     s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0; s->do_step = 0;
     s->iword = -1;
     ev_push<T>(s, EV_ITER_BEGIN, (T)(s->iter + 1));
@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_freev(Wk<T> w, Dist<T> di
     const int mode = s->cauchy_mode;
     if (mode != 1) site_reduce<T>(w, dist, site_freev(), &red);
     if (threadIdx.x != 0) return;
+    if (gf) s->lazy_z = 1;   // k_formk_cmprlb did not store xcp (state bit 2 tells where d = -g)
     if (mode != 1) {
         s->nintol = s->nintol + s->nseg;
         s->nfree = red.iv[0];
@@ -555,6 +556,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_bt(Wk<T> w, Dist<T> dist,
     if (red.rv[0] < alpha) { alpha = red.rv[0]; ibd = red.iv[0]; }
     s->alpha = alpha;
     s->ibd = ibd;   // global variable index (k_bt_alpha adds the shard offset)
+    s->lazy_z = 0;  // k_bt_apply stores the backtracked point in z
     (void)index_offset;
 }
 
@@ -616,6 +618,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_init(Wk<T> w, Dist<T> 
         s->ifun += 1; s->nfgv += 1; s->iback = s->ifun - 1;
         s->do_step = 1;
         s->step_done = (s->spec_step && s->lsinit_done && s->stp == one) ? 1 : 0;   // x already holds z
+        s->z_in_x = s->step_done;   // ... and z itself was not stored
         s->go = 0; s->in_body = 0;   // return to the caller for f and g
     } else {
         // cannot happen on the first entry (dcsrch 'START' returns 'FG' or 'ERROR')
@@ -647,7 +650,14 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_trial(Wk<T> w, Dist<T>
         ls_failure<T>(s, false);
         return;
     }
-    if (more) { s->do_step = 1; s->go = 0; return; }
+    if (more) {
+        s->do_step = 1; s->go = 0;
+        if (s->z_in_x) {   // the Newton point lives only in x (speculative step)
+            if (s->stp == (T)1) s->step_done = 1;            // asked for again (:2265): x is already there
+            else { s->save_z = 1; s->z_in_x = 0; }           // x moves on: k_ls_step keeps a copy in z first
+        }
+        return;
+    }
     // accepted: NEW_X (:775-787)
     s->iter += 1;
     s->sbgnrm = red.rv[1];
@@ -660,10 +670,10 @@ __global__ void s_call_begin(Wk<T> w, T f, int entry_task) {
     if (threadIdx.x != 0) return;
     DevState<T>* s = w.s;
     s->go = 1; s->in_body = 0; s->restart = 0; s->need_walk = 0;
-    s->do_step = 0; s->do_restore = 0; s->do_update = 0;
+    s->do_step = 0; s->do_restore = 0; s->do_update = 0; s->save_z = 0;
     s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0;
     s->fuse_uc = 0; s->classify_done = 0; s->lsinit_done = 0;
-    s->spec_step = 0; s->step_done = 0; s->do_unstep = 0; s->lazy_gcp = 0; s->fuse_gf = 0;
+    s->spec_step = 0; s->step_done = 0; s->do_unstep = 0; s->lazy_gcp = 0; s->fuse_gf = 0; s->lazy_z = 0;
     s->ev_n = 0;
     s->f = f;
     (void)entry_task;
@@ -677,8 +687,9 @@ __global__ void s_start(Wk<T> w, T factr, T pgtol, int host_err_task) {
     const T zero = (T)0;
     s->go = 1; s->in_body = 0; s->restart = 0; s->need_walk = 0; s->cauchy_mode = 0;
     s->do_subspace = s->do_formk = s->do_delta = s->do_backtrack = s->do_update = s->do_step = s->do_restore = 0;
+    s->z_in_x = 0; s->save_z = 0;
     s->fuse_uc = 0; s->classify_done = 0; s->lsinit_done = 0; s->ev_n = 0;
-    s->spec_step = 0; s->step_done = 0; s->do_unstep = 0; s->lazy_gcp = 0; s->fuse_gf = 0;
+    s->spec_step = 0; s->step_done = 0; s->do_unstep = 0; s->lazy_gcp = 0; s->fuse_gf = 0; s->lazy_z = 0;
     s->task = TK_START; s->csave = CS_BLANK; s->info = 0;
     s->col = 0; s->head = 1; s->theta = (T)1; s->iupdat = 0; s->updatd = 0;
     s->iback = 0; s->itail = 0; s->iword = 0; s->nact = 0; s->nleave = 0; s->nenter = 0;

@@ -310,9 +310,19 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_ls_init(Wk<T> w) {
     T acc[2]; acc[0] = (T)0; acc[1] = (T)0;
     T smx = LB_INF(T);
     const T* xs = s->spec_step ? w.t : w.x;   // after a speculative step the iterate is in t
+    const bool lz = s->lazy_z != 0;           // xcp not stored (fuse_gf without a subspace step): form and store it here
+    const T tsum = s->tsum;
+    const bool axpy = tsum != (T)0;
     LB_FOR_TILES(T, n, base) {
         T z[VEC], x[VEC], g[VEC], d[VEC];
-        ldv<T>(w.z, base, n, z); ldv<T>(xs, base, n, x); ldv<T>(w.g, base, n, g);
+        ldv<T>(xs, base, n, x); ldv<T>(w.g, base, n, g);
+        if (lz) {
+            int st[VEC];
+            ldvb<T>(w.state, base, n, st);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) z[v] = axpy ? (x[v] + tsum * ((st[v] & 4) ? -g[v] : (T)0)) : x[v];
+            stv<T>(w.z, base, n, z);
+        } else ldv<T>(w.z, base, n, z);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             d[v] = z[v] - x[v];
@@ -361,8 +371,10 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_ls_step(Wk<T> w) {
     if (stp == (T)1) {
         LB_FOR_TILES(T, n, base) { T z[VEC]; ldv<T>(w.z, base, n, z); stv<T>(w.x, base, n, z); }
     } else {
+        const bool keep = s->save_z != 0;   // x is the only copy of the Newton point z: store it before x moves on
         LB_FOR_TILES(T, n, base) {
             T d[VEC], t[VEC], x[VEC];
+            if (keep) { ldv<T>(w.x, base, n, x); stv<T>(w.z, base, n, x); }
             ldv<T>(w.d, base, n, d); ldv<T>(w.t, base, n, t);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) x[v] = stp * d[v] + t[v];

@@ -661,13 +661,14 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
                 const int old = st[v] & 1;
                 nfr += f ? 1 : 0;
                 if (cnt) { nen += (f && !old) ? 1 : 0; nle += (inr && !f && old) ? 1 : 0; }
-                st[v] = (f ? 1 : 0) | ((cnt ? old : (f ? 1 : 0)) << 1);
+                // bit 2: the variable moves along the Cauchy direction (d = -g): with it xcp can be formed again
+                // from x and g by the subspace pass, and is not stored here (lazy_z)
+                st[v] = (f ? 1 : 0) | ((cnt ? old : (f ? 1 : 0)) << 1) | ((iw[v] == 0 || iw[v] == -1) ? 4 : 0);
                 fr[v] = f; any |= f;
                 z[v] = axpy ? (x[v] + tsum * cauchy_dir<T>(iw[v], g[v])) : x[v];
                 r[v] = uc ? -g[v] : (-theta * (z[v] - x[v]) - g[v]);
             }
             stvb<T>(w.state, base, n, st);
-            stv<T>(w.z, base, n, z);
             if (!any && !gram) return;
         } else {
 #pragma unroll
@@ -749,6 +750,12 @@ template <typename T, int MT> constexpr unsigned smem_formk_cmprlb() { return pi
 // into x and neither z, nor the backup xp (:2787), nor the direction r (read only by the backtrack) are
 // stored.  If the backtrack is needed after all, xcp is still intact in z, the iterate is in t, and PASS 1
 // of this kernel (same arithmetic, no other effect) writes the direction into r.
+//
+// With lazy_z, xcp is not read from memory either: it is x + tsum*d with d = -g on the variables whose state
+// bit 2 is set (one multiply-add from streams that pass through this kernel anyway); PASS 1 then also stores
+// xcp for the backtrack.  (Forming cmprlb's reduced gradient r again here in the same way was measured and
+// rejected: its 2*col dependent additions per variable double the dependency chain of this pass, which is
+// latency-bound at 8 warps per SM, and cost as much time as the 16 bytes per variable saved.)
 // ---------------------------------------------------------------------------
 template <typename T, int MT, int PASS>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
@@ -769,16 +776,22 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
     const int col = s->col, head0 = s->head - 1;
     const T theta = s->theta, rtheta = (T)1 / theta;
     const bool bounds = (s->cnstnd && s->iter != 0);
-    constexpr unsigned OZ = 0, OX = G::REAL_SLOT, OG = 2 * G::REAL_SLOT, OR = 3 * G::REAL_SLOT, OL = 4 * G::REAL_SLOT,
-                       OU = 5 * G::REAL_SLOT, OW = 6 * G::REAL_SLOT;
+    // lz: xcp was not stored by k_formk_cmprlb (fuse_gf); it is x + tsum*d with d = -g where state bit 2 is set
+    const bool lz = s->lazy_z != 0;
+    const T tsum = s->tsum;
+    const bool axpy = tsum != (T)0;
+    constexpr unsigned OX = 0, OG = G::REAL_SLOT, OL = 2 * G::REAL_SLOT, OU = 3 * G::REAL_SLOT, OR = 4 * G::REAL_SLOT,
+                       OZ = 5 * G::REAL_SLOT;
+    const unsigned OW = (lz ? 5u : 6u) * G::REAL_SLOT;
     if (threadIdx.x == 0) {
         pipe_begin(&ps);
-        pipe_add(&ps, w.z, sizeof(T), G::REAL_SLOT);
-        pipe_add(&ps, w.x, sizeof(T), G::REAL_SLOT);
+        // PASS 1 runs after PASS 0 stepped speculatively (x = z): the iterate is then in t
+        pipe_add(&ps, PASS == 1 ? w.t : w.x, sizeof(T), G::REAL_SLOT);
         pipe_add(&ps, w.g, sizeof(T), G::REAL_SLOT);
-        pipe_add(&ps, w.r, sizeof(T), G::REAL_SLOT);
         pipe_add(&ps, w.l, sizeof(T), G::REAL_SLOT);
         pipe_add(&ps, w.u, sizeof(T), G::REAL_SLOT);
+        pipe_add(&ps, w.r, sizeof(T), G::REAL_SLOT);
+        if (!lz) pipe_add(&ps, w.z, sizeof(T), G::REAL_SLOT);
         pipe_add_w<T>(&ps, w, head0, col, G::REAL_SLOT);
         pipe_add(&ps, w.nbd, 4, G::INT_SLOT);
         pipe_add(&ps, w.state, 1, G::BYTE_SLOT);
@@ -797,9 +810,16 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
         bool fr[VEC]; bool any = false;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { fr[v] = (base + v < n) && (st[v] & 1); any |= fr[v]; }
-        if (PASS == 1) {   // the direction only (for the backtrack after a speculative step)
-            if (!any) return;
-            T dk[VEC];
+        if (PASS == 1 && !any && !lz) return;
+        T z[VEC], x[VEC], g[VEC];
+        lds_real<T>(sb, OX, lt, x); lds_real<T>(sb, OG, lt, g);
+        if (lz) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) z[v] = axpy ? (x[v] + tsum * ((st[v] & 4) ? -g[v] : (T)0)) : x[v];
+        } else lds_real<T>(sb, OZ, lt, z);
+        // the Newton direction of subsm on this sub-tile (free variables), from cmprlb's reduced gradient
+        T dk[VEC];
+        if (any) {
             lds_real<T>(sb, OR, lt, dk);
 #pragma unroll
             for (int j = 0; j < MT; ++j) {
@@ -812,31 +832,20 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
                 }
             }
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) dk[v] = rtheta * dk[v];
-            stv<T>(w.r, base, n, dk);
+            for (int v = 0; v < VEC; ++v) dk[v] = rtheta * dk[v];   // dscal(nsub, one/theta, d) :2780
+        }
+        if (PASS == 1) {   // what the backtrack reads after a speculative step: the direction, and xcp in z
+            if (any) stv<T>(w.r, base, n, dk);
+            if (lz) stv<T>(w.z, base, n, z);
             return;
         }
-        T z[VEC], x[VEC], g[VEC], l[VEC], u[VEC]; int nb[VEC];
-        lds_real<T>(sb, OZ, lt, z); lds_real<T>(sb, OX, lt, x); lds_real<T>(sb, OG, lt, g);
+        T l[VEC], u[VEC]; int nb[VEC];
         lds_real<T>(sb, OL, lt, l); lds_real<T>(sb, OU, lt, u);
         lds_int<T>(sb, onb, lt, nb);
         if (!spec) stv<T>(w.xp, base, n, z);   // :2787
         if (any) {
-            T dk[VEC];
-            lds_real<T>(sb, OR, lt, dk);
-#pragma unroll
-            for (int j = 0; j < MT; ++j) {
-                if (j < col) {
-                    T wy[VEC], wsv[VEC];
-                    lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
-                    lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) dk[v] = dk[v] + wy[v] * wv1[j] / theta + wsv[v] * wv2[j];
-                }
-            }
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                dk[v] = rtheta * dk[v];   // dscal(nsub, one/theta, d) :2780
                 if (fr[v]) {
                     T xk = z[v];
                     if (nb[v] != 0) {
@@ -854,7 +863,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
                 stv<T>(w.r, base, n, dk);
                 stv<T>(w.z, base, n, z);
             }
-        }
+        } else if (!spec && lz) stv<T>(w.z, base, n, z);
         // d = z - x, dtd, gd (= dd_p :2825-2827), stpmx candidates (:2201-2227), t = x, gold = g
         T d[VEC];
 #pragma unroll

@@ -113,6 +113,19 @@ def quadratic_problem(n_local, dtype=np.float64, scale=0.5):
     return x, l, u, nbd
 
 
+def _halo_on_device(x, rank, world, dist):
+    """(halo, fpart) device tensors: halo = [last value of the left neighbour, first value of the right one]
+    (0 at the ends of the chain) from one all-gather of the two edge values, never leaving the device."""
+    import torch
+    edge = torch.stack([x[0], x[-1]])
+    allv = torch.empty(2 * world, dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(allv, edge)
+    zero = torch.zeros((), dtype=x.dtype, device=x.device)
+    xl = allv[2 * (rank - 1) + 1] if rank > 0 else zero
+    xr = allv[2 * (rank + 1)] if rank < world - 1 else zero
+    return torch.stack([xl, xr]), torch.empty(1, dtype=x.dtype, device=x.device)
+
+
 class ShardedQuadraticDevice:
     """Device f/g of the convex quadratic on a shard: halo exchange + partial-f all-reduce around
     lbfgsb_problem_quadratic_* (lbfgsb_b200.QuadraticDevice)."""
@@ -124,6 +137,11 @@ class ShardedQuadraticDevice:
         import torch
         if self.world == 1:
             return self.k(x, g, offset=self.lo)
+        if x.is_cuda and x.dtype == torch.float64:
+            halo, fpart = _halo_on_device(x, self.rank, self.world, self.dist)
+            self.k.shard_async(x, g, self.lo, halo, fpart)
+            self.dist.all_reduce(fpart)
+            return float(fpart)      # the only host round trip of the evaluation
         edge = torch.stack([x[0], x[-1]])
         allv = [torch.empty_like(edge) for _ in range(self.world)]
         self.dist.all_gather(allv, edge)
@@ -147,6 +165,11 @@ class ShardedRosenbrockDevice:
         import torch
         if self.world == 1:
             return self.k(x, g)
+        if x.is_cuda and x.dtype == torch.float64:
+            halo, fpart = _halo_on_device(x, self.rank, self.world, self.dist)
+            self.k.shard_async(x, g, 1 if self.rank == 0 else 0, 1 if self.rank == self.world - 1 else 0, halo, fpart)
+            self.dist.all_reduce(fpart)
+            return float(fpart)      # the only host round trip of the evaluation
         edge = torch.stack([x[0], x[-1]])
         allv = [torch.empty_like(edge) for _ in range(self.world)]
         self.dist.all_gather(allv, edge)
