@@ -420,7 +420,9 @@ def main():
                    "nfree": int(nfree_t), "fg_evals_per_step": fg_per_iter,
                    "l2": "working set (%.1f GB per GPU) is far larger than the 126 MB L2; no flush needed" % (
                        (2 * m + 9) * n * 8 / 1e9),
-                   "fg": "device kernel, inside the timed region"},
+                   "fg": "device kernel, inside the timed region",
+                   "rank_exchange": {0: "none (single GPU)", 1: "ncclAllGather of the reduction records",
+                                     2: "reduction records stored into the peers' memory over NVLink (CUDA IPC), flags polled by the consuming kernel"}.get(prob.exchange_mode(), "?")},
         "gpu_launches": int(launches),
         "task_after_profile_pass": prob.task_str(),
         "clocks": clocks.summary(),

@@ -122,6 +122,9 @@ int lbfgsb_dev_active_set_hash(lbfgsb_dev_t* h, uint64_t* hash, int64_t* count);
 void* lbfgsb_dev_vector(lbfgsb_dev_t* h, int32_t which);
 /* device-to-device copy of `bytes` bytes of that work vector into dst_dev (after the engine's stream drained) */
 int lbfgsb_dev_vector_copy(lbfgsb_dev_t* h, int32_t which, void* dst_dev, int64_t bytes);
+/* how the per-rank reduction records travel on a sharded workspace: 0 single GPU, 1 ncclAllGather, 2 stores into the
+ * peers' memory over NVLink (CUDA IPC; default when every rank can map every peer, LBFGSB_B200_P2P=0 switches it off) */
+int lbfgsb_dev_exchange_mode(lbfgsb_dev_t* h);
 /* counters since creation: kernels launched, host syncs, device ms per kernel family */
 int lbfgsb_dev_counters(lbfgsb_dev_t* h, int64_t* launches, int64_t* syncs);
 /* per-kernel timing: when enabled every streaming kernel is bracketed by CUDA events on the

@@ -262,6 +262,10 @@ class DeviceProblem:
             raise LbfgsbB200Error(last_error())
         return h.value, c.value
 
+    def exchange_mode(self):
+        """0 single GPU, 1 records through ncclAllGather, 2 records stored into the peers' memory (NVLink)."""
+        return int(lib().lbfgsb_dev_exchange_mode(C.c_void_p(self.h)))
+
     def counters(self):
         a, b = C.c_int64(0), C.c_int64(0)
         lib().lbfgsb_dev_counters(C.c_void_p(self.h), C.byref(a), C.byref(b))

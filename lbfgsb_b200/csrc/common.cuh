@@ -88,6 +88,7 @@ struct DevState {
     int lazy_gcp;      // cauchy's d and xcp are not materialised: xcp = x + tsum*d, d = -g or 0 by iwhere
     int fuse_gf;       // the cauchy tail (:1515) and freev (:1980-2059) run inside k_formk_cmprlb
     int lazy_z;        // ... and xcp was not stored: xcp = x + tsum*d with d = -g where state bit 2 is set, else 0
+    int p2p_timeout;   // a peer's record did not arrive (sharded runs over peer memory): the call ends in an error
     int z_in_x;        // line search: the Newton point z exists only as the current x (speculative step); persists over calls
     int save_z;        // this call's k_ls_step moves x away from it: copy it into z first (a later trial may ask for stp = 1 again)
     int task, csave, info;

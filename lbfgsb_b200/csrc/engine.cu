@@ -146,7 +146,67 @@ struct Engine : EngineBase {
     double fam_ms[F_COUNT]; i64 fam_calls[F_COUNT];
     bool x_changed = false, g_changed = false;
 
-    Dist<T> dist() const { Dist<T> d; d.R = R; d.all = rec_all; return d; }
+    // records over peer memory (kernels_dense.cuh: P2PBuf)
+    bool p2p = false;
+    P2PBuf<T>* p2p_local = nullptr;
+    Peers peers, peers_delta;
+    std::vector<void*> ipc_opened;
+    unsigned long long site_seq = 0, delta_seq = 0;
+    int cur_slot = 0;
+    Dist<T> dist() const {
+        Dist<T> d; d.R = R; d.all = rec_all;
+        d.p2p = p2p ? p2p_local : nullptr; d.slot = cur_slot; d.seq = site_seq; d.dseq = delta_seq;
+        return d;
+    }
+    // Exchange CUDA IPC handles of the P2PBuf and of delta_all through the engine's communicator and map the peers'
+    // buffers.  Any failure on any rank leaves every rank on the ncclAllGather path.
+    bool setup_p2p() {
+        if (const char* e = getenv("LBFGSB_B200_P2P")) { if (e[0] == '0') return true; }
+        struct Pack { cudaIpcMemHandle_t hb, hd; int ok; int pad[3]; };
+        Pack mine; memset(&mine, 0, sizeof mine);
+        mine.ok = 1;
+        if (cudaMalloc((void**)&p2p_local, sizeof(P2PBuf<T>)) != cudaSuccess) { p2p_local = nullptr; mine.ok = 0; cudaGetLastError(); }
+        if (mine.ok) {
+            allocs.push_back(p2p_local);
+            cudaMemset(p2p_local, 0, sizeof(P2PBuf<T>));
+            if (cudaIpcGetMemHandle(&mine.hb, p2p_local) != cudaSuccess || cudaIpcGetMemHandle(&mine.hd, delta_all) != cudaSuccess) {
+                mine.ok = 0; cudaGetLastError();
+            }
+        }
+        Pack* dsend = nullptr; Pack* drecv = nullptr;
+        if (!dalloc(&dsend, sizeof(Pack)) || !dalloc(&drecv, sizeof(Pack) * R)) return false;
+        CK(cudaMemcpy(dsend, &mine, sizeof mine, cudaMemcpyHostToDevice));
+        if (!allgather(dsend, drecv, sizeof(Pack))) return false;
+        std::vector<Pack> all(R);
+        CK(cudaMemcpyAsync(all.data(), drecv, sizeof(Pack) * R, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        bool ok = true;
+        for (int q = 0; q < R; ++q) ok = ok && all[q].ok;
+        memset(&peers, 0, sizeof peers); memset(&peers_delta, 0, sizeof peers_delta);
+        int myok = ok ? 1 : 0;
+        if (ok) {
+            for (int q = 0; q < R && myok; ++q) {
+                if (q == rank) { peers.p[q] = p2p_local; peers_delta.p[q] = delta_all; continue; }
+                void *pb = nullptr, *pd = nullptr;
+                if (cudaIpcOpenMemHandle(&pb, all[q].hb, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { myok = 0; cudaGetLastError(); break; }
+                ipc_opened.push_back(pb);
+                if (cudaIpcOpenMemHandle(&pd, all[q].hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { myok = 0; cudaGetLastError(); break; }
+                ipc_opened.push_back(pd);
+                peers.p[q] = pb; peers_delta.p[q] = pd;
+            }
+        }
+        // second round: every rank must have mapped every peer
+        int* dflag = nullptr; int* dflags = nullptr;
+        if (!dalloc(&dflag, sizeof(int)) || !dalloc(&dflags, sizeof(int) * R)) return false;
+        CK(cudaMemcpy(dflag, &myok, sizeof(int), cudaMemcpyHostToDevice));
+        if (!allgather(dflag, dflags, sizeof(int))) return false;
+        std::vector<int> oks(R);
+        CK(cudaMemcpyAsync(oks.data(), dflags, sizeof(int) * R, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        p2p = true;
+        for (int q = 0; q < R; ++q) p2p = p2p && oks[q];
+        return true;
+    }
 
     template <typename P> bool dalloc(P** p, size_t bytes) {
         void* q = nullptr;
@@ -225,10 +285,12 @@ struct Engine : EngineBase {
             if (!dalloc(&delta_all, sizeof(T) * 6 * LB_MMAX * LB_MMAX * R) || !dalloc(&delta_sum, sizeof(T) * 6 * LB_MMAX * LB_MMAX)) return false;
         }
         CK(cudaStreamSynchronize(stream));
+        if (R > 1 && !setup_p2p()) return false;
         return true;
     }
 
     ~Engine() {
+        for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
         for (void* p : allocs) cudaFree(p);
         for (DynBuf* d : {&dw_send, &dw_recv, &dw_k0, &dw_k1, &dw_v0, &dw_v1}) if (d->p) cudaFree(d->p);
         if (s_host) cudaFreeHost(s_host);
@@ -269,11 +331,18 @@ struct Engine : EngineBase {
         CK(cudaStreamSynchronize(stream));
         syncs++;
         if (profile) resolve_events();
+        if (s_host->p2p_timeout) { set_error("a peer rank's reduction record did not arrive (sharded run over peer memory)"); return false; }
         return true;
     }
     // finish + all-gather of a reduction site on sharded runs
     bool site(const SiteSpec& sp) {
         if (R <= 1) return true;
+        if (p2p) {
+            site_seq++; cur_slot = (int)(site_seq & 1ULL);
+            k_rank_finish_p2p<T><<<1, LB_SCALAR_THREADS, 0, stream>>>(w, sp, peers, R, rank, cur_slot, site_seq);
+            launches++;
+            return true;
+        }
         k_rank_finish<T><<<1, LB_SCALAR_THREADS, 0, stream>>>(w, sp, rec_local);
         launches++;
         int rc = nccl_api()->AllGather(rec_local, rec_all, sizeof(Red<T>), 0 /*ncclChar*/, comm, stream);
@@ -597,7 +666,10 @@ struct Engine : EngineBase {
             k_formk_delta_final<T><<<(6 * LB_MMAX * LB_MMAX + 255) / 256, 256, 0, stream>>>(w, fd_parts, LB_FD_GRID, delta);
             end(F_FORMK_DELTA, 5);
             if (!site(site_formk(mt))) return false;
-            if (R > 1 && !allgather(delta, delta_all, sizeof(T) * 6 * LB_MMAX * LB_MMAX)) return false;
+            if (R > 1) {
+                if (p2p) { delta_seq++; k_delta_push<T><<<1, 256, 0, stream>>>(w, delta, peers_delta, peers, R, rank, delta_seq); launches++; }
+                else if (!allgather(delta, delta_all, sizeof(T) * 6 * LB_MMAX * LB_MMAX)) return false;
+            }
             begin(F_SCALAR); s_formk_dense<T><<<LS>>>(w, dist(), mt, R > 1 ? delta_all : delta, delta_sum); end(F_SCALAR);
             if (!fused) { begin(F_CMPRLB_WV); MTCALL(k_cmprlb_wv, smem_cmprlb, w); end(F_CMPRLB_WV); }
             if (!site(site_wv(mt))) return false;
@@ -1386,6 +1458,12 @@ int lbfgsb_dev_vector_copy(lbfgsb_dev_t* h, int32_t which, void* dst_dev, int64_
     if (!src || !dst_dev || bytes < 0) return 1;
     if (cudaDeviceSynchronize() != cudaSuccess) return 1;
     return cudaMemcpy(dst_dev, src, (size_t)bytes, cudaMemcpyDeviceToDevice) != cudaSuccess;
+}
+int lbfgsb_dev_exchange_mode(lbfgsb_dev_t* h) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b) return -1;
+    if (b->real_kind == 8) { Engine<double>* e = (Engine<double>*)b; return e->R <= 1 ? 0 : (e->p2p ? 2 : 1); }
+    Engine<float>* e = (Engine<float>*)b; return e->R <= 1 ? 0 : (e->p2p ? 2 : 1);
 }
 int lbfgsb_dev_counters(lbfgsb_dev_t* h, int64_t* launches, int64_t* syncs) {
     EngineBase* b = (EngineBase*)h;

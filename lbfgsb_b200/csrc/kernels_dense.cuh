@@ -95,17 +95,104 @@ __device__ void site_combine_ranks(const Red<T>* all, int R, const SiteSpec sp, 
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------
+// Exchange of the per-rank records over peer memory (NVLink / NVSwitch).  Every rank owns one P2PBuf; the
+// finish kernel of a reduction site stores its record straight into slot [rank] of every peer's buffer
+// (remote stores), fences, and then publishes the site's sequence number in the peer's flag word; the scalar
+// kernel that consumes the site spins on its own R flag words.  No collective launch sits between a streaming
+// pass and the 2m x 2m algebra that needs its sums.  Two slots alternate: a rank can be at most one site ahead
+// of the slowest rank's *production*, because consuming site k needs every rank's record of site k, and a rank
+// produces site k+1 only after it consumed (or skipped, identically on all ranks) site k.
+// ---------------------------------------------------------------------------
+#ifndef LB_MAXR
+#define LB_MAXR 16
+#endif
+#define LB_P2P_SPIN_LIMIT (20000000000LL)   // ~10 s of SM clocks: a lost peer ends in an error, not in a hung GPU
+template <typename T>
+struct P2PBuf {
+    Red<T> rec[2][LB_MAXR];
+    unsigned long long flag[2][LB_MAXR];
+    unsigned long long dflag[LB_MAXR];     // formk's entering/leaving corrections (delta_all) of rank q are complete
+};
+struct Peers { void* p[LB_MAXR]; };
+
 // Distribution context passed to every scalar kernel.
 template <typename T>
 struct Dist {
     int R;                 // ranks (1: single GPU)
-    const Red<T>* all;     // [R] gathered records (R > 1)
+    Red<T>* all;           // [R] gathered records (R > 1)
+    P2PBuf<T>* p2p;        // this rank's peer-memory buffer (nullptr: the records came through ncclAllGather)
+    int slot;              // which of the two record slots the current site uses
+    unsigned long long seq;   // sequence number of the current site
+    unsigned long long dseq;  // sequence number of the current delta exchange
 };
+
+// wait until every rank's word equals seq (threads 0..R-1 spin), then make the peers' stores visible
+template <typename T>
+__device__ __forceinline__ void p2p_wait(const Wk<T>& w, volatile unsigned long long* flags, int R, unsigned long long seq) {
+    if ((int)threadIdx.x < R) {
+        const long long t0 = clock64();
+        while (flags[threadIdx.x] != seq) {
+            if (clock64() - t0 > LB_P2P_SPIN_LIMIT) { w.s->p2p_timeout = 1; break; }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+}
 
 template <typename T>
 __device__ __forceinline__ void site_reduce(const Wk<T>& w, const Dist<T>& dist, const SiteSpec sp, Red<T>* red) {
-    if (dist.R <= 1) site_finish_local<T>(w, sp, red);
-    else site_combine_ranks<T>(dist.all, dist.R, sp, red);
+    if (dist.R <= 1) { site_finish_local<T>(w, sp, red); return; }
+    if (dist.p2p) {
+        p2p_wait<T>(w, dist.p2p->flag[dist.slot], dist.R, dist.seq);
+        // copy the records out of the peer-written buffer (volatile: never from a stale L1 line)
+        const int words = (int)(sizeof(Red<T>) / 8);
+        for (int q = 0; q < dist.R; ++q) {
+            const volatile unsigned long long* src = (const volatile unsigned long long*)&dist.p2p->rec[dist.slot][q];
+            unsigned long long* dst = (unsigned long long*)&dist.all[q];
+            for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src[k];
+        }
+        __syncthreads();
+    }
+    site_combine_ranks<T>(dist.all, dist.R, sp, red);
+}
+
+// Rank-local finish of a site, stored into every peer's buffer (see P2PBuf).
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) k_rank_finish_p2p(Wk<T> w, SiteSpec sp, Peers peers, int R, int rank, int slot,
+                                                                      unsigned long long seq) {
+    __shared__ Red<T> red;
+    site_finish_local<T>(w, sp, &red);
+    for (int q = 0; q < R; ++q) {
+        Red<T>* dst = &((P2PBuf<T>*)peers.p[q])->rec[slot][rank];
+        for (int k = threadIdx.x; k < LB_KMAX; k += blockDim.x) dst->rv[k] = (k < sp.nreal) ? red.rv[k] : (T)0;
+        for (int k = threadIdx.x; k < LB_IMAX; k += blockDim.x) dst->iv[k] = (k < sp.nint) ? red.iv[k] : 0;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < R) {
+        __threadfence_system();
+        *(volatile unsigned long long*)&((P2PBuf<T>*)peers.p[threadIdx.x])->flag[slot][rank] = seq;
+    }
+}
+// formk's entering/leaving corrections of this rank into every peer's delta_all[rank] (only when they are needed:
+// do_delta is the same on every rank)
+template <typename T>
+__global__ void __launch_bounds__(256) k_delta_push(Wk<T> w, const T* delta, Peers peers_delta, Peers peers, int R, int rank,
+                                                    unsigned long long dseq) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_delta) return;
+    const int ne = 6 * LB_MMAX * LB_MMAX;
+    for (int q = 0; q < R; ++q) {
+        T* dst = (T*)peers_delta.p[q] + (i64)rank * ne;
+        for (int e = threadIdx.x; e < ne; e += blockDim.x) dst[e] = delta[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < R) {
+        __threadfence_system();
+        *(volatile unsigned long long*)&((P2PBuf<T>*)peers.p[threadIdx.x])->dflag[rank] = dseq;
+    }
 }
 
 // Rank-local finish of a site into a global record (sharded runs; followed by an all-gather).
@@ -409,10 +496,13 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist
     const bool newrow = s->do_formk && s->updatd;
     if (newrow) site_reduce<T>(w, dist, site_formk(mt), &red);
     if (dist.R > 1 && s->do_delta) {
-        // sharded: `delta` holds the all-gathered per-rank corrections [R][6*MMAX*MMAX]; add them in rank order
+        // sharded: `delta` holds the per-rank corrections [R][6*MMAX*MMAX] (all-gathered, or pushed by the peers);
+        // add them in rank order
+        if (dist.p2p) p2p_wait<T>(w, dist.p2p->dflag, dist.R, dist.dseq);
+        const volatile T* dv = delta;
         for (int e = threadIdx.x; e < 6 * LB_MMAX * LB_MMAX; e += blockDim.x) {
-            T acc = delta[e];
-            for (int q = 1; q < dist.R; ++q) acc = acc + delta[(i64)q * (6 * LB_MMAX * LB_MMAX) + e];
+            T acc = dv[e];
+            for (int q = 1; q < dist.R; ++q) acc = acc + dv[(i64)q * (6 * LB_MMAX * LB_MMAX) + e];
             delta_sum[e] = acc;
         }
         __syncthreads();
