@@ -137,8 +137,8 @@ void lbfgsb_dev_profile_reset(lbfgsb_dev_t* h);
  * equal t): which members of the group end up fixed depends on the order in which they are popped, and the
  * reference pops them in the order of its heap (hpsolb, :2079-2157).  The engine then replays that heap on the
  * device (one thread; single-GPU workspaces) if the call has at most `max_breakpoints` breakpoints (default
- * 2^21, environment LBFGSB_B200_TIE_LIMIT; 0 switches the replay off).  Beyond the limit, and on sharded
- * workspaces, such a group is taken in variable order and the event is counted.
+ * 2^21, environment LBFGSB_B200_TIE_LIMIT; 0 switches the replay off).  Beyond the limit such a group is taken in
+ * variable order and the event is counted; sharded workspaces always use (t, global index) order.
  * tie_stats: replays done, exits inside a tie group that were not replayed (since START).            */
 void lbfgsb_dev_set_tie_limit(lbfgsb_dev_t* h, int64_t max_breakpoints);
 int lbfgsb_dev_tie_stats(lbfgsb_dev_t* h, int64_t* replays, int64_t* not_replayed);
