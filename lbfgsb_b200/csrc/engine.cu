@@ -363,7 +363,10 @@ struct Engine : EngineBase {
         if constexpr (fused_passes_ok<T, MT>()) k_update_classify<T, MT><<<LBFGSB_GRID, LB_TMA_THREADS, smem_update_classify<T, MT>(), stream>>>(w);
     }
     template <int MT> void launch_formk_cmprlb() {
-        if constexpr (fused_passes_ok<T, MT>()) k_formk_cmprlb<T, MT><<<LBFGSB_GRID, LB_TMA_THREADS, smem_formk_cmprlb<T, MT>(), stream>>>(w);
+        if constexpr (fused_passes_ok<T, MT>()) k_formk_cmprlb<T, MT, false><<<LBFGSB_GRID, LB_TMA_THREADS, smem_formk_cmprlb<T, MT>(), stream>>>(w);
+    }
+    template <int MT> void launch_formk_cmprlb_gf() {
+        if constexpr (fused_passes_ok<T, MT>()) k_formk_cmprlb<T, MT, true><<<LBFGSB_GRID, LB_TMA_THREADS, smem_formk_cmprlb<T, MT>(), stream>>>(w);
     }
     template <int MT> void launch_subsm_lsinit() {
         if constexpr (fused_passes_ok<T, MT>()) k_subsm_lsinit<T, MT, 0><<<LBFGSB_GRID, LB_TMA_THREADS, smem_subsm<T, MT>(), stream>>>(w);
@@ -382,7 +385,8 @@ struct Engine : EngineBase {
         CK(cudaFuncSetAttribute(k_subsm_step<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_subsm<T, MT>()));
         if constexpr (fused_passes_ok<T, MT>()) {
             CK(cudaFuncSetAttribute(k_update_classify<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_update_classify<T, MT>()));
-            CK(cudaFuncSetAttribute(k_formk_cmprlb<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk_cmprlb<T, MT>()));
+            CK(cudaFuncSetAttribute(k_formk_cmprlb<T, MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk_cmprlb<T, MT>()));
+            CK(cudaFuncSetAttribute(k_formk_cmprlb<T, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk_cmprlb<T, MT>()));
             CK(cudaFuncSetAttribute(k_subsm_lsinit<T, MT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_subsm<T, MT>()));
             CK(cudaFuncSetAttribute(k_subsm_lsinit<T, MT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_subsm<T, MT>()));
         }
@@ -652,7 +656,11 @@ struct Engine : EngineBase {
                 if (!site(site_freev())) return false;
             }
             begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global, 0); end(F_SCALAR);
-            if (fused) { begin(F_FORMK_CMPRLB); MTFUSED(launch_formk_cmprlb); end(F_FORMK_CMPRLB); }
+            if (fused) {
+                begin(F_FORMK_CMPRLB);
+                if (gf) MTFUSED(launch_formk_cmprlb_gf); else MTFUSED(launch_formk_cmprlb);
+                end(F_FORMK_CMPRLB);
+            }
             else { begin(F_FORMK_GRAM); MTCALL(k_formk_gram, smem_formk, w); end(F_FORMK_GRAM); }
             if (gf) {
                 if (!site(site_freev())) return false;

@@ -591,7 +591,7 @@ template <typename T, int MT> constexpr unsigned smem_update_classify() { return
 // on sy, wt and c and is therefore computed before this pass (s_freev).
 // part : as k_formk_gram (written when the Gram row is needed)     part2 : as k_cmprlb_wv
 // ---------------------------------------------------------------------------
-template <typename T, int MT>
+template <typename T, int MT, bool GF>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<MT>::v;
@@ -604,9 +604,11 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
     __shared__ i64 smi[LBFGSB_BLOCK / 32];
     const DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->do_subspace) return;
-    // gf: the tail of cauchy (xcp = x + tsum*d, :1515) and freev (:1980-2059) are part of this pass; the flags
-    // do_subspace / do_formk are then s_freev's tentative values (the counts are only known after this pass)
-    const bool gf = s->fuse_gf != 0;
+    // GF: the tail of cauchy (xcp = x + tsum*d, :1515) and freev (:1980-2059) are part of this pass; the flags
+    // do_subspace / do_formk are then s_freev's tentative values (the counts are only known after this pass).
+    // The host launches the instantiation that matches the device flag (it has read fuse_gf back by then).
+    constexpr bool gf = GF;
+    if ((s->fuse_gf != 0) != GF) return;
     const bool gram = s->do_formk && s->updatd;
     const i64 n = w.n;
     const int col = s->col, head0 = s->head - 1;
@@ -616,7 +618,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
     const bool axpy = tsum != (T)0;            // daxpy early-out (:49-50)
     const bool cnt = (s->iter > 0 && s->cnstnd);
     constexpr unsigned OG = 0, OX = G::REAL_SLOT, OZ = 2 * G::REAL_SLOT;
-    const unsigned OW = (gf ? 2u : 3u) * G::REAL_SLOT;
+    constexpr unsigned OW = (gf ? 2u : 3u) * G::REAL_SLOT;
     if (threadIdx.x == 0) {
         pipe_begin(&ps);
         pipe_add(&ps, w.g, sizeof(T), G::REAL_SLOT);
