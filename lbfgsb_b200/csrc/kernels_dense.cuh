@@ -229,6 +229,18 @@ __host__ __device__ inline SiteSpec site_lstrial() { SiteSpec s = make_site(2, 0
 __host__ __device__ inline SiteSpec site_update(int mt) { return make_site(2 * mt + 1, 0); }
 __host__ __device__ inline SiteSpec site_hash() { return make_site(0, 2); }
 
+// The 2m x 2m algebra runs in one thread (reference operation order), and that thread would meet every element of
+// the small matrices as a dependent load from global memory.  The block therefore copies them into shared memory
+// first (and back afterwards where they were changed): same arithmetic, a fraction of the latency.
+template <typename T>
+__device__ __forceinline__ void stage_in(T* dst, const T* src, int count) {
+    for (int q = threadIdx.x; q < count; q += blockDim.x) dst[q] = src[q];
+}
+template <typename T>
+__device__ __forceinline__ void stage_out(T* dst, const T* src, int count) {
+    for (int q = threadIdx.x; q < count; q += blockDim.x) dst[q] = src[q];
+}
+
 // "refresh the lbfgs memory" (:625-630 and the four other sites)
 template <typename T> __device__ inline void reset_memory(DevState<T>* s) {
     s->info = 0; s->col = 0; s->head = 1; s->theta = (T)1; s->iupdat = 0; s->updatd = 0;
@@ -337,32 +349,43 @@ __global__ void s_newx_tests(Wk<T> w, int fused_supported) {
 template <typename T>
 __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_update_dense(Wk<T> w, Dist<T> dist, int mt) {
     __shared__ Red<T> red;
+    __shared__ T ssy[LB_MMAX * LB_MMAX], sss[LB_MMAX * LB_MMAX], swt[LB_MMAX * LB_MMAX];
     DevState<T>* s = w.s;
     if (!s->go) return;
     const bool upd = s->do_update;
-    if (upd) site_reduce<T>(w, dist, site_update(mt), &red);
-    if (threadIdx.x != 0) return;
+    const int mm = s->m * s->m;
     if (upd) {
-        const int m = s->m, col = s->col;
-        s->rr = red.rv[0];
-        s->theta = s->rr / s->dr;
-        T* sy = s->sy; T* ss = s->ss;
-        if (s->iupdat > m) {  // :2324-2330
-            for (int j = 1; j <= col - 1; ++j) {
-                for (int q = 0; q < j; ++q) ss[q + (j - 1) * m] = ss[(1 + q) + j * m];             // dcopy(j,Ss(2,j+1),Ss(1,j))
-                for (int q = 0; q < col - j; ++q) sy[(j - 1 + q) + (j - 1) * m] = sy[(j + q) + j * m];  // dcopy(col-j,Sy(j+1,j+1),Sy(j,j))
-            }
-        }
-        for (int j = 1; j <= col - 1; ++j) {
-            sy[(col - 1) + (j - 1) * m] = red.rv[1 + (j - 1)];
-            ss[(j - 1) + (col - 1) * m] = red.rv[1 + mt + (j - 1)];
-        }
-        ss[(col - 1) + (col - 1) * m] = (s->stp == (T)1) ? s->dtd : s->stp * s->stp * s->dtd;
-        sy[(col - 1) + (col - 1) * m] = s->dr;
-        int info = dense::formt<T>(m, s->wt, sy, ss, col, s->theta);
-        if (info != 0) { ev_push<T>(s, EV_FORMT_FAIL); reset_memory<T>(s); }   // :851-863
+        site_reduce<T>(w, dist, site_update(mt), &red);
+        stage_in<T>(ssy, s->sy, mm); stage_in<T>(sss, s->ss, mm); stage_in<T>(swt, s->wt, mm);
+        __syncthreads();
     }
-    begin_body<T>(s);
+    if (threadIdx.x == 0) {
+        if (upd) {
+            const int m = s->m, col = s->col;
+            s->rr = red.rv[0];
+            s->theta = s->rr / s->dr;
+            T* sy = ssy; T* ss = sss;
+            if (s->iupdat > m) {  // :2324-2330
+                for (int j = 1; j <= col - 1; ++j) {
+                    for (int q = 0; q < j; ++q) ss[q + (j - 1) * m] = ss[(1 + q) + j * m];             // dcopy(j,Ss(2,j+1),Ss(1,j))
+                    for (int q = 0; q < col - j; ++q) sy[(j - 1 + q) + (j - 1) * m] = sy[(j + q) + j * m];  // dcopy(col-j,Sy(j+1,j+1),Sy(j,j))
+                }
+            }
+            for (int j = 1; j <= col - 1; ++j) {
+                sy[(col - 1) + (j - 1) * m] = red.rv[1 + (j - 1)];
+                ss[(j - 1) + (col - 1) * m] = red.rv[1 + mt + (j - 1)];
+            }
+            ss[(col - 1) + (col - 1) * m] = (s->stp == (T)1) ? s->dtd : s->stp * s->stp * s->dtd;
+            sy[(col - 1) + (col - 1) * m] = s->dr;
+            int info = dense::formt<T>(m, swt, sy, ss, col, s->theta);
+            if (info != 0) { ev_push<T>(s, EV_FORMT_FAIL); reset_memory<T>(s); }   // :851-863
+        }
+        begin_body<T>(s);
+    }
+    if (upd) {
+        __syncthreads();
+        stage_out<T>(s->sy, ssy, mm); stage_out<T>(s->ss, sss, mm); stage_out<T>(s->wt, swt, mm);
+    }
 }
 
 // Host asked for another pass of the body after a memory reset ("cycle main_loop").
@@ -382,9 +405,12 @@ __global__ void s_restart_body(Wk<T> w) {
 template <typename T>
 __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> dist, int mt, int fused_supported) {
     __shared__ Red<T> red;
+    __shared__ T ssy[LB_MMAX * LB_MMAX], swt[LB_MMAX * LB_MMAX];
     DevState<T>* s = w.s;
     if (!s->go || !s->in_body || s->cauchy_mode != 0) return;
     site_reduce<T>(w, dist, site_cauchy(mt), &red);
+    stage_in<T>(ssy, s->sy, s->m * s->m); stage_in<T>(swt, s->wt, s->m * s->m);
+    __syncthreads();
     if (threadIdx.x != 0) return;
     s->classify_done = 0;
     const int col = s->col, col2 = 2 * col, m = s->m;
@@ -404,7 +430,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
     s->f2 = -s->theta * s->f1;
     s->f2_org = s->f2;
     if (col > 0) {
-        int info = dense::bmv<T>(m, s->sy, s->wt, col, s->p, s->v);
+        int info = dense::bmv<T>(m, ssy, swt, col, s->p, s->v);
         if (info != 0) {   // :620-635
             ev_push<T>(s, EV_CAUCHY_SINGULAR);
             reset_memory<T>(s);
@@ -432,7 +458,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
     // counts of freev, and with them nfree == 0 / wrk, are evaluated after that pass (s_freev phase 1).  If
     // the product fails, the separate passes run and s_freev reports the failure in the reference's order.
     if (fused_supported && col > 0 && s->cnstnd) {
-        if (dense::bmv<T>(m, s->sy, s->wt, col, s->c, s->a) == 0) s->fuse_gf = 1;
+        if (dense::bmv<T>(m, ssy, swt, col, s->c, s->a) == 0) s->fuse_gf = 1;
     }
 }
 
@@ -508,9 +534,15 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist
         __syncthreads();
         delta = delta_sum;
     }
-    if (threadIdx.x != 0) return;
+    __shared__ T swn[4 * LB_MMAX * LB_MMAX], swn1[4 * LB_MMAX * LB_MMAX];
+    const bool stage = s->do_formk != 0;
+    if (stage) {
+        stage_in<T>(swn, s->wn, 4 * s->m * s->m); stage_in<T>(swn1, s->wn1, 4 * s->m * s->m);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
     const int m = s->m, col = s->col, m2 = 2 * m;
-    T* wn = s->wn; T* wn1 = s->wn1;
+    T* wn = swn; T* wn1 = swn1;
 #define WN(i, j) wn[((i)-1) + ((j)-1) * m2]
 #define WN1(i, j) wn1[((i)-1) + ((j)-1) * m2]
     if (s->do_formk) {
@@ -583,11 +615,15 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist
             ev_push<T>(s, EV_FORMK_FAIL);
             reset_memory<T>(s);
             s->restart = 1; s->in_body = 0;
-            return;
         }
     }
 #undef WN
 #undef WN1
+    }
+    if (stage) {
+        __syncthreads();
+        stage_out<T>(s->wn, swn, 4 * s->m * s->m); stage_out<T>(s->wn1, swn1, 4 * s->m * s->m);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -599,13 +635,16 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_dense(Wk<T> w, Dist
     DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->do_subspace) return;
     site_reduce<T>(w, dist, site_wv(mt), &red);
+    __shared__ T swn[4 * LB_MMAX * LB_MMAX];
+    stage_in<T>(swn, s->wn, 4 * s->m * s->m);
+    __syncthreads();
     if (threadIdx.x != 0) return;
     const int m = s->m, col = s->col, m2 = 2 * m, col2 = 2 * col;
     for (int i = 0; i < col; ++i) { s->wv[i] = red.rv[i]; s->wv[col + i] = s->theta * red.rv[mt + i]; }
-    int info = dense::dtrsl<T>(s->wn, m2, col2, s->wv, 11);
+    int info = dense::dtrsl<T>(swn, m2, col2, s->wv, 11);
     if (info == 0) {
         for (int i = 0; i < col; ++i) s->wv[i] = -s->wv[i];
-        info = dense::dtrsl<T>(s->wn, m2, col2, s->wv, 1);
+        info = dense::dtrsl<T>(swn, m2, col2, s->wv, 1);
     }
     if (info != 0) {   // :694-710
         ev_push<T>(s, EV_SUBSM_SINGULAR);
