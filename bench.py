@@ -301,12 +301,12 @@ def main():
         fgk = lbfgsb_b200.QuadraticDevice(np.float64, seed=QUAD_SEED, stream=stream)
         fg_one = (lambda: fgk(xd, gd, offset=0))
         if world > 1:
-            fg_sh = sharded.ShardedQuadraticDevice(fgk, off, rank, world, dist, dev)
+            fg_sh = sharded.ShardedQuadraticDevice(fgk, off, rank, world, dist, dev, engine=prob)
     else:
         fgk = lbfgsb_b200.RosenbrockDevice(np.float64, stream=stream)
         fg_one = (lambda: fgk(xd, gd))
         if world > 1:
-            fg_sh = sharded.ShardedRosenbrockDevice(fgk, rank, world, dist, dev)
+            fg_sh = sharded.ShardedRosenbrockDevice(fgk, rank, world, dist, dev, engine=prob)
 
     def fg():
         nfg[0] += 1

@@ -155,6 +155,12 @@ int64_t lbfgsb_problem_scratch_bytes(void);
  * in f_part_dev[0] (device), nothing is synchronised -- the caller all-reduces f_part_dev on the same stream */
 int lbfgsb_problem_rosenbrock_halo_f64(int64_t n, const double* x_dev, double* g_dev, double* f_part_dev, void* cuda_stream,
                                        int32_t first, int32_t last, const double* halo_dev, void* scratch_dev);
+/* the same two objectives on a sharded workspace whose ranks exchange over peer memory (lbfgsb_dev_exchange_mode == 2):
+ * halo values and the per-rank parts of f travel as stores into the neighbours' / peers' memory, f (summed in rank
+ * order, identical on every rank) is read back once.  kind 0: Rosenbrock, 1: quadratic (seed).  x, g: this rank's
+ * shard, evaluated on the workspace's stream.  Returns 0, 1 on a CUDA failure, 2 when the workspace does not exchange
+ * over peer memory (use the *_halo_* variants with your own collectives then).                                        */
+int lbfgsb_problem_sharded_f64(lbfgsb_dev_t* h, int32_t kind, const double* x_dev, double* g_dev, double* f_out, uint64_t seed);
 int lbfgsb_problem_quadratic_halo_f64(int64_t n, const double* x_dev, double* g_dev, double* f_part_dev, void* cuda_stream,
                                       int64_t index_offset, uint64_t seed, const double* halo_dev, void* scratch_dev);
 

@@ -262,6 +262,19 @@ class DeviceProblem:
             raise LbfgsbB200Error(last_error())
         return h.value, c.value
 
+    def sharded_fg(self, kind, x, g, seed=0):
+        """Sample objective (0 Rosenbrock, 1 quadratic) of this rank's shard with halo and partial-f exchange over peer
+        memory (include/lbfgsb_b200.h: lbfgsb_problem_sharded_f64).  Returns f, or None when the workspace does not
+        exchange over peer memory."""
+        out = C.c_double(0.0)
+        rc = lib().lbfgsb_problem_sharded_f64(C.c_void_p(self.h), C.c_int32(kind), C.c_void_p(x.data_ptr()),
+                                              C.c_void_p(g.data_ptr()), C.byref(out), C.c_uint64(int(seed)))
+        if rc == 2:
+            return None
+        if rc != 0:
+            raise LbfgsbB200Error("sharded objective failed: " + last_error())
+        return out.value
+
     def exchange_mode(self):
         """0 single GPU, 1 records through ncclAllGather, 2 records stored into the peers' memory (NVLink)."""
         return int(lib().lbfgsb_dev_exchange_mode(C.c_void_p(self.h)))

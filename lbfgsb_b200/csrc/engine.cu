@@ -151,7 +151,8 @@ struct Engine : EngineBase {
     P2PBuf<T>* p2p_local = nullptr;
     Peers peers, peers_delta;
     std::vector<void*> ipc_opened;
-    unsigned long long site_seq = 0, delta_seq = 0;
+    unsigned long long site_seq = 0, delta_seq = 0, fg_seq = 0;
+    T* fg_scratch = nullptr; T* fg_out = nullptr; T* fg_host = nullptr;
     int cur_slot = 0;
     Dist<T> dist() const {
         Dist<T> d; d.R = R; d.all = rec_all;
@@ -293,6 +294,7 @@ struct Engine : EngineBase {
         for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
         for (void* p : allocs) cudaFree(p);
         for (DynBuf* d : {&dw_send, &dw_recv, &dw_k0, &dw_k1, &dw_v0, &dw_v1}) if (d->p) cudaFree(d->p);
+        if (fg_host) cudaFreeHost(fg_host);
         if (s_host) cudaFreeHost(s_host);
         if (ctl_host) cudaFreeHost(ctl_host);
         for (auto e : pool) cudaEventDestroy(e);
@@ -1243,6 +1245,57 @@ static int quadratic_impl(i64 n, const T* x, T* g, T* f_out, void* st, i64 off, 
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// The chain-coupled sample objectives on a sharded workspace, exchanged over peer memory: every rank stores its two
+// boundary values of x into its neighbours' P2PBuf, the objective kernel's blocks poll the local flags before they
+// read the halo, the per-rank parts of f are stored into every peer and summed in rank order.  One host read of f per
+// evaluation; no collective launch, no host round trip for the halo.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void k_fg_halo_push(const T* x, i64 n, Peers peers, int R, int rank, int slot, unsigned long long seq) {
+    if (threadIdx.x != 0) return;
+    P2PBuf<T>* left = rank > 0 ? (P2PBuf<T>*)peers.p[rank - 1] : nullptr;
+    P2PBuf<T>* right = rank < R - 1 ? (P2PBuf<T>*)peers.p[rank + 1] : nullptr;
+    if (left) left->halo[slot][1] = x[0];
+    if (right) right->halo[slot][0] = x[n - 1];
+    __threadfence_system();
+    if (left) *(volatile unsigned long long*)&left->hflag[slot][1] = seq;
+    if (right) *(volatile unsigned long long*)&right->hflag[slot][0] = seq;
+}
+// blocks of the objective kernel: wait for the neighbours' values of this evaluation, leave them in halo_out[0..1]
+template <typename T>
+__global__ void k_fg_halo_wait(Wk<T> w, P2PBuf<T>* mine, int R, int rank, int slot, unsigned long long seq, T* halo_out) {
+    if (threadIdx.x != 0) return;
+    const long long t0 = clock64();
+    for (int side = 0; side < 2; ++side) {
+        const bool need = side == 0 ? rank > 0 : rank < R - 1;
+        T v = (T)0;
+        if (need) {
+            volatile unsigned long long* f = &mine->hflag[slot][side];
+            while (*f != seq) { if (clock64() - t0 > LB_P2P_SPIN_LIMIT) { w.s->p2p_timeout = 1; break; } }
+            __threadfence_system();
+            v = *(volatile T*)&mine->halo[slot][side];
+        }
+        halo_out[side] = v;
+    }
+}
+template <typename T>
+__global__ void k_fg_fsum_push(const T* fpart_local, Peers peers, int R, int rank, int slot, unsigned long long seq) {
+    if ((int)threadIdx.x >= R) return;
+    P2PBuf<T>* dst = (P2PBuf<T>*)peers.p[threadIdx.x];
+    dst->fpart[slot][rank] = fpart_local[0];
+    __threadfence_system();
+    *(volatile unsigned long long*)&dst->fflag[slot][rank] = seq;
+}
+template <typename T>
+__global__ void k_fg_fsum_wait(Wk<T> w, P2PBuf<T>* mine, int R, int slot, unsigned long long seq, T* f_out) {
+    p2p_wait<T>(w, mine->fflag[slot], R, seq);
+    if (threadIdx.x != 0) return;
+    T acc = *(volatile T*)&mine->fpart[slot][0];
+    for (int q = 1; q < R; ++q) acc = acc + *(volatile T*)&mine->fpart[slot][q];
+    f_out[0] = acc;
+}
+
 // Shard variants without a host round trip: the neighbours' boundary values are read from halo_dev[0..1] and the
 // shard's part of f is left in f_part_dev[0]; nothing is synchronised (the caller all-reduces f_part_dev on the
 // same stream and reads it once).
@@ -1540,6 +1593,38 @@ int lbfgsb_problem_rosenbrock_halo_f64(int64_t n, const double* x, double* g, do
 int lbfgsb_problem_quadratic_halo_f64(int64_t n, const double* x, double* g, double* f_part_dev, void* st, int64_t off,
                                       uint64_t seed, const double* halo_dev, void* scratch) {
     return quadratic_halo_impl<double>(n, x, g, f_part_dev, st, off, seed, halo_dev, scratch);
+}
+int lbfgsb_problem_sharded_f64(lbfgsb_dev_t* hh, int32_t kind, const double* x, double* g, double* f_out, uint64_t seed) {
+    EngineBase* b = (EngineBase*)hh;
+    if (!b || b->real_kind != 8) return 2;
+    Engine<double>* e = (Engine<double>*)b;
+    if (e->R <= 1 || !e->p2p) return 2;   // the caller falls back to its own halo exchange and all-reduce
+    typedef double T;
+    if (!e->fg_scratch) {
+        if (!e->dalloc(&e->fg_scratch, sizeof(T) * (LBFGSB_GRID + 8)) || !e->dalloc(&e->fg_out, sizeof(T) * 8)) return 1;
+        if (cudaMallocHost((void**)&e->fg_host, sizeof(T) * 8) != cudaSuccess) return 1;
+    }
+    cudaStream_t st = e->stream;
+    const unsigned long long seq = ++e->fg_seq;
+    const int slot = (int)(seq & 1ULL);
+    T* halo = e->fg_out + 2;       // [2]
+    T* fpart = e->fg_out + 4;      // [1]
+    k_fg_halo_push<T><<<1, 32, 0, st>>>(x, e->n, e->peers, e->R, e->rank, slot, seq);
+    k_fg_halo_wait<T><<<1, 32, 0, st>>>(e->w, e->p2p_local, e->R, e->rank, slot, seq, halo);
+    if (kind == 0) {
+        k_rosenbrock<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, st>>>(e->n, x, g, e->fg_scratch, e->rank == 0 ? 1 : 0, e->rank == e->R - 1 ? 1 : 0, (T)0, (T)0, halo);
+        k_rosenbrock_final<T><<<1, 32, 0, st>>>(e->fg_scratch, fpart);
+    } else {
+        const unsigned long long seedp = seed * 0x9E3779B97F4A7C15ULL;
+        k_quadratic<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, st>>>(e->n, x, g, e->fg_scratch, e->offset, seedp, (T)0, (T)0, halo);
+        k_sum_final<T><<<1, 32, 0, st>>>(e->fg_scratch, fpart);
+    }
+    k_fg_fsum_push<T><<<1, 32, 0, st>>>(fpart, e->peers, e->R, e->rank, slot, seq);
+    k_fg_fsum_wait<T><<<1, 32, 0, st>>>(e->w, e->p2p_local, e->R, slot, seq, e->fg_out);
+    if (cudaMemcpyAsync(e->fg_host, e->fg_out, sizeof(T), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("sharded objective failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
+    *f_out = e->fg_host[0];
+    return 0;
 }
 int lbfgsb_problem_quadratic_f64(int64_t n, const double* x, double* g, double* f_out, void* st, int64_t off, uint64_t seed,
                                  double xl, double xr, void* scratch) {

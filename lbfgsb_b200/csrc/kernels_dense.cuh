@@ -113,6 +113,12 @@ struct P2PBuf {
     Red<T> rec[2][LB_MAXR];
     unsigned long long flag[2][LB_MAXR];
     unsigned long long dflag[LB_MAXR];     // formk's entering/leaving corrections (delta_all) of rank q are complete
+    // chain-coupled sample objectives on a shard (lbfgsb_problem_sharded_f64): the neighbours' boundary values and the
+    // per-rank parts of f, two alternating slots like the records
+    T halo[2][2];                          // [slot][0]: last x of the left neighbour, [slot][1]: first x of the right one
+    unsigned long long hflag[2][2];
+    T fpart[2][LB_MAXR];
+    unsigned long long fflag[2][LB_MAXR];
 };
 struct Peers { void* p[LB_MAXR]; };
 

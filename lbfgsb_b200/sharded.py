@@ -130,13 +130,18 @@ class ShardedQuadraticDevice:
     """Device f/g of the convex quadratic on a shard: halo exchange + partial-f all-reduce around
     lbfgsb_problem_quadratic_* (lbfgsb_b200.QuadraticDevice)."""
 
-    def __init__(self, kernel, lo, rank, world, dist, device):
+    def __init__(self, kernel, lo, rank, world, dist, device, engine=None):
         self.k, self.lo, self.rank, self.world, self.dist, self.device = kernel, lo, rank, world, dist, device
+        self.engine = engine     # a sharded DeviceProblem: its peer-memory exchange carries halo and partial f
 
     def __call__(self, x, g):
         import torch
         if self.world == 1:
             return self.k(x, g, offset=self.lo)
+        if self.engine is not None and x.is_cuda and x.dtype == torch.float64:
+            f = self.engine.sharded_fg(1, x, g, seed=self.k.seed)
+            if f is not None:
+                return f
         if x.is_cuda and x.dtype == torch.float64:
             halo, fpart = _halo_on_device(x, self.rank, self.world, self.dist)
             self.k.shard_async(x, g, self.lo, halo, fpart)
@@ -158,13 +163,18 @@ class ShardedRosenbrockDevice:
     """Device f/g of the sample problem on a shard: halo exchange + partial-f all-reduce around
     lbfgsb_problem_rosenbrock_* (lbfgsb_b200.RosenbrockDevice)."""
 
-    def __init__(self, kernel, rank, world, dist, device):
+    def __init__(self, kernel, rank, world, dist, device, engine=None):
         self.k, self.rank, self.world, self.dist, self.device = kernel, rank, world, dist, device
+        self.engine = engine     # a sharded DeviceProblem: its peer-memory exchange carries halo and partial f
 
     def __call__(self, x, g):
         import torch
         if self.world == 1:
             return self.k(x, g)
+        if self.engine is not None and x.is_cuda and x.dtype == torch.float64:
+            f = self.engine.sharded_fg(0, x, g)
+            if f is not None:
+                return f
         if x.is_cuda and x.dtype == torch.float64:
             halo, fpart = _halo_on_device(x, self.rank, self.world, self.dist)
             self.k.shard_async(x, g, 1 if self.rank == 0 else 0, 1 if self.rank == self.world - 1 else 0, halo, fpart)

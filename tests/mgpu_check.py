@@ -37,6 +37,8 @@ def solve(n_local, off, n_global, m, l_odd, iters, shard, fg_factory, dev, rank,
     g = torch.zeros_like(x)
     prob = lbfgsb_b200.DeviceProblem(n_local, m, np.float64, shard=shard)
     fg = fg_factory()
+    if shard is not None and hasattr(fg, "engine") and os.environ.get("MGPU_FG", "peer") == "peer":
+        fg.engine = prob      # halo and partial f over the workspace's peer-memory exchange (else: torch collectives)
     rows = []
     while True:
         prob.setulb_dev(x, l, u, nbd, g, 0.0, 0.0)

@@ -19,9 +19,13 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("args", [("200000", "5", "1.0", "30"), ("100001", "10", "1.1", "25"), ("4099", "7", "1.5", "20"),
-                                  ("150001", "10", "0", "25", "quadratic")])
-def test_sharded_matches_single_gpu(args):
+@pytest.mark.parametrize("args,fg", [(("200000", "5", "1.0", "30"), "peer"), (("100001", "10", "1.1", "25"), "peer"),
+                                     (("4099", "7", "1.5", "20"), "peer"), (("4099", "7", "1.5", "20"), "torch"),
+                                     (("150001", "10", "0", "25", "quadratic"), "peer"),
+                                     (("150001", "10", "0", "25", "quadratic"), "torch")])
+def test_sharded_matches_single_gpu(args, fg):
+    """fg = "peer": the sample objective's halo and partial f travel over the workspace's peer-memory exchange
+    (lbfgsb_problem_sharded_f64); "torch": through torch.distributed collectives (lbfgsb_problem_*_halo_f64)."""
     import torch
     ng = torch.cuda.device_count()
     if ng < 2:
@@ -30,5 +34,7 @@ def test_sharded_matches_single_gpu(args):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "mgpu_check.py")] + list(args)
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    env = dict(os.environ)
+    env["MGPU_FG"] = fg
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0 and "MGPU_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
