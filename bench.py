@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--n", type=int, default=None, help="variables per GPU (default 1e8; 1.25e8 for the quadratic)")
     ap.add_argument("--m", type=int, default=10)
     ap.add_argument("--cpu-n", type=int, default=2_000_000, help="sample size of the CPU baseline")
+    ap.add_argument("--plain-fg", action="store_true", help="objective kernels without the line-search epilogue")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-family table here (JSON)")
@@ -297,16 +298,21 @@ def main():
         shard = (off, n_global, comm, rank, world)
     prob = lbfgsb_b200.DeviceProblem(n, m, np.float64, stream=stream, shard=shard)
     nfg = [0]
+    # The objective kernels run with their line-search epilogue (gd = g.d and max |proj g| formed while the gradient is
+    # in registers; include/lbfgsb_b200.h "Objective with line-search epilogue") unless --plain-fg asks for the plain ones.
+    epi = (ld, ud, nd) if not a.plain_fg else (None, None, None)
     if quad:
         fgk = lbfgsb_b200.QuadraticDevice(np.float64, seed=QUAD_SEED, stream=stream)
-        fg_one = (lambda: fgk(xd, gd, offset=0))
+        fg_one = (lambda: prob.fused_fg(1, xd, gd, *epi, seed=QUAD_SEED))
         if world > 1:
             fg_sh = sharded.ShardedQuadraticDevice(fgk, off, rank, world, dist, dev, engine=prob)
+            fg_sh.bounds = None if a.plain_fg else epi
     else:
         fgk = lbfgsb_b200.RosenbrockDevice(np.float64, stream=stream)
-        fg_one = (lambda: fgk(xd, gd))
+        fg_one = (lambda: prob.fused_fg(0, xd, gd, *epi))
         if world > 1:
             fg_sh = sharded.ShardedRosenbrockDevice(fgk, rank, world, dist, dev, engine=prob)
+            fg_sh.bounds = None if a.plain_fg else epi
 
     def fg():
         nfg[0] += 1
@@ -424,7 +430,9 @@ def main():
                    "nfree": int(nfree_t), "fg_evals_per_step": fg_per_iter,
                    "l2": "working set (%.1f GB per GPU) is far larger than the 126 MB L2; no flush needed" % (
                        (2 * m + 9) * n * 8 / 1e9),
-                   "fg": "device kernel, inside the timed region",
+                   "fg": "device kernel, inside the timed region" + ("" if a.plain_fg else
+                         "; it also forms the line-search sums g.d and max |proj g| (lbfgsb_problem_fused_f64), so the "
+                         "engine's own pass for them (k_ls_trial) is not launched"),
                    "rank_exchange": {0: "none (single GPU)", 1: "ncclAllGather of the reduction records",
                                      2: "reduction records stored into the peers' memory over NVLink (CUDA IPC), flags polled by the consuming kernel"}.get(prob.exchange_mode(), "?")},
         "gpu_launches": int(launches),

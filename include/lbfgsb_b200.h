@@ -155,12 +155,21 @@ int64_t lbfgsb_problem_scratch_bytes(void);
  * in f_part_dev[0] (device), nothing is synchronised -- the caller all-reduces f_part_dev on the same stream */
 int lbfgsb_problem_rosenbrock_halo_f64(int64_t n, const double* x_dev, double* g_dev, double* f_part_dev, void* cuda_stream,
                                        int32_t first, int32_t last, const double* halo_dev, void* scratch_dev);
-/* the same two objectives on a sharded workspace whose ranks exchange over peer memory (lbfgsb_dev_exchange_mode == 2):
- * halo values and the per-rank parts of f travel as stores into the neighbours' / peers' memory, f (summed in rank
- * order, identical on every rank) is read back once.  kind 0: Rosenbrock, 1: quadratic (seed).  x, g: this rank's
- * shard, evaluated on the workspace's stream.  Returns 0, 1 on a CUDA failure, 2 when the workspace does not exchange
- * over peer memory (use the *_halo_* variants with your own collectives then).                                        */
-int lbfgsb_problem_sharded_f64(lbfgsb_dev_t* h, int32_t kind, const double* x_dev, double* g_dev, double* f_out, uint64_t seed);
+/* Objective with line-search epilogue.  While the gradient of a trial point is still in
+ * registers, the objective kernel also forms gd = g.d (lnsrlb, src/lbfgsb.f90:2244) and max |proj g| (projgr :2610-2620)
+ * in the engine's fixed reduction shape (include/lbfgsb_b200_shape.h) and leaves the block partials where the engine's
+ * own pass (k_ls_trial) would; the next lbfgsb_setulb_dev call on the workspace skips that pass (44 bytes per variable).
+ * Same products in the same order: results are bit-identical.  Pass l, u, nbd (device pointers, as given to setulb) to
+ * get the epilogue, NULL to leave it out.  kind 0: Rosenbrock, 1: quadratic (seed).  Evaluated on the workspace's
+ * stream; f is read back once.  Returns 0, 1 on a CUDA failure, 2 when the workspace is of the wrong kind.
+ *   lbfgsb_problem_fused_f64   -- single-GPU workspace
+ *   lbfgsb_problem_sharded_f64 -- sharded workspace whose ranks exchange over peer memory (lbfgsb_dev_exchange_mode == 2):
+ *     halo values and the per-rank parts of f travel as stores into the neighbours' / peers' memory; f is summed in rank
+ *     order (identical on every rank).  Returns 2 otherwise (use the *_halo_* variants with your own collectives).   */
+int lbfgsb_problem_fused_f64(lbfgsb_dev_t* h, int32_t kind, const double* x_dev, double* g_dev, const double* l_dev,
+                             const double* u_dev, const int32_t* nbd_dev, double* f_out, uint64_t seed);
+int lbfgsb_problem_sharded_f64(lbfgsb_dev_t* h, int32_t kind, const double* x_dev, double* g_dev, const double* l_dev,
+                               const double* u_dev, const int32_t* nbd_dev, double* f_out, uint64_t seed);
 int lbfgsb_problem_quadratic_halo_f64(int64_t n, const double* x_dev, double* g_dev, double* f_part_dev, void* cuda_stream,
                                       int64_t index_offset, uint64_t seed, const double* halo_dev, void* scratch_dev);
 

@@ -262,13 +262,30 @@ class DeviceProblem:
             raise LbfgsbB200Error(last_error())
         return h.value, c.value
 
-    def sharded_fg(self, kind, x, g, seed=0):
+    @staticmethod
+    def _opt(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+    def fused_fg(self, kind, x, g, l=None, u=None, nbd=None, seed=0):
+        """Sample objective (0 Rosenbrock, 1 quadratic) on this single-GPU workspace's stream.  With l, u, nbd the
+        kernel also forms the line-search sums gd = g.d and max |proj g| (include/lbfgsb_b200.h:
+        lbfgsb_problem_fused_f64), and the next setulb_dev call skips its own pass over g, d, x, l, u, nbd."""
+        out = C.c_double(0.0)
+        rc = lib().lbfgsb_problem_fused_f64(C.c_void_p(self.h), C.c_int32(kind), C.c_void_p(x.data_ptr()),
+                                            C.c_void_p(g.data_ptr()), self._opt(l), self._opt(u), self._opt(nbd),
+                                            C.byref(out), C.c_uint64(int(seed)))
+        if rc != 0:
+            raise LbfgsbB200Error("objective kernel failed (rc %d): %s" % (rc, last_error()))
+        return out.value
+
+    def sharded_fg(self, kind, x, g, l=None, u=None, nbd=None, seed=0):
         """Sample objective (0 Rosenbrock, 1 quadratic) of this rank's shard with halo and partial-f exchange over peer
-        memory (include/lbfgsb_b200.h: lbfgsb_problem_sharded_f64).  Returns f, or None when the workspace does not
-        exchange over peer memory."""
+        memory (include/lbfgsb_b200.h: lbfgsb_problem_sharded_f64); with l, u, nbd also the line-search sums, as
+        fused_fg.  Returns f, or None when the workspace does not exchange over peer memory."""
         out = C.c_double(0.0)
         rc = lib().lbfgsb_problem_sharded_f64(C.c_void_p(self.h), C.c_int32(kind), C.c_void_p(x.data_ptr()),
-                                              C.c_void_p(g.data_ptr()), C.byref(out), C.c_uint64(int(seed)))
+                                              C.c_void_p(g.data_ptr()), self._opt(l), self._opt(u), self._opt(nbd),
+                                              C.byref(out), C.c_uint64(int(seed)))
         if rc == 2:
             return None
         if rc != 0:

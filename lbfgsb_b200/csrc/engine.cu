@@ -151,6 +151,7 @@ struct Engine : EngineBase {
     P2PBuf<T>* p2p_local = nullptr;
     Peers peers, peers_delta;
     std::vector<void*> ipc_opened;
+    bool trial_ready = false;   // the caller's objective kernel already left k_ls_trial's partials in w.part (TrialSums)
     unsigned long long site_seq = 0, delta_seq = 0, fg_seq = 0;
     T* fg_scratch = nullptr; T* fg_out = nullptr; T* fg_host = nullptr;
     int cur_slot = 0;
@@ -719,6 +720,8 @@ struct Engine : EngineBase {
     bool call(int entry, int aux, T* x, const T* l, const T* u, const int* nbd, T* f, T* g, T factr, T pgtol) {
         w.x = x; w.l = l; w.u = u; w.nbd = nbd; w.g = g;
         x_changed = false; g_changed = false;
+        const bool ts_ready = trial_ready;   // valid only for the call that follows the objective evaluation
+        trial_ready = false;
         if (entry == 0) {
             int host_err = 0;
             if (factr < (T)0) host_err = TK_ERR_FACTR;
@@ -756,7 +759,7 @@ struct Engine : EngineBase {
             begin(F_SCALAR); s_fg_start<T><<<LS>>>(w, dist()); end(F_SCALAR);
             if (!enqueue_body()) return false;
         } else if (entry == 2) {
-            begin(F_LS_TRIAL); k_ls_trial<T><<<LG>>>(w); end(F_LS_TRIAL);
+            if (!ts_ready) { begin(F_LS_TRIAL); k_ls_trial<T><<<LG>>>(w); end(F_LS_TRIAL); }
             if (!site(site_lstrial())) return false;
             begin(F_SCALAR); s_ls_trial<T><<<LS>>>(w, dist()); end(F_SCALAR);
             begin(F_LS_STEP); k_ls_step<T><<<LG>>>(w); end(F_LS_STEP);
@@ -1127,12 +1130,32 @@ static void setulb_host_impl(const int32_t* n, const int32_t* m, T* x, const T* 
 // ---------------------------------------------------------------------------
 // sample problem (test/driver1.f90:274-289) on the device
 // ---------------------------------------------------------------------------
+// Line-search epilogue of an objective kernel (lnsrlb :2244, projgr :2610-2620): while the
+// gradient of a trial point is still in registers the kernel also forms gd = g.d and max |proj g| in the engine's
+// fixed reduction shape -- the same products in the same order as k_ls_trial, which the next setulb call then skips.
+template <typename T>
+struct TrialSums {
+    const T* d; const T* l; const T* u; const int* nbd;   // search direction (engine), bounds (caller)
+    T* gd_part; T* pg_part;                                // block partials: the engine's slots of k_ls_trial
+};
+template <typename T>
+__device__ __forceinline__ void trial_sums_store(const TrialSums<T>& ts, T agd, T pg, T* sm) {
+    T a[1]; a[0] = agd;
+    __syncthreads();
+    block_sum_store<T, 1>(a, 1, sm, ts.gd_part);
+    __syncthreads();
+    T r = block_max<T>(pg, sm);
+    if (threadIdx.x == 0) ts.pg_part[blockIdx.x] = r;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(LBFGSB_BLOCK) k_rosenbrock(i64 n, const T* __restrict__ x, T* __restrict__ g,
-                                                            T* part, int first, int last, T xl, T xr, const T* halo) {
+                                                            T* part, int first, int last, T xl, T xr, const T* halo,
+                                                            TrialSums<T> ts) {
     constexpr int VEC = Real<T>::VEC;
     __shared__ T sm[LBFGSB_BLOCK / 32];
     if (halo) { xl = halo[0]; xr = halo[1]; }   // the neighbours' boundary values, still on the device
+    T agd = (T)0, pgm = (T)0;
     T acc[1]; acc[0] = (T)0;
     LB_FOR_TILES(T, n, base) {
         T xv[VEC], gv[VEC];
@@ -1159,8 +1182,19 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_rosenbrock(i64 n, const T* __r
             } else gv[v] = (T)0;
         }
         stv<T>(g, base, n, gv);
+        if (ts.d) {
+            T d[VEC], l[VEC], u[VEC]; int nb[VEC];
+            ldv<T>(ts.d, base, n, d); ldv<T>(ts.l, base, n, l); ldv<T>(ts.u, base, n, u); ldvi<T>(ts.nbd, base, n, nb);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (base + v < n) {
+                    agd = agd + gv[v] * d[v];
+                    pgm = dense::tmax(pgm, projg_one<T>(xv[v], gv[v], l[v], u[v], nb[v]));
+                }
+        }
     }
     block_sum_store<T, 1>(acc, 1, sm, part);
+    if (ts.d) trial_sums_store<T>(ts, agd, pgm, sm);
 }
 template <typename T>
 __global__ void k_rosenbrock_final(const T* part, T* out) {
@@ -1172,7 +1206,7 @@ static int rosenbrock_impl(i64 n, const T* x, T* g, T* f_out, void* st, int firs
     cudaStream_t s = (cudaStream_t)st;
     T* part = (T*)scratch;
     T* out = part + LBFGSB_GRID;
-    k_rosenbrock<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, first, last, xl, xr, nullptr);
+    k_rosenbrock<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, first, last, xl, xr, nullptr, TrialSums<T>{});
     k_rosenbrock_final<T><<<1, 32, 0, s>>>(part, out);
     if (cudaMemcpyAsync(f_out, out, sizeof(T), cudaMemcpyDeviceToHost, s) != cudaSuccess) return 1;
     if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("rosenbrock kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
@@ -1198,10 +1232,12 @@ __device__ __forceinline__ void quad_coeff(unsigned long long gi, unsigned long 
 }
 template <typename T>
 __global__ void __launch_bounds__(LBFGSB_BLOCK) k_quadratic(i64 n, const T* __restrict__ x, T* __restrict__ g, T* part,
-                                                           i64 off, unsigned long long seedp, T xl, T xr, const T* halo) {
+                                                           i64 off, unsigned long long seedp, T xl, T xr, const T* halo,
+                                                           TrialSums<T> ts) {
     constexpr int VEC = Real<T>::VEC;
     __shared__ T sm[LBFGSB_BLOCK / 32];
     if (halo) { xl = halo[0]; xr = halo[1]; }
+    T agd = (T)0, pgm = (T)0;
     T acc[1]; acc[0] = (T)0;
     LB_FOR_TILES(T, n, base) {
         T xv[VEC], gv[VEC];
@@ -1224,8 +1260,19 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_quadratic(i64 n, const T* __re
             }
         }
         stv<T>(g, base, n, gv);
+        if (ts.d) {
+            T d[VEC], l[VEC], u[VEC]; int nb[VEC];
+            ldv<T>(ts.d, base, n, d); ldv<T>(ts.l, base, n, l); ldv<T>(ts.u, base, n, u); ldvi<T>(ts.nbd, base, n, nb);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (base + v < n) {
+                    agd = agd + gv[v] * d[v];
+                    pgm = dense::tmax(pgm, projg_one<T>(xv[v], gv[v], l[v], u[v], nb[v]));
+                }
+        }
     }
     block_sum_store<T, 1>(acc, 1, sm, part);
+    if (ts.d) trial_sums_store<T>(ts, agd, pgm, sm);
 }
 template <typename T>
 __global__ void k_sum_final(const T* part, T* out) {
@@ -1238,7 +1285,7 @@ static int quadratic_impl(i64 n, const T* x, T* g, T* f_out, void* st, i64 off, 
     T* part = (T*)scratch;
     T* out = part + LBFGSB_GRID;
     const unsigned long long seedp = seed * 0x9E3779B97F4A7C15ULL;
-    k_quadratic<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, off, seedp, xl, xr, nullptr);
+    k_quadratic<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, off, seedp, xl, xr, nullptr, TrialSums<T>{});
     k_sum_final<T><<<1, 32, 0, s>>>(part, out);
     if (cudaMemcpyAsync(f_out, out, sizeof(T), cudaMemcpyDeviceToHost, s) != cudaSuccess) return 1;
     if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("quadratic kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
@@ -1303,7 +1350,7 @@ template <typename T>
 static int rosenbrock_halo_impl(i64 n, const T* x, T* g, T* f_part_dev, void* st, int first, int last, const T* halo_dev, void* scratch) {
     cudaStream_t s = (cudaStream_t)st;
     T* part = (T*)scratch;
-    k_rosenbrock<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, first, last, (T)0, (T)0, halo_dev);
+    k_rosenbrock<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, first, last, (T)0, (T)0, halo_dev, TrialSums<T>{});
     k_rosenbrock_final<T><<<1, 32, 0, s>>>(part, f_part_dev);
     return cudaGetLastError() != cudaSuccess;
 }
@@ -1312,7 +1359,7 @@ static int quadratic_halo_impl(i64 n, const T* x, T* g, T* f_part_dev, void* st,
     cudaStream_t s = (cudaStream_t)st;
     T* part = (T*)scratch;
     const unsigned long long seedp = seed * 0x9E3779B97F4A7C15ULL;
-    k_quadratic<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, off, seedp, (T)0, (T)0, halo_dev);
+    k_quadratic<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, s>>>(n, x, g, part, off, seedp, (T)0, (T)0, halo_dev, TrialSums<T>{});
     k_sum_final<T><<<1, 32, 0, s>>>(part, f_part_dev);
     return cudaGetLastError() != cudaSuccess;
 }
@@ -1375,6 +1422,18 @@ __global__ void k_test_heap_order(unsigned long long* k, int* v, i64 n, int* ord
     }
 }
 __global__ void k_test_setctl(SortCtl* c, i64 n) { if (threadIdx.x == 0) { c->count = n; c->cur = 0; c->skip = 0; } }
+
+// Single-GPU objective with the line-search epilogue (and the shared implementation of the epilogue's bookkeeping).
+template <typename T>
+static TrialSums<T> trial_sums_of(Engine<T>* e, const T* l, const T* u, const int32_t* nbd) {
+    TrialSums<T> ts; memset(&ts, 0, sizeof ts);
+    if (l && u && nbd) {
+        ts.d = e->w.d; ts.l = l; ts.u = u; ts.nbd = nbd;
+        ts.gd_part = LB_SLOT(e->w.part, 0); ts.pg_part = LB_SLOT(e->w.part, 1);
+        e->trial_ready = true;    // consumed (or dropped) by the next setulb call on this workspace
+    }
+    return ts;
+}
 
 // ---------------------------------------------------------------------------
 // C ABI
@@ -1594,12 +1653,40 @@ int lbfgsb_problem_quadratic_halo_f64(int64_t n, const double* x, double* g, dou
                                       uint64_t seed, const double* halo_dev, void* scratch) {
     return quadratic_halo_impl<double>(n, x, g, f_part_dev, st, off, seed, halo_dev, scratch);
 }
-int lbfgsb_problem_sharded_f64(lbfgsb_dev_t* hh, int32_t kind, const double* x, double* g, double* f_out, uint64_t seed) {
+int lbfgsb_problem_fused_f64(lbfgsb_dev_t* hh, int32_t kind, const double* x, double* g, const double* l, const double* u,
+                             const int32_t* nbd, double* f_out, uint64_t seed) {
+    EngineBase* b = (EngineBase*)hh;
+    if (!b || b->real_kind != 8) return 2;
+    Engine<double>* e = (Engine<double>*)b;
+    if (e->R > 1) return 2;
+    typedef double T;
+    if (!e->fg_scratch) {
+        if (!e->dalloc(&e->fg_scratch, sizeof(T) * (LBFGSB_GRID + 8)) || !e->dalloc(&e->fg_out, sizeof(T) * 8)) return 1;
+        if (cudaMallocHost((void**)&e->fg_host, sizeof(T) * 8) != cudaSuccess) return 1;
+    }
+    cudaStream_t st = e->stream;
+    const TrialSums<T> ts = trial_sums_of<T>(e, l, u, nbd);
+    if (kind == 0) {
+        k_rosenbrock<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, st>>>(e->n, x, g, e->fg_scratch, 1, 1, (T)0, (T)0, nullptr, ts);
+        k_rosenbrock_final<T><<<1, 32, 0, st>>>(e->fg_scratch, e->fg_out);
+    } else {
+        const unsigned long long seedp = seed * 0x9E3779B97F4A7C15ULL;
+        k_quadratic<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, st>>>(e->n, x, g, e->fg_scratch, 0, seedp, (T)0, (T)0, nullptr, ts);
+        k_sum_final<T><<<1, 32, 0, st>>>(e->fg_scratch, e->fg_out);
+    }
+    if (cudaMemcpyAsync(e->fg_host, e->fg_out, sizeof(T), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("objective kernel failed: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
+    *f_out = e->fg_host[0];
+    return 0;
+}
+int lbfgsb_problem_sharded_f64(lbfgsb_dev_t* hh, int32_t kind, const double* x, double* g, const double* l, const double* u,
+                               const int32_t* nbd, double* f_out, uint64_t seed) {
     EngineBase* b = (EngineBase*)hh;
     if (!b || b->real_kind != 8) return 2;
     Engine<double>* e = (Engine<double>*)b;
     if (e->R <= 1 || !e->p2p) return 2;   // the caller falls back to its own halo exchange and all-reduce
     typedef double T;
+    const TrialSums<T> ts = trial_sums_of<T>(e, l, u, nbd);
     if (!e->fg_scratch) {
         if (!e->dalloc(&e->fg_scratch, sizeof(T) * (LBFGSB_GRID + 8)) || !e->dalloc(&e->fg_out, sizeof(T) * 8)) return 1;
         if (cudaMallocHost((void**)&e->fg_host, sizeof(T) * 8) != cudaSuccess) return 1;
@@ -1612,11 +1699,11 @@ int lbfgsb_problem_sharded_f64(lbfgsb_dev_t* hh, int32_t kind, const double* x, 
     k_fg_halo_push<T><<<1, 32, 0, st>>>(x, e->n, e->peers, e->R, e->rank, slot, seq);
     k_fg_halo_wait<T><<<1, 32, 0, st>>>(e->w, e->p2p_local, e->R, e->rank, slot, seq, halo);
     if (kind == 0) {
-        k_rosenbrock<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, st>>>(e->n, x, g, e->fg_scratch, e->rank == 0 ? 1 : 0, e->rank == e->R - 1 ? 1 : 0, (T)0, (T)0, halo);
+        k_rosenbrock<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, st>>>(e->n, x, g, e->fg_scratch, e->rank == 0 ? 1 : 0, e->rank == e->R - 1 ? 1 : 0, (T)0, (T)0, halo, ts);
         k_rosenbrock_final<T><<<1, 32, 0, st>>>(e->fg_scratch, fpart);
     } else {
         const unsigned long long seedp = seed * 0x9E3779B97F4A7C15ULL;
-        k_quadratic<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, st>>>(e->n, x, g, e->fg_scratch, e->offset, seedp, (T)0, (T)0, halo);
+        k_quadratic<T><<<LBFGSB_GRID, LBFGSB_BLOCK, 0, st>>>(e->n, x, g, e->fg_scratch, e->offset, seedp, (T)0, (T)0, halo, ts);
         k_sum_final<T><<<1, 32, 0, st>>>(e->fg_scratch, fpart);
     }
     k_fg_fsum_push<T><<<1, 32, 0, st>>>(fpart, e->peers, e->R, e->rank, slot, seq);

@@ -133,13 +133,14 @@ class ShardedQuadraticDevice:
     def __init__(self, kernel, lo, rank, world, dist, device, engine=None):
         self.k, self.lo, self.rank, self.world, self.dist, self.device = kernel, lo, rank, world, dist, device
         self.engine = engine     # a sharded DeviceProblem: its peer-memory exchange carries halo and partial f
+        self.bounds = None       # (l, u, nbd) device tensors: the kernel then also forms the line-search sums
 
     def __call__(self, x, g):
         import torch
         if self.world == 1:
             return self.k(x, g, offset=self.lo)
         if self.engine is not None and x.is_cuda and x.dtype == torch.float64:
-            f = self.engine.sharded_fg(1, x, g, seed=self.k.seed)
+            f = self.engine.sharded_fg(1, x, g, *(self.bounds or (None, None, None)), seed=self.k.seed)
             if f is not None:
                 return f
         if x.is_cuda and x.dtype == torch.float64:
@@ -166,13 +167,14 @@ class ShardedRosenbrockDevice:
     def __init__(self, kernel, rank, world, dist, device, engine=None):
         self.k, self.rank, self.world, self.dist, self.device = kernel, rank, world, dist, device
         self.engine = engine     # a sharded DeviceProblem: its peer-memory exchange carries halo and partial f
+        self.bounds = None       # (l, u, nbd) device tensors: the kernel then also forms the line-search sums
 
     def __call__(self, x, g):
         import torch
         if self.world == 1:
             return self.k(x, g)
         if self.engine is not None and x.is_cuda and x.dtype == torch.float64:
-            f = self.engine.sharded_fg(0, x, g)
+            f = self.engine.sharded_fg(0, x, g, *(self.bounds or (None, None, None)))
             if f is not None:
                 return f
         if x.is_cuda and x.dtype == torch.float64:

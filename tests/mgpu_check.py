@@ -39,6 +39,7 @@ def solve(n_local, off, n_global, m, l_odd, iters, shard, fg_factory, dev, rank,
     fg = fg_factory()
     if shard is not None and hasattr(fg, "engine") and os.environ.get("MGPU_FG", "peer") == "peer":
         fg.engine = prob      # halo and partial f over the workspace's peer-memory exchange (else: torch collectives)
+        fg.bounds = (l, u, nbd)   # ... and the objective kernel forms the line-search sums (k_ls_trial is skipped)
     rows = []
     while True:
         prob.setulb_dev(x, l, u, nbd, g, 0.0, 0.0)

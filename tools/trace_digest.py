@@ -61,7 +61,10 @@ def run_case(case):
         prob.setulb_dev(x, l, u, nbd, g, factr, pgtol)
         t = prob.task_str()
         if t[:2] == "FG":
-            prob.f[0] = fg(x, g)
+            if dt == "f64" and os.environ.get("LBFGSB_DIGEST_FUSED_FG") == "1":
+                prob.f[0] = prob.fused_fg(0, x, g, l, u, nbd)     # objective kernel with the line-search epilogue
+            else:
+                prob.f[0] = fg(x, g)
         elif t[:5] == "NEW_X":
             hh, _ = prob.active_set_hash()
             i, d = prob.isave, prob.dsave
