@@ -31,6 +31,7 @@ module lbfgsb_module
 
    public :: setulb, setulb_dev
    public :: lbfgsb_dev_create, lbfgsb_dev_destroy, lbfgsb_host_release
+   public :: lbfgsb_dev_set_tie_limit, lbfgsb_dev_checkpoint_write, lbfgsb_dev_checkpoint_read
 
    interface
 
@@ -85,6 +86,28 @@ module lbfgsb_module
          import :: c_int32_t
          integer(c_int32_t), intent(inout) :: isave(44)
       end subroutine lbfgsb_host_release
+
+      !> Heap replay of equal breakpoints at the exit of the Cauchy search (hpsolb's pop order, src/lbfgsb.f90:2079-2157):
+      !> up to max_breakpoints breakpoints per call (default 2**21; 0 = ties in variable order).
+      subroutine lbfgsb_dev_set_tie_limit(h, max_breakpoints) bind(C, name='lbfgsb_dev_set_tie_limit')
+         import :: c_ptr, c_int64_t
+         type(c_ptr), value :: h
+         integer(c_int64_t), value :: max_breakpoints
+      end subroutine lbfgsb_dev_set_tie_limit
+
+      !> Device workspace to / from a file (the reference's wa, iwa); path is a C string (trim(name)//c_null_char).
+      function lbfgsb_dev_checkpoint_write(h, path) result(rc) bind(C, name='lbfgsb_dev_checkpoint_write')
+         import :: c_ptr, c_char, c_int
+         type(c_ptr), value :: h
+         character(kind=c_char), intent(in) :: path(*)
+         integer(c_int) :: rc
+      end function lbfgsb_dev_checkpoint_write
+      function lbfgsb_dev_checkpoint_read(h, path) result(rc) bind(C, name='lbfgsb_dev_checkpoint_read')
+         import :: c_ptr, c_char, c_int
+         type(c_ptr), value :: h
+         character(kind=c_char), intent(in) :: path(*)
+         integer(c_int) :: rc
+      end function lbfgsb_dev_checkpoint_read
 
    end interface
 
