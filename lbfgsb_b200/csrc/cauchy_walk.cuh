@@ -986,6 +986,14 @@ __global__ void __launch_bounds__(1024) k_heap_replay(Wk<T> w, WalkBuf<T> b) {
 // ---------------------------------------------------------------------------
 #define LB_FD_GRID 592
 #define LB_FD_ROWS 32
+#define LB_FD_TB 4          // a thread owns a 4 x 4 block of (i, j) pairs of one of the three products
+// Work decomposition: the (i, j) space of each product is cut into 4 x 4 blocks -- Wy_i Wy_j and Ws_i Ws_j only on and
+// below the diagonal (formk uses jy <= iy, :1802-1826), Ws_i Wy_j in full (:1830-1851) -- and the 256 threads are
+// NSUB copies of that block list, copy s taking the rows r = s, s + NSUB, ... of every 32-row tile.  Per row a thread
+// reads 4 + 4 values from the shared tile and does 16 multiply-adds (the old mapping read two values per
+// multiply-add and ran at the shared-memory limit).  The NSUB partial sums are added in copy order at the end.
+__host__ __device__ inline int fd_tiles_1d(int col) { return (col + LB_FD_TB - 1) / LB_FD_TB; }
+__host__ __device__ inline int fd_ntiles(int col) { const int t = fd_tiles_1d(col); return t * (t + 1) + t * t; }
 template <typename T>
 __global__ void __launch_bounds__(256) k_formk_delta(Wk<T> w, const int* list, const SortCtl* ctl, T* out) {
     const DevState<T>* s = w.s;
@@ -997,50 +1005,83 @@ __global__ void __launch_bounds__(256) k_formk_delta(Wk<T> w, const int* list, c
     i64 end = beg + chunk; if (end > nel) end = nel;
     __shared__ T tile[LB_FD_ROWS][2 * LB_MMAX + 1];
     __shared__ int ent[LB_FD_ROWS];
-    constexpr int PMAX = (3 * LB_MMAX * LB_MMAX + 255) / 256;
-    T accE[PMAX], accL[PMAX];
+    __shared__ T accs[6 * LB_MMAX * LB_MMAX];
+    // this thread's block of pairs
+    const int t1 = fd_tiles_1d(col), ntl = fd_ntiles(col), ntri = t1 * (t1 + 1) / 2;
+    const int nsub = 256 / ntl;
+    const int sub = threadIdx.x / ntl, tl = threadIdx.x % ntl;
+    const bool active = sub < nsub;
+    int blk, ti, tj;   // product (0: Wy.Wy, 1: Ws.Ws, 2: Ws.Wy), block row, block column
+    if (tl < 2 * ntri) {
+        blk = tl / ntri;
+        int k = tl % ntri; ti = 0;
+        while (k >= ti + 1) { k -= ti + 1; ++ti; }
+        tj = k;
+    } else { blk = 2; const int k = tl - 2 * ntri; ti = k / t1; tj = k % t1; }
+    const int ca0 = ((blk == 0) ? 0 : col) + ti * LB_FD_TB;    // tile columns of the i factors
+    const int cb0 = ((blk == 1) ? col : 0) + tj * LB_FD_TB;    // ... of the j factors
+    T accE[LB_FD_TB][LB_FD_TB], accL[LB_FD_TB][LB_FD_TB];
 #pragma unroll
-    for (int q = 0; q < PMAX; ++q) { accE[q] = (T)0; accL[q] = (T)0; }
-    const int npairs = 3 * col * col;
+    for (int a = 0; a < LB_FD_TB; ++a)
+#pragma unroll
+        for (int b = 0; b < LB_FD_TB; ++b) { accE[a][b] = (T)0; accL[a][b] = (T)0; }
+    for (int e = threadIdx.x; e < 6 * LB_MMAX * LB_MMAX; e += 256) accs[e] = (T)0;
+    // the columns a 4-wide block reads beyond 2*col (col not a multiple of 4) must be finite: zero them once
+    for (int e = threadIdx.x; e < LB_FD_ROWS * LB_FD_TB; e += 256) { const int c = col2 + e / LB_FD_ROWS; if (c < 2 * LB_MMAX + 1) tile[e % LB_FD_ROWS][c] = (T)0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     for (i64 r0 = beg; r0 < end; r0 += LB_FD_ROWS) {
         const int nr = (int)((end - r0 < LB_FD_ROWS) ? (end - r0) : LB_FD_ROWS);
-        for (int e = threadIdx.x; e < nr * col2; e += 256) {
-            const int r = e % nr, c = e / nr;
-            const int var = list[r0 + r];
-            const int ring = c < col ? c : c - col;
-            int pj = head0 + ring; if (pj >= m) pj -= m;
-            tile[r][c] = (c < col) ? w.wy[(i64)pj * w.ldw + var] : w.ws[(i64)pj * w.ldw + var];
+        // gather: lane = listed row (its variable index is read once), the 8 warps share the 2*col columns
+        if (lane < nr) {
+            const i64 var = list[r0 + lane];
+            if (wrp == 0) ent[lane] = (w.state[var] & 1);   // free now => entering
+            for (int c = wrp; c < col2; c += 8) {
+                const int ring = c < col ? c : c - col;
+                int pj = head0 + ring; if (pj >= m) pj -= m;
+                tile[lane][c] = (c < col) ? w.wy[(i64)pj * w.ldw + var] : w.ws[(i64)pj * w.ldw + var];
+            }
         }
-        for (int r = threadIdx.x; r < nr; r += 256) ent[r] = (w.state[list[r0 + r]] & 1);   // free now => entering
         __syncthreads();
+        if (active) {
+            for (int r = sub; r < nr; r += nsub) {
+                T av[LB_FD_TB], bv[LB_FD_TB];
 #pragma unroll
-        for (int q = 0; q < PMAX; ++q) {
-            const int pr = threadIdx.x + q * 256;
-            if (pr < npairs) {
-                const int blk = pr / (col * col), ij = pr % (col * col);
-                const int i = ij % col, j = ij / col;
-                // blk 0: Wy_i*Wy_j ; 1: Ws_i*Ws_j ; 2: Ws_i*Wy_j
-                const int ca = (blk == 0) ? i : col + i;
-                const int cb = (blk == 1) ? col + j : j;
-                for (int r = 0; r < nr; ++r) {
-                    const T pv = tile[r][ca] * tile[r][cb];
-                    if (ent[r]) accE[q] = accE[q] + pv; else accL[q] = accL[q] + pv;
+                for (int a = 0; a < LB_FD_TB; ++a) { av[a] = tile[r][ca0 + a]; bv[a] = tile[r][cb0 + a]; }
+                if (ent[r]) {
+#pragma unroll
+                    for (int a = 0; a < LB_FD_TB; ++a)
+#pragma unroll
+                        for (int b = 0; b < LB_FD_TB; ++b) accE[a][b] = accE[a][b] + av[a] * bv[b];
+                } else {
+#pragma unroll
+                    for (int a = 0; a < LB_FD_TB; ++a)
+#pragma unroll
+                        for (int b = 0; b < LB_FD_TB; ++b) accL[a][b] = accL[a][b] + av[a] * bv[b];
                 }
             }
         }
         __syncthreads();
     }
+    // add the NSUB copies in copy order (fixed), then one partial per block of the grid
+    for (int sb = 0; sb < nsub; ++sb) {
+        if (active && sub == sb) {
 #pragma unroll
-    for (int q = 0; q < PMAX; ++q) {
-        const int pr = threadIdx.x + q * 256;
-        if (pr < npairs) {
-            const int blk = pr / (col * col), ij = pr % (col * col);
-            const int i = ij % col, j = ij / col;
-            T* o = out + (i64)blockIdx.x * (6 * LB_MMAX * LB_MMAX);
-            o[(blk)*LB_MMAX * LB_MMAX + i + j * LB_MMAX] = accE[q];
-            o[(3 + blk) * LB_MMAX * LB_MMAX + i + j * LB_MMAX] = accL[q];
+            for (int a = 0; a < LB_FD_TB; ++a)
+#pragma unroll
+                for (int b = 0; b < LB_FD_TB; ++b) {
+                    const int i = ti * LB_FD_TB + a, j = tj * LB_FD_TB + b;
+                    if (i < col && j < col) {
+                        const int e = i + j * LB_MMAX;
+                        accs[blk * LB_MMAX * LB_MMAX + e] = accs[blk * LB_MMAX * LB_MMAX + e] + accE[a][b];
+                        accs[(3 + blk) * LB_MMAX * LB_MMAX + e] = accs[(3 + blk) * LB_MMAX * LB_MMAX + e] + accL[a][b];
+                    }
+                }
         }
+        __syncthreads();
     }
+    T* o = out + (i64)blockIdx.x * (6 * LB_MMAX * LB_MMAX);
+    for (int e = threadIdx.x; e < 6 * LB_MMAX * LB_MMAX; e += 256) o[e] = accs[e];
 }
 
 // sum the per-block partials in block order (one thread per entry, serial: fixed order)

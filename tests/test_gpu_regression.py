@@ -6,7 +6,9 @@ shape -- the fused passes (k_update_classify, k_formk_cmprlb) must give exactly 
 separate passes they replace.  tests/golden/gpu_trace_digest.json was recorded on a B200 (first with the
 unfused kernels; re-recorded for the two cases whose Cauchy search crosses a round boundary when the
 breakpoint walk was split into rounds, which re-associates the prefix sums there -- every case still
-passes the oracle parity tests); it is compared here with a fresh run, with the fused passes on and off.
+passes the oracle parity tests; and once more for n100001_m5 when formk's entering/leaving corrections got a
+register-tiled kernel, which adds the listed rows in a different order); it is compared here with a fresh run, with
+the fused passes on and off.
 """
 import json
 import os

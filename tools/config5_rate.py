@@ -22,6 +22,7 @@ st = torch.cuda.current_stream().cuda_stream
 prob = lbfgsb_b200.DeviceProblem(n, m, np.float32, stream=st)
 fg = lbfgsb_b200.RosenbrockDevice(np.float32, stream=st)
 import time
+prob.profile(True)
 rows = []
 nfg = 0
 torch.cuda.synchronize(); t0 = time.perf_counter(); nfg_last = 0
@@ -46,3 +47,5 @@ for r in rows:
     it, col, nseg, nfree, nf, ms, f = r
     canon = n * (35 * w + 40) + nfree * (12 * w + 20) + 2 * col * w * (2 * n + nfree + 3 * nfree)
     print("  %3d  col %2d  nseg %9d  nfree %9d  fg %d  %8.2f ms  canonical %6.1f GB -> %6.0f GB/s   f %.6e" % (it, col, nseg, nfree, nf, ms, canon / 1e9, canon / ms / 1e6, f))
+pr = prob.profile_read()
+print("kernel families over the whole run (total ms, calls):", {k: (round(v["ms"], 1), v["calls"]) for k, v in pr.items() if v["ms"] > 5})
