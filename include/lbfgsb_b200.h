@@ -162,10 +162,27 @@ int lbfgsb_problem_rosenbrock_halo_f64(int64_t n, const double* x_dev, double* g
  * Same products in the same order: results are bit-identical.  Pass l, u, nbd (device pointers, as given to setulb) to
  * get the epilogue, NULL to leave it out.  kind 0: Rosenbrock, 1: quadratic (seed).  Evaluated on the workspace's
  * stream; f is read back once.  Returns 0, 1 on a CUDA failure, 2 when the workspace is of the wrong kind.
+ * (The built-in objectives use the caller-side hook below, lbfgsb_dev_trial_sums / _commit.)
  *   lbfgsb_problem_fused_f64   -- single-GPU workspace
  *   lbfgsb_problem_sharded_f64 -- sharded workspace whose ranks exchange over peer memory (lbfgsb_dev_exchange_mode == 2):
  *     halo values and the per-rank parts of f travel as stores into the neighbours' / peers' memory; f is summed in rank
  *     order (identical on every rank).  Returns 2 otherwise (use the *_halo_* variants with your own collectives).   */
+/* The same hook for a caller's own gradient kernel.  lbfgsb_dev_trial_sums gives the search direction d and the two
+ * arrays of `grid` block partials; the kernel must walk the variables in the fixed shape of lbfgsb_b200_shape.h
+ * (`grid` blocks of `block` threads, tiles of block*VEC*unroll variables, VEC = 16 / real_kind), add g_i*d_i into one
+ * accumulator per thread in that order, combine lanes by xor-butterfly and warps serially (block_sum_store in
+ * lbfgsb_b200/csrc/common.cuh), store the block's sum in gd_part_dev[blockIdx.x] and the block's maximum of
+ * |proj g|_i (projgr :2611-2619) in pg_part_dev[blockIdx.x]; then call lbfgsb_dev_trial_sums_commit before the next
+ * setulb_dev (task FG_LNSRCH).  Without the commit the engine computes the sums itself.                              */
+typedef struct {
+    const void* d_dev;      /* search direction of the current line search, n reals                       */
+    void* gd_part_dev;      /* [grid] block partials of sum g_i d_i                                        */
+    void* pg_part_dev;      /* [grid] block partials of max |proj g|_i                                     */
+    int64_t n;
+    int32_t grid, block, unroll, real_kind;
+} lbfgsb_trial_sums_t;
+int lbfgsb_dev_trial_sums(lbfgsb_dev_t* h, lbfgsb_trial_sums_t* out);
+void lbfgsb_dev_trial_sums_commit(lbfgsb_dev_t* h);
 int lbfgsb_problem_fused_f64(lbfgsb_dev_t* h, int32_t kind, const double* x_dev, double* g_dev, const double* l_dev,
                              const double* u_dev, const int32_t* nbd_dev, double* f_out, uint64_t seed);
 int lbfgsb_problem_sharded_f64(lbfgsb_dev_t* h, int32_t kind, const double* x_dev, double* g_dev, const double* l_dev,

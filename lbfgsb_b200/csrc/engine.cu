@@ -1424,13 +1424,17 @@ __global__ void k_test_heap_order(unsigned long long* k, int* v, i64 n, int* ord
 __global__ void k_test_setctl(SortCtl* c, i64 n) { if (threadIdx.x == 0) { c->count = n; c->cur = 0; c->skip = 0; } }
 
 // Single-GPU objective with the line-search epilogue (and the shared implementation of the epilogue's bookkeeping).
+// (the built-in objectives go through the same two public calls a caller's own kernel would use)
+extern "C" int lbfgsb_dev_trial_sums(lbfgsb_dev_t* h, lbfgsb_trial_sums_t* out);
+extern "C" void lbfgsb_dev_trial_sums_commit(lbfgsb_dev_t* h);
 template <typename T>
 static TrialSums<T> trial_sums_of(Engine<T>* e, const T* l, const T* u, const int32_t* nbd) {
     TrialSums<T> ts; memset(&ts, 0, sizeof ts);
-    if (l && u && nbd) {
-        ts.d = e->w.d; ts.l = l; ts.u = u; ts.nbd = nbd;
-        ts.gd_part = LB_SLOT(e->w.part, 0); ts.pg_part = LB_SLOT(e->w.part, 1);
-        e->trial_ready = true;    // consumed (or dropped) by the next setulb call on this workspace
+    lbfgsb_trial_sums_t pub;
+    if (l && u && nbd && lbfgsb_dev_trial_sums((lbfgsb_dev_t*)e, &pub) == 0) {
+        ts.d = (const T*)pub.d_dev; ts.l = l; ts.u = u; ts.nbd = nbd;
+        ts.gd_part = (T*)pub.gd_part_dev; ts.pg_part = (T*)pub.pg_part_dev;
+        lbfgsb_dev_trial_sums_commit((lbfgsb_dev_t*)e);
     }
     return ts;
 }
@@ -1652,6 +1656,26 @@ int lbfgsb_problem_rosenbrock_halo_f64(int64_t n, const double* x, double* g, do
 int lbfgsb_problem_quadratic_halo_f64(int64_t n, const double* x, double* g, double* f_part_dev, void* st, int64_t off,
                                       uint64_t seed, const double* halo_dev, void* scratch) {
     return quadratic_halo_impl<double>(n, x, g, f_part_dev, st, off, seed, halo_dev, scratch);
+}
+int lbfgsb_dev_trial_sums(lbfgsb_dev_t* h, lbfgsb_trial_sums_t* out) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b || !out) return 1;
+    memset(out, 0, sizeof *out);
+    if (b->real_kind == 8) {
+        Engine<double>* e = (Engine<double>*)b;
+        out->d_dev = e->w.d; out->gd_part_dev = LB_SLOT(e->w.part, 0); out->pg_part_dev = LB_SLOT(e->w.part, 1); out->n = e->n;
+    } else {
+        Engine<float>* e = (Engine<float>*)b;
+        out->d_dev = e->w.d; out->gd_part_dev = LB_SLOT(e->w.part, 0); out->pg_part_dev = LB_SLOT(e->w.part, 1); out->n = e->n;
+    }
+    out->grid = LBFGSB_GRID; out->block = LBFGSB_BLOCK; out->unroll = LBFGSB_UNROLL; out->real_kind = b->real_kind;
+    return 0;
+}
+void lbfgsb_dev_trial_sums_commit(lbfgsb_dev_t* h) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b) return;
+    if (b->real_kind == 8) ((Engine<double>*)b)->trial_ready = true;   // consumed (or dropped) by the next setulb call
+    else ((Engine<float>*)b)->trial_ready = true;
 }
 int lbfgsb_problem_fused_f64(lbfgsb_dev_t* hh, int32_t kind, const double* x, double* g, const double* l, const double* u,
                              const int32_t* nbd, double* f_out, uint64_t seed) {
