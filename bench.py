@@ -143,7 +143,7 @@ def reference_arm(a):
     world = max(1, a.gpus)
     full_n = a.n * world
     v = 1.0 / (spi * full_n / n)
-    sample = ("CPU oracle port of src/lbfgsb.f90 (g++ -O2, serial like the reference), time inside setulb only, "
+    sample = ("CPU oracle port of src/lbfgsb.f90 (g++ -O3 -funroll-loops, serial like the reference), time inside setulb only, "
               "n=%d sample of the same problem, %d iterations after %d warm-up; scaled linearly to n=%d" % (
                   n, k, a.warmup, full_n))
     out = {
