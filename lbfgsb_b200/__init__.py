@@ -102,6 +102,14 @@ def lib():
                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, cr, cr, C.c_void_p]
             getattr(L, "lbfgsb_problem_quadratic_" + sfx).argtypes = [
                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, cr, cr, C.c_void_p]
+        L.lbfgsb_problem_rosenbrock_halo_f64.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                                         C.c_int32, C.c_void_p, C.c_void_p]
+        L.lbfgsb_problem_quadratic_halo_f64.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                                        C.c_uint64, C.c_void_p, C.c_void_p]
+        for nm in ("lbfgsb_problem_fused_f64", "lbfgsb_problem_sharded_f64"):
+            getattr(L, nm).argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_uint64]
+        L.lbfgsb_dev_exchange_mode.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 

@@ -15,7 +15,7 @@
 typedef long long i64;
 
 #define LB_MMAX 20               // largest history size m supported by the kernels
-#define LB_KMAX (4 * LB_MMAX + 16)  // real-valued reduction slots per site
+#define LB_KMAX (6 * LB_MMAX + 8)   // real-valued reduction slots per site (the merged freev+formk+wv record: 6m)
 #define LB_IMAX 8                // integer reduction slots per site
 
 // task codes (mainlb's character(60) Task, decoded on the host)
@@ -24,6 +24,8 @@ enum {
     TK_ABNORMAL = 6, TK_RESTART = 7, TK_STOP = 8,
     TK_ERR_N = 10, TK_ERR_M = 11, TK_ERR_FACTR = 12, TK_ERR_NBD = 13, TK_ERR_INFEAS = 14
 };
+// resume points of the general pipeline after a pause of the fast one (Engine::enqueue_body)
+enum { PAUSE_NONE = 0, PAUSE_CLASSIFY = 1, PAUSE_WALK = 2, PAUSE_GCP_FREEV = 3, PAUSE_DELTA = 4, PAUSE_BACKTRACK = 5, PAUSE_LSINIT = 6 };
 // dcsrch task codes (Csave)
 enum {
     CS_START = 0, CS_FG = 1, CS_CONV = 2, CS_WARN_ROUND = 3, CS_WARN_XTOL = 4, CS_WARN_STPMAX = 5,
@@ -74,6 +76,9 @@ template <typename T>
 struct DevState {
     // ---- pipeline control (device-side predication of the enqueued kernels) ----
     int go;            // 1: keep executing the enqueued pipeline; 0: a return point was reached
+    int pause;         // fast pipeline (engine.cu "fast path"): a merged scalar kernel met a branch that the common-path
+                       // sequence does not cover; everything enqueued after it returns at once and the host resumes the
+                       // general pipeline at this stage (PAUSE_* below)
     int in_body;       // 1: the "prelims + first lnsrlb" kernels are enabled
     int restart;       // 1: L-BFGS memory was reset; host must enqueue the body again
     int need_walk;     // cauchy: the breakpoint walk (sort + scans) is required

@@ -145,6 +145,7 @@ struct Engine : EngineBase {
     std::vector<cudaEvent_t> pool;
     double fam_ms[F_COUNT]; i64 fam_calls[F_COUNT];
     bool x_changed = false, g_changed = false;
+    bool started = false;            // this workspace has seen task = 'START' (or a checkpoint of a started run)
 
     // records over peer memory (kernels_dense.cuh: P2PBuf)
     bool p2p = false;
@@ -155,9 +156,11 @@ struct Engine : EngineBase {
     unsigned long long site_seq = 0, delta_seq = 0, fg_seq = 0;
     T* fg_scratch = nullptr; T* fg_out = nullptr; T* fg_host = nullptr;
     int cur_slot = 0;
-    Dist<T> dist() const {
+    bool site_pending = false;   // a producer was launched and its consumer not yet: the next dist() carries wait = 1
+    Dist<T> dist() {
         Dist<T> d; d.R = R; d.all = rec_all;
         d.p2p = p2p ? p2p_local : nullptr; d.slot = cur_slot; d.seq = site_seq; d.dseq = delta_seq;
+        d.wait = site_pending ? 1 : 0; site_pending = false;
         return d;
     }
     // Exchange CUDA IPC handles of the P2PBuf and of delta_all through the engine's communicator and map the peers'
@@ -226,6 +229,9 @@ struct Engine : EngineBase {
         mt = (m <= 5) ? 5 : (m <= 10 ? 10 : 20);
         fused = (mt == 5 ? fused_passes_ok<T, 5>() : (mt == 10 ? fused_passes_ok<T, 10>() : fused_passes_ok<T, 20>()));
         if (const char* e = getenv("LBFGSB_B200_NO_FUSION")) { if (e[0] == '1') fused = false; }
+        fast = fused;   // the fast NEW_X pipeline is built from the fused passes
+        if (const char* e = getenv("LBFGSB_B200_NO_FAST")) { if (e[0] == '1') fast = false; }
+        if (const char* e = getenv("LBFGSB_B200_NO_TIMERS")) { if (e[0] == '1') timers = false; }
         if (!(mt == 5 ? set_smem_attrs<5>() : (mt == 10 ? set_smem_attrs<10>() : set_smem_attrs<20>()))) return false;
         for (int q = 0; q < F_COUNT; ++q) { fam_ms[q] = 0; fam_calls[q] = 0; }
         if (st) stream = st;
@@ -303,6 +309,32 @@ struct Engine : EngineBase {
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 
+    // ---- phase timers dsave(7:9) = cachyt, sbtime, lnscht (src/lbfgsb.f90:616-637, 655-713, 723-777) -------------
+    // CUDA events on the engine's stream at the phase boundaries of a call, resolved after the call's last read-back.
+    // On the fused paths a phase is the group of kernels that carries it: "cauchy" = the S/Y update + per-variable
+    // pass + its scalar kernel (+ walk), "subspace" = the formk/cmprlb pass through the subspace pass (which also
+    // forms lnsrlb's first-entry sums), "line search" = the scalar kernels of lnsrlb/dcsrch and the trial-point passes.
+    enum { PH_CAUCHY = 0, PH_SUBSPACE = 1, PH_LNSRCH = 2, PH_END = 3 };
+    struct Mark { int ph; cudaEvent_t e; };
+    std::vector<Mark> marks;
+    double ph_time[3] = {0, 0, 0};
+    bool timers = true;
+    void phase(int ph) {
+        if (!timers) return;
+        Mark mk; mk.ph = ph; mk.e = get_event();
+        cudaEventRecord(mk.e, stream);
+        marks.push_back(mk);
+    }
+    void resolve_phases() {
+        for (size_t i = 0; i + 1 < marks.size(); ++i) {
+            if (marks[i].ph == PH_END) continue;
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, marks[i].e, marks[i + 1].e) == cudaSuccess) ph_time[marks[i].ph] += (double)ms * 1e-3;
+        }
+        for (auto& mk : marks) pool.push_back(mk.e);
+        marks.clear();
+    }
+
     // ---- launch helpers ----------------------------------------------------
     cudaEvent_t get_event() {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
@@ -340,6 +372,7 @@ struct Engine : EngineBase {
     // finish + all-gather of a reduction site on sharded runs
     bool site(const SiteSpec& sp) {
         if (R <= 1) return true;
+        site_pending = true;
         if (p2p) {
             site_seq++; cur_slot = (int)(site_seq & 1ULL);
             k_rank_finish_p2p<T><<<1, LB_SCALAR_THREADS, 0, stream>>>(w, sp, peers, R, rank, cur_slot, site_seq);
@@ -350,6 +383,19 @@ struct Engine : EngineBase {
         launches++;
         int rc = nccl_api()->AllGather(rec_local, rec_all, sizeof(Red<T>), 0 /*ncclChar*/, comm, stream);
         if (rc != 0) { set_error("ncclAllGather failed: %d", rc); return false; }
+        return true;
+    }
+    // the same for a merged record of the fast pipeline (kernels_dense.cuh: MSite)
+    bool site_m(const MSite& ms) {
+        if (R <= 1) return true;
+        site_pending = true;
+        if (p2p) { site_seq++; cur_slot = (int)(site_seq & 1ULL); }
+        k_rank_finish_m<T><<<1, LB_SCALAR_THREADS, 0, stream>>>(w, ms, rec_local, peers, R, rank, cur_slot, site_seq, p2p ? 1 : 0);
+        launches++;
+        if (!p2p) {
+            int rc = nccl_api()->AllGather(rec_local, rec_all, sizeof(Red<T>), 0 /*ncclChar*/, comm, stream);
+            if (rc != 0) { set_error("ncclAllGather failed: %d", rc); return false; }
+        }
         return true;
     }
 #define LG LBFGSB_GRID, LBFGSB_BLOCK, 0, stream
@@ -639,75 +685,139 @@ struct Engine : EngineBase {
         return true;
     }
 
-    // ---- prelims + first lnsrlb (:601-773) ----------------------------------
-    bool enqueue_body() {
+    // ---- prelims + first lnsrlb (:601-773): the general pipeline -------------------------------
+    // `from` = where to enter: PAUSE_NONE for the whole body, or the stage at which the fast pipeline paused
+    // (common.cuh PAUSE_*; the device state is then exactly what this sequence would have produced up to there,
+    // and s_host is current).
+    bool enqueue_body(int from = PAUSE_NONE) {
         for (;;) {
-            begin(F_CLASSIFY); MTCALL(k_cauchy_classify, smem_classify, w); end(F_CLASSIFY);
-            if (!site(site_cauchy(mt))) return false;
-            begin(F_SCALAR); s_cauchy<T><<<LS>>>(w, dist(), mt, fused ? 1 : 0); end(F_SCALAR);
             bool gf = false;   // cauchy's tail and freev run inside k_formk_cmprlb (decided by s_cauchy)
-            if (s_host->cnstnd) {
-                if (!sync_state()) return false;
-                if (s_host->go && s_host->in_body && s_host->need_walk) {
-                    begin(F_WALK_COMPACT); k_materialize<T><<<LG>>>(w); end(F_WALK_COMPACT);
-                    if (!enqueue_walk_rounds()) return false;
+            if (from <= PAUSE_CLASSIFY) {
+                phase(PH_CAUCHY);
+                begin(F_CLASSIFY); MTCALL(k_cauchy_classify, smem_classify, w); end(F_CLASSIFY);
+                if (!site(site_cauchy(mt))) return false;
+                begin(F_SCALAR); s_cauchy<T><<<LS>>>(w, dist(), mt, fused ? 1 : 0); end(F_SCALAR);
+            }
+            if (from <= PAUSE_WALK) {
+                if (s_host->cnstnd) {
+                    if (from != PAUSE_WALK && !sync_state()) return false;
+                    if (s_host->go && s_host->in_body && s_host->need_walk) {
+                        begin(F_WALK_COMPACT); k_materialize<T><<<LG>>>(w); end(F_WALK_COMPACT);
+                        if (!enqueue_walk_rounds()) return false;
+                    }
+                    gf = fused && s_host->go && s_host->in_body && s_host->fuse_gf;
                 }
-                gf = fused && s_host->go && s_host->in_body && s_host->fuse_gf;
             }
-            if (!gf) {
-                begin(F_GCP_FREEV); k_gcp_freev<T><<<LG>>>(w); end(F_GCP_FREEV);
-                if (!site(site_freev())) return false;
+            if (from <= PAUSE_GCP_FREEV) {
+                phase(PH_SUBSPACE);
+                if (!gf) {
+                    begin(F_GCP_FREEV); k_gcp_freev<T><<<LG>>>(w); end(F_GCP_FREEV);
+                    if (!site(site_freev())) return false;
+                }
+                begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global, 0); end(F_SCALAR);
+                if (fused) {
+                    begin(F_FORMK_CMPRLB);
+                    if (gf) MTFUSED(launch_formk_cmprlb_gf); else MTFUSED(launch_formk_cmprlb);
+                    end(F_FORMK_CMPRLB);
+                }
+                else { begin(F_FORMK_GRAM); MTCALL(k_formk_gram, smem_formk, w); end(F_FORMK_GRAM); }
+                if (gf) {
+                    if (!site(site_freev())) return false;
+                    begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global, 1); end(F_SCALAR);
+                }
             }
-            begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global, 0); end(F_SCALAR);
-            if (fused) {
-                begin(F_FORMK_CMPRLB);
-                if (gf) MTFUSED(launch_formk_cmprlb_gf); else MTFUSED(launch_formk_cmprlb);
-                end(F_FORMK_CMPRLB);
+            if (from <= PAUSE_DELTA) {
+                if (from == PAUSE_DELTA) phase(PH_SUBSPACE);
+                begin(F_FORMK_DELTA);
+                k_flag_count<T, 1><<<LG>>>(w, tile_counts);
+                k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 1, tile_counts, tile_offsets, ntiles, ctl_el);
+                k_flag_write<T, 1><<<LG>>>(w, tile_offsets, wb.k0, wb.v0);
+                k_formk_delta<T><<<LB_FD_GRID, 256, 0, stream>>>(w, wb.v0, ctl_el, fd_parts);
+                k_formk_delta_final<T><<<(6 * LB_MMAX * LB_MMAX + 255) / 256, 256, 0, stream>>>(w, fd_parts, LB_FD_GRID, delta);
+                end(F_FORMK_DELTA, 5);
+                if (!site(site_formk(mt))) return false;
+                if (R > 1) {
+                    if (p2p) { delta_seq++; k_delta_push<T><<<1, 256, 0, stream>>>(w, delta, peers_delta, peers, R, rank, delta_seq); launches++; }
+                    else if (!allgather(delta, delta_all, sizeof(T) * 6 * LB_MMAX * LB_MMAX)) return false;
+                }
+                begin(F_SCALAR); s_formk_dense<T><<<LS>>>(w, dist(), mt, R > 1 ? delta_all : delta, delta_sum); end(F_SCALAR);
+                if (!fused) { begin(F_CMPRLB_WV); MTCALL(k_cmprlb_wv, smem_cmprlb, w); end(F_CMPRLB_WV); }
+                if (!site(site_wv(mt))) return false;
+                begin(F_SCALAR); s_subsm_dense<T><<<LS>>>(w, dist(), mt, fused ? 1 : 0); end(F_SCALAR);
+                if (fused) { begin(F_SUBSM_LSINIT); MTFUSED(launch_subsm_lsinit); end(F_SUBSM_LSINIT); }
+                else { begin(F_SUBSM_STEP); MTCALL(k_subsm_step, smem_subsm, w); end(F_SUBSM_STEP); }
+                if (!site(site_subsm())) return false;
+                begin(F_SCALAR); s_subsm_post<T><<<LS>>>(w, dist(), fused ? 1 : 0); end(F_SCALAR);
             }
-            else { begin(F_FORMK_GRAM); MTCALL(k_formk_gram, smem_formk, w); end(F_FORMK_GRAM); }
-            if (gf) {
-                if (!site(site_freev())) return false;
-                begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global, 1); end(F_SCALAR);
+            if (from <= PAUSE_BACKTRACK) {
+                if (from == PAUSE_BACKTRACK) phase(PH_SUBSPACE);
+                begin(F_BACKTRACK);
+                if (fused) { MTFUSED(launch_subsm_dir); launches++; }   // direction for the backtrack after a speculative step
+                k_bt_alpha<T><<<LG>>>(w);
+                if (!site(site_bt())) return false;
+                s_bt<T><<<LS>>>(w, dist(), offset);
+                k_bt_apply<T><<<LG>>>(w);
+                end(F_BACKTRACK, 3);
             }
-            begin(F_FORMK_DELTA);
-            k_flag_count<T, 1><<<LG>>>(w, tile_counts);
-            k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 1, tile_counts, tile_offsets, ntiles, ctl_el);
-            k_flag_write<T, 1><<<LG>>>(w, tile_offsets, wb.k0, wb.v0);
-            k_formk_delta<T><<<LB_FD_GRID, 256, 0, stream>>>(w, wb.v0, ctl_el, fd_parts);
-            k_formk_delta_final<T><<<(6 * LB_MMAX * LB_MMAX + 255) / 256, 256, 0, stream>>>(w, fd_parts, LB_FD_GRID, delta);
-            end(F_FORMK_DELTA, 5);
-            if (!site(site_formk(mt))) return false;
-            if (R > 1) {
-                if (p2p) { delta_seq++; k_delta_push<T><<<1, 256, 0, stream>>>(w, delta, peers_delta, peers, R, rank, delta_seq); launches++; }
-                else if (!allgather(delta, delta_all, sizeof(T) * 6 * LB_MMAX * LB_MMAX)) return false;
-            }
-            begin(F_SCALAR); s_formk_dense<T><<<LS>>>(w, dist(), mt, R > 1 ? delta_all : delta, delta_sum); end(F_SCALAR);
-            if (!fused) { begin(F_CMPRLB_WV); MTCALL(k_cmprlb_wv, smem_cmprlb, w); end(F_CMPRLB_WV); }
-            if (!site(site_wv(mt))) return false;
-            begin(F_SCALAR); s_subsm_dense<T><<<LS>>>(w, dist(), mt, fused ? 1 : 0); end(F_SCALAR);
-            if (fused) { begin(F_SUBSM_LSINIT); MTFUSED(launch_subsm_lsinit); end(F_SUBSM_LSINIT); }
-            else { begin(F_SUBSM_STEP); MTCALL(k_subsm_step, smem_subsm, w); end(F_SUBSM_STEP); }
-            if (!site(site_subsm())) return false;
-            begin(F_SCALAR); s_subsm_post<T><<<LS>>>(w, dist(), fused ? 1 : 0); end(F_SCALAR);
-            begin(F_BACKTRACK);
-            if (fused) { MTFUSED(launch_subsm_dir); launches++; }   // direction for the backtrack after a speculative step
-            k_bt_alpha<T><<<LG>>>(w);
-            if (!site(site_bt())) return false;
-            s_bt<T><<<LS>>>(w, dist(), offset);
-            k_bt_apply<T><<<LG>>>(w);
-            end(F_BACKTRACK, 3);
+            phase(PH_LNSRCH);
             begin(F_LS_INIT); k_ls_init<T><<<LG>>>(w); end(F_LS_INIT);
             if (!site(site_lsinit())) return false;
             begin(F_SCALAR); s_ls_init<T><<<LS>>>(w, dist()); end(F_SCALAR);
             begin(F_LS_STEP); k_ls_step<T><<<LG>>>(w); end(F_LS_STEP);
+            phase(PH_END);
             if (!sync_state()) return false;
             if (s_host->do_step) x_changed = true;
             if (!s_host->restart) break;
             // "refresh the lbfgs memory and restart the iteration": run the prelims again
             begin(F_SCALAR); s_restart_body<T><<<1, 32, 0, stream>>>(w); end(F_SCALAR);
+            from = PAUSE_NONE;
         }
         return true;
     }
+
+    // ---- NEW_X entry, fast pipeline (kernels_dense.cuh "Fast pipeline") ---------------------------------
+    // Three streaming passes and four scalar kernels with one host read-back at the end; any branch off the
+    // common path pauses the sequence on the device and the general pipeline takes over at that stage.
+    bool fast = false;
+    bool fast_newx(T f) {
+        begin(F_SCALAR); f_head<T><<<1, 32, 0, stream>>>(w, f, 1); end(F_SCALAR);
+        phase(PH_CAUCHY);
+        begin(F_UPDATE_CLASSIFY); MTFUSED(launch_update_classify); end(F_UPDATE_CLASSIFY);
+        if (!site_m(msite_ucf(mt))) return false;
+        begin(F_SCALAR); f_ucf<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);
+        phase(PH_SUBSPACE);
+        begin(F_FORMK_CMPRLB); MTFUSED(launch_formk_cmprlb_gf); end(F_FORMK_CMPRLB);
+        if (!site_m(msite_mid(mt))) return false;
+        begin(F_SCALAR); f_mid<T><<<LS>>>(w, dist(), mt, n_global); end(F_SCALAR);
+        begin(F_SUBSM_LSINIT); MTFUSED(launch_subsm_lsinit); end(F_SUBSM_LSINIT);
+        if (!site_m(msite_tail())) return false;
+        phase(PH_LNSRCH);
+        begin(F_SCALAR); f_tail<T><<<LS>>>(w, dist()); end(F_SCALAR);
+        phase(PH_END);
+        if (!sync_state()) return false;
+        if (s_host->pause != PAUSE_NONE) {
+            const int from = s_host->pause;
+            fast_pauses++;
+            s_resume<T><<<1, 32, 0, stream>>>(w); launches++;
+            return enqueue_body(from);
+        }
+        if (s_host->restart) {
+            begin(F_SCALAR); s_restart_body<T><<<1, 32, 0, stream>>>(w); end(F_SCALAR);
+            return enqueue_body();
+        }
+        return finish_step();
+    }
+    // lnsrlb's trial point after the state came back: nothing to do when the subspace pass already stepped
+    bool finish_step() {
+        if (s_host->do_unstep || (s_host->do_step && !s_host->step_done)) {
+            begin(F_LS_STEP); k_ls_step<T><<<LG>>>(w); end(F_LS_STEP);
+            CK(cudaStreamSynchronize(stream));
+            if (profile) resolve_events();
+        }
+        if (s_host->do_step) x_changed = true;
+        return true;
+    }
+    i64 fast_pauses = 0;
 
     bool check_launch() {
         cudaError_t e = cudaGetLastError();
@@ -720,9 +830,13 @@ struct Engine : EngineBase {
     bool call(int entry, int aux, T* x, const T* l, const T* u, const int* nbd, T* f, T* g, T factr, T pgtol) {
         w.x = x; w.l = l; w.u = u; w.nbd = nbd; w.g = g;
         x_changed = false; g_changed = false;
+        for (auto& mk : marks) pool.push_back(mk.e);
+        marks.clear();
         const bool ts_ready = trial_ready;   // valid only for the call that follows the objective evaluation
         trial_ready = false;
         if (entry == 0) {
+            started = true;
+            ph_time[0] = ph_time[1] = ph_time[2] = 0;
             int host_err = 0;
             if (factr < (T)0) host_err = TK_ERR_FACTR;
             s_start<T><<<1, 32, 0, stream>>>(w, factr, pgtol, host_err); launches++;
@@ -752,26 +866,36 @@ struct Engine : EngineBase {
             s_host->task = TK_FG_START;
             return true;
         }
-        s_call_begin<T><<<1, 32, 0, stream>>>(w, *f, entry); launches++;
         if (entry == 1) {
+            s_call_begin<T><<<1, 32, 0, stream>>>(w, *f, entry); launches++;
             begin(F_PROJGR); k_projgr<T><<<LG>>>(w); end(F_PROJGR);
             if (!site(site_projgr())) return false;
             begin(F_SCALAR); s_fg_start<T><<<LS>>>(w, dist()); end(F_SCALAR);
             if (!enqueue_body()) return false;
         } else if (entry == 2) {
+            // the scalar kernel opens the call itself (call_begin = 1); the trial point, or the restored iterate,
+            // is written after the state came back, and only when there is something to write
+            phase(PH_LNSRCH);
             if (!ts_ready) { begin(F_LS_TRIAL); k_ls_trial<T><<<LG>>>(w); end(F_LS_TRIAL); }
             if (!site(site_lstrial())) return false;
-            begin(F_SCALAR); s_ls_trial<T><<<LS>>>(w, dist()); end(F_SCALAR);
-            begin(F_LS_STEP); k_ls_step<T><<<LG>>>(w); end(F_LS_STEP);
-            begin(F_RESTORE); k_restore<T><<<LG>>>(w); end(F_RESTORE);
+            begin(F_SCALAR); s_ls_trial<T><<<LS>>>(w, dist(), 1, *f); end(F_SCALAR);
+            phase(PH_END);
             if (!sync_state()) return false;
-            if (s_host->do_step) x_changed = true;
-            if (s_host->do_restore) { x_changed = true; g_changed = true; }
+            if (s_host->do_restore) {
+                begin(F_RESTORE); k_restore<T><<<LG>>>(w); end(F_RESTORE);
+                CK(cudaStreamSynchronize(stream));
+                if (profile) resolve_events();
+                x_changed = true; g_changed = true;
+            }
+            if (!finish_step()) return false;
             if (s_host->restart) {
                 begin(F_SCALAR); s_restart_body<T><<<1, 32, 0, stream>>>(w); end(F_SCALAR);
                 if (!enqueue_body()) return false;
             }
+        } else if (fast && s_host->cnstnd) {   // NEW_X, fast pipeline
+            if (!fast_newx(*f)) return false;
         } else {   // NEW_X
+            s_call_begin<T><<<1, 32, 0, stream>>>(w, *f, entry); launches++;
             begin(F_SCALAR); s_newx_tests<T><<<1, 32, 0, stream>>>(w, fused ? 1 : 0); end(F_SCALAR);
             if (fused) { begin(F_UPDATE_CLASSIFY); MTFUSED(launch_update_classify); end(F_UPDATE_CLASSIFY); }
             begin(F_UPDATE); MTCALL(k_update, smem_update, w); end(F_UPDATE);
@@ -780,17 +904,20 @@ struct Engine : EngineBase {
             if (!enqueue_body()) return false;
         }
         *f = s_host->f;
+        resolve_phases();
         return check_launch();
     }
 
     // ---- checkpoint / resume (include/lbfgsb_b200.h section 4) --------------------------------
     struct CkHeader { char magic[8]; i64 n, ldw, n_global, offset; int m, real_kind, R, rank; i64 state_bytes; };
     bool checkpoint_io(const char* path, bool write) {
-        FILE* fp = fopen(path, write ? "wb" : "rb");
-        if (!fp) { set_error("cannot open checkpoint file %s", path); return false; }
         CK(cudaStreamSynchronize(stream));
+        // written under a temporary name and renamed on success: a failure never truncates the previous checkpoint
+        const std::string tmp = std::string(path) + ".tmp";
+        FILE* fp = fopen(write ? tmp.c_str() : path, write ? "wb" : "rb");
+        if (!fp) { set_error("cannot open checkpoint file %s", write ? tmp.c_str() : path); return false; }
         CkHeader hd; memset(&hd, 0, sizeof hd);
-        memcpy(hd.magic, "LBB2CKP1", 8);
+        memcpy(hd.magic, "LBB2CKP2", 8);
         hd.n = n; hd.ldw = w.ldw; hd.n_global = n_global; hd.offset = offset; hd.m = m; hd.real_kind = (int)sizeof(T); hd.R = R; hd.rank = rank;
         hd.state_bytes = (i64)sizeof(DevState<T>);
         bool ok = true;
@@ -802,6 +929,10 @@ struct Engine : EngineBase {
                  in.R == hd.R && in.rank == hd.rank && in.state_bytes == hd.state_bytes;
             if (!ok) set_error("checkpoint %s does not match this workspace (n, m, real kind or shard differ)", path);
         }
+        // the heap-replay limit is a property of this workspace (lbfgsb_dev_set_tie_limit / LBFGSB_B200_TIE_LIMIT), not of
+        // the run that wrote the checkpoint
+        i64 my_tie_limit = 0;
+        if (ok && !write) ok = cudaMemcpy(&my_tie_limit, &s_dev->tie_limit, sizeof my_tie_limit, cudaMemcpyDeviceToHost) == cudaSuccess;
         const size_t CH = (size_t)64 << 20;
         void* stage = nullptr;
         if (ok && cudaMallocHost(&stage, CH) != cudaSuccess) { set_error("cudaMallocHost failed"); ok = false; }
@@ -821,8 +952,15 @@ struct Engine : EngineBase {
         xfer(w.z, vb); xfer(w.r, vb); xfer(w.d, vb); xfer(w.t, vb); xfer(w.xp, vb); xfer(w.gold, vb);
         xfer(w.iwhere, (size_t)w.ldw * 4); xfer(w.state, (size_t)w.ldw);
         if (stage) cudaFreeHost(stage);
+        if (ok && !write) ok = cudaMemcpy(&s_dev->tie_limit, &my_tie_limit, sizeof my_tie_limit, cudaMemcpyHostToDevice) == cudaSuccess;
         if (ok && !write) ok = cudaMemcpy(s_host, s_dev, header_bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (ok && !write) started = true;
+        if (write && ok) ok = fflush(fp) == 0;
         if (fclose(fp) != 0) ok = false;
+        if (write) {
+            if (ok) ok = rename(tmp.c_str(), path) == 0;
+            else remove(tmp.c_str());
+        }
         if (!ok && g_last_error.empty()) set_error("checkpoint %s failed on %s", write ? "write" : "read", path);
         return ok;
     }
@@ -911,7 +1049,8 @@ static void export_state(const Engine<T>* e, char* task, char* csave, int32_t* l
     isave[40] = clamp32(s->nenter);
     isave[42] = s->brackt; isave[43] = s->stage;
     dsave[0] = s->theta; dsave[1] = s->fold; dsave[2] = s->tol; dsave[3] = s->dnorm; dsave[4] = s->epsmch;
-    dsave[5] = 0; dsave[6] = 0; dsave[7] = 0; dsave[8] = 0; dsave[9] = 0;
+    dsave[5] = 0; dsave[9] = 0;   // cpu1, time1: host clock readings of the reference, not kept here
+    dsave[6] = (T)e->ph_time[0]; dsave[7] = (T)e->ph_time[1]; dsave[8] = (T)e->ph_time[2];   // cachyt, sbtime, lnscht (seconds)
     dsave[10] = s->gd; dsave[11] = s->stpmx; dsave[12] = s->sbgnrm; dsave[13] = s->stp; dsave[14] = s->gdold; dsave[15] = s->dtd;
     for (int q = 0; q < 13; ++q) dsave[16 + q] = s->ls[q];
     put60(task, task_text(s->task));
@@ -983,6 +1122,14 @@ static void setulb_dev_impl(lbfgsb_dev_t* hh, T* x, const T* l, const T* u, cons
         e->pr.t0 = std::chrono::steady_clock::now();
         e->pr.word[0] = e->pr.word[1] = e->pr.word[2] = '-';
         e->pr.open_file();
+    }
+    e->x_changed = false; e->g_changed = false;   // (a plain STOP leaves x and g untouched, like the reference's finish())
+    if (entry != 0 && !e->started) {
+        // the reference would run on whatever the caller's isave/dsave hold; here the state is the workspace's, and a
+        // workspace that never saw START has none (same answer as the host twin)
+        put60(task, "ERROR: SETULB CALLED WITHOUT A VALID START");
+        set_error("setulb_dev called with task other than START on a fresh workspace");
+        return;
     }
     if (entry == 4 && !aux) { print_after_call<T>(e, 4, x, l, u, g, *f, task); return; }   // finish(): only prn3lb
     if ((((uintptr_t)x) | ((uintptr_t)l) | ((uintptr_t)u) | ((uintptr_t)nbd) | ((uintptr_t)g)) & 15) {

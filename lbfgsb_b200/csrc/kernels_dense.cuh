@@ -33,9 +33,10 @@ struct SiteSpec {
     int buf;              // 0: partials in w.part / w.ipart ; 1: in w.part2 / w.ipart2
 };
 
-// Finish the local block partials of a site into red (shared memory), using all warps.
+// Finish the local block partials of a site into red (shared memory), using all warps.  The site's real slots land
+// at red->rv[roff + k], its integer slots at red->iv[ioff + k] (a merged record holds several sites back to back).
 template <typename T>
-__device__ void site_finish_local(const Wk<T>& w, const SiteSpec sp, Red<T>* red) {
+__device__ void site_finish_local(const Wk<T>& w, const SiteSpec sp, Red<T>* red, int roff = 0, int ioff = 0) {
     const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
     const T* part = sp.buf ? w.part2 : w.part;
     const i64* ipart = sp.buf ? w.ipart2 : w.ipart;
@@ -45,11 +46,11 @@ __device__ void site_finish_local(const Wk<T>& w, const SiteSpec sp, Red<T>* red
         if (k == sp.argmin_slot) {
             i64 idx;
             final_argmin_warp<T>(p, LB_SLOT(ipart, 0), r, idx);
-            if (lane == 0) red->iv[0] = idx;
+            if (lane == 0) red->iv[ioff] = idx;
         } else if (k >= sp.max_from && k < sp.max_to) r = final_max_warp<T>(p);
         else if (k >= sp.min_from && k < sp.min_to) r = final_min_warp<T>(p);
         else r = final_sum_warp<T>(p);
-        if (lane == 0) red->rv[k] = r;
+        if (lane == 0) red->rv[roff + k] = r;
     }
     for (int k = wid; k < sp.nint; k += nw) {
         if (k == 0 && sp.argmin_slot >= 0) continue;
@@ -58,38 +59,38 @@ __device__ void site_finish_local(const Wk<T>& w, const SiteSpec sp, Red<T>* red
         if (k >= sp.imin_from && k < sp.imin_to) r = final_imin_warp(p);
         else if (k >= sp.imax_from && k < sp.imax_to) r = final_imax_warp(p);
         else r = final_isum_warp(p);
-        if (lane == 0) red->iv[k] = r;
+        if (lane == 0) red->iv[ioff + k] = r;
     }
     __syncthreads();
 }
 
-// Combine the per-rank records (rank order) into red.
+// Combine the per-rank records (rank order) into red; the site sits at (roff, ioff) inside each record.
 template <typename T>
-__device__ void site_combine_ranks(const Red<T>* all, int R, const SiteSpec sp, Red<T>* red) {
+__device__ void site_combine_ranks(const Red<T>* all, int R, const SiteSpec sp, Red<T>* red, int roff = 0, int ioff = 0) {
     for (int k = threadIdx.x; k < sp.nreal; k += blockDim.x) {
-        T r = all[0].rv[k];
+        T r = all[0].rv[roff + k];
         if (k == sp.argmin_slot) {
-            i64 idx = all[0].iv[0];
+            i64 idx = all[0].iv[ioff];
             for (int q = 1; q < R; ++q) {
-                T ov = all[q].rv[k]; i64 oi = all[q].iv[0];
+                T ov = all[q].rv[roff + k]; i64 oi = all[q].iv[ioff];
                 if (ov < r || (ov == r && oi < idx)) { r = ov; idx = oi; }
             }
             red->iv[0] = idx;
         } else if (k >= sp.max_from && k < sp.max_to) {
-            for (int q = 1; q < R; ++q) r = all[q].rv[k] > r ? all[q].rv[k] : r;
+            for (int q = 1; q < R; ++q) r = all[q].rv[roff + k] > r ? all[q].rv[roff + k] : r;
         } else if (k >= sp.min_from && k < sp.min_to) {
-            for (int q = 1; q < R; ++q) r = all[q].rv[k] < r ? all[q].rv[k] : r;
+            for (int q = 1; q < R; ++q) r = all[q].rv[roff + k] < r ? all[q].rv[roff + k] : r;
         } else {
-            for (int q = 1; q < R; ++q) r = r + all[q].rv[k];
+            for (int q = 1; q < R; ++q) r = r + all[q].rv[roff + k];
         }
         red->rv[k] = r;
     }
     for (int k = threadIdx.x; k < sp.nint; k += blockDim.x) {
         if (k == 0 && sp.argmin_slot >= 0) continue;
-        i64 r = all[0].iv[k];
-        if (k >= sp.imin_from && k < sp.imin_to) { for (int q = 1; q < R; ++q) r = all[q].iv[k] < r ? all[q].iv[k] : r; }
-        else if (k >= sp.imax_from && k < sp.imax_to) { for (int q = 1; q < R; ++q) r = all[q].iv[k] > r ? all[q].iv[k] : r; }
-        else { for (int q = 1; q < R; ++q) r += all[q].iv[k]; }
+        i64 r = all[0].iv[ioff + k];
+        if (k >= sp.imin_from && k < sp.imin_to) { for (int q = 1; q < R; ++q) r = all[q].iv[ioff + k] < r ? all[q].iv[ioff + k] : r; }
+        else if (k >= sp.imax_from && k < sp.imax_to) { for (int q = 1; q < R; ++q) r = all[q].iv[ioff + k] > r ? all[q].iv[ioff + k] : r; }
+        else { for (int q = 1; q < R; ++q) r += all[q].iv[ioff + k]; }
         red->iv[k] = r;
     }
     __syncthreads();
@@ -100,9 +101,13 @@ __device__ void site_combine_ranks(const Red<T>* all, int R, const SiteSpec sp, 
 // finish kernel of a reduction site stores its record straight into slot [rank] of every peer's buffer
 // (remote stores), fences, and then publishes the site's sequence number in the peer's flag word; the scalar
 // kernel that consumes the site spins on its own R flag words.  No collective launch sits between a streaming
-// pass and the 2m x 2m algebra that needs its sums.  Two slots alternate: a rank can be at most one site ahead
-// of the slowest rank's *production*, because consuming site k needs every rank's record of site k, and a rank
-// produces site k+1 only after it consumed (or skipped, identically on all ranks) site k.
+// pass and the 2m x 2m algebra that needs its sums.  Two slots alternate, and the protocol is safe by construction:
+//   * every launched producer has exactly one consumer kernel, launched right after it on every rank (the host
+//     sequence is identical on all ranks because every decision is taken from bit-identical combined records);
+//   * that consumer ALWAYS waits for all R flags of its site and copies the records out BEFORE it tests any
+//     predicate that could make it skip its work (site_fetch at the top of every scalar kernel).
+// Hence a rank produces site j+2 (same slot as j) only after its consumer of j+1 saw every rank's record of j+1,
+// which each rank stored after its own consumer of j had finished reading slot j (stream order).
 // ---------------------------------------------------------------------------
 #ifndef LB_MAXR
 #define LB_MAXR 16
@@ -131,6 +136,7 @@ struct Dist {
     int slot;              // which of the two record slots the current site uses
     unsigned long long seq;   // sequence number of the current site
     unsigned long long dseq;  // sequence number of the current delta exchange
+    int wait;              // a producer of this kernel's record was launched right before it (site_fetch waits iff set)
 };
 
 // wait until every rank's word equals seq (threads 0..R-1 spin), then make the peers' stores visible
@@ -146,22 +152,32 @@ __device__ __forceinline__ void p2p_wait(const Wk<T>& w, volatile unsigned long 
     __syncthreads();
 }
 
+// First statement of every scalar kernel on a sharded run: wait for the R records of the site produced right before
+// this kernel and copy them out of the peer-written buffer -- unconditionally (see the protocol above).
 template <typename T>
-__device__ __forceinline__ void site_reduce(const Wk<T>& w, const Dist<T>& dist, const SiteSpec sp, Red<T>* red) {
-    if (dist.R <= 1) { site_finish_local<T>(w, sp, red); return; }
-    if (dist.p2p) {
-        p2p_wait<T>(w, dist.p2p->flag[dist.slot], dist.R, dist.seq);
-        // copy the records out of the peer-written buffer (volatile: never from a stale L1 line)
-        const int words = (int)(sizeof(Red<T>) / 8);
-        for (int q = 0; q < dist.R; ++q) {
-            const volatile unsigned long long* src = (const volatile unsigned long long*)&dist.p2p->rec[dist.slot][q];
-            unsigned long long* dst = (unsigned long long*)&dist.all[q];
-            for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src[k];
-        }
-        __syncthreads();
+__device__ __forceinline__ void site_fetch(const Wk<T>& w, const Dist<T>& dist) {
+    if (dist.R <= 1 || !dist.p2p || !dist.wait) return;
+    p2p_wait<T>(w, dist.p2p->flag[dist.slot], dist.R, dist.seq);
+    // volatile: never from a stale L1 line
+    const int words = (int)(sizeof(Red<T>) / 8);
+    for (int q = 0; q < dist.R; ++q) {
+        const volatile unsigned long long* src = (const volatile unsigned long long*)&dist.p2p->rec[dist.slot][q];
+        unsigned long long* dst = (unsigned long long*)&dist.all[q];
+        for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src[k];
     }
-    site_combine_ranks<T>(dist.all, dist.R, sp, red);
+    __syncthreads();
 }
+// The reduced values of one site: local block partials on a single GPU, the fetched (or all-gathered) per-rank
+// records combined in rank order on a sharded run.
+template <typename T>
+__device__ __forceinline__ void site_reduce(const Wk<T>& w, const Dist<T>& dist, const SiteSpec sp, Red<T>* red, int roff = 0,
+                                            int ioff = 0) {
+    if (dist.R <= 1) { site_finish_local<T>(w, sp, red); return; }
+    site_combine_ranks<T>(dist.all, dist.R, sp, red, roff, ioff);
+}
+
+// A record that carries up to three sites back to back (the fast pipeline's merged scalar kernels).
+struct MSite { int nsub; SiteSpec sp[3]; int roff[3]; int ioff[3]; };
 
 // Rank-local finish of a site, stored into every peer's buffer (see P2PBuf).
 template <typename T>
@@ -173,6 +189,32 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) k_rank_finish_p2p(Wk<T> w, 
         Red<T>* dst = &((P2PBuf<T>*)peers.p[q])->rec[slot][rank];
         for (int k = threadIdx.x; k < LB_KMAX; k += blockDim.x) dst->rv[k] = (k < sp.nreal) ? red.rv[k] : (T)0;
         for (int k = threadIdx.x; k < LB_IMAX; k += blockDim.x) dst->iv[k] = (k < sp.nint) ? red.iv[k] : 0;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < R) {
+        __threadfence_system();
+        *(volatile unsigned long long*)&((P2PBuf<T>*)peers.p[threadIdx.x])->flag[slot][rank] = seq;
+    }
+}
+// The same for a merged record; p2p = 0: into `out` for the all-gather that follows.
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) k_rank_finish_m(Wk<T> w, MSite ms, Red<T>* out, Peers peers, int R, int rank,
+                                                                    int slot, unsigned long long seq, int p2p) {
+    __shared__ Red<T> red;
+    for (int k = threadIdx.x; k < LB_KMAX; k += blockDim.x) red.rv[k] = (T)0;
+    for (int k = threadIdx.x; k < LB_IMAX; k += blockDim.x) red.iv[k] = 0;
+    __syncthreads();
+    for (int q = 0; q < ms.nsub; ++q) site_finish_local<T>(w, ms.sp[q], &red, ms.roff[q], ms.ioff[q]);
+    if (!p2p) {
+        for (int k = threadIdx.x; k < LB_KMAX; k += blockDim.x) out->rv[k] = red.rv[k];
+        for (int k = threadIdx.x; k < LB_IMAX; k += blockDim.x) out->iv[k] = red.iv[k];
+        return;
+    }
+    for (int q = 0; q < R; ++q) {
+        Red<T>* dst = &((P2PBuf<T>*)peers.p[q])->rec[slot][rank];
+        for (int k = threadIdx.x; k < LB_KMAX; k += blockDim.x) dst->rv[k] = red.rv[k];
+        for (int k = threadIdx.x; k < LB_IMAX; k += blockDim.x) dst->iv[k] = red.iv[k];
     }
     __threadfence_system();
     __syncthreads();
@@ -267,63 +309,24 @@ template <typename T> __device__ inline void begin_body(DevState<T>* s) {
     s->tsum = (T)0;
 }
 
-// ---------------------------------------------------------------------------
-// START, part 1: errclb (:1601-1643) result.
-// ---------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_errclb(Wk<T> w, Dist<T> dist, i64 index_offset) {
-    __shared__ Red<T> red;
-    site_reduce<T>(w, dist, site_errclb(), &red);
-    if (threadIdx.x != 0) return;
-    DevState<T>* s = w.s;
-    i64 k6 = red.iv[0], k7 = red.iv[1];
-    // Each offending i overwrites (task, info, k); the last one wins.  On a shard the
-    // indices are local, so they are globalised by the caller through index_offset.
-    if (dist.R <= 1) { if (k6 >= 0) k6 += index_offset; if (k7 >= 0) k7 += index_offset; }
-    if (k6 >= 0 || k7 >= 0) {
-        if (k6 > k7) { s->task = TK_ERR_NBD; s->info = -6; s->errk = k6 + 1; }
-        else { s->task = TK_ERR_INFEAS; s->info = -7; s->errk = k7 + 1; }
-        s->go = 0;
-    } else if (s->task >= TK_ERR_N) s->go = 0;   // factr < 0 stands when no array error overwrites it
+// ===========================================================================
+// The scalar steps of mainlb as single-thread device functions (t0_*: thread 0 of a scalar kernel), shared by the
+// general pipeline's kernels (s_*) and the fast pipeline's merged kernels (f_*), so that both produce the same bits.
+// ===========================================================================
+
+// clear the per-call flags at the start of every setulb call
+template <typename T> __device__ inline void t0_call_begin(DevState<T>* s, T f) {
+    s->go = 1; s->pause = 0; s->in_body = 0; s->restart = 0; s->need_walk = 0;
+    s->do_step = 0; s->do_restore = 0; s->do_update = 0; s->save_z = 0;
+    s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0;
+    s->fuse_uc = 0; s->classify_done = 0; s->lsinit_done = 0;
+    s->spec_step = 0; s->step_done = 0; s->do_unstep = 0; s->lazy_gcp = 0; s->fuse_gf = 0; s->lazy_z = 0;
+    s->ev_n = 0;
+    s->f = f;
 }
 
-// START, part 2: active (:965-1040) flags; then start() (:884-890).
-template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_active(Wk<T> w, Dist<T> dist) {
-    __shared__ Red<T> red;
-    if (!w.s->go) return;
-    site_reduce<T>(w, dist, site_active(), &red);
-    if (threadIdx.x != 0) return;
-    DevState<T>* s = w.s;
-    s->nbdd = red.iv[0];
-    s->prjctd = red.iv[1] > 0; s->cnstnd = red.iv[2] > 0; s->boxed = !(red.iv[3] > 0);
-    s->task = TK_FG_START;
-    s->go = 0;
-}
-
-// ---------------------------------------------------------------------------
-// FG_START entry (:579-596): sbgnrm, first termination test, open the body.
-// ---------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_fg_start(Wk<T> w, Dist<T> dist) {
-    __shared__ Red<T> red;
-    site_reduce<T>(w, dist, site_projgr(), &red);
-    if (threadIdx.x != 0) return;
-    DevState<T>* s = w.s;
-    s->nfgv = 1;
-    s->sbgnrm = red.rv[0];
-    if (s->sbgnrm <= s->pgtol) { s->task = TK_CONV_PG; s->go = 0; return; }
-    begin_body<T>(s);
-}
-
-// ---------------------------------------------------------------------------
-// NEW_X entry, part 1 (:795-834, :838-839, matupd :2303-2309): termination
-// tests, skip rule, ring pointers.
-// ---------------------------------------------------------------------------
-template <typename T>
-__global__ void s_newx_tests(Wk<T> w, int fused_supported) {
-    if (threadIdx.x != 0) return;
-    DevState<T>* s = w.s;
+// NEW_X entry, part 1 (:795-834, :838-839, matupd :2303-2309): termination tests, skip rule, ring pointers.
+template <typename T> __device__ inline void t0_newx_tests(DevState<T>* s, int fused_supported) {
     const T one = (T)1;
     s->fuse_uc = 0; s->classify_done = 0;
     if (s->sbgnrm <= s->pgtol) { s->task = TK_CONV_PG; s->go = 0; return; }
@@ -350,74 +353,31 @@ __global__ void s_newx_tests(Wk<T> w, int fused_supported) {
     }
 }
 
-// NEW_X entry, part 2: matupd's small matrices (:2318-2344) + formt (:1926-1963),
-// then open the body.
-template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_update_dense(Wk<T> w, Dist<T> dist, int mt) {
-    __shared__ Red<T> red;
-    __shared__ T ssy[LB_MMAX * LB_MMAX], sss[LB_MMAX * LB_MMAX], swt[LB_MMAX * LB_MMAX];
-    DevState<T>* s = w.s;
-    if (!s->go) return;
-    const bool upd = s->do_update;
-    const int mm = s->m * s->m;
-    if (upd) {
-        site_reduce<T>(w, dist, site_update(mt), &red);
-        stage_in<T>(ssy, s->sy, mm); stage_in<T>(sss, s->ss, mm); stage_in<T>(swt, s->wt, mm);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        if (upd) {
-            const int m = s->m, col = s->col;
-            s->rr = red.rv[0];
-            s->theta = s->rr / s->dr;
-            T* sy = ssy; T* ss = sss;
-            if (s->iupdat > m) {  // :2324-2330
-                for (int j = 1; j <= col - 1; ++j) {
-                    for (int q = 0; q < j; ++q) ss[q + (j - 1) * m] = ss[(1 + q) + j * m];             // dcopy(j,Ss(2,j+1),Ss(1,j))
-                    for (int q = 0; q < col - j; ++q) sy[(j - 1 + q) + (j - 1) * m] = sy[(j + q) + j * m];  // dcopy(col-j,Sy(j+1,j+1),Sy(j,j))
-                }
-            }
-            for (int j = 1; j <= col - 1; ++j) {
-                sy[(col - 1) + (j - 1) * m] = red.rv[1 + (j - 1)];
-                ss[(j - 1) + (col - 1) * m] = red.rv[1 + mt + (j - 1)];
-            }
-            ss[(col - 1) + (col - 1) * m] = (s->stp == (T)1) ? s->dtd : s->stp * s->stp * s->dtd;
-            sy[(col - 1) + (col - 1) * m] = s->dr;
-            int info = dense::formt<T>(m, swt, sy, ss, col, s->theta);
-            if (info != 0) { ev_push<T>(s, EV_FORMT_FAIL); reset_memory<T>(s); }   // :851-863
+// NEW_X entry, part 2: matupd's small matrices (:2318-2344) + formt (:1926-1963).  sy, ss, wt: staged copies.
+template <typename T> __device__ inline void t0_update_dense(DevState<T>* s, const Red<T>& red, int mt, T* sy, T* ss, T* swt) {
+    const int m = s->m, col = s->col;
+    s->rr = red.rv[0];
+    s->theta = s->rr / s->dr;
+    if (s->iupdat > m) {  // :2324-2330
+        for (int j = 1; j <= col - 1; ++j) {
+            for (int q = 0; q < j; ++q) ss[q + (j - 1) * m] = ss[(1 + q) + j * m];             // dcopy(j,Ss(2,j+1),Ss(1,j))
+            for (int q = 0; q < col - j; ++q) sy[(j - 1 + q) + (j - 1) * m] = sy[(j + q) + j * m];  // dcopy(col-j,Sy(j+1,j+1),Sy(j,j))
         }
-        begin_body<T>(s);
     }
-    if (upd) {
-        __syncthreads();
-        stage_out<T>(s->sy, ssy, mm); stage_out<T>(s->ss, sss, mm); stage_out<T>(s->wt, swt, mm);
+    for (int j = 1; j <= col - 1; ++j) {
+        sy[(col - 1) + (j - 1) * m] = red.rv[1 + (j - 1)];
+        ss[(j - 1) + (col - 1) * m] = red.rv[1 + mt + (j - 1)];
     }
+    ss[(col - 1) + (col - 1) * m] = (s->stp == (T)1) ? s->dtd : s->stp * s->stp * s->dtd;
+    sy[(col - 1) + (col - 1) * m] = s->dr;
+    int info = dense::formt<T>(m, swt, sy, ss, col, s->theta);
+    if (info != 0) { ev_push<T>(s, EV_FORMT_FAIL); reset_memory<T>(s); }   // :851-863
 }
 
-// Host asked for another pass of the body after a memory reset ("cycle main_loop").
-template <typename T>
-__global__ void s_restart_body(Wk<T> w) {
-    if (threadIdx.x != 0) return;
-    DevState<T>* s = w.s;
-    s->go = 1;
-    s->classify_done = 0;
-    begin_body<T>(s);
-}
-
-// ---------------------------------------------------------------------------
-// cauchy after the per-variable pass (:1337-1366) and the first-segment exit
-// test (:1384-1416 with iter == 1).
-// ---------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> dist, int mt, int fused_supported) {
-    __shared__ Red<T> red;
-    __shared__ T ssy[LB_MMAX * LB_MMAX], swt[LB_MMAX * LB_MMAX];
-    DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || s->cauchy_mode != 0) return;
-    site_reduce<T>(w, dist, site_cauchy(mt), &red);
-    stage_in<T>(ssy, s->sy, s->m * s->m); stage_in<T>(swt, s->wt, s->m * s->m);
-    __syncthreads();
-    if (threadIdx.x != 0) return;
+// cauchy after the per-variable pass (:1337-1366) and the first-segment exit test (:1384-1416 with iter == 1).
+// ssy, swt: staged copies of sy, wt.
+template <typename T> __device__ inline void t0_cauchy(DevState<T>* s, const Red<T>& red, int mt, const T* ssy, const T* swt,
+                                                       int fused_supported) {
     s->classify_done = 0;
     const int col = s->col, col2 = 2 * col, m = s->m;
     const T zero = (T)0, one = (T)1;
@@ -468,28 +428,10 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
     }
 }
 
-// ---------------------------------------------------------------------------
-// after freev (:638-648): counters, wrk, what of the subspace phase runs.
-// ---------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_freev(Wk<T> w, Dist<T> dist, i64 n_global, int phase) {
-    __shared__ Red<T> red;
-    DevState<T>* s = w.s;
-    if (!s->go || !s->in_body) return;
-    // phase 0: after k_gcp_freev (the separate pass).  With fuse_gf the counts do not exist yet: the subspace
-    // flags are set tentatively (col > 0 holds; the Gram row is wanted iff updatd) and phase 1, after
-    // k_formk_cmprlb, evaluates them.  phase 1 does nothing without fuse_gf.
-    const bool gf = s->fuse_gf != 0;
-    if (phase == 1 && !gf) return;
-    if (phase == 0 && gf) {
-        if (threadIdx.x == 0) { s->do_subspace = 1; s->do_formk = s->updatd; s->do_delta = 0; }
-        return;
-    }
-    const int mode = s->cauchy_mode;
-    if (mode != 1) site_reduce<T>(w, dist, site_freev(), &red);
-    if (threadIdx.x != 0) return;
+// after freev (:638-648): counters, wrk, what of the subspace phase runs.  `have` = the counts exist (cauchy_mode != 1).
+template <typename T> __device__ inline void t0_freev(DevState<T>* s, const Red<T>& red, i64 n_global, bool gf, bool have) {
     if (gf) s->lazy_z = 1;   // k_formk_cmprlb did not store xcp (state bit 2 tells where d = -g)
-    if (mode != 1) {
+    if (have) {
         s->nintol = s->nintol + s->nseg;
         s->nfree = red.iv[0];
         s->nenter = red.iv[1];
@@ -513,42 +455,12 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_freev(Wk<T> w, Dist<T> di
     }
 }
 
-// ---------------------------------------------------------------------------
-// formk, everything after the long sums (:1735-1744 shift, :1772-1792 new
-// row/column, :1821-1847 corrections, :1853-1906 assembly and factorisation),
-// then cmprlb's bmv (:1569).
+// formk, everything after the long sums (:1735-1744 shift, :1772-1792 new row/column, :1821-1847 corrections,
+// :1853-1906 assembly and factorisation).  wn, wn1: staged copies.
 // delta: [3][2m][2m] enter-minus-leave sums of Wy.Wy, Ws.Ws, Ws.Wy over ring positions
 //        (dE - dL kept separately: delta[0..2] enter, delta[3..5] leave)
-// ---------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist<T> dist, int mt, const T* delta, T* delta_sum) {
-    __shared__ Red<T> red;
-    DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || !s->do_subspace) return;
-    const bool newrow = s->do_formk && s->updatd;
-    if (newrow) site_reduce<T>(w, dist, site_formk(mt), &red);
-    if (dist.R > 1 && s->do_delta) {
-        // sharded: `delta` holds the per-rank corrections [R][6*MMAX*MMAX] (all-gathered, or pushed by the peers);
-        // add them in rank order
-        if (dist.p2p) p2p_wait<T>(w, dist.p2p->dflag, dist.R, dist.dseq);
-        const volatile T* dv = delta;
-        for (int e = threadIdx.x; e < 6 * LB_MMAX * LB_MMAX; e += blockDim.x) {
-            T acc = dv[e];
-            for (int q = 1; q < dist.R; ++q) acc = acc + dv[(i64)q * (6 * LB_MMAX * LB_MMAX) + e];
-            delta_sum[e] = acc;
-        }
-        __syncthreads();
-        delta = delta_sum;
-    }
-    __shared__ T swn[4 * LB_MMAX * LB_MMAX], swn1[4 * LB_MMAX * LB_MMAX];
-    const bool stage = s->do_formk != 0;
-    if (stage) {
-        stage_in<T>(swn, s->wn, 4 * s->m * s->m); stage_in<T>(swn1, s->wn1, 4 * s->m * s->m);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
+template <typename T> __device__ inline void t0_formk_dense(DevState<T>* s, const Red<T>& red, int mt, const T* delta, T* wn, T* wn1) {
     const int m = s->m, col = s->col, m2 = 2 * m;
-    T* wn = swn; T* wn1 = swn1;
 #define WN(i, j) wn[((i)-1) + ((j)-1) * m2]
 #define WN1(i, j) wn1[((i)-1) + ((j)-1) * m2]
     if (s->do_formk) {
@@ -625,26 +537,10 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist
     }
 #undef WN
 #undef WN1
-    }
-    if (stage) {
-        __syncthreads();
-        stage_out<T>(s->wn, swn, 4 * s->m * s->m); stage_out<T>(s->wn1, swn1, 4 * s->m * s->m);
-    }
 }
 
-// ---------------------------------------------------------------------------
-// subsm: wv = K^{-1} wv (:2751-2766)
-// ---------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_dense(Wk<T> w, Dist<T> dist, int mt, int fused_lsinit) {
-    __shared__ Red<T> red;
-    DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || !s->do_subspace) return;
-    site_reduce<T>(w, dist, site_wv(mt), &red);
-    __shared__ T swn[4 * LB_MMAX * LB_MMAX];
-    stage_in<T>(swn, s->wn, 4 * s->m * s->m);
-    __syncthreads();
-    if (threadIdx.x != 0) return;
+// subsm: wv = K^{-1} wv (:2751-2766).  swn: staged copy of wn.
+template <typename T> __device__ inline void t0_subsm_dense(DevState<T>* s, const Red<T>& red, int mt, const T* swn, int fused_lsinit) {
     const int m = s->m, col = s->col, m2 = 2 * m, col2 = 2 * col;
     for (int i = 0; i < col; ++i) { s->wv[i] = red.rv[i]; s->wv[col + i] = s->theta * red.rv[mt + i]; }
     int info = dense::dtrsl<T>(swn, m2, col2, s->wv, 11);
@@ -664,13 +560,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_dense(Wk<T> w, Dist
 }
 
 // subsm: projection outcome (:2820-2828)
-template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_post(Wk<T> w, Dist<T> dist, int fused_lsinit) {
-    __shared__ Red<T> red;
-    DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || !s->do_subspace) return;
-    site_reduce<T>(w, dist, site_subsm(), &red);
-    if (threadIdx.x != 0) return;
+template <typename T> __device__ inline void t0_subsm_post(DevState<T>* s, const Red<T>& red, int fused_lsinit) {
     s->iword = red.iv[0] > 0 ? 1 : 0;
     s->dd_p = red.rv[0];
     s->do_backtrack = (s->iword == 1 && s->dd_p > (T)0);
@@ -679,25 +569,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_post(Wk<T> w, Dist<
     s->lsinit_done = (fused_lsinit && !s->do_backtrack) ? 1 : 0;
 }
 
-// subsm: backtrack step length (:2836-2863)
-template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_bt(Wk<T> w, Dist<T> dist, i64 index_offset) {
-    __shared__ Red<T> red;
-    DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || !s->do_backtrack) return;
-    site_reduce<T>(w, dist, site_bt(), &red);
-    if (threadIdx.x != 0) return;
-    T alpha = (T)1; i64 ibd = -1;
-    if (red.rv[0] < alpha) { alpha = red.rv[0]; ibd = red.iv[0]; }
-    s->alpha = alpha;
-    s->ibd = ibd;   // global variable index (k_bt_alpha adds the shard offset)
-    s->lazy_z = 0;  // k_bt_apply stores the backtracked point in z
-    (void)index_offset;
-}
-
-// ---------------------------------------------------------------------------
 // lnsrlb first entry (:2196-2273) and mainlb's handling of its outcome (:734-773)
-// ---------------------------------------------------------------------------
 template <typename T>
 __device__ inline void ls_failure(DevState<T>* s, bool at_first_entry) {
     // :734-769 ; x = t, g = r, f = fold
@@ -718,14 +590,7 @@ __device__ inline void ls_failure(DevState<T>* s, bool at_first_entry) {
         s->restart = 1; s->in_body = 0;
     }
 }
-
-template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_init(Wk<T> w, Dist<T> dist) {
-    __shared__ Red<T> red;
-    DevState<T>* s = w.s;
-    if (!s->go || !s->in_body) return;
-    site_reduce<T>(w, dist, site_lsinit(), &red);
-    if (threadIdx.x != 0) return;
+template <typename T> __device__ inline void t0_ls_init(DevState<T>* s, const Red<T>& red) {
     const T zero = (T)0, one = (T)1, big = (T)1.0e+10, ftol = (T)1.0e-3, gtol = (T)0.9, xtol = (T)0.1;
     s->dtd = red.rv[0];
     s->dnorm = sqrt(s->dtd);
@@ -762,12 +627,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_init(Wk<T> w, Dist<T> 
 }
 
 // lnsrlb re-entry (:2244-2273) and the outcome (:734-788)
-template <typename T>
-__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_trial(Wk<T> w, Dist<T> dist) {
-    __shared__ Red<T> red;
-    DevState<T>* s = w.s;
-    site_reduce<T>(w, dist, site_lstrial(), &red);
-    if (threadIdx.x != 0) return;
+template <typename T> __device__ inline void t0_ls_trial(DevState<T>* s, const Red<T>& red) {
     const T zero = (T)0, ftol = (T)1.0e-3, gtol = (T)0.9, xtol = (T)0.1;
     s->gd = red.rv[0];
     if (s->ifun == 0) {   // only after a dcsrch input error on the first entry; kept for fidelity
@@ -799,18 +659,243 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_trial(Wk<T> w, Dist<T>
     s->go = 0;
 }
 
-// clear the per-call flags at the start of every setulb call
+// ===========================================================================
+// General pipeline: one scalar kernel per reduction site.
+// ===========================================================================
+
+// START, part 1: errclb (:1601-1643) result.
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_errclb(Wk<T> w, Dist<T> dist, i64 index_offset) {
+    __shared__ Red<T> red;
+    site_fetch<T>(w, dist);
+    site_reduce<T>(w, dist, site_errclb(), &red);
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    i64 k6 = red.iv[0], k7 = red.iv[1];
+    // Each offending i overwrites (task, info, k); the last one wins.  On a shard the
+    // indices are local, so they are globalised by the caller through index_offset.
+    if (dist.R <= 1) { if (k6 >= 0) k6 += index_offset; if (k7 >= 0) k7 += index_offset; }
+    if (k6 >= 0 || k7 >= 0) {
+        if (k6 > k7) { s->task = TK_ERR_NBD; s->info = -6; s->errk = k6 + 1; }
+        else { s->task = TK_ERR_INFEAS; s->info = -7; s->errk = k7 + 1; }
+        s->go = 0;
+    } else if (s->task >= TK_ERR_N) s->go = 0;   // factr < 0 stands when no array error overwrites it
+}
+
+// START, part 2: active (:965-1040) flags; then start() (:884-890).
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_active(Wk<T> w, Dist<T> dist) {
+    __shared__ Red<T> red;
+    site_fetch<T>(w, dist);
+    if (!w.s->go) return;
+    site_reduce<T>(w, dist, site_active(), &red);
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    s->nbdd = red.iv[0];
+    s->prjctd = red.iv[1] > 0; s->cnstnd = red.iv[2] > 0; s->boxed = !(red.iv[3] > 0);
+    s->task = TK_FG_START;
+    s->go = 0;
+}
+
+// FG_START entry (:579-596): sbgnrm, first termination test, open the body.
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_fg_start(Wk<T> w, Dist<T> dist) {
+    __shared__ Red<T> red;
+    site_fetch<T>(w, dist);
+    site_reduce<T>(w, dist, site_projgr(), &red);
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    s->nfgv = 1;
+    s->sbgnrm = red.rv[0];
+    if (s->sbgnrm <= s->pgtol) { s->task = TK_CONV_PG; s->go = 0; return; }
+    begin_body<T>(s);
+}
+
+template <typename T>
+__global__ void s_newx_tests(Wk<T> w, int fused_supported) {
+    if (threadIdx.x != 0) return;
+    t0_newx_tests<T>(w.s, fused_supported);
+}
+
+// NEW_X entry, part 2: matupd's small matrices + formt, then open the body.
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_update_dense(Wk<T> w, Dist<T> dist, int mt) {
+    __shared__ Red<T> red;
+    __shared__ T ssy[LB_MMAX * LB_MMAX], sss[LB_MMAX * LB_MMAX], swt[LB_MMAX * LB_MMAX];
+    DevState<T>* s = w.s;
+    site_fetch<T>(w, dist);
+    if (!s->go) return;
+    const bool upd = s->do_update;
+    const int mm = s->m * s->m;
+    if (upd) {
+        site_reduce<T>(w, dist, site_update(mt), &red);
+        stage_in<T>(ssy, s->sy, mm); stage_in<T>(sss, s->ss, mm); stage_in<T>(swt, s->wt, mm);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (upd) t0_update_dense<T>(s, red, mt, ssy, sss, swt);
+        begin_body<T>(s);
+    }
+    if (upd) {
+        __syncthreads();
+        stage_out<T>(s->sy, ssy, mm); stage_out<T>(s->ss, sss, mm); stage_out<T>(s->wt, swt, mm);
+    }
+}
+
+// Host asked for another pass of the body after a memory reset ("cycle main_loop").
+template <typename T>
+__global__ void s_restart_body(Wk<T> w) {
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    s->go = 1; s->pause = 0;
+    s->classify_done = 0;
+    begin_body<T>(s);
+}
+// The host resumes the general pipeline after a pause of the fast one.
+template <typename T>
+__global__ void s_resume(Wk<T> w) {
+    if (threadIdx.x == 0) w.s->pause = 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> dist, int mt, int fused_supported) {
+    __shared__ Red<T> red;
+    __shared__ T ssy[LB_MMAX * LB_MMAX], swt[LB_MMAX * LB_MMAX];
+    DevState<T>* s = w.s;
+    site_fetch<T>(w, dist);
+    if (!s->go || !s->in_body || s->cauchy_mode != 0) return;
+    site_reduce<T>(w, dist, site_cauchy(mt), &red);
+    stage_in<T>(ssy, s->sy, s->m * s->m); stage_in<T>(swt, s->wt, s->m * s->m);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    t0_cauchy<T>(s, red, mt, ssy, swt, fused_supported);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_freev(Wk<T> w, Dist<T> dist, i64 n_global, int phase) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    site_fetch<T>(w, dist);
+    if (!s->go || !s->in_body) return;
+    // phase 0: after k_gcp_freev (the separate pass).  With fuse_gf the counts do not exist yet: the subspace
+    // flags are set tentatively (col > 0 holds; the Gram row is wanted iff updatd) and phase 1, after
+    // k_formk_cmprlb, evaluates them.  phase 1 does nothing without fuse_gf.
+    const bool gf = s->fuse_gf != 0;
+    if (phase == 1 && !gf) return;
+    if (phase == 0 && gf) {
+        if (threadIdx.x == 0) { s->do_subspace = 1; s->do_formk = s->updatd; s->do_delta = 0; }
+        return;
+    }
+    const int mode = s->cauchy_mode;
+    if (mode != 1) site_reduce<T>(w, dist, site_freev(), &red);
+    if (threadIdx.x != 0) return;
+    t0_freev<T>(s, red, n_global, gf, mode != 1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist<T> dist, int mt, const T* delta, T* delta_sum) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    site_fetch<T>(w, dist);
+    if (!s->go || !s->in_body || !s->do_subspace) return;
+    const bool newrow = s->do_formk && s->updatd;
+    if (newrow) site_reduce<T>(w, dist, site_formk(mt), &red);
+    if (dist.R > 1 && s->do_delta) {
+        // sharded: `delta` holds the per-rank corrections [R][6*MMAX*MMAX] (all-gathered, or pushed by the peers);
+        // add them in rank order
+        if (dist.p2p) p2p_wait<T>(w, dist.p2p->dflag, dist.R, dist.dseq);
+        const volatile T* dv = delta;
+        for (int e = threadIdx.x; e < 6 * LB_MMAX * LB_MMAX; e += blockDim.x) {
+            T acc = dv[e];
+            for (int q = 1; q < dist.R; ++q) acc = acc + dv[(i64)q * (6 * LB_MMAX * LB_MMAX) + e];
+            delta_sum[e] = acc;
+        }
+        __syncthreads();
+        delta = delta_sum;
+    }
+    __shared__ T swn[4 * LB_MMAX * LB_MMAX], swn1[4 * LB_MMAX * LB_MMAX];
+    const bool stage = s->do_formk != 0;
+    if (stage) {
+        stage_in<T>(swn, s->wn, 4 * s->m * s->m); stage_in<T>(swn1, s->wn1, 4 * s->m * s->m);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) t0_formk_dense<T>(s, red, mt, delta, swn, swn1);
+    if (stage) {
+        __syncthreads();
+        stage_out<T>(s->wn, swn, 4 * s->m * s->m); stage_out<T>(s->wn1, swn1, 4 * s->m * s->m);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_dense(Wk<T> w, Dist<T> dist, int mt, int fused_lsinit) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    site_fetch<T>(w, dist);
+    if (!s->go || !s->in_body || !s->do_subspace) return;
+    site_reduce<T>(w, dist, site_wv(mt), &red);
+    __shared__ T swn[4 * LB_MMAX * LB_MMAX];
+    stage_in<T>(swn, s->wn, 4 * s->m * s->m);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    t0_subsm_dense<T>(s, red, mt, swn, fused_lsinit);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_post(Wk<T> w, Dist<T> dist, int fused_lsinit) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    site_fetch<T>(w, dist);
+    if (!s->go || !s->in_body || !s->do_subspace) return;
+    site_reduce<T>(w, dist, site_subsm(), &red);
+    if (threadIdx.x != 0) return;
+    t0_subsm_post<T>(s, red, fused_lsinit);
+}
+
+// subsm: backtrack step length (:2836-2863)
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_bt(Wk<T> w, Dist<T> dist, i64 index_offset) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    site_fetch<T>(w, dist);
+    if (!s->go || !s->in_body || !s->do_backtrack) return;
+    site_reduce<T>(w, dist, site_bt(), &red);
+    if (threadIdx.x != 0) return;
+    T alpha = (T)1; i64 ibd = -1;
+    if (red.rv[0] < alpha) { alpha = red.rv[0]; ibd = red.iv[0]; }
+    s->alpha = alpha;
+    s->ibd = ibd;   // global variable index (k_bt_alpha adds the shard offset)
+    s->lazy_z = 0;  // k_bt_apply stores the backtracked point in z
+    (void)index_offset;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_init(Wk<T> w, Dist<T> dist) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    site_fetch<T>(w, dist);
+    if (!s->go || !s->in_body) return;
+    site_reduce<T>(w, dist, site_lsinit(), &red);
+    if (threadIdx.x != 0) return;
+    t0_ls_init<T>(s, red);
+}
+
+// lnsrlb re-entry.  call_begin != 0: this kernel opens the setulb call itself (the FG_LNSRCH entry launches nothing
+// in front of it that reads the per-call flags).
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_ls_trial(Wk<T> w, Dist<T> dist, int call_begin, T f) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    site_fetch<T>(w, dist);
+    site_reduce<T>(w, dist, site_lstrial(), &red);
+    if (threadIdx.x != 0) return;
+    if (call_begin) t0_call_begin<T>(s, f);
+    t0_ls_trial<T>(s, red);
+}
+
 template <typename T>
 __global__ void s_call_begin(Wk<T> w, T f, int entry_task) {
     if (threadIdx.x != 0) return;
-    DevState<T>* s = w.s;
-    s->go = 1; s->in_body = 0; s->restart = 0; s->need_walk = 0;
-    s->do_step = 0; s->do_restore = 0; s->do_update = 0; s->save_z = 0;
-    s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0; s->do_backtrack = 0;
-    s->fuse_uc = 0; s->classify_done = 0; s->lsinit_done = 0;
-    s->spec_step = 0; s->step_done = 0; s->do_unstep = 0; s->lazy_gcp = 0; s->fuse_gf = 0; s->lazy_z = 0;
-    s->ev_n = 0;
-    s->f = f;
+    t0_call_begin<T>(w.s, f);
     (void)entry_task;
 }
 
@@ -820,7 +905,7 @@ __global__ void s_start(Wk<T> w, T factr, T pgtol, int host_err_task) {
     if (threadIdx.x != 0) return;
     DevState<T>* s = w.s;
     const T zero = (T)0;
-    s->go = 1; s->in_body = 0; s->restart = 0; s->need_walk = 0; s->cauchy_mode = 0;
+    s->go = 1; s->pause = 0; s->in_body = 0; s->restart = 0; s->need_walk = 0; s->cauchy_mode = 0;
     s->do_subspace = s->do_formk = s->do_delta = s->do_backtrack = s->do_update = s->do_step = s->do_restore = 0;
     s->z_in_x = 0; s->save_z = 0;
     s->fuse_uc = 0; s->classify_done = 0; s->lsinit_done = 0; s->ev_n = 0;
@@ -842,4 +927,137 @@ __global__ void s_start(Wk<T> w, T factr, T pgtol, int host_err_task) {
     for (int q = 0; q < 13; ++q) s->ls[q] = zero;
     s->f = zero; s->rr = zero; s->dr = zero; s->ddum = zero; s->tsum = zero; s->dtm = zero;
     if (host_err_task != 0) { s->task = host_err_task; }   // n<=0 / m<=0 / factr<0 (:1618-1620); array errors overwrite
+}
+
+// ===========================================================================
+// Fast pipeline (Engine::fast_newx): the common path of one NEW_X entry -- bounds present, S/Y update not skipped,
+// the Cauchy search ends in its first segment, no variable enters or leaves the free set, no backtrack -- is
+//     f_head -> k_update_classify -> f_ucf -> k_formk_cmprlb<gf> -> f_mid -> k_subsm_lsinit -> f_tail
+// three streaming passes and four scalar kernels, each scalar kernel consuming ONE merged record (MSite) on a
+// sharded run.  A merged kernel that meets any other branch leaves the state exactly as the general pipeline
+// would have it at that point, sets s->pause to the stage at which the host must resume it (PAUSE_*), and
+// everything enqueued after it returns at once.
+// ===========================================================================
+__host__ __device__ inline MSite msite_ucf(int mt) {
+    MSite ms; ms.nsub = 2;
+    ms.sp[0] = site_update(mt); ms.roff[0] = 0; ms.ioff[0] = 0;
+    ms.sp[1] = site_cauchy(mt); ms.roff[1] = 2 * mt + 1; ms.ioff[1] = 0;
+    ms.sp[2] = make_site(0, 0); ms.roff[2] = 0; ms.ioff[2] = 0;
+    return ms;
+}
+__host__ __device__ inline MSite msite_mid(int mt) {
+    MSite ms; ms.nsub = 3;
+    ms.sp[0] = site_freev(); ms.roff[0] = 0; ms.ioff[0] = 0;
+    ms.sp[1] = site_formk(mt); ms.roff[1] = 0; ms.ioff[1] = 3;
+    ms.sp[2] = site_wv(mt); ms.roff[2] = 4 * mt; ms.ioff[2] = 3;
+    return ms;
+}
+__host__ __device__ inline MSite msite_tail() {
+    MSite ms; ms.nsub = 2;
+    ms.sp[0] = site_subsm(); ms.roff[0] = 0; ms.ioff[0] = 0;
+    ms.sp[1] = site_lsinit(); ms.roff[1] = 1; ms.ioff[1] = 1;
+    ms.sp[2] = make_site(0, 0); ms.roff[2] = 0; ms.ioff[2] = 0;
+    return ms;
+}
+
+// NEW_X entry: s_call_begin + s_newx_tests.
+template <typename T>
+__global__ void f_head(Wk<T> w, T f, int fused_supported) {
+    if (threadIdx.x != 0) return;
+    t0_call_begin<T>(w.s, f);
+    t0_newx_tests<T>(w.s, fused_supported);
+}
+
+// s_update_dense + s_cauchy + s_freev(phase 0 with fuse_gf).
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) f_ucf(Wk<T> w, Dist<T> dist, int mt) {
+    __shared__ Red<T> red;
+    __shared__ T ssy[LB_MMAX * LB_MMAX], sss[LB_MMAX * LB_MMAX], swt[LB_MMAX * LB_MMAX];
+    __shared__ int cont;
+    DevState<T>* s = w.s;
+    const MSite ms = msite_ucf(mt);
+    site_fetch<T>(w, dist);
+    if (!s->go) return;
+    const bool upd = s->do_update;
+    const int mm = s->m * s->m;
+    stage_in<T>(ssy, s->sy, mm); stage_in<T>(swt, s->wt, mm);
+    if (upd) {
+        site_reduce<T>(w, dist, ms.sp[0], &red, ms.roff[0], ms.ioff[0]);
+        stage_in<T>(sss, s->ss, mm);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (upd) t0_update_dense<T>(s, red, mt, ssy, sss, swt);
+        begin_body<T>(s);
+        // the fast sequence goes on only into cauchy's full per-variable pass done by k_update_classify
+        cont = (s->cauchy_mode == 0 && s->classify_done) ? 1 : 0;
+        if (!cont) s->pause = PAUSE_CLASSIFY;
+    }
+    __syncthreads();
+    if (upd) { stage_out<T>(s->sy, ssy, mm); stage_out<T>(s->ss, sss, mm); stage_out<T>(s->wt, swt, mm); }
+    if (!cont) return;
+    site_reduce<T>(w, dist, ms.sp[1], &red, ms.roff[1], ms.ioff[1]);   // (ends with a barrier: the staged sy, wt are final)
+    if (threadIdx.x != 0) return;
+    t0_cauchy<T>(s, red, mt, ssy, swt, 1);
+    if (!s->in_body) return;                                 // singular bmv: memory reset, the host restarts the body
+    if (s->need_walk) { s->pause = PAUSE_WALK; return; }
+    if (!s->fuse_gf) { s->pause = PAUSE_GCP_FREEV; return; }
+    s->do_subspace = 1; s->do_formk = s->updatd; s->do_delta = 0;   // s_freev phase 0 with fuse_gf
+}
+
+// s_freev(phase 1) + s_formk_dense + s_subsm_dense.
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) f_mid(Wk<T> w, Dist<T> dist, int mt, i64 n_global) {
+    __shared__ Red<T> red;
+    __shared__ T swn[4 * LB_MMAX * LB_MMAX], swn1[4 * LB_MMAX * LB_MMAX];
+    __shared__ int cont;
+    DevState<T>* s = w.s;
+    const MSite ms = msite_mid(mt);
+    site_fetch<T>(w, dist);
+    if (!s->go || s->pause || !s->in_body) return;
+    site_reduce<T>(w, dist, ms.sp[0], &red, ms.roff[0], ms.ioff[0]);
+    if (threadIdx.x == 0) {
+        t0_freev<T>(s, red, n_global, true, true);
+        cont = 1;
+        if (!s->do_subspace) { s->pause = PAUSE_LSINIT; cont = 0; }        // no free variable: straight to the line search
+        else if (s->do_delta) { s->pause = PAUSE_DELTA; cont = 0; }        // variables entered / left: formk's corrections first
+    }
+    __syncthreads();
+    if (!cont) return;
+    const bool newrow = s->do_formk && s->updatd;
+    if (newrow) site_reduce<T>(w, dist, ms.sp[1], &red, ms.roff[1], ms.ioff[1]);
+    const bool stage = s->do_formk != 0;
+    const int m4 = 4 * s->m * s->m;
+    stage_in<T>(swn, s->wn, m4);
+    if (stage) stage_in<T>(swn1, s->wn1, m4);
+    __syncthreads();
+    if (threadIdx.x == 0) t0_formk_dense<T>(s, red, mt, (const T*)nullptr, swn, swn1);
+    __syncthreads();
+    if (stage) { stage_out<T>(s->wn, swn, m4); stage_out<T>(s->wn1, swn1, m4); }
+    if (!s->in_body) return;                                 // formk failed: memory reset, the host restarts the body
+    site_reduce<T>(w, dist, ms.sp[2], &red, ms.roff[2], ms.ioff[2]);
+    if (threadIdx.x != 0) return;
+    t0_subsm_dense<T>(s, red, mt, swn, 1);
+}
+
+// s_subsm_post + s_ls_init.
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) f_tail(Wk<T> w, Dist<T> dist) {
+    __shared__ Red<T> red;
+    __shared__ int cont;
+    DevState<T>* s = w.s;
+    const MSite ms = msite_tail();
+    site_fetch<T>(w, dist);
+    if (!s->go || s->pause || !s->in_body || !s->do_subspace) return;
+    site_reduce<T>(w, dist, ms.sp[0], &red, ms.roff[0], ms.ioff[0]);
+    if (threadIdx.x == 0) {
+        t0_subsm_post<T>(s, red, 1);
+        cont = 1;
+        if (s->do_backtrack) { s->pause = PAUSE_BACKTRACK; cont = 0; }
+    }
+    __syncthreads();
+    if (!cont) return;
+    site_reduce<T>(w, dist, ms.sp[1], &red, ms.roff[1], ms.ioff[1]);
+    if (threadIdx.x != 0) return;
+    t0_ls_init<T>(s, red);
 }

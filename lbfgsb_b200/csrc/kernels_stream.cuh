@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_restore(Wk<T> w) {
 template <typename T>
 __global__ void __launch_bounds__(LBFGSB_BLOCK) k_ls_trial(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
-    if (!w.s->go) return;
+    // (launched only on the FG_LNSRCH entry, in front of the scalar kernel that opens the call: no predicate)
     const i64 n = w.n;
     __shared__ T sm[LBFGSB_BLOCK / 32];
     __shared__ T smm[LBFGSB_BLOCK / 32];

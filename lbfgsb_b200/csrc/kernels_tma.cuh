@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
     __shared__ T coef[2 * MT];
     __shared__ i64 smi[LBFGSB_BLOCK / 32];
     const DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || !s->do_subspace) return;
+    if (!s->go || s->pause || !s->in_body || !s->do_subspace) return;
     // GF: the tail of cauchy (xcp = x + tsum*d, :1515) and freev (:1980-2059) are part of this pass; the flags
     // do_subspace / do_formk are then s_freev's tentative values (the counts are only known after this pass).
     // The host launches the instantiation that matches the device flag (it has read fuse_gf back by then).
@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
     __shared__ T smm[LBFGSB_BLOCK / 32];
     __shared__ i64 smi[LBFGSB_BLOCK / 32];
     const DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || !s->do_subspace) return;
+    if (!s->go || s->pause || !s->in_body || !s->do_subspace) return;
     const bool spec = s->spec_step != 0;
     if (PASS == 1 && !(spec && s->do_backtrack)) return;
     const i64 n = w.n;

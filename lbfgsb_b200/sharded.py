@@ -194,6 +194,47 @@ class ShardedRosenbrockDevice:
         return float(ft)
 
 
+class HostShard:
+    """Host-buffer front of one rank's shard of a sharded problem: the staging that the C-ABI host twin
+    (lbfgsb_setulb_f64, single GPU) does around the device variant, done here around lbfgsb_setulb_dev_* of a sharded
+    workspace.  The caller keeps x, l, u, nbd, g of its shard in (preferably pinned) host arrays and drives the same
+    `task` protocol (src/lbfgsb.f90:88-89); per call g goes host -> device on an 'FG' re-entry and x comes back
+    whenever the call moved it."""
+
+    def __init__(self, n_local, lo, n_global, m, comm, rank, world, dtype=np.float64):
+        import torch
+        import lbfgsb_b200
+        self.torch = torch
+        tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+        self.prob = lbfgsb_b200.DeviceProblem(n_local, m, dtype, shard=(lo, n_global, comm, rank, world))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.xd, self.ld, self.ud, self.gd = (torch.empty(n_local, dtype=tdt, device=dev) for _ in range(4))
+        self.nd = torch.empty(n_local, dtype=torch.int32, device=dev)
+
+    def setulb(self, x, l, u, nbd, f, g, factr, pgtol, task, iprint, csave, lsave, isave, dsave):
+        torch = self.torch
+        p = self.prob
+        t_in = bytes(task[:5])
+        if t_in == b"START":
+            for d, h in ((self.xd, x), (self.ld, l), (self.ud, u), (self.nd, nbd)):
+                d.copy_(torch.from_numpy(h), non_blocking=True)
+        elif t_in[:2] == b"FG":
+            self.gd.copy_(torch.from_numpy(g), non_blocking=True)
+        torch.cuda.synchronize()
+        p.task, p.csave, p.lsave, p.isave, p.dsave, p.f = task, csave, lsave, isave, dsave, f
+        p.setulb_dev(self.xd, self.ld, self.ud, self.nd, self.gd, factr, pgtol)
+        t_out = bytes(task[:5])
+        if t_in == b"START" or t_out[:2] == b"FG":
+            torch.from_numpy(x).copy_(self.xd, non_blocking=True)          # projected start / next trial point
+        elif t_out != b"NEW_X":
+            torch.from_numpy(x).copy_(self.xd, non_blocking=True)          # termination: x (and g) may have been restored
+            torch.from_numpy(g).copy_(self.gd, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def close(self):
+        self.prob.close()
+
+
 def nccl_comm_for_engine(rank, world, dist, device):
     """Creates the engine's own NCCL communicator: the 128-byte unique id is made on rank 0 and
     broadcast through torch.distributed."""

@@ -66,6 +66,26 @@ def solve(n_local, off, n_global, m, l_odd, iters, shard, fg_factory, dev, rank,
     return rows, task, x
 
 
+def compare(rows, task, ref, rtask):
+    """Sharded trace `rows` against the single-GPU trace `ref`: every discrete field and the active-set hash equal at
+    every iterate, f within 1e-10 (first 10 iterates) / 1e-6.  Returns (ok, message, worst relative difference of f)."""
+    ok, msg, worst = True, "", 0.0
+    if task != rtask or len(rows) != len(ref):
+        ok, msg = False, "task/len %r %r %d %d" % (task, rtask, len(rows), len(ref))
+    for a, b in zip(rows, ref):
+        for k in ("iter", "nfgv", "nseg", "nfree", "nact", "iword", "iback", "nenter", "col", "hash", "hcount"):
+            if a[k] != b[k]:
+                ok, msg = False, msg + " | it %d %s: %r != %r" % (b["iter"], k, a[k], b[k])
+        rel = abs(a["f"] - b["f"]) / max(abs(b["f"]), 1e-300)
+        worst = max(worst, rel)
+        tol = 1e-10 if b["iter"] <= 10 else 1e-6
+        if rel > tol:
+            ok, msg = False, msg + " | it %d f rel %.2e" % (b["iter"], rel)
+        if not ok:
+            break
+    return ok, msg, worst
+
+
 def main():
     n_global = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
     m = int(sys.argv[2]) if len(sys.argv) > 2 else 5
@@ -91,23 +111,9 @@ def main():
     rows, task, x = solve(hi - lo, lo, n_global, m, l_odd, iters, (lo, n_global, comm, rank, world),
                           mk_sharded, dev, rank, world, kind)
     ok = True
-    msg = ""
     if rank == 0:
         ref, rtask, xr = solve(n_global, 0, n_global, m, l_odd, iters, None, mk_single, dev, 0, 1, kind)
-        if task != rtask or len(rows) != len(ref):
-            ok, msg = False, "task/len %r %r %d %d" % (task, rtask, len(rows), len(ref))
-        worst = 0.0
-        for a, b in zip(rows, ref):
-            for k in ("iter", "nfgv", "nseg", "nfree", "nact", "iword", "iback", "nenter", "col", "hash", "hcount"):
-                if a[k] != b[k]:
-                    ok, msg = False, msg + " | it %d %s: %r != %r" % (b["iter"], k, a[k], b[k])
-            rel = abs(a["f"] - b["f"]) / max(abs(b["f"]), 1e-300)
-            worst = max(worst, rel)
-            tol = 1e-10 if b["iter"] <= 10 else 1e-6
-            if rel > tol:
-                ok, msg = False, msg + " | it %d f rel %.2e" % (b["iter"], rel)
-            if not ok:
-                break
+        ok, msg, worst = compare(rows, task, ref, rtask)
         walks = [r["nseg"] for r in ref if r["nseg"] > 1]
         print("MGPU_CHECK %s %s world=%d n=%d m=%d l_odd=%g iterations=%d walks(nseg>1)=%s worst_rel_f=%.2e %s" % (
             "OK" if ok else "FAIL", kind, world, n_global, m, l_odd, len(ref), walks[:6], worst, msg[:600]), flush=True)
