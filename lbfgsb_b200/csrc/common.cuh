@@ -689,3 +689,134 @@ save:
 }
 
 }  // namespace dense
+
+// ---------------------------------------------------------------------------
+// The same small dense routines run by ONE WARP (all 32 lanes call; `lane` = threadIdx.x & 31).  Every matrix
+// or vector entry is formed by exactly the operations of the single-thread versions above, in the same order
+// -- only entries that do not depend on one another are formed by different lanes at the same time -- so the
+// results are bit-identical (tests/test_gpu_kernels.py compares both with the oracle).  What this buys is
+// latency: the chains of dependent FP divisions and the shared-memory round trips of the 2m x 2m algebra are
+// what the scalar kernels spend their time on.
+// ---------------------------------------------------------------------------
+namespace wdense {
+
+#define LB_FULL 0xffffffffu
+
+// dpofa, row by row: at step k the diagonal entry of column k (its sum of squares runs over rows 0..k-1 in order,
+// as LINPACK accumulates it), then row k of every column j > k, one lane per column.
+template <typename T> __device__ inline int dpofa(T* a, int lda, int n) {
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < n; ++k) {
+        int bad = 0;
+        if (lane == 0) {
+            T s = (T)0;
+            for (int q = 0; q < k; ++q) { const T t = a[q + k * lda]; s = s + t * t; }
+            s = a[k + k * lda] - s;
+            if (s <= (T)0) bad = 1;
+            else a[k + k * lda] = sqrt(s);
+        }
+        bad = __shfl_sync(LB_FULL, bad, 0);
+        if (bad) return k + 1;
+        __syncwarp();
+        const T dk = a[k + k * lda];
+        for (int j = k + 1 + lane; j < n; j += 32) {
+            T t = a[k + j * lda] - dense::ddot<T>(k, a + k * lda, a + j * lda);
+            t = t / dk;
+            a[k + j * lda] = t;
+        }
+        __syncwarp();
+    }
+    return 0;
+}
+
+// dtrsl, jobs 01 and 11, n <= 64: lane q owns entries q and q + 32 of b.
+template <typename T> __device__ inline int dtrsl(const T* t, int ldt, int n, T* b, int job) {
+    const int lane = threadIdx.x & 31;
+    unsigned z0 = __ballot_sync(LB_FULL, lane < n && t[lane + lane * ldt] == (T)0);
+    unsigned z1 = __ballot_sync(LB_FULL, lane + 32 < n && t[(lane + 32) + (lane + 32) * ldt] == (T)0);
+    if (z0) return __ffs(z0);
+    if (z1) return 32 + __ffs(z1);
+    T b0 = lane < n ? b[lane] : (T)0, b1 = lane + 32 < n ? b[lane + 32] : (T)0;
+    if (job == 1) {   // t*x = b, t upper: b(j) final from the last row up; then b(i) += (-b(j)) t(i,j) for i < j (:136-146)
+        for (int j = n - 1; j >= 0; --j) {
+            const int own = j & 31;
+            T bj = (j < 32) ? b0 : b1;
+            if (lane == own) { bj = bj / t[j + j * ldt]; if (j < 32) b0 = bj; else b1 = bj; }
+            bj = __shfl_sync(LB_FULL, bj, own);
+            const T temp = -bj;
+            if (temp != (T)0) {   // daxpy's early-out (:49-50)
+                if (lane < j) b0 = b0 + temp * t[lane + j * ldt];
+                if (lane + 32 < j) b1 = b1 + temp * t[(lane + 32) + j * ldt];
+            }
+        }
+    } else {          // trans(t)*x = b, t upper: b(j) = (b(j) - sum_{i<j} t(i,j) b(i)) / t(j,j), the sum in i order (:159-166)
+        T s0 = (T)0, s1 = (T)0;
+        for (int i = 0; i < n; ++i) {
+            const int own = i & 31;
+            T bi = (i < 32) ? b0 : b1;
+            if (lane == own) {
+                if (i > 0) bi = bi - ((i < 32) ? s0 : s1);
+                bi = bi / t[i + i * ldt];
+                if (i < 32) b0 = bi; else b1 = bi;
+            }
+            bi = __shfl_sync(LB_FULL, bi, own);
+            if (lane > i && lane < n) s0 = s0 + t[i + lane * ldt] * bi;
+            if (lane + 32 > i && lane + 32 < n) s1 = s1 + t[i + (lane + 32) * ldt] * bi;
+        }
+    }
+    if (lane < n) b[lane] = b0;
+    if (lane + 32 < n) b[lane + 32] = b1;
+    __syncwarp();
+    return 0;
+}
+
+// bmv (src/lbfgsb.f90:1057-1123); v and p must not overlap
+template <typename T>
+__device__ inline int bmv(int m, const T* sy, const T* wt, int col, const T* v, T* p) {
+    const int lane = threadIdx.x & 31;
+    if (col == 0) return 0;
+    for (int i = 1 + lane; i <= col; i += 32) {
+        if (i == 1) { p[col] = v[col]; continue; }
+        T sum = (T)0;
+        for (int k = 1; k <= i - 1; ++k)
+            sum = sum + sy[(i - 1) + (k - 1) * m] * v[k - 1] / sy[(k - 1) + (k - 1) * m];
+        p[col + i - 1] = v[col + i - 1] + sum;
+    }
+    __syncwarp();
+    int info = dtrsl<T>(wt, m, col, p + col, 11);
+    if (info != 0) return info;
+    for (int i = lane; i < col; i += 32) p[i] = v[i] / sqrt(sy[i + i * m]);
+    __syncwarp();
+    info = dtrsl<T>(wt, m, col, p + col, 1);
+    if (info != 0) return info;
+    for (int i = 1 + lane; i <= col; i += 32) {
+        T pi = -p[i - 1] / sqrt(sy[(i - 1) + (i - 1) * m]);
+        T sum = (T)0;
+        for (int k = i + 1; k <= col; ++k)
+            sum = sum + sy[(k - 1) + (i - 1) * m] * p[col + k - 1] / sy[(i - 1) + (i - 1) * m];
+        p[i - 1] = pi + sum;
+    }
+    __syncwarp();
+    return 0;
+}
+
+// formt (src/lbfgsb.f90:1926-1963): the entries of T one per lane, then dpofa
+template <typename T>
+__device__ inline int formt(int m, T* wt, const T* sy, const T* ss, int col, T theta) {
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < col * col; e += 32) {
+        const int i = e % col + 1, j = e / col + 1;
+        if (i > j) continue;
+        if (i == 1) { wt[0 + (j - 1) * m] = theta * ss[0 + (j - 1) * m]; continue; }
+        const int k1 = i - 1;   // min(i, j) - 1 with i <= j
+        T ddum = (T)0;
+        for (int k = 1; k <= k1; ++k)
+            ddum = ddum + sy[(i - 1) + (k - 1) * m] * sy[(j - 1) + (k - 1) * m] / sy[(k - 1) + (k - 1) * m];
+        wt[(i - 1) + (j - 1) * m] = ddum + theta * ss[(i - 1) + (j - 1) * m];
+    }
+    __syncwarp();
+    int info = dpofa<T>(wt, m, col);
+    return info != 0 ? -3 : 0;
+}
+
+}  // namespace wdense

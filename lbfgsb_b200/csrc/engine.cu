@@ -1543,8 +1543,33 @@ static int test_sum_impl(i64 n, const T* a, const T* b, T* out) {
     return e != cudaSuccess;
 }
 
-__global__ void k_test_dense(int op, int m, int col, double theta, double* a, double* b, double* c, int* info) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// ops 0-4: the single-thread routines (dense::); 10-14: the same by one warp (wdense::), as the scalar kernels run
+// them; 15: the dense tail of formk (w_formk_dense with no new pair and no entering/leaving variable)
+__global__ void k_test_dense(int op, int m, int col, double theta, double* a, double* b, double* c, int* info, DevState<double>* st) {
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    int r = 0;
+    if (op >= 10 && op <= 14) {
+        if (op == 10) r = wdense::dpofa<double>(a, m, col);
+        else if (op == 11) r = wdense::dtrsl<double>(a, m, col, b, 1);
+        else if (op == 12) r = wdense::dtrsl<double>(a, m, col, b, 11);
+        else if (op == 13) r = wdense::bmv<double>(m, a, b, col, c, c + 2 * m);
+        else r = wdense::formt<double>(m, c, a, b, col, theta);
+        if (threadIdx.x == 0) *info = r;
+        return;
+    }
+    if (op == 15) {   // a = wn1 (2m x 2m, in), b = sy (m x m), c = wn (2m x 2m, out)
+        if (threadIdx.x == 0) {
+            st->m = m; st->col = col; st->theta = theta; st->do_formk = 1; st->updatd = 0; st->do_delta = 0; st->iupdat = m + 1;
+            st->restart = 0; st->in_body = 1; st->ev_n = 0;
+            for (int q = 0; q < m * m; ++q) st->sy[q] = b[q];
+        }
+        __syncwarp();
+        Red<double>* red = nullptr;
+        w_formk_dense<double>(st, *red, m <= 5 ? 5 : (m <= 10 ? 10 : 20), (const double*)nullptr, c, a);
+        if (threadIdx.x == 0) *info = st->restart ? 1 : 0;
+        return;
+    }
+    if (threadIdx.x != 0) return;
     if (op == 0) *info = dense::dpofa<double>(a, m, col);
     else if (op == 1) *info = dense::dtrsl<double>(a, m, col, b, 1);
     else if (op == 2) *info = dense::dtrsl<double>(a, m, col, b, 11);
@@ -1945,11 +1970,12 @@ int lbfgsb_test_heap_order_f64(int64_t n, const double* t, int32_t* order_out) {
     return e != cudaSuccess || cudaGetLastError() != cudaSuccess;
 }
 int lbfgsb_test_dense_f64(int32_t op, int32_t m, int32_t col, double theta, double* a, double* b, double* c, int32_t* info) {
-    int* dinfo;
-    if (cudaMalloc(&dinfo, 4)) return 1;
-    k_test_dense<<<1, 32>>>(op, m, col, theta, a, b, c, dinfo);
+    int* dinfo; DevState<double>* st;
+    if (cudaMalloc(&dinfo, 4) || cudaMalloc(&st, sizeof(DevState<double>))) return 1;
+    cudaMemset(st, 0, sizeof(DevState<double>));
+    k_test_dense<<<1, 32>>>(op, m, col, theta, a, b, c, dinfo, st);
     cudaError_t e = cudaMemcpy(info, dinfo, 4, cudaMemcpyDeviceToHost);
-    cudaFree(dinfo);
+    cudaFree(dinfo); cudaFree(st);
     return e != cudaSuccess;
 }
 int lbfgsb_test_dcsrch_f64(double f, double g, double* stp, double stpmax, int32_t* task, int32_t* isave2, double* dsave13) {

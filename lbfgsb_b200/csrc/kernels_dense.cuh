@@ -353,135 +353,180 @@ template <typename T> __device__ inline void t0_newx_tests(DevState<T>* s, int f
     }
 }
 
-// NEW_X entry, part 2: matupd's small matrices (:2318-2344) + formt (:1926-1963).  sy, ss, wt: staged copies.
-template <typename T> __device__ inline void t0_update_dense(DevState<T>* s, const Red<T>& red, int mt, T* sy, T* ss, T* swt) {
+// NEW_X entry, part 2: matupd's small matrices (:2318-2344) + formt (:1926-1963).  sy, ss, wt: staged copies (the
+// shifted entries are read from the originals in the state block).  Called by warp 0.
+template <typename T> __device__ inline void w_update_dense(DevState<T>* s, const Red<T>& red, int mt, T* sy, T* ss, T* swt) {
+    const int lane = threadIdx.x & 31;
     const int m = s->m, col = s->col;
-    s->rr = red.rv[0];
-    s->theta = s->rr / s->dr;
-    if (s->iupdat > m) {  // :2324-2330
-        for (int j = 1; j <= col - 1; ++j) {
-            for (int q = 0; q < j; ++q) ss[q + (j - 1) * m] = ss[(1 + q) + j * m];             // dcopy(j,Ss(2,j+1),Ss(1,j))
-            for (int q = 0; q < col - j; ++q) sy[(j - 1 + q) + (j - 1) * m] = sy[(j + q) + j * m];  // dcopy(col-j,Sy(j+1,j+1),Sy(j,j))
+    if (lane == 0) {
+        s->rr = red.rv[0];
+        s->theta = s->rr / s->dr;
+    }
+    if (s->iupdat > m) {  // :2324-2330: every entry moves one place up and to the left
+        for (int e = lane; e < m * m; e += 32) {
+            const int j = e / m + 1, q = e % m;   // reference loop j = 1..col-1
+            if (j > col - 1) continue;
+            if (q < j) ss[q + (j - 1) * m] = s->ss[(1 + q) + j * m];                         // dcopy(j,Ss(2,j+1),Ss(1,j))
+            if (q < col - j) sy[(j - 1 + q) + (j - 1) * m] = s->sy[(j + q) + j * m];         // dcopy(col-j,Sy(j+1,j+1),Sy(j,j))
         }
     }
-    for (int j = 1; j <= col - 1; ++j) {
+    __syncwarp();
+    for (int j = 1 + lane; j <= col - 1; j += 32) {
         sy[(col - 1) + (j - 1) * m] = red.rv[1 + (j - 1)];
         ss[(j - 1) + (col - 1) * m] = red.rv[1 + mt + (j - 1)];
     }
-    ss[(col - 1) + (col - 1) * m] = (s->stp == (T)1) ? s->dtd : s->stp * s->stp * s->dtd;
-    sy[(col - 1) + (col - 1) * m] = s->dr;
-    int info = dense::formt<T>(m, swt, sy, ss, col, s->theta);
-    if (info != 0) { ev_push<T>(s, EV_FORMT_FAIL); reset_memory<T>(s); }   // :851-863
+    if (lane == 0) {
+        ss[(col - 1) + (col - 1) * m] = (s->stp == (T)1) ? s->dtd : s->stp * s->stp * s->dtd;
+        sy[(col - 1) + (col - 1) * m] = s->dr;
+    }
+    __syncwarp();
+    int info = wdense::formt<T>(m, swt, sy, ss, col, s->theta);
+    if (info != 0 && lane == 0) { ev_push<T>(s, EV_FORMT_FAIL); reset_memory<T>(s); }   // :851-863
+    __syncwarp();
 }
 
 // cauchy after the per-variable pass (:1337-1366) and the first-segment exit test (:1384-1416 with iter == 1).
-// ssy, swt: staged copies of sy, wt.
-template <typename T> __device__ inline void t0_cauchy(DevState<T>* s, const Red<T>& red, int mt, const T* ssy, const T* swt,
-                                                       int fused_supported) {
-    s->classify_done = 0;
+// ssy, swt: staged copies of sy, wt.  Called by warp 0.
+template <typename T> __device__ inline void w_cauchy(DevState<T>* s, const Red<T>& red, int mt, const T* ssy, const T* swt,
+                                                      int fused_supported) {
+    const int lane = threadIdx.x & 31;
     const int col = s->col, col2 = 2 * col, m = s->m;
     const T zero = (T)0, one = (T)1;
-    for (int j = 0; j < col; ++j) { s->p[j] = red.rv[j]; s->p[col + j] = red.rv[mt + j]; }
-    s->f1 = -red.rv[2 * mt];
-    s->bkmin = red.rv[2 * mt + 1];
-    s->ibkmin = red.iv[0];
-    s->nbreak = red.iv[1];
-    s->nfreec = red.iv[2];
-    s->bnded = red.iv[3] > 0;
-    if (s->theta != one) for (int j = 0; j < col; ++j) s->p[col + j] = s->theta * s->p[col + j];  // :1337
-    s->tsum = zero;
-    s->lazy_gcp = 1;   // the per-variable pass did not write d and xcp = x (k_gcp_freev / k_formk_cmprlb form xcp)
-    if (s->nbreak == 0 && s->nfreec == 0) return;   // d is the zero vector (:1343-1347); nseg untouched
-    for (int j = 0; j < col2; ++j) s->c[j] = zero;
-    s->f2 = -s->theta * s->f1;
-    s->f2_org = s->f2;
+    int stop = 0;
+    if (lane == 0) {
+        s->classify_done = 0;
+        for (int j = 0; j < col; ++j) { s->p[j] = red.rv[j]; s->p[col + j] = red.rv[mt + j]; }
+        s->f1 = -red.rv[2 * mt];
+        s->bkmin = red.rv[2 * mt + 1];
+        s->ibkmin = red.iv[0];
+        s->nbreak = red.iv[1];
+        s->nfreec = red.iv[2];
+        s->bnded = red.iv[3] > 0;
+        if (s->theta != one) for (int j = 0; j < col; ++j) s->p[col + j] = s->theta * s->p[col + j];  // :1337
+        s->tsum = zero;
+        s->lazy_gcp = 1;   // the per-variable pass did not write d and xcp = x (k_gcp_freev / k_formk_cmprlb form xcp)
+        if (s->nbreak == 0 && s->nfreec == 0) stop = 1;   // d is the zero vector (:1343-1347); nseg untouched
+        else {
+            for (int j = 0; j < col2; ++j) s->c[j] = zero;
+            s->f2 = -s->theta * s->f1;
+            s->f2_org = s->f2;
+        }
+    }
+    stop = __shfl_sync(LB_FULL, stop, 0);
+    if (stop) return;
+    __syncwarp();
     if (col > 0) {
-        int info = dense::bmv<T>(m, ssy, swt, col, s->p, s->v);
+        int info = wdense::bmv<T>(m, ssy, swt, col, s->p, s->v);
         if (info != 0) {   // :620-635
-            ev_push<T>(s, EV_CAUCHY_SINGULAR);
-            reset_memory<T>(s);
-            s->restart = 1; s->in_body = 0;
+            if (lane == 0) {
+                ev_push<T>(s, EV_CAUCHY_SINGULAR);
+                reset_memory<T>(s);
+                s->restart = 1; s->in_body = 0;
+            }
+            __syncwarp();
             return;
         }
-        s->f2 = s->f2 - dense::ddot<T>(col2, s->v, s->p);
     }
-    s->dtm = -s->f1 / s->f2;
-    s->nseg = 1;
-    if (s->nbreak != 0 && !(s->dtm < s->bkmin)) {
-        // the first breakpoint is reached: the sorted walk takes over (k_materialize writes d, xcp = x first)
-        s->need_walk = 1; s->lazy_gcp = 0;
-        for (int j = 0; j < col2; ++j) { s->p0[j] = s->p[j]; s->walkA[j] = zero; s->walkB[j] = zero; }
-        s->walk_f1 = s->f1; s->walk_f2 = s->f2; s->walk_tlast = zero; s->walk_tprev2 = zero;
-        s->walk_J = -1; s->walk_done = 0; s->walk_base = 0; s->walk_rcount = 0; s->walk_lcount = 0; s->walk_rem = 0;
-        s->walk_cstart = 0; s->walk_fixn = 0; s->walk_closed = 0; s->tie_redo = 0; s->tie_round = 0;
-        return;
+    if (lane == 0) {
+        if (col > 0) s->f2 = s->f2 - dense::ddot<T>(col2, s->v, s->p);
+        s->dtm = -s->f1 / s->f2;
+        s->nseg = 1;
+        if (s->nbreak != 0 && !(s->dtm < s->bkmin)) {
+            // the first breakpoint is reached: the sorted walk takes over (k_materialize writes d, xcp = x first)
+            s->need_walk = 1; s->lazy_gcp = 0;
+            for (int j = 0; j < col2; ++j) { s->p0[j] = s->p[j]; s->walkA[j] = zero; s->walkB[j] = zero; }
+            s->walk_f1 = s->f1; s->walk_f2 = s->f2; s->walk_tlast = zero; s->walk_tprev2 = zero;
+            s->walk_J = -1; s->walk_done = 0; s->walk_base = 0; s->walk_rcount = 0; s->walk_lcount = 0; s->walk_rem = 0;
+            s->walk_cstart = 0; s->walk_fixn = 0; s->walk_closed = 0; s->tie_redo = 0; s->tie_round = 0;
+            stop = 1;
+        } else {
+            if (s->dtm <= zero) s->dtm = zero;   // :1509
+            s->tsum = s->tsum + s->dtm;
+            if (col > 0) dense::daxpy<T>(col2, s->dtm, s->p, s->c);  // :1526
+        }
     }
-    if (s->dtm <= zero) s->dtm = zero;   // :1509
-    s->tsum = s->tsum + s->dtm;
-    if (col > 0) dense::daxpy<T>(col2, s->dtm, s->p, s->c);  // :1526
+    stop = __shfl_sync(LB_FULL, stop, 0);
+    if (stop) return;
+    __syncwarp();
     // The generalized Cauchy point is known without a walk and c is final: cmprlb's a = M c (:1569) can be
     // formed here, and then the tail of cauchy (:1515) and freev run inside k_formk_cmprlb (fuse_gf).  The
     // counts of freev, and with them nfree == 0 / wrk, are evaluated after that pass (s_freev phase 1).  If
     // the product fails, the separate passes run and s_freev reports the failure in the reference's order.
     if (fused_supported && col > 0 && s->cnstnd) {
-        if (dense::bmv<T>(m, ssy, swt, col, s->c, s->a) == 0) s->fuse_gf = 1;
+        const int info = wdense::bmv<T>(m, ssy, swt, col, s->c, s->a);
+        if (info == 0 && lane == 0) s->fuse_gf = 1;
     }
+    __syncwarp();
 }
 
 // after freev (:638-648): counters, wrk, what of the subspace phase runs.  `have` = the counts exist (cauchy_mode != 1).
-template <typename T> __device__ inline void t0_freev(DevState<T>* s, const Red<T>& red, i64 n_global, bool gf, bool have) {
-    if (gf) s->lazy_z = 1;   // k_formk_cmprlb did not store xcp (state bit 2 tells where d = -g)
-    if (have) {
-        s->nintol = s->nintol + s->nseg;
-        s->nfree = red.iv[0];
-        s->nenter = red.iv[1];
-        s->nleave = red.iv[2];
-        s->wrk = (s->nleave > 0) || (s->nenter > 0) || s->updatd;
-        s->nact = n_global - s->nfree;
+// Called by warp 0.
+template <typename T> __device__ inline void w_freev(DevState<T>* s, const Red<T>& red, i64 n_global, bool gf, bool have) {
+    const int lane = threadIdx.x & 31;
+    int need_a = 0;
+    if (lane == 0) {
+        if (gf) s->lazy_z = 1;   // k_formk_cmprlb did not store xcp (state bit 2 tells where d = -g)
+        if (have) {
+            s->nintol = s->nintol + s->nseg;
+            s->nfree = red.iv[0];
+            s->nenter = red.iv[1];
+            s->nleave = red.iv[2];
+            s->wrk = (s->nleave > 0) || (s->nenter > 0) || s->updatd;
+            s->nact = n_global - s->nfree;
+        }
+        s->do_subspace = !(s->nfree == 0 || s->col == 0);
+        s->do_formk = s->do_subspace && s->wrk;
+        s->do_delta = s->do_formk && (s->nenter + s->nleave > 0);
+        // cmprlb's a = M c (:1569; not needed on the unconstrained shortcut :1560-1563).  It depends only on
+        // sy, wt and c, which are final here, and is hoisted in front of formk so that formk's Gram pass and
+        // cmprlb's pass over S/Y can run as one kernel.  A failure of either ends in the same memory reset.
+        need_a = (!gf && s->do_subspace && !(!s->cnstnd && s->col > 0)) ? 1 : 0;   // (with fuse_gf s_cauchy formed a)
     }
-    s->do_subspace = !(s->nfree == 0 || s->col == 0);
-    s->do_formk = s->do_subspace && s->wrk;
-    s->do_delta = s->do_formk && (s->nenter + s->nleave > 0);
-    // cmprlb's a = M c (:1569; not needed on the unconstrained shortcut :1560-1563).  It depends only on
-    // sy, wt and c, which are final here, and is hoisted in front of formk so that formk's Gram pass and
-    // cmprlb's pass over S/Y can run as one kernel.  A failure of either ends in the same memory reset.
-    if (!gf && s->do_subspace && !(!s->cnstnd && s->col > 0)) {   // (with fuse_gf s_cauchy formed a)
-        int info = dense::bmv<T>(s->m, s->sy, s->wt, s->col, s->c, s->a);
-        if (info != 0) {   // info = -8 -> :694-710
+    need_a = __shfl_sync(LB_FULL, need_a, 0);
+    __syncwarp();
+    if (need_a) {
+        int info = wdense::bmv<T>(s->m, s->sy, s->wt, s->col, s->c, s->a);
+        if (info != 0 && lane == 0) {   // info = -8 -> :694-710
             ev_push<T>(s, EV_SUBSM_SINGULAR);
             reset_memory<T>(s);
             s->restart = 1; s->in_body = 0; s->do_subspace = 0; s->do_formk = 0; s->do_delta = 0;
         }
     }
+    __syncwarp();
 }
 
 // formk, everything after the long sums (:1735-1744 shift, :1772-1792 new row/column, :1821-1847 corrections,
-// :1853-1906 assembly and factorisation).  wn, wn1: staged copies.
+// :1853-1906 assembly and factorisation).  wn, wn1: staged copies (the shifted entries are read from the original
+// wn1 in the state block).  Called by warp 0.
 // delta: [3][2m][2m] enter-minus-leave sums of Wy.Wy, Ws.Ws, Ws.Wy over ring positions
 //        (dE - dL kept separately: delta[0..2] enter, delta[3..5] leave)
-template <typename T> __device__ inline void t0_formk_dense(DevState<T>* s, const Red<T>& red, int mt, const T* delta, T* wn, T* wn1) {
+template <typename T> __device__ inline void w_formk_dense(DevState<T>* s, const Red<T>& red, int mt, const T* delta, T* wn, T* wn1) {
+    const int lane = threadIdx.x & 31;
     const int m = s->m, col = s->col, m2 = 2 * m;
 #define WN(i, j) wn[((i)-1) + ((j)-1) * m2]
 #define WN1(i, j) wn1[((i)-1) + ((j)-1) * m2]
+#define WN1O(i, j) s->wn1[((i)-1) + ((j)-1) * m2]
     if (s->do_formk) {
         int upcl;
         if (s->updatd) {
-            if (s->iupdat > m) {   // :1736-1744
-                for (int jy = 1; jy <= m - 1; ++jy) {
-                    int js = m + jy;
-                    for (int q = 0; q < m - jy; ++q) WN1(jy + q, jy) = WN1(jy + 1 + q, jy + 1);
-                    for (int q = 0; q < m - jy; ++q) WN1(js + q, js) = WN1(js + 1 + q, js + 1);
-                    for (int q = 0; q < m - 1; ++q) WN1(m + 1 + q, jy) = WN1(m + 2 + q, jy + 1);
+            if (s->iupdat > m) {   // :1736-1744: the three blocks move one place up and to the left
+                for (int e = lane; e < (m - 1) * m; e += 32) {
+                    const int jy = e / m + 1, q = e % m, js = m + jy;
+                    if (q < m - jy) { WN1(jy + q, jy) = WN1O(jy + 1 + q, jy + 1); WN1(js + q, js) = WN1O(js + 1 + q, js + 1); }
+                    if (q < m - 1) WN1(m + 1 + q, jy) = WN1O(m + 2 + q, jy + 1);
                 }
+                __syncwarp();
             }
             const int iy = col, is = m + col;
-            for (int jy = 1; jy <= col; ++jy) {   // :1772-1774
+            for (int jy = 1 + lane; jy <= col; jy += 32) {   // :1772-1774
                 const int js = m + jy;
                 WN1(iy, jy) = red.rv[jy - 1];
                 WN1(is, js) = red.rv[mt + jy - 1];
                 WN1(is, jy) = red.rv[2 * mt + jy - 1];
             }
-            for (int i = 1; i <= col; ++i) WN1(m + i, col) = red.rv[3 * mt + i - 1];   // :1792
+            __syncwarp();
+            for (int i = 1 + lane; i <= col; i += 32) WN1(m + i, col) = red.rv[3 * mt + i - 1];   // :1792
+            __syncwarp();
             upcl = col - 1;
         } else upcl = col;
         if (s->do_delta) {
@@ -489,74 +534,87 @@ template <typename T> __device__ inline void t0_formk_dense(DevState<T>* s, cons
             const T* eYY = delta + 0 * LB_MMAX * LB_MMAX; const T* eSS = delta + 1 * LB_MMAX * LB_MMAX;
             const T* eSY = delta + 2 * LB_MMAX * LB_MMAX; const T* lYY = delta + 3 * LB_MMAX * LB_MMAX;
             const T* lSS = delta + 4 * LB_MMAX * LB_MMAX; const T* lSY = delta + 5 * LB_MMAX * LB_MMAX;
-            for (int iy = 1; iy <= upcl; ++iy) {   // :1802-1826
-                const int is = m + iy;
-                for (int jy = 1; jy <= iy; ++jy) {
-                    const int js = m + jy;
-                    const int e = (iy - 1) + (jy - 1) * LB_MMAX;
-                    WN1(iy, jy) = WN1(iy, jy) + eYY[e] - lYY[e];
-                    WN1(is, js) = WN1(is, js) - eSS[e] + lSS[e];
+            for (int e = lane; e < upcl * upcl; e += 32) {
+                const int a = e / upcl + 1, b = e % upcl + 1;
+                if (b <= a) {   // :1802-1826 with (iy, jy) = (a, b)
+                    const int iy = a, jy = b, is = m + iy, js = m + jy;
+                    const int d = (iy - 1) + (jy - 1) * LB_MMAX;
+                    WN1(iy, jy) = WN1(iy, jy) + eYY[d] - lYY[d];
+                    WN1(is, js) = WN1(is, js) - eSS[d] + lSS[d];
+                }
+                {               // :1830-1851 with (is, jy) = (m + a, b)
+                    const int is = m + a, jy = b;
+                    const int d = (is - m - 1) + (jy - 1) * LB_MMAX;
+                    if (is <= jy + m) WN1(is, jy) = WN1(is, jy) + eSY[d] - lSY[d];
+                    else WN1(is, jy) = WN1(is, jy) - eSY[d] + lSY[d];
                 }
             }
-            for (int is = m + 1; is <= m + upcl; ++is) {   // :1830-1851
-                for (int jy = 1; jy <= upcl; ++jy) {
-                    const int e = (is - m - 1) + (jy - 1) * LB_MMAX;
-                    if (is <= jy + m) WN1(is, jy) = WN1(is, jy) + eSY[e] - lSY[e];
-                    else WN1(is, jy) = WN1(is, jy) - eSY[e] + lSY[e];
-                }
-            }
+            __syncwarp();
         }
         const T theta = s->theta;
-        for (int iy = 1; iy <= col; ++iy) {   // :1857-1873
-            const int is = col + iy, is1 = m + iy;
-            for (int jy = 1; jy <= iy; ++jy) {
-                const int js = col + jy, js1 = m + jy;
-                WN(jy, iy) = WN1(iy, jy) / theta;
+        for (int e = lane; e < col * col; e += 32) {   // :1857-1873, one (iy, jy) pair per lane
+            const int iy = e / col + 1, jy = e % col + 1;
+            const int is = col + iy, is1 = m + iy, js = col + jy, js1 = m + jy;
+            if (jy <= iy) {
+                T v = WN1(iy, jy) / theta;
+                if (jy == iy) v = v + s->sy[(iy - 1) + (iy - 1) * m];
+                WN(jy, iy) = v;
                 WN(js, is) = WN1(is1, js1) * theta;
             }
-            for (int jy = 1; jy <= iy - 1; ++jy) WN(jy, is) = -WN1(is1, jy);
-            for (int jy = iy; jy <= col; ++jy) WN(jy, is) = WN1(is1, jy);
-            WN(iy, iy) = WN(iy, iy) + s->sy[(iy - 1) + (iy - 1) * m];
+            if (jy <= iy - 1) WN(jy, is) = -WN1(is1, jy);
+            else WN(jy, is) = WN1(is1, jy);
         }
-        int info = dense::dpofa<T>(wn, m2, col);
+        __syncwarp();
+        int info = wdense::dpofa<T>(wn, m2, col);
         if (info != 0) info = -1;
         else {
             const int col2 = 2 * col;
-            for (int js = col + 1; js <= col2; ++js) dense::dtrsl<T>(wn, m2, col, &WN(1, js), 11);
-            for (int is = col + 1; is <= col2; ++is)
-                for (int js = is; js <= col2; ++js)
-                    WN(is, js) = WN(is, js) + dense::ddot<T>(col, &WN(1, is), &WN(1, js));
-            info = dense::dpofa<T>(&WN(col + 1, col + 1), m2, col);
+            for (int js = col + 1 + lane; js <= col2; js += 32) dense::dtrsl<T>(wn, m2, col, &WN(1, js), 11);
+            __syncwarp();
+            for (int e = lane; e < col * col; e += 32) {
+                const int is = col + 1 + e / col, js = col + 1 + e % col;
+                if (js >= is) WN(is, js) = WN(is, js) + dense::ddot<T>(col, &WN(1, is), &WN(1, js));
+            }
+            __syncwarp();
+            info = wdense::dpofa<T>(&WN(col + 1, col + 1), m2, col);
             if (info != 0) info = -2;
         }
-        if (info != 0) {   // :666-682
+        if (info != 0 && lane == 0) {   // :666-682
             ev_push<T>(s, EV_FORMK_FAIL);
             reset_memory<T>(s);
             s->restart = 1; s->in_body = 0;
         }
+        __syncwarp();
     }
 #undef WN
 #undef WN1
+#undef WN1O
 }
 
-// subsm: wv = K^{-1} wv (:2751-2766).  swn: staged copy of wn.
-template <typename T> __device__ inline void t0_subsm_dense(DevState<T>* s, const Red<T>& red, int mt, const T* swn, int fused_lsinit) {
+// subsm: wv = K^{-1} wv (:2751-2766).  swn: staged copy of wn.  Called by warp 0.
+template <typename T> __device__ inline void w_subsm_dense(DevState<T>* s, const Red<T>& red, int mt, const T* swn, int fused_lsinit) {
+    const int lane = threadIdx.x & 31;
     const int m = s->m, col = s->col, m2 = 2 * m, col2 = 2 * col;
-    for (int i = 0; i < col; ++i) { s->wv[i] = red.rv[i]; s->wv[col + i] = s->theta * red.rv[mt + i]; }
-    int info = dense::dtrsl<T>(swn, m2, col2, s->wv, 11);
+    for (int i = lane; i < col; i += 32) { s->wv[i] = red.rv[i]; s->wv[col + i] = s->theta * red.rv[mt + i]; }
+    __syncwarp();
+    int info = wdense::dtrsl<T>(swn, m2, col2, s->wv, 11);
     if (info == 0) {
-        for (int i = 0; i < col; ++i) s->wv[i] = -s->wv[i];
-        info = dense::dtrsl<T>(swn, m2, col2, s->wv, 1);
+        for (int i = lane; i < col; i += 32) s->wv[i] = -s->wv[i];
+        __syncwarp();
+        info = wdense::dtrsl<T>(swn, m2, col2, s->wv, 1);
     }
-    if (info != 0) {   // :694-710
-        ev_push<T>(s, EV_SUBSM_SINGULAR);
-        reset_memory<T>(s);
-        s->restart = 1; s->in_body = 0; s->do_subspace = 0;
-        return;
+    if (lane == 0) {
+        if (info != 0) {   // :694-710
+            ev_push<T>(s, EV_SUBSM_SINGULAR);
+            reset_memory<T>(s);
+            s->restart = 1; s->in_body = 0; s->do_subspace = 0;
+        } else {
+            // lnsrlb starts at stp = 1 unless this is the first iteration of a problem that is not boxed (:2229-2233):
+            // the fused subspace pass then writes that trial point (x = z, :2265) itself
+            s->spec_step = (fused_lsinit && (s->iter != 0 || s->boxed)) ? 1 : 0;
+        }
     }
-    // lnsrlb starts at stp = 1 unless this is the first iteration of a problem that is not boxed (:2229-2233):
-    // the fused subspace pass then writes that trial point (x = z, :2265) itself
-    s->spec_step = (fused_lsinit && (s->iter != 0 || s->boxed)) ? 1 : 0;
+    __syncwarp();
 }
 
 // subsm: projection outcome (:2820-2828)
@@ -732,9 +790,9 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_update_dense(Wk<T> w, Dis
         stage_in<T>(ssy, s->sy, mm); stage_in<T>(sss, s->ss, mm); stage_in<T>(swt, s->wt, mm);
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        if (upd) t0_update_dense<T>(s, red, mt, ssy, sss, swt);
-        begin_body<T>(s);
+    if (threadIdx.x < 32) {
+        if (upd) w_update_dense<T>(s, red, mt, ssy, sss, swt);
+        if (threadIdx.x == 0) begin_body<T>(s);
     }
     if (upd) {
         __syncthreads();
@@ -767,8 +825,8 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
     site_reduce<T>(w, dist, site_cauchy(mt), &red);
     stage_in<T>(ssy, s->sy, s->m * s->m); stage_in<T>(swt, s->wt, s->m * s->m);
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    t0_cauchy<T>(s, red, mt, ssy, swt, fused_supported);
+    if (threadIdx.x >= 32) return;
+    w_cauchy<T>(s, red, mt, ssy, swt, fused_supported);
 }
 
 template <typename T>
@@ -788,8 +846,8 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_freev(Wk<T> w, Dist<T> di
     }
     const int mode = s->cauchy_mode;
     if (mode != 1) site_reduce<T>(w, dist, site_freev(), &red);
-    if (threadIdx.x != 0) return;
-    t0_freev<T>(s, red, n_global, gf, mode != 1);
+    if (threadIdx.x >= 32) return;
+    w_freev<T>(s, red, n_global, gf, mode != 1);
 }
 
 template <typename T>
@@ -819,7 +877,7 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_formk_dense(Wk<T> w, Dist
         stage_in<T>(swn, s->wn, 4 * s->m * s->m); stage_in<T>(swn1, s->wn1, 4 * s->m * s->m);
         __syncthreads();
     }
-    if (threadIdx.x == 0) t0_formk_dense<T>(s, red, mt, delta, swn, swn1);
+    if (threadIdx.x < 32) w_formk_dense<T>(s, red, mt, delta, swn, swn1);
     if (stage) {
         __syncthreads();
         stage_out<T>(s->wn, swn, 4 * s->m * s->m); stage_out<T>(s->wn1, swn1, 4 * s->m * s->m);
@@ -836,8 +894,8 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_subsm_dense(Wk<T> w, Dist
     __shared__ T swn[4 * LB_MMAX * LB_MMAX];
     stage_in<T>(swn, s->wn, 4 * s->m * s->m);
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    t0_subsm_dense<T>(s, red, mt, swn, fused_lsinit);
+    if (threadIdx.x >= 32) return;
+    w_subsm_dense<T>(s, red, mt, swn, fused_lsinit);
 }
 
 template <typename T>
@@ -986,19 +1044,22 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) f_ucf(Wk<T> w, Dist<T> dist
         stage_in<T>(sss, s->ss, mm);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (upd) t0_update_dense<T>(s, red, mt, ssy, sss, swt);
-        begin_body<T>(s);
-        // the fast sequence goes on only into cauchy's full per-variable pass done by k_update_classify
-        cont = (s->cauchy_mode == 0 && s->classify_done) ? 1 : 0;
-        if (!cont) s->pause = PAUSE_CLASSIFY;
+    if (threadIdx.x < 32) {
+        if (upd) w_update_dense<T>(s, red, mt, ssy, sss, swt);
+        if (threadIdx.x == 0) {
+            begin_body<T>(s);
+            // the fast sequence goes on only into cauchy's full per-variable pass done by k_update_classify
+            cont = (s->cauchy_mode == 0 && s->classify_done) ? 1 : 0;
+            if (!cont) s->pause = PAUSE_CLASSIFY;
+        }
     }
     __syncthreads();
     if (upd) { stage_out<T>(s->sy, ssy, mm); stage_out<T>(s->ss, sss, mm); stage_out<T>(s->wt, swt, mm); }
     if (!cont) return;
     site_reduce<T>(w, dist, ms.sp[1], &red, ms.roff[1], ms.ioff[1]);   // (ends with a barrier: the staged sy, wt are final)
+    if (threadIdx.x >= 32) return;
+    w_cauchy<T>(s, red, mt, ssy, swt, 1);
     if (threadIdx.x != 0) return;
-    t0_cauchy<T>(s, red, mt, ssy, swt, 1);
     if (!s->in_body) return;                                 // singular bmv: memory reset, the host restarts the body
     if (s->need_walk) { s->pause = PAUSE_WALK; return; }
     if (!s->fuse_gf) { s->pause = PAUSE_GCP_FREEV; return; }
@@ -1016,11 +1077,13 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) f_mid(Wk<T> w, Dist<T> dist
     site_fetch<T>(w, dist);
     if (!s->go || s->pause || !s->in_body) return;
     site_reduce<T>(w, dist, ms.sp[0], &red, ms.roff[0], ms.ioff[0]);
-    if (threadIdx.x == 0) {
-        t0_freev<T>(s, red, n_global, true, true);
-        cont = 1;
-        if (!s->do_subspace) { s->pause = PAUSE_LSINIT; cont = 0; }        // no free variable: straight to the line search
-        else if (s->do_delta) { s->pause = PAUSE_DELTA; cont = 0; }        // variables entered / left: formk's corrections first
+    if (threadIdx.x < 32) {
+        w_freev<T>(s, red, n_global, true, true);
+        if (threadIdx.x == 0) {
+            cont = 1;
+            if (!s->do_subspace) { s->pause = PAUSE_LSINIT; cont = 0; }        // no free variable: straight to the line search
+            else if (s->do_delta) { s->pause = PAUSE_DELTA; cont = 0; }        // variables entered / left: formk's corrections first
+        }
     }
     __syncthreads();
     if (!cont) return;
@@ -1031,13 +1094,13 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) f_mid(Wk<T> w, Dist<T> dist
     stage_in<T>(swn, s->wn, m4);
     if (stage) stage_in<T>(swn1, s->wn1, m4);
     __syncthreads();
-    if (threadIdx.x == 0) t0_formk_dense<T>(s, red, mt, (const T*)nullptr, swn, swn1);
+    if (threadIdx.x < 32) w_formk_dense<T>(s, red, mt, (const T*)nullptr, swn, swn1);
     __syncthreads();
     if (stage) { stage_out<T>(s->wn, swn, m4); stage_out<T>(s->wn1, swn1, m4); }
     if (!s->in_body) return;                                 // formk failed: memory reset, the host restarts the body
     site_reduce<T>(w, dist, ms.sp[2], &red, ms.roff[2], ms.ioff[2]);
-    if (threadIdx.x != 0) return;
-    t0_subsm_dense<T>(s, red, mt, swn, 1);
+    if (threadIdx.x >= 32) return;
+    w_subsm_dense<T>(s, red, mt, swn, 1);
 }
 
 // s_subsm_post + s_ls_init.

@@ -1881,6 +1881,26 @@ void oracle_dtrsl_f64(const double* t, int32_t ldt, int32_t n, double* b, int32_
     LB<double>::dtrsl(t, ldt, n, b, job, inf);
     *info = inf;
 }
+// bmv :1057-1123, formt :1926-1963 and the dense tail of formk :1853-1906 on their own (per-routine parity tests)
+void oracle_bmv_f64(int32_t m, const double* sy, const double* wt, int32_t col, const double* v, double* p, int32_t* info) {
+    int inf = 0;
+    LB<double>::bmv(m, sy, wt, col, v, p, inf);
+    *info = inf;
+}
+void oracle_formt_f64(int32_t m, double* wt, const double* sy, const double* ss, int32_t col, double theta, int32_t* info) {
+    int inf = 0;
+    LB<double>::formt(m, wt, sy, ss, col, theta, inf);
+    *info = inf;
+}
+// formk with no new pair and no entering/leaving variable: WN1 stands as given and the routine is its tail --
+// assembly of WN from WN1, theta and the diagonal of SY, the two Cholesky factorisations and the column solves.
+void oracle_formk_tail_f64(int32_t m, int32_t col, double theta, double* wn, double* wn1, const double* sy, int32_t* info) {
+    int inf = 0;
+    const int ind[1] = {1}, indx2[1] = {0};
+    std::vector<double> w((size_t)m, 0.0);
+    LB<double>::formk(1, 1, ind, 0, 2, indx2, m + 1, false, wn, wn1, m, w.data(), w.data(), sy, theta, col, 1, inf);
+    *info = inf;
+}
 void oracle_hpsolb_f64(int64_t n, double* t, int32_t* iorder, int64_t iheap) {
     LB<double>::hpsolb(n, t, iorder, iheap);
 }

@@ -155,6 +155,76 @@ def test_dpofa_dtrsl_bitwise(L, m, col):
         assert np.array_equal(bd.cpu().numpy(), bref)
 
 
+@pytest.mark.parametrize("m,col", [(5, 1), (5, 5), (10, 7), (10, 10), (20, 13), (20, 20)])
+@pytest.mark.parametrize("warp", [0, 10])
+def test_bmv_formt_formk_tail_bitwise(L, m, col, warp):
+    """bmv (src/lbfgsb.f90:1057-1123), formt (:1926-1963) and the dense tail of formk (:1853-1906) against the oracle,
+    bit for bit; warp = 0: the single-thread routines, 10: the one-warp versions the scalar kernels run (dpofa, dtrsl
+    included), which form independent entries in different lanes but every entry by the same operations in the same order."""
+    rng = np.random.default_rng(1000 * m + col + warp)
+    lo = O.lib()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    info_ref = np.zeros(1, np.int32)
+    info = np.zeros(1, np.int32)
+    # S, Y with S'Y positive diagonal: sy = lower triangle of S'Y incl. diagonal, ss = S'S
+    S = rng.standard_normal((4 * m, col))
+    Y = S * rng.uniform(0.5, 2.0, (4 * m, 1)) + 0.1 * rng.standard_normal((4 * m, col))
+    sy = np.zeros((m, m), order="F"); ss = np.zeros((m, m), order="F")
+    sy[:col, :col] = S.T @ Y; ss[:col, :col] = S.T @ S
+    theta = float((Y[:, -1] @ Y[:, -1]) / (S[:, -1] @ Y[:, -1]))
+    # formt
+    wt_ref = np.zeros((m, m), order="F")
+    lo.oracle_formt_f64(m, vp(wt_ref), vp(sy), vp(ss), col, C.c_double(theta), vp(info_ref))
+    syd, ssd, wtd = _dev(sy.T), _dev(ss.T), _dev(np.zeros((m, m)))
+    assert L.lbfgsb_test_dense_f64(4 + warp, m, col, C.c_double(theta), _vp(syd), _vp(ssd), _vp(wtd), vp(info)) == 0
+    assert info[0] == info_ref[0] == 0
+    got = wtd.cpu().numpy().T
+    assert np.array_equal(np.triu(got[:col, :col]), np.triu(wt_ref[:col, :col]))
+    if warp:   # dpofa / dtrsl by one warp on this factor
+        a = _spd(rng, m, col); ref = a.copy(order="F")
+        lo.oracle_dpofa_f64(vp(ref), m, col, vp(info_ref))
+        ad = _dev(a.T); dummy = _dev(np.zeros(4 * m))
+        assert L.lbfgsb_test_dense_f64(10, m, col, C.c_double(1.0), _vp(ad), _vp(dummy), _vp(dummy), vp(info)) == 0
+        assert info[0] == info_ref[0] == 0
+        assert np.array_equal(np.triu(ad.cpu().numpy().T[:col, :col]), np.triu(ref[:col, :col]))
+        for job, op in ((1, 11), (11, 12)):
+            b = rng.standard_normal(col); bref = b.copy()
+            lo.oracle_dtrsl_f64(vp(ref), m, col, vp(bref), job, vp(info_ref))
+            bd = _dev(b)
+            assert L.lbfgsb_test_dense_f64(op, m, col, C.c_double(1.0), _vp(ad), _vp(bd), _vp(dummy), vp(info)) == 0
+            assert np.array_equal(bd.cpu().numpy(), bref)
+    # bmv with that wt
+    v = rng.standard_normal(2 * m); v[2 * col:] = 0.0
+    vv = np.zeros(2 * col); vv[:] = v[:2 * col]
+    p_ref = np.zeros(2 * col)
+    lo.oracle_bmv_f64(m, vp(sy), vp(wt_ref), col, vp(vv), vp(p_ref), vp(info_ref))
+    c = np.zeros(4 * m); c[:2 * col] = vv
+    cd = _dev(c); wtd2 = _dev(wt_ref.T)
+    assert L.lbfgsb_test_dense_f64(3 + warp, m, col, C.c_double(theta), _vp(syd), _vp(wtd2), _vp(cd), vp(info)) == 0
+    assert info[0] == info_ref[0] == 0
+    assert np.array_equal(cd.cpu().numpy()[2 * m:2 * m + 2 * col], p_ref)
+    # formk's tail: WN1 = [Y'ZZ'Y, .; L_a' + R_z', S'AA'S] from a random free/active split
+    if warp:
+        free = rng.uniform(size=4 * m) < 0.6
+        Yf, Sf, Sa, Ya = Y[free], S[free], S[~free], Y[~free]
+        wn1 = np.zeros((2 * m, 2 * m), order="F")
+        wn1[:col, :col] = np.tril(Yf.T @ Yf)
+        wn1[m:m + col, m:m + col] = np.tril(Sa.T @ Sa)
+        LR = np.zeros((col, col))
+        for i in range(col):
+            for j in range(col):
+                LR[i, j] = (Sa[:, i] @ Ya[:, j]) if i <= j else (Sf[:, i] @ Yf[:, j])
+        wn1[m:m + col, :col] = LR
+        wn_ref = np.zeros((2 * m, 2 * m), order="F"); wn1_ref = wn1.copy(order="F")
+        lo.oracle_formk_tail_f64(m, col, C.c_double(theta), vp(wn_ref), vp(wn1_ref), vp(sy), vp(info_ref))
+        wn1d, wnd = _dev(wn1.T), _dev(np.zeros((2 * m, 2 * m)))
+        assert L.lbfgsb_test_dense_f64(15, m, col, C.c_double(theta), _vp(wn1d), _vp(syd), _vp(wnd), vp(info)) == 0
+        assert (info[0] != 0) == (info_ref[0] != 0)
+        if info_ref[0] == 0:
+            got = wnd.cpu().numpy().T
+            assert np.array_equal(np.triu(got[:2 * col, :2 * col]), np.triu(wn_ref[:2 * col, :2 * col]))
+
+
 def test_dpofa_reports_non_positive_pivot(L):
     m = col = 4
     a = np.asfortranarray(np.eye(4))

@@ -109,6 +109,37 @@ def test_device_order_sum_mode_same_discrete_trace():
         assert abs(a["f"] - b["f"]) <= 1e-6 * abs(a["f"]) + 1e-18
 
 
+@pytest.mark.parametrize("n,m,l_odd,factr,pgtol", [(1_000_000, 5, 1.0, 1.0e7, 1.0e-5), (400_000, 10, 1.1, 0.0, 0.0)])
+def test_device_order_vs_reference_order_at_config_sizes(n, m, l_odd, factr, pgtol):
+    """Leg (ii) of the parity chain at the size of BASELINE.json configs[1] (n = 1e6, m = 5, the reference's stopping
+    test) and on the configs[2] problem (odd lower bound 1.1, m = 10, fixed budget): the oracle in the reference's
+    summation order and in the device's order (the mode the GPU is gated against) take the same number of iterations
+    and the same discrete decisions at every iterate (nseg, free/active counts, entering/leaving counts, line-search
+    trials, active-set identity); the drift of f, which summation order alone causes, is bounded and printed."""
+    stop = None if factr > 0 else H.iteration_budget_stop(25)
+
+    def run():
+        x, l, u, nbd = H.rosenbrock_problem(n, l_odd=l_odd)
+        return H.run_driver(O.OracleSetulb(), O.rosenbrock_fg, n, m, x, l, u, nbd, factr, pgtol, stop=stop)
+    ref = run()
+    O.set_sum_mode(1)
+    try:
+        dev = run()
+    finally:
+        O.set_sum_mode(0)
+    assert ref[1] == dev[1], (ref[1], dev[1])
+    assert len(ref[0]) == len(dev[0]), (len(ref[0]), len(dev[0]))
+    worst = 0.0
+    for a, b in zip(ref[0], dev[0]):
+        for k in ("iter", "nfgv", "nseg", "nact", "nfree", "nenter", "nleave", "iword", "iback", "col", "nskip", "hash", "hcount"):
+            assert a[k] == b[k], (k, a, b)
+        rel = abs(a["f"] - b["f"]) / max(abs(a["f"]), 1e-300)
+        worst = max(worst, rel)
+        assert rel <= (1e-10 if a["iter"] <= 5 else 1e-5), (a["iter"], rel)
+    print("n=%d m=%d: %d iterates, identical discrete trace; worst relative drift of f from summation order alone: %.2e" % (
+        n, m, len(ref[0]), worst))
+
+
 @pytest.mark.parametrize("bad", ["nbd", "lu", "factr", "m"])
 def test_errclb_messages(bad):
     """errclb :1601-1643 -- later errors overwrite earlier ones; k = last offending index."""
