@@ -226,11 +226,20 @@ class DeviceProblem:
         self.task[:len(b)] = np.frombuffer(b, dtype=np.uint8)
 
     def setulb_dev(self, x, l, u, nbd, g, factr, pgtol):
-        fa, pg = self._cr(factr), self._cr(pgtol)
-        self._fn(C.c_void_p(self.h), C.c_void_p(x.data_ptr()), C.c_void_p(l.data_ptr()), C.c_void_p(u.data_ptr()),
-                 C.c_void_p(nbd.data_ptr()), _p(self.f), C.c_void_p(g.data_ptr()), C.byref(fa), C.byref(pg),
-                 _p(self.task), C.byref(self._ip), _p(self.csave), _p(self.lsave), _p(self.isave), _p(self.dsave))
-        _check_task(self.task)
+        # the marshalled argument list is kept for as long as the same buffers come back (the hot loop of a caller)
+        key = (x.data_ptr(), l.data_ptr(), u.data_ptr(), nbd.data_ptr(), g.data_ptr(), factr, pgtol, self.f.ctypes.data,
+               self.task.ctypes.data, self.csave.ctypes.data, self.lsave.ctypes.data, self.isave.ctypes.data,
+               self.dsave.ctypes.data)
+        if key != getattr(self, "_argkey", None):
+            fa, pg = self._cr(factr), self._cr(pgtol)
+            self._argkeep = (fa, pg)
+            self._args = (C.c_void_p(self.h), C.c_void_p(key[0]), C.c_void_p(key[1]), C.c_void_p(key[2]), C.c_void_p(key[3]),
+                          _p(self.f), C.c_void_p(key[4]), C.byref(fa), C.byref(pg), _p(self.task), C.byref(self._ip),
+                          _p(self.csave), _p(self.lsave), _p(self.isave), _p(self.dsave))
+            self._argkey = key
+        self._fn(*self._args)
+        if self.task[0] == 69:     # 'E': an ERROR task -- raise for the ones that mean the engine itself failed
+            _check_task(self.task)
 
     def minimize(self, x, l, u, nbd, g, fg, factr, pgtol, max_iter=0, max_fg=0):
         """lbfgsb_minimize_dev_*: the library owns the task loop (include/lbfgsb_b200.h section 3).

@@ -263,40 +263,70 @@ __device__ __forceinline__ void block_argmin(T& v, i64& idx, T* smv, i64* smi) {
 }
 
 // ---- final stage: one warp finishes one slot over the GRID block partials ----
+// Lane t combines partials t, t+32, ... serially, then the butterfly.  The partials are first fetched into registers
+// in one batch (independent loads in flight together), then combined in the fixed order: same bits, a fraction of
+// the latency of a load-add chain.
+#define LB_FINAL_PER_LANE ((LBFGSB_GRID + 31) / 32)
+template <typename V> __device__ __forceinline__ void final_fetch(const V* part, V (&v)[LB_FINAL_PER_LANE]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < LB_FINAL_PER_LANE; ++q) {
+        const int b = lane + 32 * q;
+        v[q] = part[b < LBFGSB_GRID ? b : lane];
+    }
+}
 template <typename T> __device__ __forceinline__ T final_sum_warp(const T* part) {
     const int lane = threadIdx.x & 31;
+    T v[LB_FINAL_PER_LANE];
+    final_fetch<T>(part, v);
     T acc = (T)0;
-    for (int b = lane; b < LBFGSB_GRID; b += LBFGSB_FINAL_BLOCK) acc = acc + part[b];
+#pragma unroll
+    for (int q = 0; q < LB_FINAL_PER_LANE; ++q) if (lane + 32 * q < LBFGSB_GRID) acc = acc + v[q];
     return warp_sum<T>(acc);
 }
 template <typename T> __device__ __forceinline__ T final_max_warp(const T* part) {
     const int lane = threadIdx.x & 31;
-    T acc = part[lane < LBFGSB_GRID ? lane : 0];
-    for (int b = lane; b < LBFGSB_GRID; b += 32) acc = part[b] > acc ? part[b] : acc;
+    T v[LB_FINAL_PER_LANE];
+    final_fetch<T>(part, v);
+    T acc = v[0];
+#pragma unroll
+    for (int q = 0; q < LB_FINAL_PER_LANE; ++q) if (lane + 32 * q < LBFGSB_GRID) acc = v[q] > acc ? v[q] : acc;
     return warp_max<T>(acc);
 }
 template <typename T> __device__ __forceinline__ T final_min_warp(const T* part) {
     const int lane = threadIdx.x & 31;
-    T acc = part[lane < LBFGSB_GRID ? lane : 0];
-    for (int b = lane; b < LBFGSB_GRID; b += 32) acc = part[b] < acc ? part[b] : acc;
+    T v[LB_FINAL_PER_LANE];
+    final_fetch<T>(part, v);
+    T acc = v[0];
+#pragma unroll
+    for (int q = 0; q < LB_FINAL_PER_LANE; ++q) if (lane + 32 * q < LBFGSB_GRID) acc = v[q] < acc ? v[q] : acc;
     return warp_min<T>(acc);
 }
 __device__ __forceinline__ i64 final_isum_warp(const i64* part) {
     const int lane = threadIdx.x & 31;
+    i64 v[LB_FINAL_PER_LANE];
+    final_fetch<i64>(part, v);
     i64 acc = 0;
-    for (int b = lane; b < LBFGSB_GRID; b += 32) acc += part[b];
+#pragma unroll
+    for (int q = 0; q < LB_FINAL_PER_LANE; ++q) if (lane + 32 * q < LBFGSB_GRID) acc += v[q];
     return warp_sum<i64>(acc);
 }
 __device__ __forceinline__ i64 final_imin_warp(const i64* part) {
     const int lane = threadIdx.x & 31;
+    i64 v[LB_FINAL_PER_LANE];
+    final_fetch<i64>(part, v);
     i64 acc = 0x7fffffffffffffffLL;
-    for (int b = lane; b < LBFGSB_GRID; b += 32) acc = part[b] < acc ? part[b] : acc;
+#pragma unroll
+    for (int q = 0; q < LB_FINAL_PER_LANE; ++q) if (lane + 32 * q < LBFGSB_GRID) acc = v[q] < acc ? v[q] : acc;
     return warp_min<i64>(acc);
 }
 __device__ __forceinline__ i64 final_imax_warp(const i64* part) {
     const int lane = threadIdx.x & 31;
+    i64 v[LB_FINAL_PER_LANE];
+    final_fetch<i64>(part, v);
     i64 acc = -0x7fffffffffffffffLL;
-    for (int b = lane; b < LBFGSB_GRID; b += 32) acc = part[b] > acc ? part[b] : acc;
+#pragma unroll
+    for (int q = 0; q < LB_FINAL_PER_LANE; ++q) if (lane + 32 * q < LBFGSB_GRID) acc = v[q] > acc ? v[q] : acc;
     return warp_max<i64>(acc);
 }
 template <typename T>

@@ -100,6 +100,16 @@ static const char* fam_name[F_COUNT] = {
     "subsm_step", "backtrack", "ls_init", "ls_step", "ls_trial", "update", "restore", "walk_compact",
     "walk_sort", "walk_scan", "walk_fix", "scalar", "hash", "update_classify", "formk_cmprlb", "subsm_lsinit"};
 
+// The scalar header of the state block straight into the host's pinned mirror, then a sequence word: the host waits
+// for that word instead of enqueueing a copy and synchronising the stream (a shorter round trip per setulb call).
+__global__ void __launch_bounds__(256) k_publish(const unsigned* src, unsigned* dst_host, int words, volatile unsigned long long* flag_host,
+                                                 unsigned long long seq) {
+    for (int q = threadIdx.x; q < words; q += blockDim.x) dst_host[q] = src[q];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *flag_host = seq;
+}
+
 struct EngineBase {
     virtual ~EngineBase() {}
     int real_kind;
@@ -255,8 +265,10 @@ struct Engine : EngineBase {
         CK(cudaMemsetAsync(w.ws, 0, vb * m, stream));
         CK(cudaMemsetAsync(w.wy, 0, vb * m, stream));
         w.s = s_dev;
-        CK(cudaMallocHost((void**)&s_host, sizeof(DevState<T>)));
-        memset(s_host, 0, sizeof(DevState<T>));
+        CK(cudaHostAlloc((void**)&s_host, sizeof(DevState<T>) + 64, cudaHostAllocMapped));
+        memset(s_host, 0, sizeof(DevState<T>) + 64);
+        pub_flag = (volatile unsigned long long*)((char*)s_host + ((sizeof(DevState<T>) + 7) / 8) * 8);
+        if (const char* e = getenv("LBFGSB_B200_SYNC")) { if (e[0] == 'm') publish = false; }
         CK(cudaMallocHost((void**)&ctl_host, sizeof(SortCtl)));
         header_bytes = offsetof(DevState<T>, sy);
         // walk / compaction buffers
@@ -326,6 +338,7 @@ struct Engine : EngineBase {
         marks.push_back(mk);
     }
     void resolve_phases() {
+        if (!marks.empty()) cudaEventSynchronize(marks.back().e);
         for (size_t i = 0; i + 1 < marks.size(); ++i) {
             if (marks[i].ph == PH_END) continue;
             float ms = 0;
@@ -352,7 +365,12 @@ struct Engine : EngineBase {
         if (profile) cudaEventRecord(pending.back().b, stream);
         else fam_calls[fam] += 1;
     }
+    // the timed launches from index `from` on returned at once (the fast pipeline paused in front of them): not counted
+    void drop_events_from(size_t from) {
+        while (pending.size() > from) { pool.push_back(pending.back().a); pool.push_back(pending.back().b); pending.pop_back(); }
+    }
     void resolve_events() {
+        if (!pending.empty()) cudaEventSynchronize(pending.back().b);
         for (auto& p : pending) {
             float ms = 0;
             cudaEventElapsedTime(&ms, p.a, p.b);
@@ -361,11 +379,29 @@ struct Engine : EngineBase {
         }
         pending.clear();
     }
-    bool sync_state() {
-        CK(cudaMemcpyAsync(s_host, s_dev, header_bytes, cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
+    // state read-back: k_publish + a wait on the pinned sequence word; LBFGSB_B200_SYNC=memcpy: copy + stream synchronise
+    volatile unsigned long long* pub_flag = nullptr;
+    unsigned long long pub_seq = 0;
+    bool publish = true;
+    bool sync_state(bool resolve = true) {
+        if (publish && pub_flag) {
+            pub_seq++;
+            k_publish<<<1, 256, 0, stream>>>((const unsigned*)s_dev, (unsigned*)s_host, (int)(header_bytes / 4), pub_flag, pub_seq);
+            launches++;
+            unsigned spins = 0;
+            while (*pub_flag != pub_seq) {
+                if ((++spins & 0x3fff) == 0) {   // a faulted kernel never publishes: ask the stream now and then
+                    cudaError_t q = cudaStreamQuery(stream);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) { set_error("CUDA error %s while waiting for the state block", cudaGetErrorString(q)); return false; }
+                    if (q == cudaSuccess && *pub_flag != pub_seq) { set_error("the state block was not published (internal error)"); return false; }
+                }
+            }
+        } else {
+            CK(cudaMemcpyAsync(s_host, s_dev, header_bytes, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+        }
         syncs++;
-        if (profile) resolve_events();
+        if (profile && resolve) resolve_events();
         if (s_host->p2p_timeout) { set_error("a peer rank's reduction record did not arrive (sharded run over peer memory)"); return false; }
         return true;
     }
@@ -785,16 +821,24 @@ struct Engine : EngineBase {
         begin(F_UPDATE_CLASSIFY); MTFUSED(launch_update_classify); end(F_UPDATE_CLASSIFY);
         if (!site_m(msite_ucf(mt))) return false;
         begin(F_SCALAR); f_ucf<T><<<LS>>>(w, dist(), mt); end(F_SCALAR);
+        const size_t ev_ucf = pending.size();
         phase(PH_SUBSPACE);
         begin(F_FORMK_CMPRLB); MTFUSED(launch_formk_cmprlb_gf); end(F_FORMK_CMPRLB);
         if (!site_m(msite_mid(mt))) return false;
         begin(F_SCALAR); f_mid<T><<<LS>>>(w, dist(), mt, n_global); end(F_SCALAR);
+        const size_t ev_mid = pending.size();
         begin(F_SUBSM_LSINIT); MTFUSED(launch_subsm_lsinit); end(F_SUBSM_LSINIT);
         if (!site_m(msite_tail())) return false;
         phase(PH_LNSRCH);
         begin(F_SCALAR); f_tail<T><<<LS>>>(w, dist()); end(F_SCALAR);
         phase(PH_END);
-        if (!sync_state()) return false;
+        if (!sync_state(false)) return false;
+        if (profile) {
+            const int ps = s_host->pause;
+            if (ps == PAUSE_CLASSIFY || ps == PAUSE_WALK || ps == PAUSE_GCP_FREEV) drop_events_from(ev_ucf);
+            else if (ps == PAUSE_DELTA || ps == PAUSE_LSINIT) drop_events_from(ev_mid);
+            resolve_events();
+        }
         if (s_host->pause != PAUSE_NONE) {
             const int from = s_host->pause;
             fast_pauses++;

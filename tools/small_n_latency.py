@@ -1,39 +1,66 @@
-"""Development aid: wall time per setulb call at small n (launch/latency-bound regime)."""
-import os, sys, time
+"""Development aid: time per iteration where the fixed cost per setulb call decides it (small n, or the per-GPU share of a
+strongly scaled problem) -- ms per iteration, launches and host read-backs per iteration, and the scalar kernels' time.
+  python tools/small_n_latency.py [out.json]"""
+import json
+import os
+import sys
+import time
+
 import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
-import harness as H
-from oracle import oracle_py as O
-import lbfgsb_b200
+import torch  # noqa: E402
+import lbfgsb_b200  # noqa: E402
 
-for n, m in ((1000, 10), (100000, 10)):
-    x, l, u, nbd = H.rosenbrock_problem(n, l_odd=1.1)
-    s = lbfgsb_b200.HostSetulb()
-    t0 = time.perf_counter()
-    tr = H.run_driver(s, O.rosenbrock_fg, n, m, x, l, u, nbd, 0.0, 0.0, stop=H.iteration_budget_stop(40), want_hash=False)
-    dt = time.perf_counter() - t0
-    print("n=%d m=%d: %d iterations, %d fg, %.1f ms total, %.3f ms per iteration" % (n, m, len(tr[0]), tr[0][-1]["nfgv"], dt * 1e3, dt * 1e3 / len(tr[0])))
 
-import torch
-for n, m in ((1000, 10), (3000, 10), (100000, 10)):
-    x, l, u, nbd = H.rosenbrock_problem(n, l_odd=1.1)
-    xd, ld, ud, nd = (torch.from_numpy(a).cuda() for a in (x, l, u, nbd))
-    gd = torch.zeros_like(xd)
-    prob = lbfgsb_b200.DeviceProblem(n, m, np.float64)
-    fg = lbfgsb_b200.RosenbrockDevice(np.float64)
-    prob.profile(True)
+def run(n, m, iters=60, warm=20, profile=False):
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream()
+    x = torch.full((n,), 3.0, dtype=torch.float64, device=dev)
+    l = torch.full((n,), -100.0, dtype=torch.float64, device=dev); l[0::2] = 1.1
+    u = torch.full((n,), 100.0, dtype=torch.float64, device=dev)
+    nbd = torch.full((n,), 2, dtype=torch.int32, device=dev)
+    g = torch.zeros_like(x)
+    torch.cuda.synchronize()
+    prob = lbfgsb_b200.DeviceProblem(n, m, np.float64, stream=st.cuda_stream)
+    t0 = l0 = s0 = None
+    nfg = 0
     while True:
-        prob.setulb_dev(xd, ld, ud, nd, gd, 0.0, 0.0)
-        t = prob.task_str()
-        if t[:2] == "FG":
-            prob.f[0] = fg(xd, gd)
-        elif t[:5] == "NEW_X":
-            if prob.isave[29] >= 30:
+        prob.setulb_dev(x, l, u, nbd, g, 0.0, 0.0)
+        t = bytes(prob.task[:5])
+        if t[:2] == b"FG":
+            prob.f[0] = prob.fused_fg(0, x, g, l, u, nbd); nfg += 1
+        elif t == b"NEW_X":
+            it = int(prob.isave[29])
+            if it == warm:
+                torch.cuda.synchronize()
+                if profile:
+                    prob.profile(True); prob.profile_reset()
+                t0 = time.perf_counter(); (l0, s0) = prob.counters(); f0 = nfg
+            if it >= warm + iters:
                 break
         else:
             break
-    pr = prob.profile_read()
-    print("n=%d" % n, {k: (round(v["ms"] / max(v["calls"], 1), 3), v["calls"]) for k, v in pr.items() if v["calls"]})
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    l1, s1 = prob.counters()
+    k = int(prob.isave[29]) - warm
+    out = {"n": n, "m": m, "iterations": k, "ms_per_iteration": dt / k * 1e3, "launches_per_iteration": (l1 - l0 + 2 * (nfg - f0)) / k,
+           "host_readbacks_per_iteration": (s1 - s0 + (nfg - f0)) / k, "fg_per_iteration": (nfg - f0) / k, "task": prob.task_str()}
+    if profile:
+        pr = prob.profile_read()
+        out["families_us_per_call"] = {a: (round(v["ms"] / v["calls"] * 1e3, 1), v["calls"]) for a, v in pr.items() if v["calls"]}
     prob.close()
+    return out
+
+
+res = []
+for n in (1000, 100000, 1000000, 12500000):
+    res.append(run(n, 10))
+    print(json.dumps(res[-1]), flush=True)
+res.append(run(12500000, 10, profile=True))
+print(json.dumps(res[-1]), flush=True)
+if len(sys.argv) > 1:
+    json.dump(res, open(sys.argv[1], "w"), indent=1)
