@@ -647,6 +647,20 @@ def solve_to_convergence(cx, n, m, l_odd, factr, pgtol):
     return out
 
 
+def batched_rate(nprob=1000, n=25, m=5):
+    """nprob copies of test/driver1.f90 (perturbed starting points) solved to the reference's
+    stopping test by lbfgsb_batch_setulb_dev_f64, one CTA per problem; next to the CPU oracle on a 200-problem sample."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import batch_rate as BR
+    g = BR.gpu_rate(nprob, n, m)
+    c = BR.cpu_rate(200, n, m)
+    return {"workload": "%d x driver1 (n=%d, m=%d, factr=1e7, pgtol=1e-5), perturbed x0" % (nprob, n, m), "baseline_config": "configs[0]",
+            "metric": "problems_per_s", "value": g["problems_per_s"], "unit": "problems/s", "iterations_per_s": g["iterations_per_s"],
+            "seconds": g["seconds"], "calls": g["calls"], "converged": g["converged"], "gpu_launches": 2 * g["calls"],
+            "cpu_baseline": {"value": c["problems_per_s"], "unit": "problems/s", "cores": 1, "kind": "port",
+                             "sample": "CPU oracle port, 200 of the problems one after the other through its driver loop"}}
+
+
 def parity_check(cx, n_global=200_000, m=5, l_odd=1.0, iters=30):
     """N > 1: the sample problem sharded over the ranks and, on rank 0, on one GPU -- discrete trace and active-set hash
     equal at every iterate, f within 1e-10 (first 10 iterates) / 1e-6 (the logic of tests/mgpu_check.py)."""
@@ -734,6 +748,7 @@ def main():
                 r = measure(cx, "driver3_f32", d3["n"], d3["m"], d3["dtype"], d3["l_odd"], W, min(K, 12), True, profile_k=4, want_clocks=False)
                 extras["configs[4] driver3-style n=4e8, m=20, REAL32"] = slim(r, "driver3_f32", d3["n"], d3["m"], d3["dtype"], d3["l_odd"], "single")
                 extras["configs[1] n=1e6, m=5 to convergence"] = solve_to_convergence(cx, 1_000_000, 5, 1.0, 1.0e7, 1.0e-5)
+                extras["configs[0] x 1000: batched small problems (one CTA per problem)"] = batched_rate()
             else:
                 other = "weak" if strong else "strong"
                 ng = a.n * world if strong else a.n

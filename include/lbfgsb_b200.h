@@ -135,10 +135,12 @@ int lbfgsb_dev_profile_read(lbfgsb_dev_t* h, int32_t cap, char* names /* cap*32 
 void lbfgsb_dev_profile_reset(lbfgsb_dev_t* h);
 /* Equal breakpoints at the exit of the generalized-Cauchy-point search (src/lbfgsb.f90:1416 inside a group of
  * equal t): which members of the group end up fixed depends on the order in which they are popped, and the
- * reference pops them in the order of its heap (hpsolb, :2079-2157).  The engine then replays that heap on the
- * device (one thread; single-GPU workspaces) if the call has at most `max_breakpoints` breakpoints (default
- * 2^21, environment LBFGSB_B200_TIE_LIMIT; 0 switches the replay off).  Beyond the limit such a group is taken in
- * variable order and the event is counted; sharded workspaces always use (t, global index) order.
+ * reference pops them in the order of its heap (hpsolb, :2079-2157).  The engine then replays that heap (single-GPU
+ * workspaces): by one device thread for calls with up to 16 384 breakpoints, on the engine's host thread from a copy of
+ * the breakpoint list beyond that (tens of nanoseconds per heap operation, as the reference pays on every walk), up to
+ * `max_breakpoints` breakpoints per call (default 2^28, environment LBFGSB_B200_TIE_LIMIT; 0 switches the replay
+ * off).  Beyond the limit such a group is taken in variable order and the event is counted; sharded workspaces always
+ * use (t, global index) order.  The batched small-problem path (section 6) pops the reference's heap itself.
  * tie_stats: replays done, exits inside a tie group that were not replayed (since START).            */
 void lbfgsb_dev_set_tie_limit(lbfgsb_dev_t* h, int64_t max_breakpoints);
 int lbfgsb_dev_tie_stats(lbfgsb_dev_t* h, int64_t* replays, int64_t* not_replayed);
@@ -202,6 +204,39 @@ int lbfgsb_problem_quadratic_f64(int64_t n, const double* x_dev, double* g_dev, 
 int lbfgsb_problem_quadratic_f32(int64_t n, const float* x_dev, float* g_dev, float* f_out, void* cuda_stream,
                                  int64_t index_offset, uint64_t seed, float xl, float xr, void* scratch_dev);
 
+/* ---- (6) batched small problems ----------------------------------------------
+ * The reference keeps no state between calls (src/lbfgsb.f90:52-56): a caller with many small boxes runs many
+ * independent copies of the task loop of test/driver1.f90:263-292.  A batch holds nprob problems of the same
+ * n and m; ONE call advances every problem from its own task to its next return point of mainlb, one CTA per
+ * problem (n <= 65 536 real64 / 131 072 real32 variables).  Same protocol per problem: task and csave are
+ * [nprob][60] blank-padded, lsave [nprob][4], isave [nprob][44], dsave [nprob][29] (host arrays, same meaning as
+ * in setulb); x, l, u, g are [nprob][n] device arrays, nbd [nprob][n] device int32, and f is a DEVICE array
+ * [nprob] (the caller's batched objective kernel writes it; no host round trip for f).  Problems whose task is a
+ * terminal one ('CONVERGENCE...', 'ABNORMAL...', 'ERROR...', 'STOP...') are left alone, so the caller simply keeps
+ * calling until lbfgsb_batch_counts reports no 'FG' and no 'NEW_X' task.  'STOP' with task(7:9)='CPU' restores the
+ * previous iterate of that problem (:565-571).  Equal breakpoints are taken in hpsolb's order (the Cauchy search of
+ * a small problem is the reference's own sequential loop, :1378-1497). */
+typedef struct lbfgsb_batch lbfgsb_batch_t;
+lbfgsb_batch_t* lbfgsb_batch_create(int32_t nprob, int64_t n, int32_t m, int32_t real_kind, void* cuda_stream);
+void lbfgsb_batch_destroy(lbfgsb_batch_t* h);
+void lbfgsb_batch_setulb_dev_f64(lbfgsb_batch_t* h, double* x_dev, const double* l_dev, const double* u_dev, const int32_t* nbd_dev,
+                                 double* f_dev, double* g_dev, const double* factr, const double* pgtol, char* task, char* csave,
+                                 int32_t* lsave, int32_t* isave, double* dsave);
+void lbfgsb_batch_setulb_dev_f32(lbfgsb_batch_t* h, float* x_dev, const float* l_dev, const float* u_dev, const int32_t* nbd_dev,
+                                 float* f_dev, float* g_dev, const float* factr, const float* pgtol, char* task, char* csave,
+                                 int32_t* lsave, int32_t* isave, float* dsave);
+/* after a call: how many problems ask for f and g, how many returned 'NEW_X', how many are finished */
+int lbfgsb_batch_counts(lbfgsb_batch_t* h, int32_t* n_fg, int32_t* n_newx, int32_t* n_done);
+void* lbfgsb_batch_stream(lbfgsb_batch_t* h);   /* the cudaStream_t the batch works on */
+/* device int32 [nprob], refreshed by every call: 1 where the problem's task now asks for f and g */
+void* lbfgsb_batch_fg_mask(lbfgsb_batch_t* h);
+/* the sample objective (test/driver1.f90:274-289) for a batch: problem p from x_dev[p][.] into g_dev[p][.], f_dev[p];
+ * mask_dev (may be NULL): int32 [nprob], problems with 0 are skipped */
+int lbfgsb_problem_rosenbrock_batch_f64(int32_t nprob, int64_t n, const double* x_dev, double* g_dev, double* f_dev,
+                                        const int32_t* mask_dev, void* cuda_stream);
+int lbfgsb_problem_rosenbrock_batch_f32(int32_t nprob, int64_t n, const float* x_dev, float* g_dev, float* f_dev,
+                                        const int32_t* mask_dev, void* cuda_stream);
+
 /* ---- single-kernel entry points for the per-routine parity tests (device pointers) ---------- */
 int lbfgsb_test_projgr_f64(int64_t n, const double* l, const double* u, const int32_t* nbd, const double* x,
                            const double* g, double* sbgnrm_out);
@@ -211,7 +246,9 @@ int lbfgsb_test_sort_f64(int64_t n, const double* t_dev, int32_t* order_out_dev,
 /* hpsolb (:2079-2157) replayed on the device: heap built over t(1..n), popped n times; order_out = iorder of the pops */
 int lbfgsb_test_heap_order_f64(int64_t n, const double* t_dev, int32_t* order_out_dev);
 int lbfgsb_test_dense_f64(int32_t op, int32_t m, int32_t col, double theta, double* a, double* b, double* c,
-                          int32_t* info);   /* op 0 dpofa(a,lda=m,n=col) 1 dtrsl job01 2 dtrsl job11 3 bmv 4 formt */
+                          int32_t* info);   /* op 0 dpofa(a,lda=m,n=col) 1 dtrsl job01 2 dtrsl job11 3 bmv 4 formt (one thread);
+                                               10-14 the same by one warp, as the scalar kernels run them; 15 formk's dense
+                                               tail (:1853-1906): a = wn1 (2m x 2m), b = sy, c = wn (out) */
 int lbfgsb_test_dcsrch_f64(double f, double g, double* stp, double stpmax, int32_t* task, int32_t* isave2,
                            double* dsave13);
 

@@ -23,7 +23,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.path.join(_HERE, "liblbfgsb_b200.so")
 _SOURCES = ["engine.cu", "common.cuh", "kernels_stream.cuh", "kernels_dense.cuh", "cauchy_walk.cuh", "kernels_tma.cuh",
-            "tma_pipe.cuh"]
+            "tma_pipe.cuh", "cauchy_walk_dist.cuh", "batch.cuh", "host_print.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               # no fused multiply-add: the dense 2m x 2m algebra and dcsrch/dcstep must round like the
               # reference (gfortran x86-64 default has no FMA), see DESIGN.md "Numerics"
@@ -110,6 +110,19 @@ def lib():
             getattr(L, nm).argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_uint64]
         L.lbfgsb_dev_exchange_mode.argtypes = [C.c_void_p]
+        L.lbfgsb_batch_create.restype = C.c_void_p
+        L.lbfgsb_batch_create.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+        L.lbfgsb_batch_destroy.argtypes = [C.c_void_p]
+        L.lbfgsb_batch_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lbfgsb_batch_stream.restype = C.c_void_p
+        L.lbfgsb_batch_stream.argtypes = [C.c_void_p]
+        L.lbfgsb_batch_fg_mask.restype = C.c_void_p
+        L.lbfgsb_batch_fg_mask.argtypes = [C.c_void_p]
+        for sfx in ("f64", "f32"):
+            getattr(L, "lbfgsb_batch_setulb_dev_" + sfx).restype = None
+            getattr(L, "lbfgsb_batch_setulb_dev_" + sfx).argtypes = [C.c_void_p] * 14
+            getattr(L, "lbfgsb_problem_rosenbrock_batch_" + sfx).argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                                             C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -429,3 +442,90 @@ class QuadraticDevice:
             C.c_void_p(self.scratch.data_ptr()))
         if rc != 0:
             raise LbfgsbB200Error("quadratic kernel failed")
+
+
+class BatchProblem:
+    """Batched small problems (include/lbfgsb_b200.h section 6): nprob independent problems of the same n and m, one
+    CTA per problem, one call per reverse-communication step of the whole batch.  x, l, u, g are [nprob, n] CUDA tensors,
+    nbd [nprob, n] int32, f a CUDA tensor [nprob]; task / csave / lsave / isave / dsave are per-problem host arrays with
+    the reference's meaning (src/lbfgsb.f90:194-242)."""
+
+    def __init__(self, nprob, n, m, dtype=np.float64, stream=None):
+        self.nprob, self.n, self.m = int(nprob), int(n), int(m)
+        self.dtype = np.dtype(dtype)
+        kind = 8 if self.dtype == np.float64 else 4
+        self.h = lib().lbfgsb_batch_create(self.nprob, self.n, self.m, kind, stream)
+        if not self.h:
+            raise LbfgsbB200Error("lbfgsb_batch_create failed: " + last_error())
+        self.task = np.full((self.nprob, 60), ord(" "), dtype=np.uint8)
+        self.task[:, :5] = np.frombuffer(b"START", dtype=np.uint8)
+        self.csave = np.full((self.nprob, 60), ord(" "), dtype=np.uint8)
+        self.lsave = np.zeros((self.nprob, 4), dtype=np.int32)
+        self.isave = np.zeros((self.nprob, 44), dtype=np.int32)
+        self.dsave = np.zeros((self.nprob, 29), dtype=self.dtype)
+        sfx, self._cr = _REAL[self.dtype]
+        self._fn = getattr(lib(), "lbfgsb_batch_setulb_dev_" + sfx)
+        self._fg = getattr(lib(), "lbfgsb_problem_rosenbrock_batch_" + sfx)
+        self.stream = lib().lbfgsb_batch_stream(C.c_void_p(self.h))
+        self.fg_mask_ptr = lib().lbfgsb_batch_fg_mask(C.c_void_p(self.h))
+
+    def task_str(self, p):
+        return bytes(self.task[p]).decode().rstrip()
+
+    def set_task(self, p, text):
+        self.task[p, :] = ord(" ")
+        b = text.encode()
+        self.task[p, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+
+    def setulb_dev(self, x, l, u, nbd, f, g, factr, pgtol):
+        fa, pg = self._cr(factr), self._cr(pgtol)
+        self._fn(C.c_void_p(self.h), C.c_void_p(x.data_ptr()), C.c_void_p(l.data_ptr()), C.c_void_p(u.data_ptr()),
+                 C.c_void_p(nbd.data_ptr()), C.c_void_p(f.data_ptr()), C.c_void_p(g.data_ptr()), C.byref(fa), C.byref(pg),
+                 _p(self.task), _p(self.csave), _p(self.lsave), _p(self.isave), _p(self.dsave))
+        if (self.task[:, 0] == 69).any():
+            for p in range(self.nprob):
+                _check_task(self.task[p])
+
+    def counts(self):
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        lib().lbfgsb_batch_counts(C.c_void_p(self.h), C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def rosenbrock_fg(self, x, g, f, all_problems=False):
+        """Sample objective (test/driver1.f90:274-289) on the batch's stream, for the problems whose task asks for f and g
+        (the batch's own device mask), or for every problem."""
+        rc = self._fg(self.nprob, self.n, C.c_void_p(x.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(f.data_ptr()),
+                      None if all_problems else C.c_void_p(self.fg_mask_ptr), C.c_void_p(self.stream))
+        if rc != 0:
+            raise LbfgsbB200Error("batched objective kernel failed")
+
+    def solve(self, x, l, u, nbd, f, g, factr, pgtol, fg=None, max_iter=0, on_newx=None):
+        """The task loop of test/driver1.f90:263-292 for the whole batch.  fg(x, g, f) evaluates every problem (default:
+        the sample objective); max_iter > 0 stops a problem at that many iterations as driver2.f90:174-181 does."""
+        fg = fg or (lambda xx, gg, ff: self.rosenbrock_fg(xx, gg, ff))
+        calls = 0
+        while True:
+            self.setulb_dev(x, l, u, nbd, f, g, factr, pgtol)
+            calls += 1
+            nfg, nnew, _ = self.counts()
+            if nfg == 0 and nnew == 0:
+                return calls
+            if nfg:
+                fg(x, g, f)
+            if nnew:
+                if on_newx is not None:
+                    on_newx(self)
+                if max_iter > 0:
+                    for p in np.nonzero((self.task[:, 0] == 78) & (self.isave[:, 29] >= max_iter))[0]:
+                        self.set_task(int(p), "STOP: TOTAL NO. of ITERATIONS REACHED LIMIT")
+
+    def close(self):
+        if self.h:
+            lib().lbfgsb_batch_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

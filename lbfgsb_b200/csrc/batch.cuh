@@ -34,6 +34,7 @@ struct BatchWk {
     T* delta;                             // [nprob][6*MMAX*MMAX]
     DevState<T>* s;                       // [nprob]
     const int* entry;                     // [nprob] what the caller's task asks for (BE_*)
+    int* fgmask;                          // [nprob] out: 1 where the problem's new task asks for f and g
     T factr, pgtol;
 };
 enum { BE_START = 0, BE_FG_START = 1, BE_FG_LNSRCH = 2, BE_NEW_X = 3, BE_STOP = 4, BE_STOP_CPU = 5, BE_OTHER = 6, BE_IDLE = 7 };
@@ -726,7 +727,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_batch_setulb(BatchWk<T> bw) {
     const int p = blockIdx.x;
     if (p >= bw.nprob) return;
     const int entry = bw.entry[p];
-    if (entry == BE_IDLE) return;
+    if (entry == BE_IDLE) { if (threadIdx.x == 0) bw.fgmask[p] = 0; return; }
     Wk<T> w;
     w.n = bw.n; w.ldw = bw.ldw; w.off = 0; w.m = bw.m;
     w.ws = bw.ws + (i64)p * bw.m * bw.ldw; w.wy = bw.wy + (i64)p * bw.m * bw.ldw;
@@ -742,16 +743,20 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_batch_setulb(BatchWk<T> bw) {
     DevState<T>* s = w.s;
     const T f = bw.f[p];
 
-    if (entry == BE_START) { batch::start<T>(w, sm, bw.factr, bw.pgtol); return; }
+    if (entry == BE_START) {
+        batch::start<T>(w, sm, bw.factr, bw.pgtol);
+        if (threadIdx.x == 0) bw.fgmask[p] = (s->task == TK_FG_START) ? 1 : 0;
+        return;
+    }
     if (entry == BE_STOP || entry == BE_STOP_CPU) {
         if (entry == BE_STOP_CPU) {   // :565-571
             batch::restore<T>(w);
             if (threadIdx.x == 0) { s->f = s->fold; bw.f[p] = s->fold; }
         }
-        if (threadIdx.x == 0) s->task = TK_STOP;
+        if (threadIdx.x == 0) { s->task = TK_STOP; bw.fgmask[p] = 0; }
         return;
     }
-    if (entry == BE_OTHER) { if (threadIdx.x == 0) s->task = TK_FG_START; return; }
+    if (entry == BE_OTHER) { if (threadIdx.x == 0) { s->task = TK_FG_START; bw.fgmask[p] = 1; } return; }
 
     if (entry == BE_FG_START) {
         if (threadIdx.x == 0) t0_call_begin<T>(s, f);
@@ -788,5 +793,5 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_batch_setulb(BatchWk<T> bw) {
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) bw.f[p] = s->f;
+    if (threadIdx.x == 0) { bw.f[p] = s->f; bw.fgmask[p] = (s->task == TK_FG_START || s->task == TK_FG_LNSRCH) ? 1 : 0; }
 }

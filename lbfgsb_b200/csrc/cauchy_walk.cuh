@@ -889,7 +889,7 @@ __global__ void __launch_bounds__(256) k_walk_fix(Wk<T> w, WalkBuf<T> b) {
 // The popped members of the group, in order, become the sorted list of the next round.
 // ---------------------------------------------------------------------------
 template <typename K>
-__device__ inline void heap_build(K* t, int* io, i64 n) {   // t, io: 1-based views; hpsolb :2096-2119
+__host__ __device__ inline void heap_build(K* t, int* io, i64 n) {   // t, io: 1-based views; hpsolb :2096-2119
     for (i64 k = 2; k <= n; ++k) {
         const K ddum = t[k];
         const int indxin = io[k];
@@ -904,7 +904,7 @@ __device__ inline void heap_build(K* t, int* io, i64 n) {   // t, io: 1-based vi
 }
 // least member out, the rest re-heaped as t(1..n-1); the reference leaves the least member in t(n)  (:2125-2155)
 template <typename K>
-__device__ inline void heap_pop(K* t, int* io, i64 n, K& out, int& indxou) {
+__host__ __device__ inline void heap_pop(K* t, int* io, i64 n, K& out, int& indxou) {
     out = t[1]; indxou = io[1];
     if (n > 1) {
         i64 i = 1;
@@ -971,6 +971,20 @@ __global__ void __launch_bounds__(1024) k_heap_replay(Wk<T> w, WalkBuf<T> b) {
         if (out > tk) break;
         if (out == tk) { b.k1[cnt] = out; b.v1[cnt] = var; cnt++; }
     }
+    b.ctl->count = cnt; b.ctl->cur = 1; b.ctl->skip = 0;
+    s->walk_lcount = cnt; s->walk_rcount = cnt; s->walk_rem = s->nbreak - s->walk_base;
+    s->walk_J = -1; s->walk_done = 0; s->walk_fixn = 0;
+    s->tie_round = 1;
+}
+
+// The replay done on the host (long breakpoint lists: a single device thread would take a second per million heap
+// insertions, a host core takes a few tens of nanoseconds each): the host has popped the heap from a copy of b.k0 / b.v0
+// and left the group in heap order in b.k1 / b.v1; this sets what k_heap_replay sets at its end.
+template <typename T>
+__global__ void k_heap_replay_commit(Wk<T> w, WalkBuf<T> b, i64 cnt) {
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || s->walk_closed) return;
     b.ctl->count = cnt; b.ctl->cur = 1; b.ctl->skip = 0;
     s->walk_lcount = cnt; s->walk_rcount = cnt; s->walk_rem = s->nbreak - s->walk_base;
     s->walk_J = -1; s->walk_done = 0; s->walk_fixn = 0;

@@ -21,6 +21,7 @@
 #include "cauchy_walk.cuh"
 #include "kernels_tma.cuh"
 #include "cauchy_walk_dist.cuh"
+#include "batch.cuh"
 #include "host_print.h"
 #include <algorithm>
 
@@ -86,6 +87,8 @@ static NcclApi* nccl_api() {
     }
     return &api;
 }
+
+#define LB_TIE_DEVICE_MAX 16384   // breakpoints of a call up to which the heap replay runs on the device (one thread)
 
 // ---------------------------------------------------------------------------
 // kernel families (profiling / launch accounting)
@@ -258,7 +261,8 @@ struct Engine : EngineBase {
         if (!dalloc(&s_dev, sizeof(DevState<T>))) return false;
         CK(cudaMemsetAsync(s_dev, 0, sizeof(DevState<T>), stream));
         {
-            i64 lim = (i64)1 << 21;   // heap replay of tied breakpoints at the exit: up to 2M breakpoints by default
+            i64 lim = (i64)1 << 28;   // heap replay of tied breakpoints at the exit: up to 2.7e8 breakpoints by default
+                                      // (on the device up to LB_TIE_DEVICE_MAX, beyond that on the engine's host thread)
             if (const char* e = getenv("LBFGSB_B200_TIE_LIMIT")) lim = atoll(e);
             CK(cudaMemcpyAsync(&s_dev->tie_limit, &lim, sizeof lim, cudaMemcpyHostToDevice, stream));
         }
@@ -526,13 +530,56 @@ struct Engine : EngineBase {
         k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 2, tile_counts, tile_offsets, ntiles, wb.ctl);
         k_flag_write<T, 2><<<LG>>>(w, tile_offsets, wb.k0, wb.v0);
         end(F_WALK_COMPACT, 3);
-        begin(F_WALK_SORT); k_heap_replay<T><<<1, 1024, 0, stream>>>(w, wb); end(F_WALK_SORT);
+        if (s_host->nbreak <= LB_TIE_DEVICE_MAX) {
+            begin(F_WALK_SORT); k_heap_replay<T><<<1, 1024, 0, stream>>>(w, wb); end(F_WALK_SORT);
+        } else if (!heap_replay_on_host(tk)) return -1;
         if (!sync_state()) return -1;
         tie_replays++;
         if (s_host->walk_lcount <= 0) { set_error("heap replay: empty tie group (internal error)"); return -1; }
         if (!round_scan_single(s_host->walk_lcount)) return -1;
         if (!sync_state()) return -1;
         return s_host->walk_closed ? 1 : 0;
+    }
+    // hpsolb's pop order of the group of breakpoints equal to tk, on the host (cauchy_walk.cuh "heap replay"): wb.k0 / wb.v0
+    // hold every breakpoint of this cauchy call in variable order.  The reference pays the same sequential heap.
+    bool heap_replay_on_host(unsigned long long tk64) {
+        typedef typename Real<T>::key_t K;
+        SortCtl hc;
+        CK(cudaMemcpyAsync(&hc, wb.ctl, sizeof hc, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream)); syncs++;
+        const i64 nb = hc.count;
+        if (nb <= 0) { set_error("heap replay: no breakpoints (internal error)"); return false; }
+        std::vector<K> hk((size_t)nb); std::vector<int> hv((size_t)nb);
+        CK(cudaMemcpyAsync(hk.data(), wb.k0, sizeof(K) * (size_t)nb, cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(hv.data(), wb.v0, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        const K tk = (K)tk64;
+        const int vmin = (int)(s_host->ibkmin - offset);
+        K kfirst; { T bk = s_host->bkmin; memcpy(&kfirst, &bk, sizeof kfirst); }
+        std::vector<K> gk; std::vector<int> gv;
+        if (kfirst == tk) { gk.push_back(tk); gv.push_back(vmin); }   // the first breakpoint is taken before the heap exists (:1384-1389)
+        i64 spos = -1;
+        for (i64 i = 0; i < nb; ++i) if (hv[(size_t)i] == vmin) spos = i;
+        K* t = hk.data() - 1; int* io = hv.data() - 1;   // 1-based
+        const i64 ib = spos + 1;
+        if (ib >= 1 && ib != nb) { t[ib] = t[nb]; io[ib] = io[nb]; }   // :1394-1397
+        i64 nleft = nb - 1;
+        heap_build<K>(t, io, nleft);
+        while (nleft > 0) {
+            K out; int var;
+            heap_pop<K>(t, io, nleft, out, var);
+            nleft--;
+            if (out > tk) break;
+            if (out == tk) { gk.push_back(out); gv.push_back(var); }
+        }
+        const i64 cnt = (i64)gk.size();
+        if (cnt > 0) {
+            CK(cudaMemcpyAsync(wb.k1, gk.data(), sizeof(K) * (size_t)cnt, cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(wb.v1, gv.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, stream));
+        }
+        k_heap_replay_commit<T><<<1, 32, 0, stream>>>(w, wb, cnt); launches++;
+        CK(cudaStreamSynchronize(stream));   // gk, gv are locals
+        return true;
     }
     // ---- the breakpoint walk, in rounds over increasing ranges of t (cauchy_walk.cuh) -------
     bool enqueue_walk_rounds() {
@@ -1078,9 +1125,8 @@ static const char* csave_text(int code) {
 
 // save_locals (:904-947): device mirror -> the caller's isave / dsave / lsave
 template <typename T>
-static void export_state(const Engine<T>* e, char* task, char* csave, int32_t* lsave, int32_t* isave, T* dsave) {
-    const DevState<T>* s = e->s_host;
-    const i64 ng = e->n_global;
+static void export_state_of(const DevState<T>* s, i64 ng, const double* ph_time, char* task, char* csave, int32_t* lsave, int32_t* isave,
+                            T* dsave) {
     auto clamp32 = [](i64 v) { return (int32_t)(v > 2147483647LL ? 2147483647LL : v); };
     lsave[0] = s->prjctd; lsave[1] = s->cnstnd; lsave[2] = s->boxed; lsave[3] = s->updatd;
     isave[21] = clamp32(s->nintol);
@@ -1094,11 +1140,15 @@ static void export_state(const Engine<T>* e, char* task, char* csave, int32_t* l
     isave[42] = s->brackt; isave[43] = s->stage;
     dsave[0] = s->theta; dsave[1] = s->fold; dsave[2] = s->tol; dsave[3] = s->dnorm; dsave[4] = s->epsmch;
     dsave[5] = 0; dsave[9] = 0;   // cpu1, time1: host clock readings of the reference, not kept here
-    dsave[6] = (T)e->ph_time[0]; dsave[7] = (T)e->ph_time[1]; dsave[8] = (T)e->ph_time[2];   // cachyt, sbtime, lnscht (seconds)
+    dsave[6] = (T)ph_time[0]; dsave[7] = (T)ph_time[1]; dsave[8] = (T)ph_time[2];   // cachyt, sbtime, lnscht (seconds)
     dsave[10] = s->gd; dsave[11] = s->stpmx; dsave[12] = s->sbgnrm; dsave[13] = s->stp; dsave[14] = s->gdold; dsave[15] = s->dtd;
     for (int q = 0; q < 13; ++q) dsave[16 + q] = s->ls[q];
     put60(task, task_text(s->task));
     if (s->csave != CS_BLANK) put60(csave, csave_text(s->csave));
+}
+template <typename T>
+static void export_state(const Engine<T>* e, char* task, char* csave, int32_t* lsave, int32_t* isave, T* dsave) {
+    export_state_of<T>(e->s_host, e->n_global, e->ph_time, task, csave, lsave, isave, dsave);
 }
 
 // Text output of one setulb call (host_print.h), in the reference's order: the iterate-0 lines, the logged
@@ -1656,6 +1706,159 @@ static TrialSums<T> trial_sums_of(Engine<T>* e, const T* l, const T* u, const in
 }
 
 // ---------------------------------------------------------------------------
+// Batched small problems (batch.cuh; include/lbfgsb_b200.h section 6)
+// ---------------------------------------------------------------------------
+struct BatchBase {
+    virtual ~BatchBase() {}
+    int real_kind;
+};
+template <typename T>
+struct BatchEngine : BatchBase {
+    BatchWk<T> bw;
+    cudaStream_t stream = 0;
+    bool own_stream = false;
+    std::vector<void*> allocs;
+    int* entry_dev = nullptr; int* entry_host = nullptr;
+    char* hdr_host = nullptr;          // [nprob][header_bytes], pinned
+    size_t header_bytes = 0;
+    std::vector<char> started;
+    int n_fg = 0, n_newx = 0, n_done = 0;
+    i64 launches = 0;
+    template <typename P> bool dalloc(P** p, size_t bytes) {
+        void* q = nullptr;
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return false; }
+        allocs.push_back(q);
+        *p = (P*)q;
+        return true;
+    }
+    template <int MT> bool set_attr() {
+        CK(cudaFuncSetAttribute(k_batch_setulb<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BatchSm<T>)));
+        return true;
+    }
+    bool init(int nprob, i64 n, int m, cudaStream_t st) {
+        real_kind = (int)sizeof(T);
+        memset(&bw, 0, sizeof bw);
+        bw.nprob = nprob; bw.n = n; bw.m = m; bw.mt = (m <= 5) ? 5 : (m <= 10 ? 10 : 20);
+        bw.ldw = (n + 31) / 32 * 32;
+        if (st) stream = st;
+        else { CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
+        const size_t P = (size_t)nprob, vb = (size_t)bw.ldw * sizeof(T);
+        if (!dalloc(&bw.ws, P * vb * m) || !dalloc(&bw.wy, P * vb * m)) return false;
+        if (!dalloc(&bw.z, P * vb) || !dalloc(&bw.r, P * vb) || !dalloc(&bw.d, P * vb) || !dalloc(&bw.t, P * vb) || !dalloc(&bw.xp, P * vb) ||
+            !dalloc(&bw.gold, P * vb) || !dalloc(&bw.bpt, P * vb)) return false;
+        if (!dalloc(&bw.iwhere, P * bw.ldw * 4) || !dalloc(&bw.bpo, P * bw.ldw * 4) || !dalloc(&bw.state, P * bw.ldw)) return false;
+        if (!dalloc(&bw.delta, P * sizeof(T) * 6 * LB_MMAX * LB_MMAX) || !dalloc(&bw.s, P * sizeof(DevState<T>))) return false;
+        if (!dalloc(&entry_dev, P * sizeof(int)) || !dalloc(&bw.fgmask, P * sizeof(int))) return false;
+        CK(cudaMemsetAsync(bw.fgmask, 0, P * sizeof(int), stream));
+        CK(cudaMemsetAsync(bw.s, 0, P * sizeof(DevState<T>), stream));
+        CK(cudaMemsetAsync(bw.ws, 0, P * vb * m, stream));
+        CK(cudaMemsetAsync(bw.wy, 0, P * vb * m, stream));
+        CK(cudaMemsetAsync(bw.delta, 0, P * sizeof(T) * 6 * LB_MMAX * LB_MMAX, stream));
+        header_bytes = offsetof(DevState<T>, sy);
+        CK(cudaMallocHost((void**)&hdr_host, P * header_bytes));
+        CK(cudaMallocHost((void**)&entry_host, P * sizeof(int)));
+        started.assign(P, 0);
+        if (!(bw.mt == 5 ? set_attr<5>() : (bw.mt == 10 ? set_attr<10>() : set_attr<20>()))) return false;
+        CK(cudaStreamSynchronize(stream));
+        return true;
+    }
+    ~BatchEngine() {
+        for (void* p : allocs) cudaFree(p);
+        if (hdr_host) cudaFreeHost(hdr_host);
+        if (entry_host) cudaFreeHost(entry_host);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+    bool call(T* x, const T* l, const T* u, const int32_t* nbd, T* f, T* g, T factr, T pgtol, char* task, char* csave, int32_t* lsave,
+              int32_t* isave, T* dsave) {
+        const int P = bw.nprob;
+        bool any = false;
+        for (int p = 0; p < P; ++p) {
+            const char* t = task + 60 * (size_t)p;
+            int e;
+            if (eq60(t, "START")) { e = BE_START; started[p] = 1; }
+            else if (started[p] == 2) e = BE_IDLE;   // ended by a STOP of its caller
+            else if (!started[p]) { put60(task + 60 * (size_t)p, "ERROR: SETULB CALLED WITHOUT A VALID START"); e = BE_IDLE; }
+            else if (pre60(t, "FG_LN")) e = BE_FG_LNSRCH;
+            else if (pre60(t, "NEW_X")) e = BE_NEW_X;
+            else if (pre60(t, "FG_ST")) e = BE_FG_START;
+            else if (pre60(t, "STOP")) { e = (memcmp(t + 6, "CPU", 3) == 0) ? BE_STOP_CPU : BE_IDLE; started[p] = 2; }   // a plain STOP only ends the problem
+            else if (pre60(t, "CONV") || pre60(t, "ABNO") || pre60(t, "ERROR")) e = BE_IDLE;
+            else e = BE_OTHER;
+            entry_host[p] = e;
+            any = any || e != BE_IDLE;
+        }
+        n_fg = n_newx = n_done = 0;
+        if (any) {
+            bw.x = x; bw.l = l; bw.u = u; bw.nbd = nbd; bw.g = g; bw.f = f; bw.factr = factr; bw.pgtol = pgtol;
+            bw.entry = entry_dev;
+            CK(cudaMemcpyAsync(entry_dev, entry_host, sizeof(int) * P, cudaMemcpyHostToDevice, stream));
+            const size_t smem = sizeof(BatchSm<T>);
+            if (bw.mt == 5) k_batch_setulb<T, 5><<<P, LBFGSB_BLOCK, smem, stream>>>(bw);
+            else if (bw.mt == 10) k_batch_setulb<T, 10><<<P, LBFGSB_BLOCK, smem, stream>>>(bw);
+            else k_batch_setulb<T, 20><<<P, LBFGSB_BLOCK, smem, stream>>>(bw);
+            launches++;
+            CK(cudaMemcpy2DAsync(hdr_host, header_bytes, bw.s, sizeof(DevState<T>), header_bytes, P, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            cudaError_t le = cudaGetLastError();
+            if (le != cudaSuccess) { set_error("batch kernel failed: %s", cudaGetErrorString(le)); return false; }
+        }
+        const double ph[3] = {0, 0, 0};
+        for (int p = 0; p < P; ++p) {
+            char* t = task + 60 * (size_t)p;
+            const int e = entry_host[p];
+            if (e != BE_IDLE) {
+                const DevState<T>* s = (const DevState<T>*)(hdr_host + (size_t)p * header_bytes);
+                if (e == BE_STOP_CPU) { /* the caller's STOP text stays in task; x, g, f were restored */ }
+                else {
+                    export_state_of<T>(s, bw.n, ph, t, csave + 60 * (size_t)p, lsave + 4 * (size_t)p, isave + 44 * (size_t)p, dsave + 29 * (size_t)p);
+                    if (e == BE_START && pre60(t, "ERROR")) { isave[44 * (size_t)p + 34] = s->info; isave[44 * (size_t)p + 41] = (int32_t)s->errk; }
+                }
+            }
+            if (pre60(t, "FG")) n_fg++;
+            else if (pre60(t, "NEW_X")) n_newx++;
+            else n_done++;
+        }
+        return true;
+    }
+};
+
+// sample objective for a batch (test/driver1.f90:274-289, one CTA per problem): the arithmetic and the summation shape
+// of k_rosenbrock, f_dev[p] = 4 * sum
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_rosenbrock_batch(int nprob, i64 n, const T* __restrict__ xall, T* __restrict__ gall,
+                                                                  T* __restrict__ f, const int* __restrict__ entry) {
+    extern __shared__ __align__(16) unsigned char bsm_raw[];
+    BatchSm<T>& sm = *reinterpret_cast<BatchSm<T>*>(bsm_raw);
+    const int p = blockIdx.x;
+    if (p >= nprob) return;
+    if (entry && entry[p] == 0) return;   // this problem did not ask for f and g
+    const T* x = xall + (i64)p * n;
+    T* g = gall + (i64)p * n;
+    B_TILES(T, n, tl) {
+        T acc[1]; acc[0] = (T)0;
+        B_ELEMS(T, n, tl, i) {
+            const T xi = x[i];
+            const T xprev = (i > 0) ? x[i - 1] : (T)0;
+            const T xnext = (i + 1 < n) ? x[i + 1] : (T)0;
+            const T t2 = xi - xprev * xprev;
+            const T t1 = xnext - xi * xi;
+            if (i == 0) {
+                g[i] = (T)2 * (xi - (T)1) - (T)16 * xi * t1;
+                acc[0] = acc[0] + (T)0.25 * (xi - (T)1) * (xi - (T)1);
+            } else {
+                acc[0] = acc[0] + t2 * t2;
+                g[i] = (i == n - 1) ? (T)8 * t2 : ((T)8 * t2 - (T)16 * xi * t1);
+            }
+        }
+        batch::tile_sum<T, 1>(acc, 1, tl, sm);
+    }
+    batch::final_sums<T>(1, n, sm, sm.red.rv);
+    if (threadIdx.x == 0) f[p] = (T)4 * sm.red.rv[0];
+}
+
+// ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
 extern "C" {
@@ -2035,4 +2238,73 @@ int lbfgsb_test_dcsrch_f64(double f, double g, double* stp, double stpmax, int32
     return e != cudaSuccess;
 }
 
+// ---- batched small problems ----
+lbfgsb_batch_t* lbfgsb_batch_create(int32_t nprob, int64_t n, int32_t m, int32_t real_kind, void* cuda_stream) {
+    if (nprob <= 0 || n <= 0 || m <= 0 || m > LB_MMAX) { set_error("lbfgsb_batch_create: need nprob > 0, n > 0 and 0 < m <= %d", LB_MMAX); return nullptr; }
+    const int64_t nmax = (int64_t)LB_BATCH_MAXTILES * LBFGSB_BLOCK * LBFGSB_UNROLL * (16 / real_kind);
+    if (real_kind != 8 && real_kind != 4) { set_error("real_kind must be 8 or 4"); return nullptr; }
+    if (n > nmax) { set_error("lbfgsb_batch_create: n = %lld exceeds the one-CTA-per-problem limit of %lld variables", (long long)n, (long long)nmax); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device (lbfgsb_b200 has no CPU path)"); return nullptr; }
+    if (real_kind == 8) {
+        BatchEngine<double>* e = new BatchEngine<double>();
+        if (!e->init(nprob, n, m, (cudaStream_t)cuda_stream)) { delete e; return nullptr; }
+        return (lbfgsb_batch_t*)e;
+    }
+    BatchEngine<float>* e = new BatchEngine<float>();
+    if (!e->init(nprob, n, m, (cudaStream_t)cuda_stream)) { delete e; return nullptr; }
+    return (lbfgsb_batch_t*)e;
+}
+void lbfgsb_batch_destroy(lbfgsb_batch_t* h) { delete (BatchBase*)h; }
+void lbfgsb_batch_setulb_dev_f64(lbfgsb_batch_t* h, double* x, const double* l, const double* u, const int32_t* nbd, double* f_dev, double* g,
+                                 const double* factr, const double* pgtol, char* task, char* csave, int32_t* lsave, int32_t* isave,
+                                 double* dsave) {
+    BatchBase* b = (BatchBase*)h;
+    if (!b || b->real_kind != 8) { set_error("invalid batch handle"); if (task) put60(task, "ERROR: INVALID LBFGSB_B200 HANDLE"); return; }
+    BatchEngine<double>* e = (BatchEngine<double>*)b;
+    if (!e->call(x, l, u, nbd, f_dev, g, *factr, *pgtol, task, csave, lsave, isave, dsave))
+        for (int p = 0; p < e->bw.nprob; ++p) put60(task + 60 * (size_t)p, "ERROR: CUDA FAILURE (see lbfgsb_b200_last_error)");
+}
+void lbfgsb_batch_setulb_dev_f32(lbfgsb_batch_t* h, float* x, const float* l, const float* u, const int32_t* nbd, float* f_dev, float* g,
+                                 const float* factr, const float* pgtol, char* task, char* csave, int32_t* lsave, int32_t* isave,
+                                 float* dsave) {
+    BatchBase* b = (BatchBase*)h;
+    if (!b || b->real_kind != 4) { set_error("invalid batch handle"); if (task) put60(task, "ERROR: INVALID LBFGSB_B200 HANDLE"); return; }
+    BatchEngine<float>* e = (BatchEngine<float>*)b;
+    if (!e->call(x, l, u, nbd, f_dev, g, *factr, *pgtol, task, csave, lsave, isave, dsave))
+        for (int p = 0; p < e->bw.nprob; ++p) put60(task + 60 * (size_t)p, "ERROR: CUDA FAILURE (see lbfgsb_b200_last_error)");
+}
+int lbfgsb_batch_counts(lbfgsb_batch_t* h, int32_t* n_fg, int32_t* n_newx, int32_t* n_done) {
+    BatchBase* b = (BatchBase*)h;
+    if (!b) return 1;
+    if (b->real_kind == 8) { BatchEngine<double>* e = (BatchEngine<double>*)b; *n_fg = e->n_fg; *n_newx = e->n_newx; *n_done = e->n_done; }
+    else { BatchEngine<float>* e = (BatchEngine<float>*)b; *n_fg = e->n_fg; *n_newx = e->n_newx; *n_done = e->n_done; }
+    return 0;
+}
+void* lbfgsb_batch_fg_mask(lbfgsb_batch_t* h) {
+    BatchBase* b = (BatchBase*)h;
+    if (!b) return nullptr;
+    return b->real_kind == 8 ? (void*)((BatchEngine<double>*)b)->bw.fgmask : (void*)((BatchEngine<float>*)b)->bw.fgmask;
+}
+void* lbfgsb_batch_stream(lbfgsb_batch_t* h) {
+    BatchBase* b = (BatchBase*)h;
+    if (!b) return nullptr;
+    return b->real_kind == 8 ? (void*)((BatchEngine<double>*)b)->stream : (void*)((BatchEngine<float>*)b)->stream;
+}
+int lbfgsb_problem_rosenbrock_batch_f64(int32_t nprob, int64_t n, const double* x_dev, double* g_dev, double* f_dev, const int32_t* mask_dev,
+                                        void* st) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_rosenbrock_batch<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BatchSm<double>)); attr = true; }
+    k_rosenbrock_batch<double><<<nprob, LBFGSB_BLOCK, sizeof(BatchSm<double>), (cudaStream_t)st>>>(nprob, n, x_dev, g_dev, f_dev, mask_dev);
+    return cudaGetLastError() != cudaSuccess;
+}
+int lbfgsb_problem_rosenbrock_batch_f32(int32_t nprob, int64_t n, const float* x_dev, float* g_dev, float* f_dev, const int32_t* mask_dev,
+                                        void* st) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_rosenbrock_batch<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BatchSm<float>)); attr = true; }
+    k_rosenbrock_batch<float><<<nprob, LBFGSB_BLOCK, sizeof(BatchSm<float>), (cudaStream_t)st>>>(nprob, n, x_dev, g_dev, f_dev, mask_dev);
+    return cudaGetLastError() != cudaSuccess;
+}
+
 }  // extern "C"
+

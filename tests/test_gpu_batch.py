@@ -1,0 +1,175 @@
+"""Batched small problems (include/lbfgsb_b200.h section 6): one CTA per problem, the reference's
+task protocol per problem.  Every problem of a batch is compared with the oracle run on that problem alone -- the loop of
+test/driver1.f90:263-292 -- in device-order summation mode: the discrete trace of every iterate (iteration and evaluation
+counts, Cauchy segments, free / active / entering / leaving counts, line-search trials, skipped updates) must be equal and
+f, |proj g| agree to rounding; the final task strings must be equal."""
+import numpy as np
+import pytest
+
+import harness as H
+from oracle import oracle_py as O
+from test_gpu_drivers import RTOL_EARLY, RTOL_LATE
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("iter", "nfgv", "nseg", "nact", "nfree", "nenter", "nleave", "iword", "iback", "col", "nskip", "nintol")
+
+
+def _problems(nprob, n, dtype, l_odd, spread, seed):
+    rng = np.random.default_rng(seed)
+    x0 = (3.0 + spread * rng.uniform(-1.0, 1.0, (nprob, n))).astype(dtype)
+    l = np.empty((nprob, n), dtype=dtype); u = np.full((nprob, n), 100.0, dtype=dtype)
+    l[:, 0::2] = l_odd; l[:, 1::2] = -100.0
+    nbd = np.full((nprob, n), 2, dtype=np.int32)
+    return x0, l, u, nbd
+
+
+def _run_batch(x0, l, u, nbd, m, factr, pgtol, max_iter=0):
+    import torch
+    import lbfgsb_b200
+    nprob, n = x0.shape
+    dt = x0.dtype
+    xd, ld, ud, nd = (torch.from_numpy(a.copy()).cuda() for a in (x0, l, u, nbd))
+    gd = torch.zeros_like(xd)
+    fd = torch.zeros(nprob, dtype=xd.dtype, device="cuda")
+    torch.cuda.synchronize()
+    b = lbfgsb_b200.BatchProblem(nprob, n, m, dt)
+    traces = [[] for _ in range(nprob)]
+
+    def on_newx(bp):
+        fh = fd.cpu().numpy()
+        for p in np.nonzero(bp.task[:, 0] == ord("N"))[0]:
+            i, d = bp.isave[p], bp.dsave[p]
+            traces[p].append({"iter": int(i[29]), "nfgv": int(i[33]), "nseg": int(i[32]), "nact": int(i[38]), "nfree": int(i[37]),
+                              "nenter": int(i[40]), "nleave": int(n + 1 - i[39]), "iword": int(i[36]), "iback": int(i[24]),
+                              "col": int(i[27]), "nskip": int(i[25]), "nintol": int(i[21]), "f": float(fh[p]),
+                              "sbgnrm": float(d[12]), "stp": float(d[13])})
+    calls = b.solve(xd, ld, ud, nd, fd, gd, factr, pgtol, max_iter=max_iter, on_newx=on_newx)
+    tasks = [b.task_str(p) for p in range(nprob)]
+    x = xd.cpu().numpy(); f = fd.cpu().numpy()
+    b.close()
+    return traces, tasks, x, f, calls
+
+
+def _run_oracle(x0, l, u, nbd, m, factr, pgtol, max_iter=0):
+    O.set_sum_mode(1)
+    try:
+        x = x0.copy()
+        n = x.shape[0]
+        stop = H.iteration_budget_stop(max_iter) if max_iter > 0 else None
+        return H.run_driver(O.OracleSetulb(x.dtype), O.rosenbrock_fg, n, m, x, l.copy(), u.copy(), nbd.copy(), factr, pgtol, stop=stop,
+                            want_hash=False)
+    finally:
+        O.set_sum_mode(0)
+
+
+def _compare(tr, ref, early=10, upto=None):
+    rows = list(zip(tr, ref[0]))[:upto]
+    for a, b in rows:
+        for k in FIELDS:
+            assert a[k] == b[k], (k, a, b)
+        tol = RTOL_EARLY if b["iter"] <= early else RTOL_LATE
+        assert abs(a["f"] - b["f"]) <= tol * abs(b["f"]) + 1e-300, (a, b)
+        assert abs(a["sbgnrm"] - b["sbgnrm"]) <= 100 * tol * abs(b["sbgnrm"]) + 1e-300, (a, b)
+
+
+def test_thousand_driver1_problems_match_the_oracle():
+    """1000 copies of test/driver1.f90 (n = 25, m = 5, factr = 1e7, pgtol = 1e-5) with perturbed starting points."""
+    nprob, n, m = 1000, 25, 5
+    x0, l, u, nbd = _problems(nprob, n, np.float64, 1.0, 0.5, 7)
+    x0[0, :] = 3.0                      # problem 0 is driver1 itself
+    tr, tasks, x, f, calls = _run_batch(x0, l, u, nbd, m, 1.0e7, 1.0e-5)
+    assert len(tr[0]) == 23 and tr[0][-1]["nfgv"] == 28 and tasks[0] == "CONVERGENCE: REL_REDUCTION_OF_F_<=_FACTR*EPSMCH"
+    assert abs(f[0] - 1.083490083461424e-09) <= 1e-7 * 1.083490083461424e-09
+    worst = 0.0
+    for p in range(nprob):
+        ref = _run_oracle(x0[p], l[p], u[p], nbd[p], m, 1.0e7, 1.0e-5)
+        assert tasks[p] == ref[1], (p, tasks[p], ref[1])
+        assert len(tr[p]) == len(ref[0]), (p, len(tr[p]), len(ref[0]))
+        _compare(tr[p], ref)
+        worst = max(worst, float(np.max(np.abs(x[p] - ref[2]))))
+    assert worst < 1e-6, worst
+
+
+@pytest.mark.parametrize("n,m,l_odd,nprob", [(1000, 10, 1.1, 16), (4099, 7, 1.5, 6), (20000, 5, 1.0, 4), (65001, 3, 1.1, 2)])
+def test_larger_problems_with_breakpoint_walks(n, m, l_odd, nprob):
+    """The Cauchy search passes breakpoints (nseg up to n at iteration 1), variables enter and leave the free set (formk's
+    corrections), several tiles per problem (n > 2048) up to the one-CTA limit."""
+    x0, l, u, nbd = _problems(nprob, n, np.float64, l_odd, 0.25, n)
+    tr, tasks, x, f, calls = _run_batch(x0, l, u, nbd, m, 0.0, 0.0, max_iter=25)
+    for p in range(nprob):
+        ref = _run_oracle(x0[p], l[p], u[p], nbd[p], m, 0.0, 0.0, max_iter=25)
+        assert len(tr[p]) == len(ref[0]) == 25
+        assert any(r["nseg"] > 1 for r in ref[0])
+        _compare(tr[p], ref)
+
+
+@pytest.mark.parametrize("n,m,l_odd,x0v", [(1000, 5, 2.0, 3.0), (3001, 3, 2.5, 5.0)])
+def test_equal_breakpoints_are_taken_in_heap_order(n, m, l_odd, x0v):
+    """Problems whose Cauchy search ends inside a group of equal breakpoints (tests/test_gpu_rare_paths.py): the batch
+    kernel pops hpsolb's heap like the reference, so the active set follows the reference's tie order by construction
+    (the oracle run with ties in variable order gives a different trace on these problems)."""
+    nprob = 3
+    x0 = np.full((nprob, n), x0v); l = np.empty((nprob, n)); u = np.full((nprob, n), 100.0)
+    l[:, 0::2] = l_odd; l[:, 1::2] = -100.0
+    nbd = np.full((nprob, n), 2, dtype=np.int32)
+    ref = _run_oracle(x0[0], l[0], u[0], nbd[0], m, 0.0, 0.0, max_iter=12)
+    O.set_tie_mode(1)
+    try:
+        other = _run_oracle(x0[0], l[0], u[0], nbd[0], m, 0.0, 0.0, max_iter=12)
+    finally:
+        O.set_tie_mode(0)
+    assert any(a["nact"] != b["nact"] or a["nfgv"] != b["nfgv"] for a, b in list(zip(ref[0], other[0]))[:8]), \
+        "tie order makes no difference on this problem: the case proves nothing"
+    tr, tasks, x, f, calls = _run_batch(x0, l, u, nbd, m, 0.0, 0.0, max_iter=12)
+    for p in range(nprob):
+        _compare(tr[p], ref, upto=8)
+
+
+def test_float32_batch():
+    nprob, n, m = 32, 500, 10
+    x0, l, u, nbd = _problems(nprob, n, np.float32, 1.0, 0.25, 3)
+    tr, tasks, x, f, calls = _run_batch(x0, l, u, nbd, m, 0.0, 0.0, max_iter=6)
+    for p in range(nprob):
+        ref = _run_oracle(x0[p], l[p], u[p], nbd[p], m, 0.0, 0.0, max_iter=6)
+        for a, b in list(zip(tr[p], ref[0]))[:4]:
+            for k in ("iter", "nfgv", "nseg", "col"):
+                assert a[k] == b[k], (k, a, b)
+            assert abs(a["f"] - b["f"]) <= 1e-3 * abs(b["f"]), (a, b)
+
+
+def test_protocol_errors_and_stop_per_problem():
+    """errclb per problem (:1601-1643), a problem stopped by its caller with STOP/CPU (:565-571) while the others go on."""
+    import torch
+    import lbfgsb_b200
+    nprob, n, m = 4, 40, 4
+    x0, l, u, nbd = _problems(nprob, n, np.float64, 1.0, 0.1, 11)
+    nbd[1, 7] = 9                     # invalid nbd in problem 1
+    l[2, 5] = 200.0                   # l > u in problem 2
+    xd, ld, ud, nd = (torch.from_numpy(a.copy()).cuda() for a in (x0, l, u, nbd))
+    gd = torch.zeros_like(xd); fd = torch.zeros(nprob, dtype=torch.float64, device="cuda")
+    b = lbfgsb_b200.BatchProblem(nprob, n, m, np.float64)
+    b.setulb_dev(xd, ld, ud, nd, fd, gd, 1e7, 1e-5)
+    assert b.task_str(0) == "FG_START" and b.task_str(3) == "FG_START"
+    assert b.task_str(1) == "ERROR: INVALID NBD" and int(b.isave[1, 41]) == 8
+    assert b.task_str(2) == "ERROR: NO FEASIBLE SOLUTION" and int(b.isave[2, 41]) == 6
+    seen = 0
+    xprev = None
+    while True:
+        nfg, nnew, ndone = b.counts()
+        if nfg == 0 and nnew == 0:
+            break
+        if nfg:
+            b.rosenbrock_fg(xd, gd, fd)
+        if nnew and b.task_str(3) == "NEW_X":
+            seen += 1
+            if seen == 3:
+                xprev = xd[3].clone()
+            if seen == 4:             # give up on problem 3 and take the previous iterate back
+                b.set_task(3, "STOP: CPU")
+        b.setulb_dev(xd, ld, ud, nd, fd, gd, 1e7, 1e-5)
+    assert b.task_str(0).startswith("CONVERGENCE")
+    assert b.task_str(3) == "STOP: CPU"
+    assert torch.equal(xd[3], xprev)
+    assert b.task_str(1) == "ERROR: INVALID NBD"
+    b.close()

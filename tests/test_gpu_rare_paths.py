@@ -86,6 +86,15 @@ def test_exit_inside_tied_breakpoints_follows_the_heap_and_backtrack_follows(n, 
     _compare(gpu, ref, min(len(ref[0]), it + 4))
 
 
+def test_tie_exit_among_millions_of_breakpoints_is_replayed_on_the_host():
+    """The same exit inside a group of equal breakpoints at n = 4e6 (2e6 breakpoints in the call, far beyond what one
+    device thread can replay): the heap is popped on the engine's host thread from a copy of the breakpoint list, and the
+    active set (hash) of every iterate equals the oracle's."""
+    gpu, ref, ev, total = _run_pair(4_000_001, 3, 2.5, 5.0, np.float64, 6)
+    assert total[0] >= 1, "the oracle did not backtrack on this problem: the case no longer covers the branch"
+    _compare(gpu, ref, min(len(ref[0]), 6))
+
+
 @pytest.mark.parametrize("n,m,l_odd,x0", CASES[:3])
 def test_without_heap_replay_ties_are_taken_in_variable_order(n, m, l_odd, x0):
     """Replay switched off (what happens beyond the replay limit and on sharded workspaces): the engine equals the
