@@ -171,7 +171,8 @@ int lbfgsb_problem_rosenbrock_halo_f64(int64_t n, const double* x_dev, double* g
  *     order (identical on every rank).  Returns 2 otherwise (use the *_halo_* variants with your own collectives).   */
 /* The same hook for a caller's own gradient kernel.  lbfgsb_dev_trial_sums gives the search direction d and the two
  * arrays of `grid` block partials; the kernel must walk the variables in the fixed shape of lbfgsb_b200_shape.h
- * (`grid` blocks of `block` threads, tiles of block*VEC*unroll variables, VEC = 16 / real_kind), add g_i*d_i into one
+ * (`grid` blocks of `block` threads, tiles of block*vec*unroll variables: thread t owns the `vec` variables at
+ * t*vec + k*block*vec, k = 0..unroll-1, of a tile), add g_i*d_i into one
  * accumulator per thread in that order, combine lanes by xor-butterfly and warps serially (block_sum_store in
  * lbfgsb_b200/csrc/common.cuh), store the block's sum in gd_part_dev[blockIdx.x] and the block's maximum of
  * |proj g|_i (projgr :2611-2619) in pg_part_dev[blockIdx.x]; then call lbfgsb_dev_trial_sums_commit before the next
@@ -182,6 +183,7 @@ typedef struct {
     void* pg_part_dev;      /* [grid] block partials of max |proj g|_i                                     */
     int64_t n;
     int32_t grid, block, unroll, real_kind;
+    int32_t vec, reserved;
 } lbfgsb_trial_sums_t;
 int lbfgsb_dev_trial_sums(lbfgsb_dev_t* h, lbfgsb_trial_sums_t* out);
 void lbfgsb_dev_trial_sums_commit(lbfgsb_dev_t* h);
@@ -230,6 +232,9 @@ int lbfgsb_batch_counts(lbfgsb_batch_t* h, int32_t* n_fg, int32_t* n_newx, int32
 void* lbfgsb_batch_stream(lbfgsb_batch_t* h);   /* the cudaStream_t the batch works on */
 /* device int32 [nprob], refreshed by every call: 1 where the problem's task now asks for f and g */
 void* lbfgsb_batch_fg_mask(lbfgsb_batch_t* h);
+/* iwhere of every problem copied to the host, int32 [nprob][n] -- what the reference keeps in iwa(2n+1:3n)
+ * (src/lbfgsb.f90:258; codes -3, -1, 0, 1, 2, 3 of cauchy :1203-1213).  Returns 0 on success. */
+int lbfgsb_batch_get_iwhere(lbfgsb_batch_t* h, int32_t* iwhere_host);
 /* the sample objective (test/driver1.f90:274-289) for a batch: problem p from x_dev[p][.] into g_dev[p][.], f_dev[p];
  * mask_dev (may be NULL): int32 [nprob], problems with 0 are skipped */
 int lbfgsb_problem_rosenbrock_batch_f64(int32_t nprob, int64_t n, const double* x_dev, double* g_dev, double* f_dev,

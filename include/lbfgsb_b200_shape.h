@@ -7,7 +7,12 @@
  *
  *   - LBFGSB_GRID blocks of LBFGSB_BLOCK threads; block b walks tiles
  *     b, b+GRID, b+2*GRID, ...; a tile is BLOCK*VEC*UNROLL consecutive
- *     variables with VEC = 16/sizeof(real) (one 128-bit load per thread);
+ *     variables.  VEC = 2 for both real kinds: one 128-bit load per thread per
+ *     stream in REAL64, one 64-bit load in REAL32, where UNROLL is doubled
+ *     instead -- a sub-tile of BLOCK*VEC variables is then 4 KB (REAL64) or
+ *     2 KB (REAL32) per stream, so that the 2*m + 8 streams of one sub-tile fit
+ *     twice in shared memory for every (kind, m) the fused passes support and
+ *     ALL threads of the block work on every staged sub-tile (tma_pipe.cuh);
  *   - in a tile, thread t owns the VEC variables at t*VEC + k*(BLOCK*VEC),
  *     k = 0..UNROLL-1, and adds their terms serially into one accumulator that
  *     lives across all of the block's tiles;
@@ -23,7 +28,12 @@
 #define LBFGSB_B200_SHAPE_H
 
 #define LBFGSB_BLOCK 256        /* threads per streaming block                  */
-#define LBFGSB_UNROLL 4         /* 128-bit loads in flight per thread per stream */
+#define LBFGSB_VEC_F64 2        /* variables per thread per load, REAL64 (128-bit) */
+#define LBFGSB_VEC_F32 2        /* variables per thread per load, REAL32 (64-bit)  */
+#define LBFGSB_UNROLL_F64 4     /* loads in flight per thread per stream, REAL64   */
+#define LBFGSB_UNROLL_F32 8     /* the same, REAL32: a tile is 4096 variables      */
+#define LBFGSB_VEC(real_bytes) ((real_bytes) == 8 ? LBFGSB_VEC_F64 : LBFGSB_VEC_F32)
+#define LBFGSB_UNROLL(real_bytes) ((real_bytes) == 8 ? LBFGSB_UNROLL_F64 : LBFGSB_UNROLL_F32)
 #define LBFGSB_GRID 592         /* 148 SMs x 4 blocks                            */
 #define LBFGSB_FINAL_BLOCK 32   /* one warp finishes one reduction slot          */
 

@@ -116,6 +116,8 @@ def lib():
         L.lbfgsb_batch_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.lbfgsb_batch_stream.restype = C.c_void_p
         L.lbfgsb_batch_stream.argtypes = [C.c_void_p]
+        L.lbfgsb_batch_get_iwhere.restype = C.c_int
+        L.lbfgsb_batch_get_iwhere.argtypes = [C.c_void_p, C.c_void_p]
         L.lbfgsb_batch_fg_mask.restype = C.c_void_p
         L.lbfgsb_batch_fg_mask.argtypes = [C.c_void_p]
         for sfx in ("f64", "f32"):
@@ -485,6 +487,13 @@ class BatchProblem:
         if (self.task[:, 0] == 69).any():
             for p in range(self.nprob):
                 _check_task(self.task[p])
+
+    def iwhere(self):
+        """iwhere of every problem ([nprob, n] int32 on the host): the reference's iwa(2n+1:3n) per problem."""
+        out = np.empty((self.nprob, self.n), dtype=np.int32)
+        if lib().lbfgsb_batch_get_iwhere(C.c_void_p(self.h), _p(out)) != 0:
+            raise LbfgsbB200Error("lbfgsb_batch_get_iwhere failed")
+        return out
 
     def counts(self):
         a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)

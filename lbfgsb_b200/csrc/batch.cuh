@@ -54,12 +54,12 @@ struct BatchSm {
 
 namespace batch {
 
-template <typename T> __device__ __forceinline__ i64 tile_size() { return (i64)LBFGSB_BLOCK * Real<T>::VEC * LBFGSB_UNROLL; }
+template <typename T> __device__ __forceinline__ i64 tile_size() { return (i64)LBFGSB_BLOCK * Real<T>::VEC * Real<T>::UNROLL; }
 template <typename T> __device__ __forceinline__ i64 ntiles_of(i64 n) { return (n + tile_size<T>() - 1) / tile_size<T>(); }
 // In tile `tl` a thread meets its elements in the order k = 0..UNROLL-1, v = 0..VEC-1 (include/lbfgsb_b200_shape.h).
 #define B_TILES(T, n, tl) for (i64 tl = 0; tl < batch::ntiles_of<T>(n); ++tl)
 #define B_ELEMS(T, n, tl, i)                                                                                         \
-    for (int _kv = 0; _kv < LBFGSB_UNROLL * Real<T>::VEC; ++_kv)                                                     \
+    for (int _kv = 0; _kv < Real<T>::UNROLL * Real<T>::VEC; ++_kv)                                                     \
         for (i64 i = (tl) * batch::tile_size<T>() + (i64)(_kv / Real<T>::VEC) * (LBFGSB_BLOCK * Real<T>::VEC) +      \
                      (i64)threadIdx.x * Real<T>::VEC + (_kv % Real<T>::VEC), _o = 1; _o && i < (n); _o = 0)
 

@@ -104,13 +104,13 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_count(Wk<T> w, int* tile_
     if (MODE == 1 && !s->do_delta) return;
     if (MODE == 2 && !s->need_walk) return;
     const i64 n = w.n;
-    const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
+    const i64 tile = (i64)LBFGSB_BLOCK * VEC * Real<T>::UNROLL;
     const i64 ntiles = (n + tile - 1) / tile;
     __shared__ i64 smi[LBFGSB_BLOCK / 32];
     for (i64 tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
         i64 c = 0;
 #pragma unroll
-        for (int k = 0; k < LBFGSB_UNROLL; ++k) {
+        for (int k = 0; k < Real<T>::UNROLL; ++k) {
             const i64 base = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC) + (i64)threadIdx.x * VEC;
             if (base >= n) continue;
             if (MODE == 2) {   // every breakpoint of this cauchy call, passed ones included (heap replay)
@@ -168,13 +168,13 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_write(Wk<T> w, const i64*
     if (MODE == 1 && !s->do_delta) return;
     if (MODE == 2 && !s->need_walk) return;
     const i64 n = w.n;
-    const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
+    const i64 tile = (i64)LBFGSB_BLOCK * VEC * Real<T>::UNROLL;
     const i64 ntiles = (n + tile - 1) / tile;
     __shared__ i64 sm[33];
     for (i64 tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
         i64 run = tile_offsets[tl];
 #pragma unroll 1
-        for (int k = 0; k < LBFGSB_UNROLL; ++k) {
+        for (int k = 0; k < Real<T>::UNROLL; ++k) {
             const i64 base = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC) + (i64)threadIdx.x * VEC;
             bool fl[VEC]; T tv[VEC];
             i64 c = 0;
@@ -633,14 +633,14 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_bp_count(Wk<T> w, BpRange rg, 
     const DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->need_walk || s->walk_closed) return;
     const i64 n = w.n;
-    const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
+    const i64 tile = (i64)LBFGSB_BLOCK * VEC * Real<T>::UNROLL;
     const i64 ntiles = (n + tile - 1) / tile;
     __shared__ i64 smi[LBFGSB_BLOCK / 32];
     i64 rem = 0, kmin = LB_I64MAX;
     for (i64 tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
         i64 c = 0;
 #pragma unroll
-        for (int k = 0; k < LBFGSB_UNROLL; ++k) {
+        for (int k = 0; k < Real<T>::UNROLL; ++k) {
             const i64 base = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC) + (i64)threadIdx.x * VEC;
             if (base >= n) continue;
             T d[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC];
@@ -678,13 +678,13 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_bp_write(Wk<T> w, BpRange rg, 
     const DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->need_walk || s->walk_closed) return;
     const i64 n = w.n;
-    const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
+    const i64 tile = (i64)LBFGSB_BLOCK * VEC * Real<T>::UNROLL;
     const i64 ntiles = (n + tile - 1) / tile;
     __shared__ i64 sm[33];
     for (i64 tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
         i64 run = tile_offsets[tl];
 #pragma unroll 1
-        for (int k = 0; k < LBFGSB_UNROLL; ++k) {
+        for (int k = 0; k < Real<T>::UNROLL; ++k) {
             const i64 base = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC) + (i64)threadIdx.x * VEC;
             bool fl[VEC]; T tv[VEC];
             i64 c = 0;

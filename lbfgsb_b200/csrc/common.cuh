@@ -54,16 +54,18 @@ enum {
 
 template <typename T> struct Real;
 template <> struct Real<double> {
-    static constexpr int VEC = 2;
+    static constexpr int VEC = LBFGSB_VEC_F64;
+    static constexpr int UNROLL = LBFGSB_UNROLL_F64;
     typedef double2 vec_t;
     typedef int2 ivec_t;
     typedef unsigned long long key_t;
     __host__ __device__ static double eps() { return DBL_EPSILON; }
 };
 template <> struct Real<float> {
-    static constexpr int VEC = 4;
-    typedef float4 vec_t;
-    typedef int4 ivec_t;
+    static constexpr int VEC = LBFGSB_VEC_F32;
+    static constexpr int UNROLL = LBFGSB_UNROLL_F32;
+    typedef float2 vec_t;
+    typedef int2 ivec_t;
     typedef unsigned int key_t;
     __host__ __device__ static float eps() { return FLT_EPSILON; }
 };
@@ -452,11 +454,11 @@ __device__ __forceinline__ void stvb(unsigned char* __restrict__ p, i64 base, i6
 
 // Tile walk of the fixed shape: body(base) sees VEC consecutive variables at `base`.
 #define LB_FOR_TILES(T, n, base)                                                               \
-    for (i64 _tl = blockIdx.x, _nt = ((n) + (i64)LBFGSB_BLOCK * Real<T>::VEC * LBFGSB_UNROLL - 1) / \
-                                     ((i64)LBFGSB_BLOCK * Real<T>::VEC * LBFGSB_UNROLL);       \
+    for (i64 _tl = blockIdx.x, _nt = ((n) + (i64)LBFGSB_BLOCK * Real<T>::VEC * Real<T>::UNROLL - 1) / \
+                                     ((i64)LBFGSB_BLOCK * Real<T>::VEC * Real<T>::UNROLL);       \
          _tl < _nt; _tl += LBFGSB_GRID)                                                        \
-        _Pragma("unroll") for (int _k = 0; _k < LBFGSB_UNROLL; ++_k)                           \
-            for (i64 base = _tl * ((i64)LBFGSB_BLOCK * Real<T>::VEC * LBFGSB_UNROLL) +         \
+        _Pragma("unroll") for (int _k = 0; _k < Real<T>::UNROLL; ++_k)                           \
+            for (i64 base = _tl * ((i64)LBFGSB_BLOCK * Real<T>::VEC * Real<T>::UNROLL) +         \
                             (i64)_k * (LBFGSB_BLOCK * Real<T>::VEC) + (i64)threadIdx.x * Real<T>::VEC, \
                      _once = 1;                                                                \
                  _once && base < (n); _once = 0)
@@ -464,11 +466,11 @@ __device__ __forceinline__ void stvb(unsigned char* __restrict__ p, i64 base, i6
 // Same walk without unrolling the k loop (kernels that stream 2*col S/Y columns already have
 // enough loads in flight per step; unrolling would only multiply register pressure).
 #define LB_FOR_TILES_NU(T, n, base)                                                            \
-    for (i64 _tl = blockIdx.x, _nt = ((n) + (i64)LBFGSB_BLOCK * Real<T>::VEC * LBFGSB_UNROLL - 1) / \
-                                     ((i64)LBFGSB_BLOCK * Real<T>::VEC * LBFGSB_UNROLL);       \
+    for (i64 _tl = blockIdx.x, _nt = ((n) + (i64)LBFGSB_BLOCK * Real<T>::VEC * Real<T>::UNROLL - 1) / \
+                                     ((i64)LBFGSB_BLOCK * Real<T>::VEC * Real<T>::UNROLL);       \
          _tl < _nt; _tl += LBFGSB_GRID)                                                        \
-        _Pragma("unroll 1") for (int _k = 0; _k < LBFGSB_UNROLL; ++_k)                         \
-            for (i64 base = _tl * ((i64)LBFGSB_BLOCK * Real<T>::VEC * LBFGSB_UNROLL) +         \
+        _Pragma("unroll 1") for (int _k = 0; _k < Real<T>::UNROLL; ++_k)                         \
+            for (i64 base = _tl * ((i64)LBFGSB_BLOCK * Real<T>::VEC * Real<T>::UNROLL) +         \
                             (i64)_k * (LBFGSB_BLOCK * Real<T>::VEC) + (i64)threadIdx.x * Real<T>::VEC, \
                      _once = 1;                                                                \
                  _once && base < (n); _once = 0)

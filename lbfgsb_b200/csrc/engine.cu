@@ -276,7 +276,7 @@ struct Engine : EngineBase {
         CK(cudaMallocHost((void**)&ctl_host, sizeof(SortCtl)));
         header_bytes = offsetof(DevState<T>, sy);
         // walk / compaction buffers
-        const i64 tile = (i64)LBFGSB_BLOCK * Real<T>::VEC * LBFGSB_UNROLL;
+        const i64 tile = (i64)LBFGSB_BLOCK * Real<T>::VEC * Real<T>::UNROLL;
         ntiles = (n + tile - 1) / tile;
         if (!dalloc(&tile_counts, sizeof(int) * (size_t)(ntiles + 1)) || !dalloc(&tile_offsets, sizeof(i64) * (size_t)(ntiles + 1))) return false;
         if (!dalloc(&rs_counts, sizeof(int) * 256 * LB_RS_GRID)) return false;
@@ -2087,7 +2087,8 @@ int lbfgsb_dev_trial_sums(lbfgsb_dev_t* h, lbfgsb_trial_sums_t* out) {
         Engine<float>* e = (Engine<float>*)b;
         out->d_dev = e->w.d; out->gd_part_dev = LB_SLOT(e->w.part, 0); out->pg_part_dev = LB_SLOT(e->w.part, 1); out->n = e->n;
     }
-    out->grid = LBFGSB_GRID; out->block = LBFGSB_BLOCK; out->unroll = LBFGSB_UNROLL; out->real_kind = b->real_kind;
+    out->grid = LBFGSB_GRID; out->block = LBFGSB_BLOCK; out->unroll = LBFGSB_UNROLL(b->real_kind); out->real_kind = b->real_kind;
+    out->vec = LBFGSB_VEC(b->real_kind);
     return 0;
 }
 void lbfgsb_dev_trial_sums_commit(lbfgsb_dev_t* h) {
@@ -2241,7 +2242,7 @@ int lbfgsb_test_dcsrch_f64(double f, double g, double* stp, double stpmax, int32
 // ---- batched small problems ----
 lbfgsb_batch_t* lbfgsb_batch_create(int32_t nprob, int64_t n, int32_t m, int32_t real_kind, void* cuda_stream) {
     if (nprob <= 0 || n <= 0 || m <= 0 || m > LB_MMAX) { set_error("lbfgsb_batch_create: need nprob > 0, n > 0 and 0 < m <= %d", LB_MMAX); return nullptr; }
-    const int64_t nmax = (int64_t)LB_BATCH_MAXTILES * LBFGSB_BLOCK * LBFGSB_UNROLL * (16 / real_kind);
+    const int64_t nmax = (int64_t)LB_BATCH_MAXTILES * LBFGSB_BLOCK * LBFGSB_UNROLL(real_kind) * LBFGSB_VEC(real_kind);
     if (real_kind != 8 && real_kind != 4) { set_error("real_kind must be 8 or 4"); return nullptr; }
     if (n > nmax) { set_error("lbfgsb_batch_create: n = %lld exceeds the one-CTA-per-problem limit of %lld variables", (long long)n, (long long)nmax); return nullptr; }
     int ndev = 0;
@@ -2285,6 +2286,15 @@ void* lbfgsb_batch_fg_mask(lbfgsb_batch_t* h) {
     BatchBase* b = (BatchBase*)h;
     if (!b) return nullptr;
     return b->real_kind == 8 ? (void*)((BatchEngine<double>*)b)->bw.fgmask : (void*)((BatchEngine<float>*)b)->bw.fgmask;
+}
+int lbfgsb_batch_get_iwhere(lbfgsb_batch_t* h, int32_t* iwhere_host) {
+    BatchBase* b = (BatchBase*)h;
+    if (!b || !iwhere_host) return 1;
+    const int* src; i64 ldw, n; int nprob; cudaStream_t st;
+    if (b->real_kind == 8) { BatchEngine<double>* e = (BatchEngine<double>*)b; src = e->bw.iwhere; ldw = e->bw.ldw; n = e->bw.n; nprob = e->bw.nprob; st = e->stream; }
+    else { BatchEngine<float>* e = (BatchEngine<float>*)b; src = e->bw.iwhere; ldw = e->bw.ldw; n = e->bw.n; nprob = e->bw.nprob; st = e->stream; }
+    if (cudaMemcpy2DAsync(iwhere_host, (size_t)n * 4, src, (size_t)ldw * 4, (size_t)n * 4, (size_t)nprob, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+    return cudaStreamSynchronize(st) != cudaSuccess;
 }
 void* lbfgsb_batch_stream(lbfgsb_batch_t* h) {
     BatchBase* b = (BatchBase*)h;

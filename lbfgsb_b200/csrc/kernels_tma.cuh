@@ -12,7 +12,20 @@
 #include "kernels_stream.cuh"
 #include "tma_pipe.cuh"
 
-template <int MT> struct SubT { static constexpr int v = (MT <= 10) ? 256 : 128; };
+// Threads per staged sub-tile: all 256 whenever the 2*MT + 8 streams of a sub-tile (256 * VEC reals each) fit twice in
+// shared memory -- REAL64 with m <= 10 and REAL32 with m <= 20 (VEC = 2 for both kinds, lbfgsb_b200_shape.h); REAL64 with
+// m > 10 stages half sub-tiles and only the 128 owning threads work on a stage.
+template <typename T, int MT> struct SubT { static constexpr int v = (sizeof(T) * MT <= 80) ? 256 : 128; };
+
+// REAL32 passes are bound by instruction issue and shared-memory latency rather than by DRAM (two resident warps per
+// scheduler, one staged load feeding a handful of single-precision operations): for them the steady state of the
+// iteration -- history full, col == MT -- gets a second instantiation of the pass body in which the ring length is a
+// compile-time constant, so that the 2*MT column steps are one branch-free block and the compiler overlaps the staged
+// loads of later columns with the arithmetic of earlier ones.  Same operations in the same order on every accumulator:
+// the bits do not change.  (Measured and rejected for REAL64, whose passes sit at the DRAM roofline: larger code, no
+// fewer stalls.)
+template <typename T> struct SpecializeFullHistory { static constexpr bool value = sizeof(T) == 4; };
+template <bool B> struct BoolC { static constexpr bool value = B; };
 
 // The stage ring starts at the (128-byte aligned) base of the dynamic shared memory.  It must stay a pointer
 // derived from `dyn` (no integer round trip): the compiler then knows the address space and reads the
@@ -39,7 +52,7 @@ __device__ __forceinline__ void pipe_add_w(PipeSrc* ps, const Wk<T>& w, int head
 template <typename T, int MT>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
-    constexpr int SUBT = SubT<MT>::v;
+    constexpr int SUBT = SubT<T, MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
@@ -94,7 +107,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update(Wk<T> w) {
     });
     block_sum_store<T, 2 * MT + 1>(acc, 2 * MT + 1, sm, w.part);
 }
-template <typename T, int MT> constexpr unsigned smem_update() { return pipe_smem_bytes<T, SubT<MT>::v>(3 + 2 * (MT - 1), 0, 0); }
+template <typename T, int MT> constexpr unsigned smem_update() { return pipe_smem_bytes<T, SubT<T, MT>::v>(3 + 2 * (MT - 1), 0, 0); }
 
 // ---------------------------------------------------------------------------
 // cauchy, one variable of the per-variable pass (:1270-1327): new iwhere, Cauchy direction,
@@ -162,7 +175,7 @@ __device__ __forceinline__ void cauchy_scan_store(const Wk<T>& w, CauchyScan<T>&
 template <typename T, int MT>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cauchy_classify(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
-    constexpr int SUBT = SubT<MT>::v;
+    constexpr int SUBT = SubT<T, MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
@@ -233,7 +246,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cauchy_classify(Wk<T> w) 
     block_sum_store<T, 2 * MT + 1>(acc, 2 * MT + 1, sm, w.part2);
     cauchy_scan_store<T, MT>(w, cs, smv, smi);
 }
-template <typename T, int MT> constexpr unsigned smem_classify() { return pipe_smem_bytes<T, SubT<MT>::v>(4 + 2 * MT, 2, 0); }
+template <typename T, int MT> constexpr unsigned smem_classify() { return pipe_smem_bytes<T, SubT<T, MT>::v>(4 + 2 * MT, 2, 0); }
 
 // ---------------------------------------------------------------------------
 // formk, new row/column of WN1 (:1756-1793): one pass over all rows of S,Y.
@@ -243,7 +256,7 @@ template <typename T, int MT> constexpr unsigned smem_classify() { return pipe_s
 template <typename T, int MT>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_gram(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
-    constexpr int SUBT = SubT<MT>::v;
+    constexpr int SUBT = SubT<T, MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
@@ -293,7 +306,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_gram(Wk<T> w) {
     });
     block_sum_store<T, 4 * MT>(acc, 4 * MT, sm, w.part);
 }
-template <typename T, int MT> constexpr unsigned smem_formk() { return pipe_smem_bytes<T, SubT<MT>::v>(2 * MT, 0, 1); }
+template <typename T, int MT> constexpr unsigned smem_formk() { return pipe_smem_bytes<T, SubT<T, MT>::v>(2 * MT, 0, 1); }
 
 // ---------------------------------------------------------------------------
 // cmprlb (:1565-1583) fused with the first half of subsm (:2742-2754):
@@ -305,7 +318,7 @@ template <typename T, int MT> constexpr unsigned smem_formk() { return pipe_smem
 template <typename T, int MT>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cmprlb_wv(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
-    constexpr int SUBT = SubT<MT>::v;
+    constexpr int SUBT = SubT<T, MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
@@ -378,7 +391,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cmprlb_wv(Wk<T> w) {
     });
     block_sum_store<T, 2 * MT>(acc, 2 * MT, sm, w.part2);
 }
-template <typename T, int MT> constexpr unsigned smem_cmprlb() { return pipe_smem_bytes<T, SubT<MT>::v>(3 + 2 * MT, 0, 1); }
+template <typename T, int MT> constexpr unsigned smem_cmprlb() { return pipe_smem_bytes<T, SubT<T, MT>::v>(3 + 2 * MT, 0, 1); }
 
 // ---------------------------------------------------------------------------
 // subsm second half (:2770-2827): Newton direction on the free set, projected
@@ -388,7 +401,7 @@ template <typename T, int MT> constexpr unsigned smem_cmprlb() { return pipe_sme
 template <typename T, int MT>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_step(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
-    constexpr int SUBT = SubT<MT>::v;
+    constexpr int SUBT = SubT<T, MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
@@ -471,7 +484,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_step(Wk<T> w) {
     i64 r0 = block_isum(iwd, smi);
     if (threadIdx.x == 0) LB_SLOT(w.ipart, 0)[blockIdx.x] = r0;
 }
-template <typename T, int MT> constexpr unsigned smem_subsm() { return pipe_smem_bytes<T, SubT<MT>::v>(6 + 2 * MT, 1, 1); }
+template <typename T, int MT> constexpr unsigned smem_subsm() { return pipe_smem_bytes<T, SubT<T, MT>::v>(6 + 2 * MT, 1, 1); }
 
 // ===========================================================================
 // Cross-routine fusions.  The iteration streams the 2*col S/Y columns once per routine in the
@@ -494,7 +507,7 @@ template <typename T, int MT> constexpr bool fused_passes_ok() { return sizeof(T
 template <typename T, int MT>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update_classify(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
-    constexpr int SUBT = SubT<MT>::v;
+    constexpr int SUBT = SubT<T, MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
@@ -528,6 +541,8 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update_classify(Wk<T> w) 
     CauchyScan<T> cs; cs.init();
     T* wsn = w.ws + (i64)itail0 * w.ldw;
     T* wyn = w.wy + (i64)itail0 * w.ldw;
+    auto pass = [&](auto full_c) {
+    constexpr bool FULLC = decltype(full_c)::value;   // col == MT at compile time
     tma_pass<T, SUBT>(n, &ps, LB_DYN_STAGES(dyn), full, [&](i64 base, const char* sb, int lt) {
         T g[VEC], y[VEC], sn[VEC];
         lds_real<T>(sb, OG, lt, g);
@@ -554,7 +569,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update_classify(Wk<T> w) 
         stvi<T>(w.iwhere, base, n, iw);   // d, xcp: see k_cauchy_classify
 #pragma unroll
         for (int j = 0; j < MT; ++j) {
-            if (j < col - 1) {
+            if (FULLC ? (j < MT - 1) : (j < col - 1)) {
                 T wy[VEC], wsv[VEC];
                 lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
                 lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
@@ -569,7 +584,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update_classify(Wk<T> w) 
                         ac[MT + j] = ac[MT + j] + wsv[v] * dc[v];
                     }
                 }
-            } else if (j == col - 1) {   // the pair being written: ring position col-1
+            } else if (FULLC ? (j == MT - 1) : (j == col - 1)) {   // the pair being written: ring position col-1
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
                     if (mv[v]) {
@@ -579,11 +594,14 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update_classify(Wk<T> w) 
             }
         }
     });
+    };
+    if constexpr (SpecializeFullHistory<T>::value) { if (col == MT) pass(BoolC<true>{}); else pass(BoolC<false>{}); }
+    else pass(BoolC<false>{});
     block_sum_store<T, 2 * MT + 1>(au, 2 * MT + 1, sm, w.part);
     block_sum_store<T, 2 * MT + 1>(ac, 2 * MT + 1, sm, w.part2);
     cauchy_scan_store<T, MT>(w, cs, smv, smi);
 }
-template <typename T, int MT> constexpr unsigned smem_update_classify() { return pipe_smem_bytes<T, SubT<MT>::v>(6 + 2 * (MT - 1), 2, 0); }
+template <typename T, int MT> constexpr unsigned smem_update_classify() { return pipe_smem_bytes<T, SubT<T, MT>::v>(6 + 2 * (MT - 1), 2, 0); }
 
 // ---------------------------------------------------------------------------
 // k_formk_gram fused with k_cmprlb_wv: the new row/column of WN1 over all rows of S,Y, the reduced
@@ -594,7 +612,7 @@ template <typename T, int MT> constexpr unsigned smem_update_classify() { return
 template <typename T, int MT, bool GF>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
-    constexpr int SUBT = SubT<MT>::v;
+    constexpr int SUBT = SubT<T, MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
@@ -633,9 +651,6 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
         const int j = threadIdx.x % MT;
         coef[threadIdx.x] = (j < col) ? ((threadIdx.x < MT) ? s->a[j] : theta * s->a[col + j]) : (T)0;
     }
-    const unsigned ost = OW + 2u * (unsigned)col * G::REAL_SLOT;
-    const unsigned oiw = ost + G::BYTE_SLOT;
-    const unsigned olast = OW + 2u * (unsigned)(col - 1) * G::REAL_SLOT;   // the newest pair sits at ring position col-1
     T af[4 * MT], aw[2 * MT];
 #pragma unroll
     for (int k = 0; k < 4 * MT; ++k) af[k] = (T)0;
@@ -646,6 +661,14 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
     // Elements at or beyond n read as zero from the stage (state 0, W = 0): their terms are +0 and leave
     // every accumulator unchanged, so the loops below carry no range checks.  The conditionals are kept
     // to a couple of instructions so that they compile to predication, not branches.
+    auto pass = [&](auto full_c) {
+    // FULLC: the steady state (history full, Gram row needed, bounds present) with col, gram, uc as compile-time constants
+    constexpr bool FULLC = decltype(full_c)::value;
+    const int colv = FULLC ? MT : col;
+    const bool gramv = FULLC ? true : gram, ucv = FULLC ? false : uc;
+    const unsigned ost = OW + 2u * (unsigned)colv * G::REAL_SLOT;
+    const unsigned oiw = ost + G::BYTE_SLOT;
+    const unsigned olast = OW + 2u * (unsigned)(colv - 1) * G::REAL_SLOT;   // the newest pair sits at ring position col-1
     tma_pass<T, SUBT>(n, &ps, LB_DYN_STAGES(dyn), full, [&](i64 base, const char* sb, int lt) {
         int st[VEC];
         lds_byte<T>(sb, ost, lt, st);
@@ -668,35 +691,55 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
                 st[v] = (f ? 1 : 0) | ((cnt ? old : (f ? 1 : 0)) << 1) | ((iw[v] == 0 || iw[v] == -1) ? 4 : 0);
                 fr[v] = f; any |= f;
                 z[v] = axpy ? (x[v] + tsum * cauchy_dir<T>(iw[v], g[v])) : x[v];
-                r[v] = uc ? -g[v] : (-theta * (z[v] - x[v]) - g[v]);
+                r[v] = ucv ? -g[v] : (-theta * (z[v] - x[v]) - g[v]);
             }
             stvb<T>(w.state, base, n, st);
-            if (!any && !gram) return;
+            if (!any && !gramv) return;
         } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { fr[v] = (st[v] & 1) != 0; any |= fr[v]; }
-            if (!any && !gram) return;
+            if (!any && !gramv) return;
             T z[VEC], x[VEC], g[VEC];
             lds_real<T>(sb, OG, lt, g); lds_real<T>(sb, OZ, lt, z); lds_real<T>(sb, OX, lt, x);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) r[v] = uc ? -g[v] : (-theta * (z[v] - x[v]) - g[v]);
+            for (int v = 0; v < VEC; ++v) r[v] = ucv ? -g[v] : (-theta * (z[v] - x[v]) - g[v]);
         }
         T wl[VEC];   // the newest pair's Wy on a free row, its Ws on an active row
-        if (gram) {
+        if (gramv) {
             T wyl[VEC], wsl[VEC];
             lds_real<T>(sb, olast, lt, wyl);
             lds_real<T>(sb, olast + G::REAL_SLOT, lt, wsl);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) wl[v] = fr[v] ? wyl[v] : wsl[v];
         }
-        if (gram || !uc) {
+        // PREF (REAL32): the staged values and coefficients of column j + 1 are requested before the arithmetic of
+        // column j (volatile, so that the loads stay where they are written); same operations, same order
+        constexpr bool PREF = SpecializeFullHistory<T>::value;
+        if (gramv || !ucv) {
+            T wyn[VEC], wsn[VEC]; T a1n = (T)0, a2n = (T)0;
+            if (PREF) {
+                lds_real_v<T>(sb, OW, lt, wyn); lds_real_v<T>(sb, OW + G::REAL_SLOT, lt, wsn);
+                a1n = *(volatile const T*)&coef[0]; a2n = *(volatile const T*)&coef[MT];
+            }
 #pragma unroll
             for (int j = 0; j < MT; ++j) {
                 if (j < col) {
-                    T wy[VEC], wsv[VEC];
-                    lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
-                    lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
-                    if (gram) {
+                    T wy[VEC], wsv[VEC]; T a1, a2;
+                    if (PREF) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) { wy[v] = wyn[v]; wsv[v] = wsn[v]; }
+                        a1 = a1n; a2 = a2n;
+                        if (j + 1 < MT) {
+                            lds_real_v<T>(sb, OW + (2 * j + 2) * G::REAL_SLOT, lt, wyn);
+                            lds_real_v<T>(sb, OW + (2 * j + 3) * G::REAL_SLOT, lt, wsn);
+                            a1n = *(volatile const T*)&coef[j + 1]; a2n = *(volatile const T*)&coef[MT + j + 1];
+                        }
+                    } else {
+                        lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
+                        lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
+                        a1 = coef[j]; a2 = coef[MT + j];
+                    }
+                    if (gramv) {
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
                             const T py = wl[v] * wy[v], psv = wl[v] * wsv[v];
@@ -704,8 +747,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
                             else { af[2 * MT + j] = af[2 * MT + j] + py; af[MT + j] = af[MT + j] + psv; }
                         }
                     }
-                    if (!uc) {
-                        const T a1 = coef[j], a2 = coef[MT + j];
+                    if (!ucv) {
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) r[v] = r[v] + wy[v] * a1 + wsv[v] * a2;
                     }
@@ -713,21 +755,36 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
             }
         }
         if (!any) return;
+        {
+            T wyn[VEC], wsn[VEC];
+            if (PREF) { lds_real_v<T>(sb, OW, lt, wyn); lds_real_v<T>(sb, OW + G::REAL_SLOT, lt, wsn); }
 #pragma unroll
-        for (int j = 0; j < MT; ++j) {
-            if (j < col) {
-                T wy[VEC], wsv[VEC];
-                lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
-                lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
+            for (int j = 0; j < MT; ++j) {
+                if (j < col) {
+                    T wy[VEC], wsv[VEC];
+                    if (PREF) {
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    const T py = wy[v] * r[v], psv = wsv[v] * r[v];
-                    if (fr[v]) { aw[j] = aw[j] + py; aw[MT + j] = aw[MT + j] + psv; }
+                        for (int v = 0; v < VEC; ++v) { wy[v] = wyn[v]; wsv[v] = wsn[v]; }
+                        if (j + 1 < MT) {
+                            lds_real_v<T>(sb, OW + (2 * j + 2) * G::REAL_SLOT, lt, wyn);
+                            lds_real_v<T>(sb, OW + (2 * j + 3) * G::REAL_SLOT, lt, wsn);
+                        }
+                    } else {
+                        lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
+                        lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
+                    }
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const T py = wy[v] * r[v], psv = wsv[v] * r[v];
+                        if (fr[v]) { aw[j] = aw[j] + py; aw[MT + j] = aw[MT + j] + psv; }
+                    }
                 }
             }
         }
         stv<T>(w.r, base, n, r);
     });
+    };
+    pass(BoolC<false>{});   // (the col == MT instantiation of this pass runs out of registers: 120 accumulators)
     if (gram) block_sum_store<T, 4 * MT>(af, 4 * MT, sm, w.part);
     block_sum_store<T, 2 * MT>(aw, 2 * MT, sm, w.part2);
     if (gf) {   // site freev
@@ -738,7 +795,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
         }
     }
 }
-template <typename T, int MT> constexpr unsigned smem_formk_cmprlb() { return pipe_smem_bytes<T, SubT<MT>::v>(3 + 2 * MT, 0, 1); }
+template <typename T, int MT> constexpr unsigned smem_formk_cmprlb() { return pipe_smem_bytes<T, SubT<T, MT>::v>(3 + 2 * MT, 0, 1); }
 
 // ---------------------------------------------------------------------------
 // k_subsm_step fused with k_ls_init: the subspace pass has z (the Newton point), x, g, l, u, nbd of every
@@ -762,7 +819,7 @@ template <typename T, int MT> constexpr unsigned smem_formk_cmprlb() { return pi
 template <typename T, int MT, int PASS>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
-    constexpr int SUBT = SubT<MT>::v;
+    constexpr int SUBT = SubT<T, MT>::v;
     typedef PipeGeom<T, SUBT> G;
     extern __shared__ __align__(128) char dyn[];
     __shared__ unsigned long long full[2 * LB_PIPE_STAGES];
@@ -799,13 +856,15 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
         pipe_add(&ps, w.state, 1, G::BYTE_SLOT);
         pipe_end(&ps);
     }
-    const unsigned onb = OW + 2u * (unsigned)col * G::REAL_SLOT, ost = onb + G::INT_SLOT;
     T wv1[MT], wv2[MT];
 #pragma unroll
     for (int j = 0; j < MT; ++j) { wv1[j] = (j < col) ? s->wv[j] : (T)0; wv2[j] = (j < col) ? s->wv[col + j] : (T)0; }
     T acc[2]; acc[0] = (T)0; acc[1] = (T)0;   // dtd, dd_p (= gd)
     T smx = LB_INF(T);
     i64 iwd = 0;
+    auto pass = [&](auto full_c) {
+    constexpr bool FULLC = decltype(full_c)::value;   // col == MT at compile time
+    const unsigned onb = OW + 2u * (unsigned)(FULLC ? MT : col) * G::REAL_SLOT, ost = onb + G::INT_SLOT;
     tma_pass<T, SUBT>(n, &ps, LB_DYN_STAGES(dyn), full, [&](i64 base, const char* sb, int lt) {
         int st[VEC];
         lds_byte<T>(sb, ost, lt, st);
@@ -825,7 +884,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
             lds_real<T>(sb, OR, lt, dk);
 #pragma unroll
             for (int j = 0; j < MT; ++j) {
-                if (j < col) {
+                if (FULLC || j < col) {
                     T wy[VEC], wsv[VEC];
                     lds_real<T>(sb, OW + (2 * j) * G::REAL_SLOT, lt, wy);
                     lds_real<T>(sb, OW + (2 * j + 1) * G::REAL_SLOT, lt, wsv);
@@ -893,6 +952,9 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_subsm_lsinit(Wk<T> w) {
             }
         }
     });
+    };
+    if constexpr (SpecializeFullHistory<T>::value && PASS == 0) { if (col == MT) pass(BoolC<true>{}); else pass(BoolC<false>{}); }
+    else pass(BoolC<false>{});
     if (PASS == 1) return;
     // site subsm: dd_p in part slot 0, iword in ipart slot 0
     T ddp[1]; ddp[0] = acc[1];

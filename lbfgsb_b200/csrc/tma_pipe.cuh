@@ -72,9 +72,9 @@ template <typename T, int SUBT>
 struct PipeGeom {
     static constexpr int VEC = Real<T>::VEC;
     static constexpr int HALVES = LBFGSB_BLOCK / SUBT;
-    static constexpr int IPT = LBFGSB_UNROLL * HALVES;            // stages per tile
+    static constexpr int IPT = Real<T>::UNROLL * HALVES;            // stages per tile
     static constexpr int ELEMS = SUBT * VEC;                      // variables per stage
-    static constexpr unsigned REAL_SLOT = ELEMS * sizeof(T);      // = SUBT * 16
+    static constexpr unsigned REAL_SLOT = ELEMS * sizeof(T);
     static constexpr unsigned INT_SLOT = ELEMS * 4;
     static constexpr unsigned BYTE_SLOT = ELEMS;
     __host__ __device__ static constexpr unsigned slot(int esz) { return (unsigned)(ELEMS * esz); }
@@ -103,10 +103,23 @@ __host__ __device__ constexpr unsigned pipe_smem_bytes(int nreal, int nint, int 
 // read this thread's VEC elements of a real / int / byte slot
 template <typename T>
 __device__ __forceinline__ void lds_real(const char* sm, unsigned off, int lt, T (&out)[Real<T>::VEC]) {
-    const typename Real<T>::vec_t q = *reinterpret_cast<const typename Real<T>::vec_t*>(sm + off + lt * 16);
+    const typename Real<T>::vec_t q = *reinterpret_cast<const typename Real<T>::vec_t*>(sm + off + lt * (int)sizeof(typename Real<T>::vec_t));
     const T* e = reinterpret_cast<const T*>(&q);
 #pragma unroll
     for (int v = 0; v < Real<T>::VEC; ++v) out[v] = e[v];
+}
+// the same through a volatile pointer: the load is issued where it is written (software prefetch of the next column)
+template <typename T>
+__device__ __forceinline__ void lds_real_v(const char* sm, unsigned off, int lt, T (&out)[Real<T>::VEC]) {
+    const volatile T* e = reinterpret_cast<const volatile T*>(sm + off + lt * (int)sizeof(typename Real<T>::vec_t));
+    if (Real<T>::VEC == 2 && sizeof(T) == 4) {
+        float a, b;
+        asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(tma::smem_u32((const void*)e)));
+        out[0] = (T)a; out[1] = (T)b;
+    } else {
+#pragma unroll
+        for (int v = 0; v < Real<T>::VEC; ++v) out[v] = e[v];
+    }
 }
 template <typename T>
 __device__ __forceinline__ void lds_int(const char* sm, unsigned off, int lt, int (&out)[Real<T>::VEC]) {
@@ -142,7 +155,7 @@ __device__ __forceinline__ void tma_pass(i64 n, const PipeSrc* ps, char* stages,
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     unsigned long long* full = bars;
     unsigned long long* empty = bars + LB_PIPE_STAGES;
-    const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
+    const i64 tile = (i64)LBFGSB_BLOCK * VEC * Real<T>::UNROLL;
     const i64 ntiles = (n + tile - 1) / tile;
     const i64 b = blockIdx.x;
     i64 nitems = 0;

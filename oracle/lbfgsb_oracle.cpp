@@ -63,8 +63,8 @@ static long long g_events[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 // LBFGSB_FINAL_BLOCK threads striding over the block partials.
 template <typename T, typename F>
 static T device_order_sum(i64 n, F term) {
-    const int VEC = (int)(16 / sizeof(T));
-    const i64 tile = (i64)LBFGSB_BLOCK * VEC * LBFGSB_UNROLL;
+    const int VEC = LBFGSB_VEC((int)sizeof(T)), UNROLL = LBFGSB_UNROLL((int)sizeof(T));
+    const i64 tile = (i64)LBFGSB_BLOCK * VEC * UNROLL;
     const i64 ntiles = (n + tile - 1) / tile;
     std::vector<T> block_partial(LBFGSB_GRID, (T)0);
     std::vector<T> lane(LBFGSB_BLOCK);
@@ -73,7 +73,7 @@ static T device_order_sum(i64 n, F term) {
         for (int t = 0; t < LBFGSB_BLOCK; ++t) {
             T acc = (T)0;
             for (i64 tl = b; tl < ntiles; tl += LBFGSB_GRID) {
-                for (int k = 0; k < LBFGSB_UNROLL; ++k) {
+                for (int k = 0; k < UNROLL; ++k) {
                     i64 base = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC) + (i64)t * VEC;
                     for (int v = 0; v < VEC; ++v) {
                         i64 i = base + v;
@@ -1917,7 +1917,7 @@ float oracle_device_order_dot_f32(int64_t n, const float* a, const float* b) {
     return device_order_sum<float>(n, [&](i64 i) { return a[i] * b[i]; });
 }
 int oracle_shape(int which) {
-    switch (which) { case 0: return LBFGSB_BLOCK; case 1: return LBFGSB_UNROLL; case 2: return LBFGSB_GRID; default: return LBFGSB_FINAL_BLOCK; }
+    switch (which) { case 0: return LBFGSB_BLOCK; case 1: return LBFGSB_UNROLL_F64; case 2: return LBFGSB_GRID; default: return LBFGSB_FINAL_BLOCK; }
 }
 
 }  // extern "C"

@@ -24,7 +24,16 @@ def _problems(nprob, n, dtype, l_odd, spread, seed):
     return x0, l, u, nbd
 
 
-def _run_batch(x0, l, u, nbd, m, factr, pgtol, max_iter=0):
+def _hash(iwhere_row):
+    """Active-set hash of one problem, as tests/harness.py records it for the oracle."""
+    import ctypes as C
+    iw = np.ascontiguousarray(iwhere_row, dtype=np.int32)
+    h, c = C.c_uint64(0), C.c_int64(0)
+    O.lib().oracle_active_set_hash(C.c_int64(iw.shape[0]), iw.ctypes.data_as(C.c_void_p), C.byref(h), C.byref(c))
+    return h.value
+
+
+def _run_batch(x0, l, u, nbd, m, factr, pgtol, max_iter=0, want_hash=False):
     import torch
     import lbfgsb_b200
     nprob, n = x0.shape
@@ -38,12 +47,15 @@ def _run_batch(x0, l, u, nbd, m, factr, pgtol, max_iter=0):
 
     def on_newx(bp):
         fh = fd.cpu().numpy()
+        iw = bp.iwhere() if want_hash else None
         for p in np.nonzero(bp.task[:, 0] == ord("N"))[0]:
             i, d = bp.isave[p], bp.dsave[p]
             traces[p].append({"iter": int(i[29]), "nfgv": int(i[33]), "nseg": int(i[32]), "nact": int(i[38]), "nfree": int(i[37]),
                               "nenter": int(i[40]), "nleave": int(n + 1 - i[39]), "iword": int(i[36]), "iback": int(i[24]),
                               "col": int(i[27]), "nskip": int(i[25]), "nintol": int(i[21]), "f": float(fh[p]),
                               "sbgnrm": float(d[12]), "stp": float(d[13])})
+            if want_hash:
+                traces[p][-1]["hash"] = _hash(iw[p])
     calls = b.solve(xd, ld, ud, nd, fd, gd, factr, pgtol, max_iter=max_iter, on_newx=on_newx)
     tasks = [b.task_str(p) for p in range(nprob)]
     x = xd.cpu().numpy(); f = fd.cpu().numpy()
@@ -51,14 +63,14 @@ def _run_batch(x0, l, u, nbd, m, factr, pgtol, max_iter=0):
     return traces, tasks, x, f, calls
 
 
-def _run_oracle(x0, l, u, nbd, m, factr, pgtol, max_iter=0):
+def _run_oracle(x0, l, u, nbd, m, factr, pgtol, max_iter=0, want_hash=False):
     O.set_sum_mode(1)
     try:
         x = x0.copy()
         n = x.shape[0]
         stop = H.iteration_budget_stop(max_iter) if max_iter > 0 else None
         return H.run_driver(O.OracleSetulb(x.dtype), O.rosenbrock_fg, n, m, x, l.copy(), u.copy(), nbd.copy(), factr, pgtol, stop=stop,
-                            want_hash=False)
+                            want_hash=want_hash)
     finally:
         O.set_sum_mode(0)
 
@@ -113,17 +125,20 @@ def test_equal_breakpoints_are_taken_in_heap_order(n, m, l_odd, x0v):
     x0 = np.full((nprob, n), x0v); l = np.empty((nprob, n)); u = np.full((nprob, n), 100.0)
     l[:, 0::2] = l_odd; l[:, 1::2] = -100.0
     nbd = np.full((nprob, n), 2, dtype=np.int32)
-    ref = _run_oracle(x0[0], l[0], u[0], nbd[0], m, 0.0, 0.0, max_iter=12)
+    ref = _run_oracle(x0[0], l[0], u[0], nbd[0], m, 0.0, 0.0, max_iter=12, want_hash=True)
     O.set_tie_mode(1)
     try:
-        other = _run_oracle(x0[0], l[0], u[0], nbd[0], m, 0.0, 0.0, max_iter=12)
+        other = _run_oracle(x0[0], l[0], u[0], nbd[0], m, 0.0, 0.0, max_iter=12, want_hash=True)
     finally:
         O.set_tie_mode(0)
-    assert any(a["nact"] != b["nact"] or a["nfgv"] != b["nfgv"] for a, b in list(zip(ref[0], other[0]))[:8]), \
+    # the problem is symmetric: which members of the tied group get fixed changes the active SET, not its size or f
+    assert any(a["hash"] != b["hash"] for a, b in list(zip(ref[0], other[0]))[:8]), \
         "tie order makes no difference on this problem: the case proves nothing"
-    tr, tasks, x, f, calls = _run_batch(x0, l, u, nbd, m, 0.0, 0.0, max_iter=12)
+    tr, tasks, x, f, calls = _run_batch(x0, l, u, nbd, m, 0.0, 0.0, max_iter=12, want_hash=True)
     for p in range(nprob):
         _compare(tr[p], ref, upto=8)
+        for a, b in list(zip(tr[p], ref[0]))[:8]:
+            assert a["hash"] == b["hash"], (p, a, b)
 
 
 def test_float32_batch():

@@ -90,9 +90,19 @@ def test_tie_exit_among_millions_of_breakpoints_is_replayed_on_the_host():
     """The same exit inside a group of equal breakpoints at n = 4e6 (2e6 breakpoints in the call, far beyond what one
     device thread can replay): the heap is popped on the engine's host thread from a copy of the breakpoint list, and the
     active set (hash) of every iterate equals the oracle's."""
-    gpu, ref, ev, total = _run_pair(4_000_001, 3, 2.5, 5.0, np.float64, 6)
-    assert total[0] >= 1, "the oracle did not backtrack on this problem: the case no longer covers the branch"
+    n, m, l_odd, x0 = 4_000_001, 3, 2.5, 5.0
+    gpu, ref, ev, total = _run_pair(n, m, l_odd, x0, np.float64, 6)
     _compare(gpu, ref, min(len(ref[0]), 6))
+    # the search of iteration 2 ends inside the tied group (nseg < breakpoints) and the tie order decides the active
+    # set there: the oracle run with ties in variable order gives another set (otherwise the case proves nothing)
+    assert 1 < ref[0][1]["nseg"] < n // 2
+    O.set_sum_mode(1); O.set_tie_mode(1)
+    try:
+        x, l, u, nbd = H.rosenbrock_problem(n, l_odd=l_odd, x0=x0)
+        other = H.run_driver(O.OracleSetulb(), O.rosenbrock_fg, n, m, x, l, u, nbd, 0.0, 0.0, stop=H.iteration_budget_stop(2))
+    finally:
+        O.set_sum_mode(0); O.set_tie_mode(0)
+    assert other[0][1]["hash"] != ref[0][1]["hash"] and gpu[0][1]["hash"] == ref[0][1]["hash"]
 
 
 @pytest.mark.parametrize("n,m,l_odd,x0", CASES[:3])
@@ -120,12 +130,13 @@ def test_abnormal_termination_in_lnsrch_matches():
     assert gpu[1] == ref[1] or len(gpu[0]) >= it + 4
 
 
-@pytest.mark.parametrize("n,m,l_odd", [(1000, 5, 1.0), (3001, 10, 1.0), (50001, 20, 1.0)])
-def test_ascent_direction_restart_withdraws_speculative_step_f32(n, m, l_odd):
+# (cases found with the oracle in REAL32 device-order mode, shape VEC = 2 / UNROLL = 8 of lbfgsb_b200_shape.h)
+@pytest.mark.parametrize("n,m,l_odd,x0", [(1500, 5, 1.0, 3.0), (10000, 10, 1.0, 3.0), (3001, 20, 1.0, 5.0), (25000, 20, 1.0, 3.0)])
+def test_ascent_direction_restart_withdraws_speculative_step_f32(n, m, l_odd, x0):
     """REAL32 near convergence: lnsrlb meets gd >= 0 at its first entry, the memory is reset and the iteration
     restarts from the unchanged iterate.  The run must stay a descent sequence from feasible points and end like
     the oracle's; the discrete trace is compared as far as rounding lets the two sides agree (up to the event)."""
-    gpu, ref, ev, total = _run_pair(n, m, l_odd, 3.0, np.float32, 120)
+    gpu, ref, ev, total = _run_pair(n, m, l_odd, x0, np.float32, 120)
     assert total[1] >= 1, "the oracle met no ascent direction on this problem: the case no longer covers the branch"
     fs = [r["f"] for r in gpu[0]]
     assert all(b <= a for a, b in zip(fs, fs[1:])), fs
@@ -134,5 +145,5 @@ def test_ascent_direction_restart_withdraws_speculative_step_f32(n, m, l_odd):
     # a restart shows as col dropping back to 1; rounding decides whether the GPU run meets the same ascent
     # direction, so it is required only for the case where it was observed (bit-reproducible run to run)
     cols = [r["col"] for r in gpu[0]]
-    if n == 1000:
+    if n == 3001:
         assert any(b < a for a, b in zip(cols, cols[1:])), cols

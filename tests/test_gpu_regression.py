@@ -7,8 +7,9 @@ separate passes they replace.  tests/golden/gpu_trace_digest.json was recorded o
 unfused kernels; re-recorded for the two cases whose Cauchy search crosses a round boundary when the
 breakpoint walk was split into rounds, which re-associates the prefix sums there -- every case still
 passes the oracle parity tests; and once more for n100001_m5 when formk's entering/leaving corrections got a
-register-tiled kernel, which adds the listed rows in a different order); it is compared here with a fresh run, with
-the fused passes on and off.
+register-tiled kernel, which adds the listed rows in a different order; the two REAL32 cases in round 2, when the REAL32
+shape became VEC = 2 / UNROLL = 8 -- same tiles, another thread -> element map inside a tile -- with all REAL64 digests
+unchanged by that build); it is compared here with a fresh run, with the fused passes on and off.
 """
 import json
 import os

@@ -24,6 +24,7 @@ fg = lbfgsb_b200.RosenbrockDevice(np.float32, stream=st)
 import time
 prob.profile(True)
 rows = []
+pr0 = None
 nfg = 0
 torch.cuda.synchronize(); t0 = time.perf_counter(); nfg_last = 0
 while True:
@@ -36,6 +37,8 @@ while True:
         t1 = time.perf_counter()
         rows.append((int(prob.isave[29]), int(prob.isave[27]), int(prob.isave[32]), int(prob.isave[37]), nfg - nfg_last, (t1 - t0) * 1e3, float(prob.f[0])))
         t0 = t1; nfg_last = nfg
+        if int(prob.isave[29]) == warm and pr0 is None:
+            pr0 = prob.profile_read()
         if int(prob.isave[29]) >= 40:
             break
     else:
@@ -49,3 +52,7 @@ for r in rows:
     print("  %3d  col %2d  nseg %9d  nfree %9d  fg %d  %8.2f ms  canonical %6.1f GB -> %6.0f GB/s   f %.6e" % (it, col, nseg, nfree, nf, ms, canon / 1e9, canon / ms / 1e6, f))
 pr = prob.profile_read()
 print("kernel families over the whole run (total ms, calls):", {k: (round(v["ms"], 1), v["calls"]) for k, v in pr.items() if v["ms"] > 5})
+if pr0 is not None:
+    print("kernel families after iteration %d, history full (ms per call, calls):" % warm,
+          {k: (round((v["ms"] - pr0.get(k, {"ms": 0})["ms"]) / max(1, v["calls"] - pr0.get(k, {"calls": 0})["calls"]), 2),
+               v["calls"] - pr0.get(k, {"calls": 0})["calls"]) for k, v in pr.items() if v["ms"] - pr0.get(k, {"ms": 0})["ms"] > 1})
