@@ -250,6 +250,14 @@ int lbfgsb_test_sum_f32(int64_t n, const float* a, const float* b, float* out);
 int lbfgsb_test_sort_f64(int64_t n, const double* t_dev, int32_t* order_out_dev, double* sorted_out_dev);
 /* hpsolb (:2079-2157) replayed on the device: heap built over t(1..n), popped n times; order_out = iorder of the pops */
 int lbfgsb_test_heap_order_f64(int64_t n, const double* t_dev, int32_t* order_out_dev);
+/* formk's entering/leaving corrections (src/lbfgsb.f90:1801-1851) on their own.  ws_dev, wy_dev: m columns of ldw reals;
+ * state_dev: one byte per variable, bit 0 = free now, bit 1 = free before (rows with the two bits different are listed);
+ * out_host: six [20 x 20] column-major sums over the listed rows -- entering rows: Wy_i Wy_j, Ws_i Ws_j (both for j <= i),
+ * Ws_i Wy_j, then the same three for leaving rows; i, j = position in the ring counted from `head` (1-based column). */
+int lbfgsb_test_formk_delta_f64(int64_t n, int32_t m, int32_t col, int32_t head, int64_t ldw, const double* ws_dev,
+                                const double* wy_dev, const unsigned char* state_dev, double* out_host);
+int lbfgsb_test_formk_delta_f32(int64_t n, int32_t m, int32_t col, int32_t head, int64_t ldw, const float* ws_dev,
+                                const float* wy_dev, const unsigned char* state_dev, float* out_host);
 int lbfgsb_test_dense_f64(int32_t op, int32_t m, int32_t col, double theta, double* a, double* b, double* c,
                           int32_t* info);   /* op 0 dpofa(a,lda=m,n=col) 1 dtrsl job01 2 dtrsl job11 3 bmv 4 formt (one thread);
                                                10-14 the same by one warp, as the scalar kernels run them; 15 formk's dense

@@ -998,27 +998,37 @@ __global__ void k_heap_replay_commit(Wk<T> w, WalkBuf<T> b, i64 cnt) {
 // 3 col^2 products are accumulated from it (enter and leave sums kept apart).
 // out: [gridDim][6][MMAX*MMAX] partials, finished by k_formk_delta_final.
 // ---------------------------------------------------------------------------
-#define LB_FD_GRID 592
+#define LB_FD_GRID 592      // capacity of the partial buffer; the launch uses fd_grid<T>() blocks
+// resident blocks per SM that the register count of k_formk_delta allows (REAL32: 3, REAL64: 2) x 148 SMs: one wave
+template <typename T> constexpr int fd_blocks_per_sm() { return sizeof(T) == 4 ? 3 : 2; }
+template <typename T> constexpr int fd_grid() { return 148 * fd_blocks_per_sm<T>(); }
 #define LB_FD_ROWS 32
 #define LB_FD_TB 4          // a thread owns a 4 x 4 block of (i, j) pairs of one of the three products
+#define LB_FD_LD (2 * LB_MMAX + 4)   // row stride of the shared tile: 16-byte aligned rows
 // Work decomposition: the (i, j) space of each product is cut into 4 x 4 blocks -- Wy_i Wy_j and Ws_i Ws_j only on and
 // below the diagonal (formk uses jy <= iy, :1802-1826), Ws_i Wy_j in full (:1830-1851) -- and the 256 threads are
-// NSUB copies of that block list, copy s taking the rows r = s, s + NSUB, ... of every 32-row tile.  Per row a thread
-// reads 4 + 4 values from the shared tile and does 16 multiply-adds (the old mapping read two values per
-// multiply-add and ran at the shared-memory limit).  The NSUB partial sums are added in copy order at the end.
+// NSUB copies of that block list, copy s taking every NSUB-th row of a 32-row tile.  Per row a thread reads its 4 + 4
+// values with two 128-bit shared loads (the Wy and Ws halves of a row start at multiples of four columns) and does 16
+// multiply-adds.  The rows of a tile are stored entering rows first, leaving rows after them (each in list order), and
+// processed in two loops, so that no warp diverges on the row type.  The tile is double-buffered: the gather of the
+// next 32 rows (lane = listed row, the 8 warps share the 2*col columns, all of a thread's loads in flight together) is
+// issued before the multiply-adds of the current tile and lands in the other buffer after them -- one barrier per tile.
+// The NSUB partial sums are added in copy order at the end.
 __host__ __device__ inline int fd_tiles_1d(int col) { return (col + LB_FD_TB - 1) / LB_FD_TB; }
 __host__ __device__ inline int fd_ntiles(int col) { const int t = fd_tiles_1d(col); return t * (t + 1) + t * t; }
+#define LB_FD_MAXC ((2 * LB_MMAX + 7) / 8)   // columns per warp in the gather
 template <typename T>
-__global__ void __launch_bounds__(256) k_formk_delta(Wk<T> w, const int* list, const SortCtl* ctl, T* out) {
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 3 : 2)) k_formk_delta(Wk<T> w, const int* list, const SortCtl* ctl, T* out) {
     const DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->do_delta) return;
     const int col = s->col, m = s->m, head0 = s->head - 1, col2 = 2 * col;
+    const int cpad = fd_tiles_1d(col) * LB_FD_TB;   // the Ws half of a row starts here
     const i64 nel = ctl->count;
     const i64 chunk = (nel + gridDim.x - 1) / gridDim.x;
     const i64 beg = (i64)blockIdx.x * chunk;
     i64 end = beg + chunk; if (end > nel) end = nel;
-    __shared__ T tile[LB_FD_ROWS][2 * LB_MMAX + 1];
-    __shared__ int ent[LB_FD_ROWS];
+    __shared__ __align__(16) T tile[2][LB_FD_ROWS][LB_FD_LD];
+    __shared__ int nent[2];
     __shared__ T accs[6 * LB_MMAX * LB_MMAX];
     // this thread's block of pairs
     const int t1 = fd_tiles_1d(col), ntl = fd_ntiles(col), ntri = t1 * (t1 + 1) / 2;
@@ -1032,49 +1042,100 @@ __global__ void __launch_bounds__(256) k_formk_delta(Wk<T> w, const int* list, c
         while (k >= ti + 1) { k -= ti + 1; ++ti; }
         tj = k;
     } else { blk = 2; const int k = tl - 2 * ntri; ti = k / t1; tj = k % t1; }
-    const int ca0 = ((blk == 0) ? 0 : col) + ti * LB_FD_TB;    // tile columns of the i factors
-    const int cb0 = ((blk == 1) ? col : 0) + tj * LB_FD_TB;    // ... of the j factors
+    const int ca0 = ((blk == 0) ? 0 : cpad) + ti * LB_FD_TB;    // tile columns of the i factors
+    const int cb0 = ((blk == 1) ? cpad : 0) + tj * LB_FD_TB;    // ... of the j factors
     T accE[LB_FD_TB][LB_FD_TB], accL[LB_FD_TB][LB_FD_TB];
 #pragma unroll
     for (int a = 0; a < LB_FD_TB; ++a)
 #pragma unroll
         for (int b = 0; b < LB_FD_TB; ++b) { accE[a][b] = (T)0; accL[a][b] = (T)0; }
     for (int e = threadIdx.x; e < 6 * LB_MMAX * LB_MMAX; e += 256) accs[e] = (T)0;
-    // the columns a 4-wide block reads beyond 2*col (col not a multiple of 4) must be finite: zero them once
-    for (int e = threadIdx.x; e < LB_FD_ROWS * LB_FD_TB; e += 256) { const int c = col2 + e / LB_FD_ROWS; if (c < 2 * LB_MMAX + 1) tile[e % LB_FD_ROWS][c] = (T)0; }
+    // the columns a 4-wide block reads beyond col in either half (col not a multiple of 4), and the rows beyond a short
+    // last tile, must be finite: zero both buffers once
+    for (int e = threadIdx.x; e < 2 * LB_FD_ROWS * LB_FD_LD; e += 256) (&tile[0][0][0])[e] = (T)0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    for (i64 r0 = beg; r0 < end; r0 += LB_FD_ROWS) {
+    // column c of the gather (c < col: Wy, else Ws) -> address offset of its ring column and its place in a tile row
+    i64 goff[LB_FD_MAXC]; int tcol[LB_FD_MAXC];
+#pragma unroll
+    for (int q = 0; q < LB_FD_MAXC; ++q) {
+        const int c = wrp + 8 * q;
+        const int ring = c < col ? c : c - col;
+        int pj = head0 + ring; if (pj >= m) pj -= m;
+        goff[q] = (i64)pj * w.ldw;
+        tcol[q] = c < col ? c : cpad + (c - col);
+    }
+    T pre[LB_FD_MAXC]; int pent = 0;
+    // the loads of one tile: this lane's row
+    auto fetch = [&](i64 r0) {
+        const bool have = r0 + lane < end;
+        const i64 var = have ? (i64)list[r0 + lane] : 0;
+        pent = have ? (int)(w.state[var] & 1) : -1;   // free now => entering; -1: no row
+#pragma unroll
+        for (int q = 0; q < LB_FD_MAXC; ++q) {
+            const int c = wrp + 8 * q;
+            pre[q] = (have && c < col2) ? ((c < col) ? w.wy[goff[q] + var] : w.ws[goff[q] + var]) : (T)0;
+        }
+    };
+    // entering rows first, leaving rows after them, each in list order
+    auto place = [&](int buf) {
+        const unsigned me = __ballot_sync(0xffffffffu, pent == 1), ml = __ballot_sync(0xffffffffu, pent == 0);
+        const unsigned below = (1u << lane) - 1u;
+        const int ne = __popc(me);
+        const int row = pent == 1 ? __popc(me & below) : ne + __popc(ml & below);
+        if (pent >= 0) {
+#pragma unroll
+            for (int q = 0; q < LB_FD_MAXC; ++q) if (wrp + 8 * q < col2) tile[buf][row][tcol[q]] = pre[q];
+        }
+        if (threadIdx.x == 0) nent[buf] = ne;
+    };
+    if (beg < end) { fetch(beg); place(0); }
+    __syncthreads();
+    int buf = 0;
+    for (i64 r0 = beg; r0 < end; r0 += LB_FD_ROWS, buf ^= 1) {
         const int nr = (int)((end - r0 < LB_FD_ROWS) ? (end - r0) : LB_FD_ROWS);
-        // gather: lane = listed row (its variable index is read once), the 8 warps share the 2*col columns
-        if (lane < nr) {
-            const i64 var = list[r0 + lane];
-            if (wrp == 0) ent[lane] = (w.state[var] & 1);   // free now => entering
-            for (int c = wrp; c < col2; c += 8) {
-                const int ring = c < col ? c : c - col;
-                int pj = head0 + ring; if (pj >= m) pj -= m;
-                tile[lane][c] = (c < col) ? w.wy[(i64)pj * w.ldw + var] : w.ws[(i64)pj * w.ldw + var];
-            }
-        }
-        __syncthreads();
+        const bool more = r0 + LB_FD_ROWS < end;
+        if (more) fetch(r0 + LB_FD_ROWS);
         if (active) {
-            for (int r = sub; r < nr; r += nsub) {
+            const int ne = nent[buf];
+            for (int r = sub; r < ne; r += nsub) {
                 T av[LB_FD_TB], bv[LB_FD_TB];
-#pragma unroll
-                for (int a = 0; a < LB_FD_TB; ++a) { av[a] = tile[r][ca0 + a]; bv[a] = tile[r][cb0 + a]; }
-                if (ent[r]) {
-#pragma unroll
-                    for (int a = 0; a < LB_FD_TB; ++a)
-#pragma unroll
-                        for (int b = 0; b < LB_FD_TB; ++b) accE[a][b] = accE[a][b] + av[a] * bv[b];
+                const T* row = &tile[buf][r][0];
+                if (sizeof(T) == 4) {
+                    const float4 qa = *reinterpret_cast<const float4*>(row + ca0), qb = *reinterpret_cast<const float4*>(row + cb0);
+                    av[0] = (T)qa.x; av[1] = (T)qa.y; av[2] = (T)qa.z; av[3] = (T)qa.w;
+                    bv[0] = (T)qb.x; bv[1] = (T)qb.y; bv[2] = (T)qb.z; bv[3] = (T)qb.w;
                 } else {
-#pragma unroll
-                    for (int a = 0; a < LB_FD_TB; ++a)
-#pragma unroll
-                        for (int b = 0; b < LB_FD_TB; ++b) accL[a][b] = accL[a][b] + av[a] * bv[b];
+                    const double2 qa0 = *reinterpret_cast<const double2*>(row + ca0), qa1 = *reinterpret_cast<const double2*>(row + ca0 + 2);
+                    const double2 qb0 = *reinterpret_cast<const double2*>(row + cb0), qb1 = *reinterpret_cast<const double2*>(row + cb0 + 2);
+                    av[0] = (T)qa0.x; av[1] = (T)qa0.y; av[2] = (T)qa1.x; av[3] = (T)qa1.y;
+                    bv[0] = (T)qb0.x; bv[1] = (T)qb0.y; bv[2] = (T)qb1.x; bv[3] = (T)qb1.y;
                 }
+#pragma unroll
+                for (int a = 0; a < LB_FD_TB; ++a)
+#pragma unroll
+                    for (int b = 0; b < LB_FD_TB; ++b) accE[a][b] = accE[a][b] + av[a] * bv[b];
+            }
+            for (int r = ne + sub; r < nr; r += nsub) {
+                T av[LB_FD_TB], bv[LB_FD_TB];
+                const T* row = &tile[buf][r][0];
+                if (sizeof(T) == 4) {
+                    const float4 qa = *reinterpret_cast<const float4*>(row + ca0), qb = *reinterpret_cast<const float4*>(row + cb0);
+                    av[0] = (T)qa.x; av[1] = (T)qa.y; av[2] = (T)qa.z; av[3] = (T)qa.w;
+                    bv[0] = (T)qb.x; bv[1] = (T)qb.y; bv[2] = (T)qb.z; bv[3] = (T)qb.w;
+                } else {
+                    const double2 qa0 = *reinterpret_cast<const double2*>(row + ca0), qa1 = *reinterpret_cast<const double2*>(row + ca0 + 2);
+                    const double2 qb0 = *reinterpret_cast<const double2*>(row + cb0), qb1 = *reinterpret_cast<const double2*>(row + cb0 + 2);
+                    av[0] = (T)qa0.x; av[1] = (T)qa0.y; av[2] = (T)qa1.x; av[3] = (T)qa1.y;
+                    bv[0] = (T)qb0.x; bv[1] = (T)qb0.y; bv[2] = (T)qb1.x; bv[3] = (T)qb1.y;
+                }
+#pragma unroll
+                for (int a = 0; a < LB_FD_TB; ++a)
+#pragma unroll
+                    for (int b = 0; b < LB_FD_TB; ++b) accL[a][b] = accL[a][b] + av[a] * bv[b];
             }
         }
+        if (more) place(buf ^ 1);
         __syncthreads();
     }
     // add the NSUB copies in copy order (fixed), then one partial per block of the grid

@@ -815,8 +815,8 @@ struct Engine : EngineBase {
                 k_flag_count<T, 1><<<LG>>>(w, tile_counts);
                 k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 1, tile_counts, tile_offsets, ntiles, ctl_el);
                 k_flag_write<T, 1><<<LG>>>(w, tile_offsets, wb.k0, wb.v0);
-                k_formk_delta<T><<<LB_FD_GRID, 256, 0, stream>>>(w, wb.v0, ctl_el, fd_parts);
-                k_formk_delta_final<T><<<(6 * LB_MMAX * LB_MMAX + 255) / 256, 256, 0, stream>>>(w, fd_parts, LB_FD_GRID, delta);
+                k_formk_delta<T><<<fd_grid<T>(), 256, 0, stream>>>(w, wb.v0, ctl_el, fd_parts);
+                k_formk_delta_final<T><<<(6 * LB_MMAX * LB_MMAX + 255) / 256, 256, 0, stream>>>(w, fd_parts, fd_grid<T>(), delta);
                 end(F_FORMK_DELTA, 5);
                 if (!site(site_formk(mt))) return false;
                 if (R > 1) {
@@ -1861,6 +1861,36 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_rosenbrock_batch(int nprob, i6
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
+// formk's entering/leaving corrections (:1801-1851) on their own: the compaction of the listed rows and k_formk_delta.
+// ws_dev, wy_dev: m columns of ldw reals; state_dev: one byte per variable (bit 0 free now, bit 1 free before);
+// out_host: six [LB_MMAX x LB_MMAX] column-major sums -- entering Wy'Wy, Ws'Ws, Ws'Wy, then the same for leaving rows.
+template <typename T>
+static int test_formk_delta_impl(int64_t n, int32_t m, int32_t col, int32_t head, int64_t ldw, const T* ws, const T* wy,
+                                 const unsigned char* state, T* out_host) {
+    if (n <= 0 || m <= 0 || m > LB_MMAX || col <= 0 || col > m || head < 1 || head > m || ldw < n) return 1;
+    std::vector<char> hs(sizeof(DevState<T>), 0);
+    DevState<T>* h = (DevState<T>*)hs.data();
+    h->go = 1; h->in_body = 1; h->do_delta = 1; h->col = col; h->m = m; h->head = head;
+    DevState<T>* st = nullptr; int* counts = nullptr; i64* offs = nullptr; int* list = nullptr; SortCtl* ctl = nullptr;
+    typename Real<T>::key_t* keys = nullptr; T* parts = nullptr; T* delta = nullptr;
+    const i64 tile = (i64)LBFGSB_BLOCK * Real<T>::VEC * Real<T>::UNROLL, ntiles = (n + tile - 1) / tile;
+    const size_t ne = (size_t)6 * LB_MMAX * LB_MMAX;
+    if (cudaMalloc(&st, sizeof(DevState<T>)) || cudaMalloc(&counts, 4 * (ntiles + 1)) || cudaMalloc(&offs, 8 * (ntiles + 1)) ||
+        cudaMalloc(&list, 4 * (size_t)n) || cudaMalloc(&keys, sizeof(typename Real<T>::key_t) * (size_t)n) || cudaMalloc(&ctl, sizeof(SortCtl)) ||
+        cudaMalloc(&parts, sizeof(T) * ne * LB_FD_GRID) || cudaMalloc(&delta, sizeof(T) * ne)) return 1;
+    cudaMemcpy(st, h, sizeof(DevState<T>), cudaMemcpyHostToDevice);
+    cudaMemset(delta, 0, sizeof(T) * ne);
+    Wk<T> w; memset(&w, 0, sizeof w);
+    w.n = n; w.m = m; w.ldw = ldw; w.ws = (T*)ws; w.wy = (T*)wy; w.state = (unsigned char*)state; w.s = st;
+    k_flag_count<T, 1><<<LBFGSB_GRID, LBFGSB_BLOCK>>>(w, counts);
+    k_tile_scan<T><<<1, 1024>>>(w, 1, counts, offs, ntiles, ctl);
+    k_flag_write<T, 1><<<LBFGSB_GRID, LBFGSB_BLOCK>>>(w, offs, keys, list);
+    k_formk_delta<T><<<fd_grid<T>(), 256>>>(w, list, ctl, parts);
+    k_formk_delta_final<T><<<(6 * LB_MMAX * LB_MMAX + 255) / 256, 256>>>(w, parts, fd_grid<T>(), delta);
+    cudaError_t e = cudaMemcpy(out_host, delta, sizeof(T) * ne, cudaMemcpyDeviceToHost);
+    cudaFree(st); cudaFree(counts); cudaFree(offs); cudaFree(list); cudaFree(keys); cudaFree(ctl); cudaFree(parts); cudaFree(delta);
+    return e != cudaSuccess || cudaGetLastError() != cudaSuccess;
+}
 extern "C" {
 
 int lbfgsb_b200_version(void) { return 100; }
@@ -2216,6 +2246,14 @@ int lbfgsb_test_heap_order_f64(int64_t n, const double* t, int32_t* order_out) {
     cudaError_t e = cudaDeviceSynchronize();
     cudaFree(k); cudaFree(v);
     return e != cudaSuccess || cudaGetLastError() != cudaSuccess;
+}
+int lbfgsb_test_formk_delta_f64(int64_t n, int32_t m, int32_t col, int32_t head, int64_t ldw, const double* ws, const double* wy,
+                                const unsigned char* state, double* out_host) {
+    return test_formk_delta_impl<double>(n, m, col, head, ldw, ws, wy, state, out_host);
+}
+int lbfgsb_test_formk_delta_f32(int64_t n, int32_t m, int32_t col, int32_t head, int64_t ldw, const float* ws, const float* wy,
+                                const unsigned char* state, float* out_host) {
+    return test_formk_delta_impl<float>(n, m, col, head, ldw, ws, wy, state, out_host);
 }
 int lbfgsb_test_dense_f64(int32_t op, int32_t m, int32_t col, double theta, double* a, double* b, double* c, int32_t* info) {
     int* dinfo; DevState<double>* st;

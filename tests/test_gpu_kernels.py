@@ -281,3 +281,41 @@ def test_dcsrch_sequence_bitwise(L):
         assert len(got) == len(ref_steps)
         for (a, sa), (b, sb) in zip(got, ref_steps):
             assert a[:2] == b[:2] and sa == sb, (got, ref_steps)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m,col,head,frac", [(1000, 5, 5, 1, 0.5), (70001, 10, 7, 4, 0.3), (300000, 20, 20, 13, 0.5),
+                                               (4099, 20, 3, 20, 1.0), (50000, 10, 10, 1, 0.001), (33, 7, 6, 2, 0.0)])
+def test_formk_delta_matches_the_reference_loops(L, n, m, col, head, frac, dtype):
+    """formk's corrections of the old blocks of WN1 for the variables that entered or left the free set
+    (src/lbfgsb.f90:1801-1851): the ordered compaction of the listed rows and k_formk_delta on random enter/leave
+    sets, against the reference's loops restated here in float64 -- for every (iy, jy), jy <= iy:
+    sum over entering rows of wy(k1,ipntr)*wy(k1,jpntr) and ws(k1,ipntr)*ws(k1,jpntr) (:1809-1813), the same over
+    leaving rows (:1815-1819); for every (is, jy): ws(k1,ipntr)*wy(k1,jpntr) over each list (:1836-1844).
+    The kernel adds the rows in another order, so the gate is a rounding bound: a few hundred eps times the sum of
+    the magnitudes of the terms (in REAL64 far below the size of a single term: a missing or doubled row fails)."""
+    rng = np.random.default_rng(n + 31 * m + col)
+    ldw = (n + 31) // 32 * 32
+    ws = rng.standard_normal((m, ldw)).astype(dtype)
+    wy = rng.standard_normal((m, ldw)).astype(dtype)
+    u = rng.uniform(0.0, 1.0, n)
+    state = np.where(u < frac / 2, 1, np.where(u < frac, 2, np.where(u < (1 + frac) / 2, 0, 3))).astype(np.uint8)
+    state |= (rng.integers(0, 2, n).astype(np.uint8) << 2)    # bit 2 belongs to another pass: must be ignored
+    out = np.zeros(6 * 20 * 20, dtype=dtype)
+    wsd, wyd, std = _dev(ws), _dev(wy), _dev(state)
+    fn = L.lbfgsb_test_formk_delta_f64 if dtype == np.float64 else L.lbfgsb_test_formk_delta_f32
+    fn.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert fn(n, m, col, head, ldw, _vp(wsd), _vp(wyd), _vp(std), out.ctypes.data_as(C.c_void_p)) == 0
+    out = out.reshape(6, 20, 20)             # [sum][j][i]: element i + 20 j
+    ring = [(head - 1 + i) % m for i in range(col)]
+    eps = np.finfo(dtype).eps
+    for which, mask in ((0, (state & 3) == 1), (1, (state & 3) == 2)):     # entering, leaving
+        Y = wy[ring][:, :n][:, mask].astype(np.float64)
+        S = ws[ring][:, :n][:, mask].astype(np.float64)
+        for blk, (A, B) in enumerate(((Y, Y), (S, S), (S, Y))):
+            ref = A @ B.T                     # ref[i, j] = sum_k A[i, k] B[j, k]
+            mag = np.abs(A) @ np.abs(B).T
+            got = out[3 * which + blk].T[:col, :col].astype(np.float64)
+            for i in range(col):
+                for j in range(col if blk == 2 else i + 1):
+                    assert abs(got[i, j] - ref[i, j]) <= 600 * eps * mag[i, j] + 1e-300, (which, blk, i, j, got[i, j], ref[i, j])

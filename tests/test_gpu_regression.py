@@ -9,7 +9,8 @@ breakpoint walk was split into rounds, which re-associates the prefix sums there
 passes the oracle parity tests; and once more for n100001_m5 when formk's entering/leaving corrections got a
 register-tiled kernel, which adds the listed rows in a different order; the two REAL32 cases in round 2, when the REAL32
 shape became VEC = 2 / UNROLL = 8 -- same tiles, another thread -> element map inside a tile -- with all REAL64 digests
-unchanged by that build); it is compared here with a fresh run, with the fused passes on and off.
+unchanged by that build; and the three cases with entering/leaving rows again when k_formk_delta got
+sorted, double-buffered tiles and a one-wave grid -- other grouping of the listed rows); it is compared here with a fresh run, with the fused passes on and off.
 """
 import json
 import os
