@@ -233,7 +233,8 @@ __device__ void classify(Wk<T>& w, BatchSm<T>& sm) {
             int iw = w.iwhere[i];
             T d = (T)0; bool mv = false;
             const T x = w.x[i];
-            cauchy_classify_one<T>(x, w.l[i], w.u[i], w.g[i], w.nbd[i], iw, d, mv, acc[2 * MT], cs, i);
+            T tbp;
+            cauchy_classify_one<T>(x, w.l[i], w.u[i], w.g[i], w.nbd[i], iw, d, mv, acc[2 * MT], cs, i, tbp);
             w.iwhere[i] = iw; w.d[i] = d; w.z[i] = x;
             if (mv) {
 #pragma unroll

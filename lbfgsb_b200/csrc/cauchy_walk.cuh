@@ -92,8 +92,8 @@ __device__ __forceinline__ bool bp_orig(T d, T g, T x, T l, T u, int nb, int iw,
 }
 
 // ---------------------------------------------------------------------------
-// Ordered compaction.  MODE 0: breakpoints -> (key = bits of t, val = variable);
-// MODE 1: entering / leaving variables -> val = variable (state bits tell which).
+// Ordered compaction.  MODE 1: entering / leaving variables -> val = variable (state bits tell which);
+// MODE 2: every breakpoint of this cauchy call, passed ones included -> (key = bits of t, val = variable).
 // ---------------------------------------------------------------------------
 template <typename T, int MODE>
 __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_count(Wk<T> w, int* tile_counts) {
@@ -115,16 +115,10 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_count(Wk<T> w, int* tile_
             if (base >= n) continue;
             if (MODE == 2) {   // every breakpoint of this cauchy call, passed ones included (heap replay)
                 T d[VEC], g[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC], iw[VEC];
-                ldv<T>(w.d, base, n, d); ldv<T>(w.g, base, n, g); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l);
+                ldv<T>(w.g, base, n, g); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l);
                 ldv<T>(w.u, base, n, u); ldvi<T>(w.nbd, base, n, nb); ldvi<T>(w.iwhere, base, n, iw);
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) { T t; if (base + v < n && bp_orig<T>(d[v], g[v], x[v], l[v], u[v], nb[v], iw[v], t)) c++; }
-            } else if (MODE == 0) {
-                T d[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC];
-                ldv<T>(w.d, base, n, d); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
-                ldvi<T>(w.nbd, base, n, nb);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) { T t; if (base + v < n && bp_of<T>(d[v], x[v], l[v], u[v], nb[v], t)) c++; }
+                for (int v = 0; v < VEC; ++v) { T t; d[v] = cauchy_dir<T>(iw[v], g[v]); if (base + v < n && bp_orig<T>(d[v], g[v], x[v], l[v], u[v], nb[v], iw[v], t)) c++; }
             } else {
                 int st[VEC];
                 ldvb<T>(w.state, base, n, st);
@@ -134,6 +128,35 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_count(Wk<T> w, int* tile_
         }
         i64 r = block_isum(c, smi);
         if (threadIdx.x == 0) tile_counts[tl] = (int)r;
+    }
+}
+
+// MODE 1 count on its own: the state bytes of a tile are 2 or 4 KB -- one warp per tile, 16 bytes per load, no block-wide
+// synchronisation (the list is short or empty in most iterations, and this pass is then all that the corrections cost).
+template <typename T>
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_el_count(Wk<T> w, int* tile_counts) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->do_delta) return;
+    const i64 n = w.n;
+    const i64 tile = (i64)LBFGSB_BLOCK * Real<T>::VEC * Real<T>::UNROLL;
+    const i64 ntiles = (n + tile - 1) / tile;
+    const int lane = threadIdx.x & 31;
+    const i64 wid = (i64)blockIdx.x * (LBFGSB_BLOCK / 32) + (threadIdx.x >> 5), nw = (i64)gridDim.x * (LBFGSB_BLOCK / 32);
+    for (i64 tl = wid; tl < ntiles; tl += nw) {
+        const i64 t0 = tl * tile;
+        int c = 0;
+        for (i64 o = (i64)lane * 16; o < tile; o += 32 * 16) {
+            const i64 i = t0 + o;
+            if (i + 16 <= n) {   // state is allocated with a multiple of 32 entries and 256-byte aligned: 16-byte loads are aligned
+                const uint4 q = *reinterpret_cast<const uint4*>(w.state + i);
+                c += __popc((q.x ^ (q.x >> 1)) & 0x01010101u) + __popc((q.y ^ (q.y >> 1)) & 0x01010101u) +
+                     __popc((q.z ^ (q.z >> 1)) & 0x01010101u) + __popc((q.w ^ (q.w >> 1)) & 0x01010101u);
+            } else {
+                for (i64 k = i; k < n && k < i + 16; ++k) c += el_of(w.state[k]) ? 1 : 0;
+            }
+        }
+        c = warp_sum<int>(c);
+        if (lane == 0) tile_counts[tl] = c;
     }
 }
 
@@ -159,7 +182,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(Wk<T> w, int mode, const int
 }
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_write(Wk<T> w, const i64* tile_offsets,
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_write(Wk<T> w, const int* tile_counts, const i64* tile_offsets,
                                                             typename Real<T>::key_t* keys, int* vals) {
     constexpr int VEC = Real<T>::VEC;
     const DevState<T>* s = w.s;
@@ -172,6 +195,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_write(Wk<T> w, const i64*
     const i64 ntiles = (n + tile - 1) / tile;
     __shared__ i64 sm[33];
     for (i64 tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        if (tile_counts[tl] == 0) continue;   // nothing to write from this tile (the common case: short lists)
         i64 run = tile_offsets[tl];
 #pragma unroll 1
         for (int k = 0; k < Real<T>::UNROLL; ++k) {
@@ -183,18 +207,13 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_flag_write(Wk<T> w, const i64*
             if (base < n) {
                 if (MODE == 2) {
                     T d[VEC], g[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC], iw[VEC];
-                    ldv<T>(w.d, base, n, d); ldv<T>(w.g, base, n, g); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l);
+                    ldv<T>(w.g, base, n, g); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l);
                     ldv<T>(w.u, base, n, u); ldvi<T>(w.nbd, base, n, nb); ldvi<T>(w.iwhere, base, n, iw);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v)
+                    for (int v = 0; v < VEC; ++v) {
+                        d[v] = cauchy_dir<T>(iw[v], g[v]);
                         if (base + v < n && bp_orig<T>(d[v], g[v], x[v], l[v], u[v], nb[v], iw[v], tv[v])) { fl[v] = true; c++; }
-                } else if (MODE == 0) {
-                    T d[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC];
-                    ldv<T>(w.d, base, n, d); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
-                    ldvi<T>(w.nbd, base, n, nb);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v)
-                        if (base + v < n && bp_of<T>(d[v], x[v], l[v], u[v], nb[v], tv[v])) { fl[v] = true; c++; }
+                    }
                 } else {
                     int st[VEC];
                     ldvb<T>(w.state, base, n, st);
@@ -366,7 +385,7 @@ __global__ void __launch_bounds__(LB_WB) k_walk_gather(Wk<T> w, WalkBuf<T> b, i6
     T wl[2 * LB_MMAX], vl[2 * LB_MMAX];
     if (ok) {
         const int var = cur_vals<T>(b)[start + j];
-        dl = w.d[var];
+        dl = cauchy_dir<T>(w.iwhere[var], w.g[var]);   // cauchy's d (:1294-1298), never stored
         ze = (dl > (T)0) ? (w.u[var] - w.x[var]) : (w.l[var] - w.x[var]);   // zibp (:1427,:1431)
         b.delta[j] = dl; b.zeta[j] = ze;
         if (col > 0) {
@@ -625,9 +644,18 @@ __device__ __forceinline__ bool bp_rem(const BpRange& r, unsigned long long k) {
 __device__ __forceinline__ bool bp_in(const BpRange& r, unsigned long long k) { return bp_rem(r, k) && k <= r.hi; }
 struct RoundRec { i64 count, rem; unsigned long long kmin; i64 pad; };   // of one rank
 
+// The breakpoint of every variable is stored once per cauchy call, in front of the first round (k_bp_count<T, true>):
+// w.r -- dead between subsm of one iteration and cmprlb of the next -- holds t_i, or -1 where the variable has none
+// (or has been fixed by an earlier round, k_walk_fix).  The passes of a round then read 8 bytes per variable
+// instead of the 36 of d, x, l, u, nbd.
+//
 // count pass of a round: per tile the breakpoints in range; per block the number of breakpoints not yet
 // passed (key > lo) and the smallest of them.  ipart slot 0: rem, slot 1: kmin (keys of t >= 0 fit in i64).
-template <typename T>
+// FIRST: the first round of a call whose per-variable pass did not expect a walk (Wk::bp_hint off) -- also writes
+// xcp = x (:1341; the walk scatters the bounds of the fixed variables into it) and the breakpoints themselves.
+// cauchy's d (:1294-1298) is never stored: it is -g where iwhere is 0 or -1 and 0 elsewhere (cauchy_dir), also after
+// the walk has fixed a variable (iwhere = 1 / 2).
+template <typename T, bool FIRST>
 __global__ void __launch_bounds__(LBFGSB_BLOCK) k_bp_count(Wk<T> w, BpRange rg, int* tile_counts) {
     constexpr int VEC = Real<T>::VEC;
     const DevState<T>* s = w.s;
@@ -643,14 +671,23 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_bp_count(Wk<T> w, BpRange rg, 
         for (int k = 0; k < Real<T>::UNROLL; ++k) {
             const i64 base = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC) + (i64)threadIdx.x * VEC;
             if (base >= n) continue;
-            T d[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC];
-            ldv<T>(w.d, base, n, d); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
-            ldvi<T>(w.nbd, base, n, nb);
+            T tk[VEC];
+            if (FIRST) {
+                int iw[VEC], nb[VEC]; T g[VEC], x[VEC], l[VEC], u[VEC], d[VEC];
+                ldvi<T>(w.iwhere, base, n, iw); ldv<T>(w.g, base, n, g); ldv<T>(w.x, base, n, x);
+                ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u); ldvi<T>(w.nbd, base, n, nb);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    d[v] = cauchy_dir<T>(iw[v], g[v]);
+                    T t;
+                    tk[v] = (base + v < n && bp_of<T>(d[v], x[v], l[v], u[v], nb[v], t)) ? t : (T)-1;
+                }
+                stv<T>(w.z, base, n, x); stv<T>(w.r, base, n, tk);
+            } else ldv<T>(w.r, base, n, tk);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                T t;
-                if (base + v < n && bp_of<T>(d[v], x[v], l[v], u[v], nb[v], t)) {
-                    const unsigned long long key = (unsigned long long)KeyBits<T>::to(t);
+                if (base + v < n && tk[v] >= (T)0) {
+                    const unsigned long long key = (unsigned long long)KeyBits<T>::to(tk[v]);
                     if (bp_rem(rg, key)) { rem++; if ((i64)key < kmin) kmin = (i64)key; }
                     if (bp_in(rg, key)) c++;
                 }
@@ -672,7 +709,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_bp_count(Wk<T> w, BpRange rg, 
 
 // ordered compaction of the breakpoints in range -> (key, local variable)
 template <typename T>
-__global__ void __launch_bounds__(LBFGSB_BLOCK) k_bp_write(Wk<T> w, BpRange rg, const i64* tile_offsets,
+__global__ void __launch_bounds__(LBFGSB_BLOCK) k_bp_write(Wk<T> w, BpRange rg, const int* tile_counts, const i64* tile_offsets,
                                                           typename Real<T>::key_t* keys, int* vals) {
     constexpr int VEC = Real<T>::VEC;
     const DevState<T>* s = w.s;
@@ -682,6 +719,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_bp_write(Wk<T> w, BpRange rg, 
     const i64 ntiles = (n + tile - 1) / tile;
     __shared__ i64 sm[33];
     for (i64 tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        if (tile_counts[tl] == 0) continue;   // nothing to write from this tile (the common case: short lists)
         i64 run = tile_offsets[tl];
 #pragma unroll 1
         for (int k = 0; k < Real<T>::UNROLL; ++k) {
@@ -691,13 +729,10 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_bp_write(Wk<T> w, BpRange rg, 
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { fl[v] = false; tv[v] = (T)0; }
             if (base < n) {
-                T d[VEC], x[VEC], l[VEC], u[VEC]; int nb[VEC];
-                ldv<T>(w.d, base, n, d); ldv<T>(w.x, base, n, x); ldv<T>(w.l, base, n, l); ldv<T>(w.u, base, n, u);
-                ldvi<T>(w.nbd, base, n, nb);
+                ldv<T>(w.r, base, n, tv);   // the stored breakpoints (k_bp_count<T, true>)
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
-                    if (base + v < n && bp_of<T>(d[v], x[v], l[v], u[v], nb[v], tv[v]) &&
-                        bp_in(rg, (unsigned long long)KeyBits<T>::to(tv[v]))) { fl[v] = true; c++; }
+                    if (base + v < n && tv[v] >= (T)0 && bp_in(rg, (unsigned long long)KeyBits<T>::to(tv[v]))) { fl[v] = true; c++; }
             }
             i64 tot;
             i64 pos = run + block_excl_scan<i64>(c, sm, tot);
@@ -871,10 +906,11 @@ __global__ void __launch_bounds__(256) k_walk_fix(Wk<T> w, WalkBuf<T> b) {
     const int* vals = cur_vals<T>(b);
     for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < J; j += (i64)gridDim.x * blockDim.x) {
         const int var = vals[j];
-        const T dl = w.d[var];
+        const T dl = cauchy_dir<T>(w.iwhere[var], w.g[var]);
+        // d = 0 from here on is implied by iwhere = 1 / 2 (cauchy_dir)
         if (dl > (T)0) { w.z[var] = w.u[var]; w.iwhere[var] = 2; }
         else { w.z[var] = w.l[var]; w.iwhere[var] = 1; }
-        w.d[var] = (T)0;
+        w.r[var] = (T)-1;   // no breakpoint any more (what bp_of gives for d = 0)
     }
 }
 

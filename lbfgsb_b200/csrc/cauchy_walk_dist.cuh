@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) k_dw_pack(Wk<T> w, WalkBuf<T> b, T* rec, 
     const int* vals = cur_vals<T>(b);
     for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += (i64)gridDim.x * blockDim.x) {
         const int var = vals[j];
-        const T dl = w.d[var];
+        const T dl = cauchy_dir<T>(w.iwhere[var], w.g[var]);
         T* r = rec + j * rs;
         r[0] = KeyBits<T>::from(keys[j]);
         r[1] = dl;
@@ -284,9 +284,9 @@ __global__ void __launch_bounds__(256) k_dw_fix(Wk<T> w, WalkBuf<T> b, const DwC
     const int* vals = cur_vals<T>(b);
     for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < J; j += (i64)gridDim.x * blockDim.x) {
         const int var = vals[j];
-        const T dl = w.d[var];
+        const T dl = cauchy_dir<T>(w.iwhere[var], w.g[var]);
         if (dl > (T)0) { w.z[var] = w.u[var]; w.iwhere[var] = 2; }
         else { w.z[var] = w.l[var]; w.iwhere[var] = 1; }
-        w.d[var] = (T)0;
+        w.r[var] = (T)-1;   // no breakpoint any more (cauchy_walk.cuh: the stored breakpoints)
     }
 }

@@ -158,6 +158,10 @@ struct Engine : EngineBase {
     std::vector<cudaEvent_t> pool;
     double fam_ms[F_COUNT]; i64 fam_calls[F_COUNT];
     bool x_changed = false, g_changed = false;
+    // breakpoint walks tend to come in runs of iterations: after an iteration that needed one, cauchy's per-variable pass of
+    // the next iteration also stores every breakpoint and xcp = x (Wk::bp_hint), and the walk's first pass reads 8 bytes
+    // per variable instead of recomputing them from x, g, l, u, nbd, iwhere
+    bool walked_prev = false, walked_now = false, body_ran = false, bp_hint_ok = true;
     bool started = false;            // this workspace has seen task = 'START' (or a checkpoint of a started run)
 
     // records over peer memory (kernels_dense.cuh: P2PBuf)
@@ -245,6 +249,7 @@ struct Engine : EngineBase {
         fast = fused;   // the fast NEW_X pipeline is built from the fused passes
         if (const char* e = getenv("LBFGSB_B200_NO_FAST")) { if (e[0] == '1') fast = false; }
         if (const char* e = getenv("LBFGSB_B200_NO_TIMERS")) { if (e[0] == '1') timers = false; }
+        if (const char* e = getenv("LBFGSB_B200_NO_BP_HINT")) { if (e[0] == '1') bp_hint_ok = false; }
         if (!(mt == 5 ? set_smem_attrs<5>() : (mt == 10 ? set_smem_attrs<10>() : set_smem_attrs<20>()))) return false;
         for (int q = 0; q < F_COUNT; ++q) { fam_ms[q] = 0; fam_calls[q] = 0; }
         if (st) stream = st;
@@ -491,9 +496,11 @@ struct Engine : EngineBase {
     // One round over the breakpoints with keys in rg.  Returns 0: go on with the next range, 1: the search is
     // closed, 2: the exit fell inside a group of equal breakpoints and the round must be redone in heap order,
     // -1: error.
-    int run_round(const BpRange& rg) {
+    int run_round(const BpRange& rg, bool first = false) {
         begin(F_WALK_COMPACT);
-        k_bp_count<T><<<LG>>>(w, rg, tile_counts);
+        // the first round of a cauchy call also writes d, xcp = x and every variable's breakpoint (cauchy_walk.cuh)
+        if (first) k_bp_count<T, true><<<LG>>>(w, rg, tile_counts);
+        else k_bp_count<T, false><<<LG>>>(w, rg, tile_counts);
         k_walk_round_local<T><<<1, 1024, 0, stream>>>(w, tile_counts, tile_offsets, ntiles, wb.ctl, rr_local);
         end(F_WALK_COMPACT, 2);
         if (R > 1 && !allgather(rr_local, rr_all, sizeof(RoundRec))) return -1;
@@ -501,7 +508,7 @@ struct Engine : EngineBase {
         if (!sync_state()) return -1;
         if (s_host->walk_closed) return 1;
         if (s_host->walk_rcount > 0) {
-            begin(F_WALK_COMPACT); k_bp_write<T><<<LG>>>(w, rg, tile_offsets, wb.k0, wb.v0); end(F_WALK_COMPACT);
+            begin(F_WALK_COMPACT); k_bp_write<T><<<LG>>>(w, rg, tile_counts, tile_offsets, wb.k0, wb.v0); end(F_WALK_COMPACT);
             begin(F_WALK_SORT); enqueue_sort(wb.k0, wb.k1, wb.v0, wb.v1, wb.ctl, s_host->walk_lcount); end(F_WALK_SORT, 0);
             if (R > 1) { if (!round_scan_sharded()) return -1; }
             else if (!round_scan_single(s_host->walk_lcount)) return -1;
@@ -528,7 +535,7 @@ struct Engine : EngineBase {
         begin(F_WALK_COMPACT);
         k_flag_count<T, 2><<<LG>>>(w, tile_counts);
         k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 2, tile_counts, tile_offsets, ntiles, wb.ctl);
-        k_flag_write<T, 2><<<LG>>>(w, tile_offsets, wb.k0, wb.v0);
+        k_flag_write<T, 2><<<LG>>>(w, tile_counts, tile_offsets, wb.k0, wb.v0);
         end(F_WALK_COMPACT, 3);
         if (s_host->nbreak <= LB_TIE_DEVICE_MAX) {
             begin(F_WALK_SORT); k_heap_replay<T><<<1, 1024, 0, stream>>>(w, wb); end(F_WALK_SORT);
@@ -593,10 +600,12 @@ struct Engine : EngineBase {
         }
         his[nr++] = 0xffffffffffffffffULL;
         BpRange rg; rg.lo = 0; rg.lo_valid = 0; rg.hi = 0;
+        bool first = true;
         for (int r = 0; r < nr;) {
             rg.hi = his[r];
             if (rg.lo_valid && rg.hi <= rg.lo) { ++r; continue; }
-            int st = run_round(rg);
+            int st = run_round(rg, first && !w.bp_hint);
+            first = false;
             if (st < 0) return false;
             if (st == 1) break;
             if (st == 2) {
@@ -773,6 +782,7 @@ struct Engine : EngineBase {
     // (common.cuh PAUSE_*; the device state is then exactly what this sequence would have produced up to there,
     // and s_host is current).
     bool enqueue_body(int from = PAUSE_NONE) {
+        body_ran = true;
         for (;;) {
             bool gf = false;   // cauchy's tail and freev run inside k_formk_cmprlb (decided by s_cauchy)
             if (from <= PAUSE_CLASSIFY) {
@@ -785,8 +795,8 @@ struct Engine : EngineBase {
                 if (s_host->cnstnd) {
                     if (from != PAUSE_WALK && !sync_state()) return false;
                     if (s_host->go && s_host->in_body && s_host->need_walk) {
-                        begin(F_WALK_COMPACT); k_materialize<T><<<LG>>>(w); end(F_WALK_COMPACT);
-                        if (!enqueue_walk_rounds()) return false;
+                        walked_now = true;
+                        if (!enqueue_walk_rounds()) return false;   // (its first count pass writes xcp and the breakpoints)
                     }
                     gf = fused && s_host->go && s_host->in_body && s_host->fuse_gf;
                 }
@@ -812,9 +822,9 @@ struct Engine : EngineBase {
             if (from <= PAUSE_DELTA) {
                 if (from == PAUSE_DELTA) phase(PH_SUBSPACE);
                 begin(F_FORMK_DELTA);
-                k_flag_count<T, 1><<<LG>>>(w, tile_counts);
+                k_el_count<T><<<LG>>>(w, tile_counts);
                 k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 1, tile_counts, tile_offsets, ntiles, ctl_el);
-                k_flag_write<T, 1><<<LG>>>(w, tile_offsets, wb.k0, wb.v0);
+                k_flag_write<T, 1><<<LG>>>(w, tile_counts, tile_offsets, wb.k0, wb.v0);
                 k_formk_delta<T><<<fd_grid<T>(), 256, 0, stream>>>(w, wb.v0, ctl_el, fd_parts);
                 k_formk_delta_final<T><<<(6 * LB_MMAX * LB_MMAX + 255) / 256, 256, 0, stream>>>(w, fd_parts, fd_grid<T>(), delta);
                 end(F_FORMK_DELTA, 5);
@@ -920,6 +930,8 @@ struct Engine : EngineBase {
     // entry: 0 START, 1 FG_START, 2 FG_LNSRCH, 3 NEW_X, 4 STOP (cpu restore flag in aux), 5 other
     bool call(int entry, int aux, T* x, const T* l, const T* u, const int* nbd, T* f, T* g, T factr, T pgtol) {
         w.x = x; w.l = l; w.u = u; w.nbd = nbd; w.g = g;
+        w.bp_hint = (entry == 3 && walked_prev && bp_hint_ok) ? 1 : 0;
+        walked_now = false; body_ran = false;
         x_changed = false; g_changed = false;
         for (auto& mk : marks) pool.push_back(mk.e);
         marks.clear();
@@ -995,6 +1007,7 @@ struct Engine : EngineBase {
             if (!enqueue_body()) return false;
         }
         *f = s_host->f;
+        if (body_ran) walked_prev = walked_now;
         resolve_phases();
         return check_launch();
     }
@@ -1882,9 +1895,9 @@ static int test_formk_delta_impl(int64_t n, int32_t m, int32_t col, int32_t head
     cudaMemset(delta, 0, sizeof(T) * ne);
     Wk<T> w; memset(&w, 0, sizeof w);
     w.n = n; w.m = m; w.ldw = ldw; w.ws = (T*)ws; w.wy = (T*)wy; w.state = (unsigned char*)state; w.s = st;
-    k_flag_count<T, 1><<<LBFGSB_GRID, LBFGSB_BLOCK>>>(w, counts);
+    k_el_count<T><<<LBFGSB_GRID, LBFGSB_BLOCK>>>(w, counts);
     k_tile_scan<T><<<1, 1024>>>(w, 1, counts, offs, ntiles, ctl);
-    k_flag_write<T, 1><<<LBFGSB_GRID, LBFGSB_BLOCK>>>(w, offs, keys, list);
+    k_flag_write<T, 1><<<LBFGSB_GRID, LBFGSB_BLOCK>>>(w, counts, offs, keys, list);
     k_formk_delta<T><<<fd_grid<T>(), 256>>>(w, list, ctl, parts);
     k_formk_delta_final<T><<<(6 * LB_MMAX * LB_MMAX + 255) / 256, 256>>>(w, parts, fd_grid<T>(), delta);
     cudaError_t e = cudaMemcpy(out_host, delta, sizeof(T) * ne, cudaMemcpyDeviceToHost);

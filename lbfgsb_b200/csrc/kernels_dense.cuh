@@ -432,7 +432,7 @@ template <typename T> __device__ inline void w_cauchy(DevState<T>* s, const Red<
         s->dtm = -s->f1 / s->f2;
         s->nseg = 1;
         if (s->nbreak != 0 && !(s->dtm < s->bkmin)) {
-            // the first breakpoint is reached: the sorted walk takes over (k_materialize writes d, xcp = x first)
+            // the first breakpoint is reached: the sorted walk takes over (its first count pass writes d, xcp = x first)
             s->need_walk = 1; s->lazy_gcp = 0;
             for (int j = 0; j < col2; ++j) { s->p0[j] = s->p[j]; s->walkA[j] = zero; s->walkB[j] = zero; }
             s->walk_f1 = s->f1; s->walk_f2 = s->f2; s->walk_tlast = zero; s->walk_tprev2 = zero;

@@ -25,6 +25,8 @@ struct Wk {               // workspace + user vectors of one problem (device poi
     i64* ipart2;          //   (cauchy's site and the W'Zr site always live here)
     DevState<T>* s;
     T* x; const T* l; const T* u; const int* nbd; T* g;   // caller's vectors
+    int bp_hint;          // cauchy's per-variable pass also stores every breakpoint (in r) and xcp = x (in z): the previous
+                          // iteration needed a breakpoint walk, so this one probably does (cauchy_walk.cuh)
 };
 
 #define LB_SLOT(part, k) ((part) + (i64)(k) * LBFGSB_GRID)
@@ -156,23 +158,7 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_projgr(Wk<T> w) {
 template <typename T>
 __device__ __forceinline__ T cauchy_dir(int iw, T g) { return (iw == 0 || iw == -1) ? -g : (T)0; }
 
-// cauchy's d and xcp = x written out (they are otherwise implied by iwhere, g, x): the breakpoint walk
-// reads d and scatters into d, xcp.  Runs only in front of that walk.
-template <typename T>
-__global__ void __launch_bounds__(LBFGSB_BLOCK) k_materialize(Wk<T> w) {
-    constexpr int VEC = Real<T>::VEC;
-    const DevState<T>* s = w.s;
-    if (!s->go || !s->in_body || !s->need_walk) return;
-    const i64 n = w.n;
-    LB_FOR_TILES(T, n, base) {
-        int iw[VEC]; T g[VEC], x[VEC], d[VEC];
-        ldvi<T>(w.iwhere, base, n, iw); ldv<T>(w.g, base, n, g); ldv<T>(w.x, base, n, x);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) d[v] = cauchy_dir<T>(iw[v], g[v]);
-        stv<T>(w.d, base, n, d); stv<T>(w.z, base, n, x);
-    }
-}
-
+// (cauchy's d and xcp = x are written out only in front of a breakpoint walk: k_bp_count<T, true>, cauchy_walk.cuh)
 template <typename T>
 __global__ void __launch_bounds__(LBFGSB_BLOCK) k_gcp_freev(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
@@ -198,11 +184,11 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_gcp_freev(Wk<T> w) {
                 for (int v = 0; v < VEC; ++v) z[v] = z[v] + tsum * cauchy_dir<T>(iw[v], g[v]);
             }
             stv<T>(w.z, base, n, z);
-        } else if (axpy) {
-            T d[VEC], z[VEC];
-            ldv<T>(w.d, base, n, d); ldv<T>(w.z, base, n, z);
+        } else if (axpy) {   // after a breakpoint walk: xcp holds the bounds of the fixed variables, whose iwhere is 1 or 2 (d = 0)
+            T g[VEC], z[VEC];
+            ldv<T>(w.g, base, n, g); ldv<T>(w.z, base, n, z);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) z[v] = z[v] + tsum * d[v];
+            for (int v = 0; v < VEC; ++v) z[v] = z[v] + tsum * cauchy_dir<T>(iw[v], g[v]);
             stv<T>(w.z, base, n, z);
         }
 #pragma unroll

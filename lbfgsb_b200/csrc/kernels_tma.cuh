@@ -121,7 +121,8 @@ struct CauchyScan {
 };
 template <typename T>
 __device__ __forceinline__ void cauchy_classify_one(T x, T l, T u, T g, int nb, int& iw, T& d, bool& mv, T& d2acc,
-                                                    CauchyScan<T>& cs, i64 gidx) {
+                                                    CauchyScan<T>& cs, i64 gidx, T& tbp) {
+    tbp = (T)-1;   // the variable's breakpoint, -1: none
     const T neggi = -g;
     T tl = (T)0, tu = (T)0;
     if (iw != 3 && iw != -1) {
@@ -142,6 +143,7 @@ __device__ __forceinline__ void cauchy_classify_one(T x, T l, T u, T g, int nb, 
         if (nb <= 2 && nb != 0 && neggi < (T)0) { tb = tl / (-neggi); hasb = true; }
         else if (nb >= 2 && neggi > (T)0) { tb = tu / neggi; hasb = true; }
         if (hasb) {
+            tbp = tb;
             cs.nbr++;
             if (tb < cs.bk) { cs.bk = tb; cs.ibk = gidx; }   // strict <: lowest index among ties (:1310)
         } else {
@@ -219,13 +221,14 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_cauchy_classify(Wk<T> w) 
         int nb[VEC], iw[VEC];
         lds_real<T>(sb, OX, lt, x); lds_real<T>(sb, OG, lt, g); lds_real<T>(sb, OL, lt, l); lds_real<T>(sb, OU, lt, u);
         lds_int<T>(sb, ONB, lt, nb); lds_int<T>(sb, OIW, lt, iw);
-        bool mv[VEC];
+        bool mv[VEC]; T tk[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            mv[v] = false; d[v] = (T)0;
-            if (base + v < n) cauchy_classify_one<T>(x[v], l[v], u[v], g[v], nb[v], iw[v], d[v], mv[v], acc[2 * MT], cs, base + v + w.off);
+            mv[v] = false; d[v] = (T)0; tk[v] = (T)-1;
+            if (base + v < n) cauchy_classify_one<T>(x[v], l[v], u[v], g[v], nb[v], iw[v], d[v], mv[v], acc[2 * MT], cs, base + v + w.off, tk[v]);
         }
-        // d and xcp = x are not written: they follow from iwhere, g and x (lazy_gcp; k_materialize writes them
+        if (w.bp_hint) { stv<T>(w.r, base, n, tk); stv<T>(w.z, base, n, x); }   // in front of a probable walk
+        // d and xcp = x are not written: they follow from iwhere, g and x (lazy_gcp; k_bp_count<T, true> writes them
         // out in front of a breakpoint walk)
         stvi<T>(w.iwhere, base, n, iw);
 #pragma unroll
@@ -560,12 +563,13 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_update_classify(Wk<T> w) 
         int nb[VEC], iw[VEC];
         lds_real<T>(sb, OX, lt, x); lds_real<T>(sb, OL, lt, l); lds_real<T>(sb, OU, lt, u);
         lds_int<T>(sb, ONB, lt, nb); lds_int<T>(sb, OIW, lt, iw);
-        bool mv[VEC];
+        bool mv[VEC]; T tk[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            mv[v] = false; dc[v] = (T)0;
-            if (base + v < n) cauchy_classify_one<T>(x[v], l[v], u[v], g[v], nb[v], iw[v], dc[v], mv[v], ac[2 * MT], cs, base + v + w.off);
+            mv[v] = false; dc[v] = (T)0; tk[v] = (T)-1;
+            if (base + v < n) cauchy_classify_one<T>(x[v], l[v], u[v], g[v], nb[v], iw[v], dc[v], mv[v], ac[2 * MT], cs, base + v + w.off, tk[v]);
         }
+        if (w.bp_hint) { stv<T>(w.r, base, n, tk); stv<T>(w.z, base, n, x); }   // in front of a probable walk
         stvi<T>(w.iwhere, base, n, iw);   // d, xcp: see k_cauchy_classify
 #pragma unroll
         for (int j = 0; j < MT; ++j) {

@@ -33,14 +33,16 @@ def _run(env_extra, tmp_path, tag):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fusion", ["fused", "unfused", "fused+fg_epilogue", "fused_general_pipeline"])
+@pytest.mark.parametrize("fusion", ["fused", "unfused", "fused+fg_epilogue", "fused_general_pipeline", "fused_no_bp_hint"])
 def test_trace_bits_match_recorded(fusion, tmp_path):
     """fused: the fast NEW_X pipeline (merged scalar kernels, pause/resume); fused_general_pipeline: the same fused passes
-    driven by the general pipeline (LBFGSB_B200_NO_FAST=1).  fused+fg_epilogue: the objective kernel forms the line-search sums itself (lbfgsb_problem_fused_f64) and the
+    driven by the general pipeline (LBFGSB_B200_NO_FAST=1); fused_no_bp_hint: cauchy's per-variable pass never stores the
+    breakpoints ahead of a walk (the walk's first pass computes them).  fused+fg_epilogue: the objective kernel forms the line-search sums itself (lbfgsb_problem_fused_f64) and the
     engine's k_ls_trial is skipped -- same products in the same order, hence the same bits."""
     gold = json.load(open(GOLD))
     got = _run({"LBFGSB_B200_NO_FUSION": "1" if fusion == "unfused" else "0",
                 "LBFGSB_B200_NO_FAST": "1" if fusion == "fused_general_pipeline" else "0",
+                "LBFGSB_B200_NO_BP_HINT": "1" if fusion == "fused_no_bp_hint" else "0",
                 "LBFGSB_DIGEST_FUSED_FG": "1" if fusion.endswith("fg_epilogue") else "0"}, tmp_path, fusion.replace("+", "_"))
     assert set(got) == set(gold)
     for name in sorted(gold):
