@@ -670,12 +670,12 @@ def parity_check(cx, n_global=200_000, m=5, l_odd=1.0, iters=30):
     torch, dist = cx.torch, cx.dist
     lo, hi = sharded.shard_bounds(n_global, cx.rank, cx.world)
     kern = lbfgsb_b200.RosenbrockDevice(np.float64)
-    rows, task, _ = MC.solve(hi - lo, lo, n_global, m, l_odd, iters, (lo, n_global, cx.comm, cx.rank, cx.world),
+    rows, task, _, _ = MC.solve(hi - lo, lo, n_global, m, l_odd, iters, (lo, n_global, cx.comm, cx.rank, cx.world),
                              lambda: sharded.ShardedRosenbrockDevice(kern, cx.rank, cx.world, dist, cx.dev), cx.dev,
                              cx.rank, cx.world, "rosenbrock")
     res = None
     if cx.rank == 0:
-        ref, rtask, _ = MC.solve(n_global, 0, n_global, m, l_odd, iters, None, lambda: kern, cx.dev, 0, 1, "rosenbrock")
+        ref, rtask, _, _ = MC.solve(n_global, 0, n_global, m, l_odd, iters, None, lambda: kern, cx.dev, 0, 1, "rosenbrock")
         ok, msg, worst = MC.compare(rows, task, ref, rtask)
         res = {"status": "ok" if ok else "FAIL", "n": n_global, "m": m, "iterates_compared": len(ref),
                "fields": "iter nfgv nseg nfree nact iword iback nenter col active-set-hash", "worst_rel_f": worst,

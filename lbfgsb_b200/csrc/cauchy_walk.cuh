@@ -367,6 +367,12 @@ template <typename T>
 __device__ __forceinline__ const typename Real<T>::key_t* cur_keys(const WalkBuf<T>& b) { return b.ctl->cur ? b.k1 : b.k0; }
 template <typename T>
 __device__ __forceinline__ const int* cur_vals(const WalkBuf<T>& b) { return b.ctl->cur ? b.v1 : b.v0; }
+// t of a sorted entry.  In a round that replays a group of equal breakpoints on a sharded workspace (tie_round = 2) the
+// sort keys are the members' positions in the reference's heap order, and t is the group's common value.
+template <typename T>
+__device__ __forceinline__ T walk_t_of(const DevState<T>* s, typename Real<T>::key_t key) {
+    return (s->tie_round == 2) ? KeyBits<T>::from((typename Real<T>::key_t)s->tie_key) : KeyBits<T>::from(key);
+}
 
 // (a) gather: w_j, v_j = M w_j, omega_j, delta_j, zeta_j; block totals of delta*w and zeta*w
 template <typename T>
@@ -501,7 +507,7 @@ __global__ void __launch_bounds__(LB_WB) k_walk_dots(Wk<T> w, WalkBuf<T> b, i64 
     const i64 j = (i64)blockIdx.x * LB_WB + threadIdx.x;
     const bool ok = j < len;
     const T dl = ok ? b.delta[j] : (T)0, ze = ok ? b.zeta[j] : (T)0;
-    const T tj = ok ? KeyBits<T>::from(cur_keys<T>(b)[start + j]) : (T)0;
+    const T tj = ok ? walk_t_of<T>(s, cur_keys<T>(b)[start + j]) : (T)0;
     T wmp = (T)0, wmc = (T)0;
     for (int c = 0; c < col2; ++c) {
         const T wv_ = ok ? b.wj[(i64)c * b.cap + j] : (T)0;
@@ -570,8 +576,8 @@ __global__ void __launch_bounds__(LB_WB) k_walk_f2(Wk<T> w, WalkBuf<T> b, i64 st
     T h = (T)0;
     if (ok) {
         const typename Real<T>::key_t* keys = cur_keys<T>(b);
-        const T tj = KeyBits<T>::from(keys[start + j]);
-        const T tp = (start + j > 0) ? KeyBits<T>::from(keys[start + j - 1]) : s->walk_tlast;   // 0, or the last key of the lower ranks
+        const T tj = walk_t_of<T>(s, keys[start + j]);
+        const T tp = (start + j > 0) ? walk_t_of<T>(s, keys[start + j - 1]) : s->walk_tlast;   // 0, or the last key of the lower ranks
         const T dt = tj - tp;
         h = dt * f2j + b.g1[j];
         b.f2a[j] = f2j;
@@ -883,15 +889,15 @@ __global__ void __launch_bounds__(LB_WB) k_walk_round_end(Wk<T> w, WalkBuf<T> b,
             }
             s->tie_events += 1;
         }
-        const T tprev = (J > 0) ? KeyBits<T>::from(keys[J - 1]) : s->walk_tlast;
+        const T tprev = (J > 0) ? walk_t_of<T>(s, keys[J - 1]) : s->walk_tlast;
         walk_close_at<T>(s, b.f1a[jl], b.f2a[jl], tprev, AJ, BJ, 1 + s->walk_base + J);
         s->walk_fixn = J;
         return;
     }
     if (threadIdx.x != 0) return;
     // every breakpoint of the round was passed
-    if (cnt >= 2) { s->walk_tprev2 = KeyBits<T>::from(keys[cnt - 2]); s->walk_tlast = KeyBits<T>::from(keys[cnt - 1]); }
-    else if (cnt == 1) { s->walk_tprev2 = s->walk_tlast; s->walk_tlast = KeyBits<T>::from(keys[0]); }
+    if (cnt >= 2) { s->walk_tprev2 = walk_t_of<T>(s, keys[cnt - 2]); s->walk_tlast = walk_t_of<T>(s, keys[cnt - 1]); }
+    else if (cnt == 1) { s->walk_tprev2 = s->walk_tlast; s->walk_tlast = walk_t_of<T>(s, keys[0]); }
     s->walk_base += cnt;
     s->walk_fixn = cnt;
     if (cnt == s->walk_rem) walk_close_all_passed<T>(s, n_global);
@@ -1016,15 +1022,17 @@ __global__ void __launch_bounds__(1024) k_heap_replay(Wk<T> w, WalkBuf<T> b) {
 // The replay done on the host (long breakpoint lists: a single device thread would take a second per million heap
 // insertions, a host core takes a few tens of nanoseconds each): the host has popped the heap from a copy of b.k0 / b.v0
 // and left the group in heap order in b.k1 / b.v1; this sets what k_heap_replay sets at its end.
+// Sharded workspaces: `cnt` = this rank's members (b.k1 = their positions in the heap order, b.v1 = local variables),
+// `cnt_all` = the size of the group over all ranks, kind = 2 (positional keys, walk_t_of).
 template <typename T>
-__global__ void k_heap_replay_commit(Wk<T> w, WalkBuf<T> b, i64 cnt) {
+__global__ void k_heap_replay_commit(Wk<T> w, WalkBuf<T> b, i64 cnt, i64 cnt_all, int kind) {
     if (threadIdx.x != 0) return;
     DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->need_walk || s->walk_closed) return;
     b.ctl->count = cnt; b.ctl->cur = 1; b.ctl->skip = 0;
-    s->walk_lcount = cnt; s->walk_rcount = cnt; s->walk_rem = s->nbreak - s->walk_base;
+    s->walk_lcount = cnt; s->walk_rcount = cnt_all; s->walk_rem = s->nbreak - s->walk_base;
     s->walk_J = -1; s->walk_done = 0; s->walk_fixn = 0;
-    s->tie_round = 1;
+    s->tie_round = kind;
 }
 
 // ---------------------------------------------------------------------------

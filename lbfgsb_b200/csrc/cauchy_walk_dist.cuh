@@ -34,7 +34,10 @@ template <typename T>
 struct WalkCarry {
     T A[2 * LB_MMAX], B[2 * LB_MMAX];
     T f1, f2, tlast, tprev2;
-    i64 found;              // 1: the exit lies in the sender's range (or before)
+    i64 found;              // 1: the exit lies in the sender's range (or before); 2: it lies inside a group of equal
+                            // breakpoints that is to be replayed in the reference's heap order (tie_key); nothing is closed
+    unsigned long long tie_key;
+    i64 tie_unreplayed;     // found = 1 inside such a group, but the heap is too long to replay: counted
     i64 fixcnt[LB_MAXR];
     // valid when found:
     T fin_f1, fin_f2, dtm, tsum;
@@ -100,7 +103,8 @@ __global__ void __launch_bounds__(256) k_dw_pack(Wk<T> w, WalkBuf<T> b, T* rec, 
         const int var = vals[j];
         const T dl = cauchy_dir<T>(w.iwhere[var], w.g[var]);
         T* r = rec + j * rs;
-        r[0] = KeyBits<T>::from(keys[j]);
+        // what the receiver sorts by: t -- or, in a replayed tie group, the member's position in the heap order
+        r[0] = (s->tie_round == 2) ? (T)(i64)keys[j] : KeyBits<T>::from(keys[j]);
         r[1] = dl;
         r[2] = (dl > (T)0) ? (w.u[var] - w.x[var]) : (w.l[var] - w.x[var]);
         int pj = head0;
@@ -220,8 +224,22 @@ __global__ void __launch_bounds__(LB_WB) k_dw_turn_end(Wk<T> w, WalkBuf<T> b, co
         }
         __syncthreads();
         if (threadIdx.x != 0) return;
+        out->tie_unreplayed = 0;
+        if (!s->tie_round) {
+            // the exit inside a group of equal breakpoints (cauchy_walk.cuh "heap replay"): the entry before the exit is
+            // the one before J in this range, or the last entry of the lower ranks' ranges (its t is the carried tlast)
+            const bool tie = (J > 0) ? (keys[J - 1] == keys[J]) : (dc->goff > 0 && KeyBits<T>::to(s->walk_tlast) == keys[0]);
+            if (tie) {
+                if (s->tie_limit > 0 && s->nbreak <= s->tie_limit) {
+                    out->found = 2; out->tie_key = (unsigned long long)keys[J];
+                    for (int q = 0; q < R; ++q) out->fixcnt[q] = 0;
+                    return;
+                }
+                out->tie_unreplayed = 1;
+            }
+        }
         const T f1 = b.f1a[jl], f2 = b.f2a[jl];
-        const T tprev = (J > 0) ? KeyBits<T>::from(keys[J - 1]) : s->walk_tlast;
+        const T tprev = (J > 0) ? walk_t_of<T>(s, keys[J - 1]) : s->walk_tlast;
         T dtm = -f1 / f2;
         if (dtm <= (T)0) dtm = (T)0;
         out->found = 1;
@@ -241,8 +259,8 @@ __global__ void __launch_bounds__(LB_WB) k_dw_turn_end(Wk<T> w, WalkBuf<T> b, co
     out->found = 0;
     for (int c = 0; c < col2; ++c) { out->A[c] = s->walkA[c]; out->B[c] = s->walkB[c]; }
     out->f1 = s->walk_f1; out->f2 = s->walk_f2;
-    if (nrecv >= 2) { out->tlast = KeyBits<T>::from(keys[nrecv - 1]); out->tprev2 = KeyBits<T>::from(keys[nrecv - 2]); }
-    else if (nrecv == 1) { out->tlast = KeyBits<T>::from(keys[0]); out->tprev2 = s->walk_tlast; }
+    if (nrecv >= 2) { out->tlast = walk_t_of<T>(s, keys[nrecv - 1]); out->tprev2 = walk_t_of<T>(s, keys[nrecv - 2]); }
+    else if (nrecv == 1) { out->tlast = walk_t_of<T>(s, keys[0]); out->tprev2 = s->walk_tlast; }
     else { out->tlast = s->walk_tlast; out->tprev2 = s->walk_tprev2; }
 }
 
@@ -256,7 +274,14 @@ __global__ void k_dw_adopt(Wk<T> w, const WalkCarry<T>* all, int turn, int R, in
     if (s->walk_J == LB_I64MAX) return;   // already closed by an earlier turn
     const WalkCarry<T>* cr = all + turn;
     const int col2 = 2 * s->col;
+    if (cr->found == 2) {   // redo the round up to the tie group, then the group in heap order (Engine::tie_replay_sharded)
+        s->tie_redo = 1; s->tie_key = cr->tie_key;
+        s->walk_J = LB_I64MAX;   // the later turns of this round do nothing
+        dc->jloc = 0;
+        return;
+    }
     if (cr->found) {
+        if (cr->tie_unreplayed) s->tie_events += 1;
         s->f1 = cr->fin_f1; s->f2 = cr->fin_f2; s->dtm = cr->dtm; s->tsum = cr->tsum; s->nseg = cr->nseg;
         for (int c = 0; c < col2; ++c) { s->p[c] = cr->p[c]; s->c[c] = cr->c[c]; }
         // my entries before the exit: everything I sent to lower ranks + my records before J on rank `turn`

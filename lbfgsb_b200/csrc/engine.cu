@@ -268,6 +268,7 @@ struct Engine : EngineBase {
         {
             i64 lim = (i64)1 << 28;   // heap replay of tied breakpoints at the exit: up to 2.7e8 breakpoints by default
                                       // (on the device up to LB_TIE_DEVICE_MAX, beyond that on the engine's host thread)
+            if (R > 1) lim = (i64)1 << 26;   // sharded: every rank holds the whole breakpoint list of the call during a replay
             if (const char* e = getenv("LBFGSB_B200_TIE_LIMIT")) lim = atoll(e);
             CK(cudaMemcpyAsync(&s_dev->tie_limit, &lim, sizeof lim, cudaMemcpyHostToDevice, stream));
         }
@@ -321,7 +322,7 @@ struct Engine : EngineBase {
     ~Engine() {
         for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
         for (void* p : allocs) cudaFree(p);
-        for (DynBuf* d : {&dw_send, &dw_recv, &dw_k0, &dw_k1, &dw_v0, &dw_v1}) if (d->p) cudaFree(d->p);
+        for (DynBuf* d : {&dw_send, &dw_recv, &dw_k0, &dw_k1, &dw_v0, &dw_v1, &tie_k, &tie_v, &tie_kall, &tie_vall}) if (d->p) cudaFree(d->p);
         if (fg_host) cudaFreeHost(fg_host);
         if (s_host) cudaFreeHost(s_host);
         if (ctl_host) cudaFreeHost(ctl_host);
@@ -522,6 +523,7 @@ struct Engine : EngineBase {
     // that group, then the group runs as a round of its own in the reference's heap order (cauchy_walk.cuh
     // "heap replay").  Returns like run_round.
     int tie_replay(const BpRange& rg) {
+        if (R > 1) return tie_replay_sharded(rg);
         const unsigned long long tk = s_host->tie_key;
         k_tie_restore<T><<<1, 32, 0, stream>>>(w); launches++;
         if (tk > 0) {
@@ -547,6 +549,112 @@ struct Engine : EngineBase {
         if (!sync_state()) return -1;
         return s_host->walk_closed ? 1 : 0;
     }
+    // The same on a sharded workspace.  The heap's history involves every breakpoint of the call, so every rank gathers
+    // all of them -- (t, global index), in variable order, exactly the reference's t / iorder arrays (:1305-1322) -- and
+    // pops the same heap on its host thread; the members of the group, in pop order, then form a round of their own whose
+    // sort keys are their positions in that order (tie_round = 2, walk_t_of): the sample sort, the exchange of the
+    // records and the scans in rank order run unchanged, and every rank fixes those of its own members that were passed.
+    DynBuf tie_k, tie_v, tie_kall, tie_vall;
+    int tie_replay_sharded(const BpRange& rg) {
+        typedef typename Real<T>::key_t K;
+        const unsigned long long tk = s_host->tie_key;
+        if (n_global >= 2147483647LL) { set_error("heap replay on a sharded workspace needs n < 2^31"); return -1; }
+        k_tie_restore<T><<<1, 32, 0, stream>>>(w); launches++;
+        if (tk > 0) {
+            BpRange ra = rg; ra.hi = tk - 1;
+            if (!(ra.lo_valid && ra.hi <= ra.lo)) {
+                const int st = run_round(ra);
+                if (st < 0) return -1;
+                if (st != 0) { set_error("heap replay: the round below the tie group did not pass (internal error)"); return -1; }
+            }
+        }
+        // this rank's breakpoints of the call, passed ones included, in variable order
+        begin(F_WALK_COMPACT);
+        k_flag_count<T, 2><<<LG>>>(w, tile_counts);
+        k_tile_scan<T><<<1, 1024, 0, stream>>>(w, 2, tile_counts, tile_offsets, ntiles, wb.ctl);
+        k_flag_write<T, 2><<<LG>>>(w, tile_counts, tile_offsets, wb.k0, wb.v0);
+        end(F_WALK_COMPACT, 3);
+        SortCtl hc;
+        CK(cudaMemcpyAsync(&hc, wb.ctl, sizeof hc, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream)); syncs++;
+        // counts and shard offsets of all ranks
+        RoundRec mine; mine.count = hc.count; mine.rem = offset; mine.kmin = 0; mine.pad = 0;
+        CK(cudaMemcpyAsync(rr_local, &mine, sizeof mine, cudaMemcpyHostToDevice, stream));
+        if (!allgather(rr_local, rr_all, sizeof(RoundRec))) return -1;
+        std::vector<RoundRec> recs((size_t)R);
+        CK(cudaMemcpyAsync(recs.data(), rr_all, sizeof(RoundRec) * R, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream)); syncs++;
+        i64 maxc = 0, nb = 0;
+        for (int q = 0; q < R; ++q) { if (recs[q].count > maxc) maxc = recs[q].count; nb += recs[q].count; }
+        if (nb <= 0) { set_error("heap replay: no breakpoints (internal error)"); return -1; }
+        if (!ensure(tie_k, sizeof(K) * (size_t)maxc) || !ensure(tie_v, 4 * (size_t)maxc) ||
+            !ensure(tie_kall, sizeof(K) * (size_t)maxc * R) || !ensure(tie_vall, 4 * (size_t)maxc * R)) return -1;
+        CK(cudaMemcpyAsync(tie_k.p, wb.k0, sizeof(K) * (size_t)hc.count, cudaMemcpyDeviceToDevice, stream));
+        CK(cudaMemcpyAsync(tie_v.p, wb.v0, 4 * (size_t)hc.count, cudaMemcpyDeviceToDevice, stream));
+        if (!allgather(tie_k.p, tie_kall.p, sizeof(K) * (size_t)maxc) || !allgather(tie_v.p, tie_vall.p, 4 * (size_t)maxc)) return -1;
+        std::vector<K> hk((size_t)nb); std::vector<int> hv((size_t)nb);
+        {
+            i64 o = 0;
+            for (int q = 0; q < R; ++q) {
+                const i64 c = recs[q].count;
+                if (c > 0) {
+                    CK(cudaMemcpyAsync(hk.data() + o, (K*)tie_kall.p + (size_t)q * maxc, sizeof(K) * (size_t)c, cudaMemcpyDeviceToHost, stream));
+                    CK(cudaMemcpyAsync(hv.data() + o, (int*)tie_vall.p + (size_t)q * maxc, 4 * (size_t)c, cudaMemcpyDeviceToHost, stream));
+                }
+                o += c;
+            }
+            CK(cudaStreamSynchronize(stream)); syncs++;
+            o = 0;
+            for (int q = 0; q < R; ++q) {   // local -> global variable index (0-based); rem carries the shard offset
+                for (i64 i = 0; i < recs[q].count; ++i) hv[(size_t)(o + i)] += (int)recs[q].rem;
+                o += recs[q].count;
+            }
+        }
+        std::vector<K> gk; std::vector<int> gv;
+        heap_group_order((K)tk, hk, hv, (int)s_host->ibkmin, gk, gv);
+        // this rank's members: key = position in the pop order, value = local variable
+        std::vector<K> lk; std::vector<int> lv;
+        const i64 g = (i64)gv.size();
+        if (sizeof(T) == 4 && g >= ((i64)1 << 24)) { set_error("heap replay on a sharded REAL32 workspace: tie group of %lld members exceeds 2^24", (long long)g); return -1; }
+        for (i64 ppos = 0; ppos < g; ++ppos) {
+            const i64 gi = gv[(size_t)ppos];
+            if (gi >= offset && gi < offset + n) { lk.push_back((K)ppos); lv.push_back((int)(gi - offset)); }
+        }
+        const i64 cnt = (i64)lk.size();
+        if (cnt > 0) {
+            CK(cudaMemcpyAsync(wb.k1, lk.data(), sizeof(K) * (size_t)cnt, cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(wb.v1, lv.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, stream));
+        }
+        k_heap_replay_commit<T><<<1, 32, 0, stream>>>(w, wb, cnt, g, 2); launches++;
+        CK(cudaStreamSynchronize(stream));   // lk, lv are locals
+        if (!sync_state()) return -1;
+        tie_replays++;
+        if (g <= 0) { set_error("heap replay: empty tie group (internal error)"); return -1; }
+        if (!round_scan_sharded()) return -1;
+        if (!sync_state()) return -1;
+        return s_host->walk_closed ? 1 : 0;
+    }
+    // hpsolb's pop order of the group of breakpoints equal to tk: hk / hv hold every breakpoint of the cauchy call in variable
+    // order (destroyed), vmin the variable of the first minimum (taken before the heap exists, :1384-1397)
+    template <typename K>
+    static void heap_group_order(K tk, std::vector<K>& hk, std::vector<int>& hv, int vmin, std::vector<K>& gk, std::vector<int>& gv) {
+        const i64 nb = (i64)hk.size();
+        i64 spos = -1;
+        for (i64 i = 0; i < nb; ++i) if (hv[(size_t)i] == vmin) spos = i;
+        if (spos >= 0 && hk[(size_t)spos] == tk) { gk.push_back(tk); gv.push_back(vmin); }
+        K* t = hk.data() - 1; int* io = hv.data() - 1;   // 1-based
+        const i64 ib = spos + 1;
+        if (ib >= 1 && ib != nb) { t[ib] = t[nb]; io[ib] = io[nb]; }   // :1394-1397
+        i64 nleft = nb - 1;
+        heap_build<K>(t, io, nleft);
+        while (nleft > 0) {
+            K out; int var;
+            heap_pop<K>(t, io, nleft, out, var);
+            nleft--;
+            if (out > tk) break;
+            if (out == tk) { gk.push_back(out); gv.push_back(var); }
+        }
+    }
     // hpsolb's pop order of the group of breakpoints equal to tk, on the host (cauchy_walk.cuh "heap replay"): wb.k0 / wb.v0
     // hold every breakpoint of this cauchy call in variable order.  The reference pays the same sequential heap.
     bool heap_replay_on_host(unsigned long long tk64) {
@@ -560,31 +668,14 @@ struct Engine : EngineBase {
         CK(cudaMemcpyAsync(hk.data(), wb.k0, sizeof(K) * (size_t)nb, cudaMemcpyDeviceToHost, stream));
         CK(cudaMemcpyAsync(hv.data(), wb.v0, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
-        const K tk = (K)tk64;
-        const int vmin = (int)(s_host->ibkmin - offset);
-        K kfirst; { T bk = s_host->bkmin; memcpy(&kfirst, &bk, sizeof kfirst); }
         std::vector<K> gk; std::vector<int> gv;
-        if (kfirst == tk) { gk.push_back(tk); gv.push_back(vmin); }   // the first breakpoint is taken before the heap exists (:1384-1389)
-        i64 spos = -1;
-        for (i64 i = 0; i < nb; ++i) if (hv[(size_t)i] == vmin) spos = i;
-        K* t = hk.data() - 1; int* io = hv.data() - 1;   // 1-based
-        const i64 ib = spos + 1;
-        if (ib >= 1 && ib != nb) { t[ib] = t[nb]; io[ib] = io[nb]; }   // :1394-1397
-        i64 nleft = nb - 1;
-        heap_build<K>(t, io, nleft);
-        while (nleft > 0) {
-            K out; int var;
-            heap_pop<K>(t, io, nleft, out, var);
-            nleft--;
-            if (out > tk) break;
-            if (out == tk) { gk.push_back(out); gv.push_back(var); }
-        }
+        heap_group_order((K)tk64, hk, hv, (int)(s_host->ibkmin - offset), gk, gv);
         const i64 cnt = (i64)gk.size();
         if (cnt > 0) {
             CK(cudaMemcpyAsync(wb.k1, gk.data(), sizeof(K) * (size_t)cnt, cudaMemcpyHostToDevice, stream));
             CK(cudaMemcpyAsync(wb.v1, gv.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, stream));
         }
-        k_heap_replay_commit<T><<<1, 32, 0, stream>>>(w, wb, cnt); launches++;
+        k_heap_replay_commit<T><<<1, 32, 0, stream>>>(w, wb, cnt, cnt, 1); launches++;
         CK(cudaStreamSynchronize(stream));   // gk, gv are locals
         return true;
     }

@@ -1,12 +1,13 @@
 """Multi-GPU parity check, launched under torchrun (one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        tests/mgpu_check.py [n_global] [m] [l_odd] [iterations] [rosenbrock|quadratic]
+        tests/mgpu_check.py [n_global] [m] [l_odd] [iterations] [rosenbrock|quadratic] [x0] [ties]
 
 Runs the sample problem sharded over the N ranks through lbfgsb_setulb_dev_f64 and, on rank 0,
 the same problem on one GPU; the per-iterate discrete trace (iter, nfgv, nseg, nfree, nact, iword,
 iback, active-set hash) must be equal and f, |proj g| agree to rounding.  Prints one line
-`MGPU_CHECK OK ...` or `MGPU_CHECK FAIL ...`; exit code 0 / 1.
+`MGPU_CHECK OK ...` or `MGPU_CHECK FAIL ...`; exit code 0 / 1.  With `ties` the sharded run must also have replayed at least
+one exit inside a group of equal breakpoints in the reference's heap order (lbfgsb_dev_tie_stats).
 """
 import os
 import sys
@@ -23,13 +24,13 @@ import lbfgsb_b200  # noqa: E402
 from lbfgsb_b200 import sharded  # noqa: E402
 
 
-def solve(n_local, off, n_global, m, l_odd, iters, shard, fg_factory, dev, rank, world, kind="rosenbrock"):
+def solve(n_local, off, n_global, m, l_odd, iters, shard, fg_factory, dev, rank, world, kind="rosenbrock", x0=3.0):
     if kind == "quadratic":      # BASELINE.json configs[3]: box [0, 0.5], start in the middle
         x = torch.full((n_local,), 0.25, dtype=torch.float64, device=dev)
         l = torch.zeros(n_local, dtype=torch.float64, device=dev)
         u = torch.full((n_local,), 0.5, dtype=torch.float64, device=dev)
     else:
-        x = torch.full((n_local,), 3.0, dtype=torch.float64, device=dev)
+        x = torch.full((n_local,), x0, dtype=torch.float64, device=dev)
         l = torch.full((n_local,), -100.0, dtype=torch.float64, device=dev)
         l[(off % 2)::2] = l_odd
         u = torch.full((n_local,), 100.0, dtype=torch.float64, device=dev)
@@ -62,8 +63,9 @@ def solve(n_local, off, n_global, m, l_odd, iters, shard, fg_factory, dev, rank,
         else:
             break
     task = prob.task_str()
+    ties = prob.tie_stats()
     prob.close()
-    return rows, task, x
+    return rows, task, x, ties
 
 
 def compare(rows, task, ref, rtask):
@@ -92,6 +94,8 @@ def main():
     l_odd = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
     iters = int(sys.argv[4]) if len(sys.argv) > 4 else 30
     kind = sys.argv[5] if len(sys.argv) > 5 else "rosenbrock"
+    x0 = float(sys.argv[6]) if len(sys.argv) > 6 else 3.0
+    want_ties = len(sys.argv) > 7 and sys.argv[7] == "ties"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -108,15 +112,17 @@ def main():
         kern = lbfgsb_b200.RosenbrockDevice(np.float64)
         mk_sharded = lambda: sharded.ShardedRosenbrockDevice(kern, rank, world, dist, dev)      # noqa: E731
         mk_single = lambda: kern                                                                # noqa: E731
-    rows, task, x = solve(hi - lo, lo, n_global, m, l_odd, iters, (lo, n_global, comm, rank, world),
-                          mk_sharded, dev, rank, world, kind)
+    rows, task, x, ties = solve(hi - lo, lo, n_global, m, l_odd, iters, (lo, n_global, comm, rank, world),
+                                mk_sharded, dev, rank, world, kind, x0)
     ok = True
     if rank == 0:
-        ref, rtask, xr = solve(n_global, 0, n_global, m, l_odd, iters, None, mk_single, dev, 0, 1, kind)
+        ref, rtask, xr, rties = solve(n_global, 0, n_global, m, l_odd, iters, None, mk_single, dev, 0, 1, kind, x0)
         ok, msg, worst = compare(rows, task, ref, rtask)
+        if want_ties and not (ties[0] >= 1 and ties[1] == 0 and rties[0] >= 1):
+            ok, msg = False, msg + " | tie replays sharded %r single %r" % (ties, rties)
         walks = [r["nseg"] for r in ref if r["nseg"] > 1]
-        print("MGPU_CHECK %s %s world=%d n=%d m=%d l_odd=%g iterations=%d walks(nseg>1)=%s worst_rel_f=%.2e %s" % (
-            "OK" if ok else "FAIL", kind, world, n_global, m, l_odd, len(ref), walks[:6], worst, msg[:600]), flush=True)
+        print("MGPU_CHECK %s %s world=%d n=%d m=%d l_odd=%g x0=%g iterations=%d walks(nseg>1)=%s tie_replays(sharded,single)=%d,%d worst_rel_f=%.2e %s" % (
+            "OK" if ok else "FAIL", kind, world, n_global, m, l_odd, x0, len(ref), walks[:6], ties[0], rties[0], worst, msg[:600]), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     lbfgsb_b200.lib().lbfgsb_dev_nccl_destroy(comm)

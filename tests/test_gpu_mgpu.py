@@ -38,3 +38,22 @@ def test_sharded_matches_single_gpu(args, fg):
     env["MGPU_FG"] = fg
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0 and "MGPU_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("args", [("1000", "5", "2.0", "12", "rosenbrock", "3.0", "ties"), ("3001", "3", "2.5", "12", "rosenbrock", "5.0", "ties"),
+                                  ("200000", "10", "1.3", "12", "rosenbrock", "5.0", "ties"), ("4000001", "3", "2.5", "6", "rosenbrock", "5.0", "ties")])
+def test_sharded_tie_exit_follows_the_heap_order(args):
+    """The problems of tests/test_gpu_rare_paths.py whose Cauchy search ends inside a group of equal breakpoints, sharded:
+    every rank gathers the breakpoints of the call, pops the reference's heap (hpsolb, src/lbfgsb.f90:2079-2157) and the
+    group runs as a round of its own in that order -- the active set (hash) of every iterate equals the single-GPU run's,
+    which the rare-path tests compare with the oracle."""
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if ng < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "mgpu_check.py")] + list(args)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ))
+    assert r.returncode == 0 and "MGPU_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -1,6 +1,10 @@
 """Turns the ncu captures brought back in gpurun_out/ into the tracked summaries under profiles/.
 
-  python tools/ncu_summary.py ROUND_TAG LAUNCHES_CSV FULL_REP N
+  python tools/ncu_summary.py ROUND_TAG LAUNCHES_CSV FULL_REP N [KEY_SUFFIX]
+
+FULL_REP is a .ncu-rep, or the csv that `ncu -i rep --page raw --csv` wrote on the GPU box (the reports of n = 4e8 runs are
+too large to bring back).  KEY_SUFFIX (e.g. "@f32m20") keys the traffic table for captures of other instantiations than
+real64 / m <= 10; launches that returned at once (< 0.05 ms) are left out.
 
   profiles/<tag>_launches.md     per-kernel share of the profiled command (gpu__time_duration pass)
   profiles/<tag>_ncu_full.md     the --set full metrics that matter for an HBM-bound kernel
@@ -17,7 +21,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FAM = {"k_update": "update", "k_cauchy_classify": "cauchy_classify", "k_formk_gram": "formk_gram",
        "k_cmprlb_wv": "cmprlb_wv", "k_subsm_step": "subsm_step", "k_ls_init": "ls_init", "k_ls_trial": "ls_trial",
        "k_ls_step": "ls_step", "k_gcp_freev": "gcp_freev", "k_iter_head": "iter_head",
-       "k_update_classify": "update_classify", "k_formk_cmprlb": "formk_cmprlb", "k_subsm_lsinit": "subsm_lsinit"}
+       "k_update_classify": "update_classify", "k_formk_cmprlb": "formk_cmprlb", "k_subsm_lsinit": "subsm_lsinit",
+       "k_formk_delta": "formk_delta"}
 
 
 def short(name):
@@ -52,8 +57,11 @@ def launches(path, out):
         fh.write("\nTotal GPU time of the profiled command: %.1f ms over %d launches (cold-cache, serialised: compare shares).\n" % (tot, sum(v[0] for v in per.values())))
 
 
-def full(rep, out, n):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def full(rep, out, n, suffix=""):
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -71,12 +79,20 @@ def full(rep, out, n):
             d = dict(zip(hdr, r))
             u = dict(zip(hdr, units))
             name = short(d["Kernel Name"])
+            try:
+                if float(d["gpu__time_duration.sum"].replace(",", "")) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(u["gpu__time_duration.sum"], 1.0) < 0.05:
+                    continue
+            except Exception:  # noqa: BLE001
+                pass
             fh.write("## `%s`\n\n| metric | value |\n|---|---|\n" % d["Kernel Name"].strip())
             for w in want:
                 if w in d:
                     fh.write("| %s | %s %s |\n" % (w, d[w], u[w]))
             stalls = [(h.replace("smsp__pcsamp_warps_issue_stalled_", ""), float(d[h].replace(",", ""))) for h in hdr
                       if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued") and d[h] not in ("", "n/a")]
+            if not stalls:
+                stalls = [(h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), float(d[h].replace(",", "")))
+                          for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and d[h] not in ("", "n/a")]
             tot = sum(v for _, v in stalls) or 1.0
             stalls.sort(key=lambda kv: -kv[1])
             fh.write("| top stall reasons | %s |\n\n" % ", ".join("%s %.0f%%" % (k, 100 * v / tot) for k, v in stalls[:5]))
@@ -86,7 +102,7 @@ def full(rep, out, n):
                 return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(un, 1.0)
             base = name.split("<")[0]
             if base in FAM and "dram__bytes_read.sum" in d:
-                traffic[FAM[base]] = {"n": int(n), "kernel": d["Kernel Name"].strip(),
+                traffic[FAM[base] + suffix] = {"n": int(n), "kernel": d["Kernel Name"].strip(),
                                       "dram_bytes_per_launch": gb(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) +
                                       gb(d["dram__bytes_write.sum"], u["dram__bytes_write.sum"]),
                                       "duration_ms_under_ncu": d["gpu__time_duration.sum"] + " " + u["gpu__time_duration.sum"]}
@@ -96,8 +112,9 @@ def full(rep, out, n):
 
 if __name__ == "__main__":
     tag, lcsv, rep, n = sys.argv[1:5]
+    suffix = sys.argv[5] if len(sys.argv) > 5 else ""
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     if os.path.exists(lcsv):
         launches(lcsv, os.path.join(ROOT, "profiles", tag + "_launches.md"))
     if os.path.exists(rep):
-        full(rep, os.path.join(ROOT, "profiles", tag + "_ncu_full.md"), n)
+        full(rep, os.path.join(ROOT, "profiles", tag + "_ncu_full.md"), n, suffix)
