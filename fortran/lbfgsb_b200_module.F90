@@ -32,6 +32,7 @@ module lbfgsb_module
    public :: setulb, setulb_dev
    public :: lbfgsb_dev_create, lbfgsb_dev_destroy, lbfgsb_host_release
    public :: lbfgsb_dev_set_tie_limit, lbfgsb_dev_checkpoint_write, lbfgsb_dev_checkpoint_read
+   public :: lbfgsb_batch_create, lbfgsb_batch_destroy, setulb_batch_dev, lbfgsb_batch_counts, lbfgsb_batch_get_iwhere
 
    interface
 
@@ -88,7 +89,7 @@ module lbfgsb_module
       end subroutine lbfgsb_host_release
 
       !> Heap replay of equal breakpoints at the exit of the Cauchy search (hpsolb's pop order, src/lbfgsb.f90:2079-2157):
-      !> up to max_breakpoints breakpoints per call (default 2**21; 0 = ties in variable order).
+      !> up to max_breakpoints breakpoints per call (default 2**28, 2**26 on a sharded workspace; 0 = ties in variable order).
       subroutine lbfgsb_dev_set_tie_limit(h, max_breakpoints) bind(C, name='lbfgsb_dev_set_tie_limit')
          import :: c_ptr, c_int64_t
          type(c_ptr), value :: h
@@ -108,6 +109,49 @@ module lbfgsb_module
          character(kind=c_char), intent(in) :: path(*)
          integer(c_int) :: rc
       end function lbfgsb_dev_checkpoint_read
+
+      !> Batched small problems: nprob independent problems of the same n and m, one call advances every problem from
+      !> its own task to its next return point (the caller's loop of test/driver1.f90:263-292, many times over).
+      !> task, csave are (60, nprob) characters, lsave (4, nprob), isave (44, nprob), dsave (29, nprob); x, l, u, g, nbd
+      !> are CUDA device pointers to (n, nprob) arrays and f to a device array (nprob).
+      function lbfgsb_batch_create(nprob, n, m, real_kind, cuda_stream) result(h) bind(C, name='lbfgsb_batch_create')
+         import :: c_int64_t, c_int32_t, c_ptr
+         integer(c_int32_t), value :: nprob, m, real_kind
+         integer(c_int64_t), value :: n
+         type(c_ptr), value :: cuda_stream
+         type(c_ptr) :: h
+      end function lbfgsb_batch_create
+      subroutine lbfgsb_batch_destroy(h) bind(C, name='lbfgsb_batch_destroy')
+         import :: c_ptr
+         type(c_ptr), value :: h
+      end subroutine lbfgsb_batch_destroy
+#ifdef REAL32
+      subroutine setulb_batch_dev(h, x, l, u, nbd, f, g, factr, pgtol, task, csave, lsave, isave, dsave) &
+         bind(C, name='lbfgsb_batch_setulb_dev_f32')
+#else
+      subroutine setulb_batch_dev(h, x, l, u, nbd, f, g, factr, pgtol, task, csave, lsave, isave, dsave) &
+         bind(C, name='lbfgsb_batch_setulb_dev_f64')
+#endif
+         import :: c_int32_t, c_char, c_ptr, wp
+         type(c_ptr), value :: h, x, l, u, nbd, f, g
+         real(wp), intent(in) :: factr, pgtol
+         character(kind=c_char), intent(inout) :: task(60, *), csave(60, *)
+         integer(c_int32_t), intent(inout) :: lsave(4, *), isave(44, *)
+         real(wp), intent(inout) :: dsave(29, *)
+      end subroutine setulb_batch_dev
+      function lbfgsb_batch_counts(h, n_fg, n_newx, n_done) result(rc) bind(C, name='lbfgsb_batch_counts')
+         import :: c_ptr, c_int32_t, c_int
+         type(c_ptr), value :: h
+         integer(c_int32_t), intent(out) :: n_fg, n_newx, n_done
+         integer(c_int) :: rc
+      end function lbfgsb_batch_counts
+      !> iwhere of every problem, (n, nprob) on the host: what the reference keeps in iwa(2n+1:3n).
+      function lbfgsb_batch_get_iwhere(h, iwhere) result(rc) bind(C, name='lbfgsb_batch_get_iwhere')
+         import :: c_ptr, c_int32_t, c_int
+         type(c_ptr), value :: h
+         integer(c_int32_t), intent(out) :: iwhere(*)
+         integer(c_int) :: rc
+      end function lbfgsb_batch_get_iwhere
 
    end interface
 

@@ -615,7 +615,9 @@ struct Engine : EngineBase {
         // this rank's members: key = position in the pop order, value = local variable
         std::vector<K> lk; std::vector<int> lv;
         const i64 g = (i64)gv.size();
-        if (sizeof(T) == 4 && g >= ((i64)1 << 24)) { set_error("heap replay on a sharded REAL32 workspace: tie group of %lld members exceeds 2^24", (long long)g); return -1; }
+        // REAL32: the position travels as a real in the exchanged record, exact below 2^24 -- a larger group is taken in
+        // variable order (what happens beyond the replay limit)
+        if (sizeof(T) == 4 && g >= ((i64)1 << 24)) std::sort(gv.begin(), gv.end());
         for (i64 ppos = 0; ppos < g; ++ppos) {
             const i64 gi = gv[(size_t)ppos];
             if (gi >= offset && gi < offset + n) { lk.push_back((K)ppos); lv.push_back((int)(gi - offset)); }
