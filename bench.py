@@ -23,8 +23,9 @@ real64, factr = pgtol = 0 and a fixed iteration budget.
   roofline      the dominant kernel family: algorithmic bytes per launch / CUDA-event time on the engine's stream
   cpu_baseline  the CPU oracle (line-by-line port of the reference; the Fortran reference cannot be built in this
                 image) on a bounded sample, 1 core
-  extra_configs BASELINE.json configs[3] (quadratic), configs[4] (n = 4e8, m = 20, REAL32) and configs[1]
-                (n = 1e6, m = 5 solved to convergence) at N = 1; the weak series at N > 1
+  extra_configs BASELINE.json configs[3] (quadratic), configs[4] (n = 4e8, m = 20, REAL32), configs[1]
+                (n = 1e6, m = 5 solved to convergence), configs[0] x 1000 as one batch and the fixed cost per iteration
+                at small n (caller loop vs the CUDA-graph loop) at N = 1; the weak series at N > 1
   parity        N > 1: a 2e5-variable problem solved sharded and on one GPU -- discrete trace and active-set hash equal
 
 Warm-up: the driver's --warmup is raised to m + 4 iterations (history full, col = m) and extended (up to 10 more)
@@ -661,6 +662,19 @@ def batched_rate(nprob=1000, n=25, m=5):
                              "sample": "CPU oracle port, 200 of the problems one after the other through its driver loop"}}
 
 
+def small_n_latency():
+    """Where the fixed cost per setulb call decides the rate: ms per iteration, launches and host read-backs per iteration
+    through the caller's loop (lbfgsb_setulb_dev_f64, objective with the line-search epilogue) and through the
+    device-resident loop (lbfgsb_minimize_graph_dev_f64: one CUDA-graph launch and one read-back per step)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import small_n_latency as SL
+    out = []
+    for n in (1000, 100000):
+        out.append(SL.run(n, 10))
+        out.append(SL.run_graph(n, 10))
+    return out
+
+
 def parity_check(cx, n_global=200_000, m=5, l_odd=1.0, iters=30):
     """N > 1: the sample problem sharded over the ranks and, on rank 0, on one GPU -- discrete trace and active-set hash
     equal at every iterate, f within 1e-10 (first 10 iterates) / 1e-6 (the logic of tests/mgpu_check.py)."""
@@ -749,6 +763,7 @@ def main():
                 extras["configs[4] driver3-style n=4e8, m=20, REAL32"] = slim(r, "driver3_f32", d3["n"], d3["m"], d3["dtype"], d3["l_odd"], "single")
                 extras["configs[1] n=1e6, m=5 to convergence"] = solve_to_convergence(cx, 1_000_000, 5, 1.0, 1.0e7, 1.0e-5)
                 extras["configs[0] x 1000: batched small problems (one CTA per problem)"] = batched_rate()
+                extras["small n: fixed cost per iteration (n=1e3, 1e5; caller loop vs lbfgsb_minimize_graph_dev_f64)"] = small_n_latency()
             else:
                 other = "weak" if strong else "strong"
                 ng = a.n * world if strong else a.n

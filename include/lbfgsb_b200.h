@@ -100,6 +100,26 @@ int lbfgsb_minimize_dev_f32(lbfgsb_dev_t* h, float* x_dev, const float* l_dev, c
                             int32_t iprint, float* f, float* g_dev, char* task, char* csave, int32_t* lsave, int32_t* isave,
                             float* dsave);
 
+/* The same loop kept on the device.  fg only ENQUEUES work on cuda_stream (kernel launches, no synchronisation, no host
+ * read-back: it is captured in a CUDA graph) and leaves f in *f_dev (device memory).  One iteration step -- the objective,
+ * the FG_LNSRCH entry of setulb, the NEW_X entry -- is then one graph launch and one read-back of the state header
+ * (src/lbfgsb.f90:36-37 @todo; the reverse-communication contract :884-890, :770-787 is kept on the device: each entry
+ * kernel opens its setulb call only if `task` in the state block asks for it).  START / FG_START, the STOP of a limit and
+ * every branch off the common path (breakpoint walk, entering/leaving variables, backtrack, restarts) go through setulb as
+ * in lbfgsb_minimize_dev_*; the results are bit-identical to that loop.  Single-GPU workspaces with bounds; otherwise the
+ * loop runs call by call with f read back from *f_dev.  No text output (iprint < 0).  Return value as lbfgsb_minimize_dev_*. */
+typedef int (*lbfgsb_fg_enqueue_f64)(void* user, int64_t n, const double* x_dev, double* g_dev, double* f_dev, void* cuda_stream);
+typedef int (*lbfgsb_fg_enqueue_f32)(void* user, int64_t n, const float* x_dev, float* g_dev, float* f_dev, void* cuda_stream);
+int lbfgsb_minimize_graph_dev_f64(lbfgsb_dev_t* h, double* x_dev, const double* l_dev, const double* u_dev, const int32_t* nbd_dev,
+                                  lbfgsb_fg_enqueue_f64 fg, void* user, double factr, double pgtol, int32_t max_iter, int32_t max_fg,
+                                  double* f, double* g_dev, char* task, char* csave, int32_t* lsave, int32_t* isave, double* dsave);
+int lbfgsb_minimize_graph_dev_f32(lbfgsb_dev_t* h, float* x_dev, const float* l_dev, const float* u_dev, const int32_t* nbd_dev,
+                                  lbfgsb_fg_enqueue_f32 fg, void* user, float factr, float pgtol, int32_t max_iter, int32_t max_fg,
+                                  float* f, float* g_dev, char* task, char* csave, int32_t* lsave, int32_t* isave, float* dsave);
+/* how many steps ran as a graph launch since the workspace was created, and how many kernels one such launch holds
+ * (the engine's; the objective's come on top) */
+int lbfgsb_dev_graph_stats(lbfgsb_dev_t* h, int64_t* graph_steps, int64_t* launches_per_step);
+
 /* ---- (4) checkpoint / resume of the device workspace ----------------------------------------------
  * The reference keeps its whole state in the caller's wa/iwa/isave/dsave/lsave/task/csave, so a caller can
  * checkpoint by saving those arrays (and test/driver3.f90:152-182 reads `t` out of wa).  Here wa/iwa live on

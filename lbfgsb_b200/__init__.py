@@ -85,6 +85,11 @@ def lib():
         L.lbfgsb_dev_vector_copy.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
         L.lbfgsb_dev_active_set_hash.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lbfgsb_dev_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lbfgsb_dev_graph_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lbfgsb_problem_rosenbrock_halo_f64.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                                         C.c_void_p, C.c_void_p]
+        L.lbfgsb_problem_quadratic_halo_f64.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64,
+                                                        C.c_void_p, C.c_void_p]
         L.lbfgsb_dev_profile.argtypes = [C.c_void_p, C.c_int32]
         L.lbfgsb_dev_profile_reset.argtypes = [C.c_void_p]
         L.lbfgsb_dev_set_tie_limit.argtypes = [C.c_void_p, C.c_int64]
@@ -280,6 +285,36 @@ class DeviceProblem:
         _check_task(self.task)
         return rc
 
+    def minimize_graph(self, x, l, u, nbd, g, fg_enqueue, factr, pgtol, max_iter=0, max_fg=0):
+        """lbfgsb_minimize_graph_dev_*: the task loop kept on the device, one CUDA-graph launch per iteration step.
+        fg_enqueue(x_ptr, g_ptr, f_dev_ptr, stream) only enqueues the objective's kernels on `stream` (it is captured in a
+        CUDA graph) and leaves f in device memory.  Returns the C return code."""
+        sfx, cr = _REAL[self.dtype]
+        CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+
+        def _cb(user, n, xp, gp, fdev, stream):
+            try:
+                fg_enqueue(xp, gp, fdev, stream)
+                return 0
+            except Exception:  # noqa: BLE001
+                return 1
+        cb = CB(_cb)
+        fn = getattr(lib(), "lbfgsb_minimize_graph_dev_" + sfx)
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p] * 5 + [CB, C.c_void_p, cr, cr, C.c_int32, C.c_int32] + [C.c_void_p] * 7
+        rc = fn(C.c_void_p(self.h), C.c_void_p(x.data_ptr()), C.c_void_p(l.data_ptr()), C.c_void_p(u.data_ptr()),
+                C.c_void_p(nbd.data_ptr()), cb, None, cr(factr), cr(pgtol), int(max_iter), int(max_fg),
+                _p(self.f), C.c_void_p(g.data_ptr()), _p(self.task), _p(self.csave), _p(self.lsave), _p(self.isave),
+                _p(self.dsave))
+        _check_task(self.task)
+        return rc
+
+    def graph_stats(self):
+        """(steps that ran as one graph launch, engine kernels per such launch)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        lib().lbfgsb_dev_graph_stats(C.c_void_p(self.h), C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def checkpoint_write(self, path):
         if lib().lbfgsb_dev_checkpoint_write(C.c_void_p(self.h), path.encode()) != 0:
             raise LbfgsbB200Error("checkpoint write failed: " + last_error())
@@ -398,13 +433,26 @@ class RosenbrockDevice:
         self._fn = getattr(lib(), "lbfgsb_problem_rosenbrock_" + sfx)
         self._f = np.zeros(1, dtype=self.dtype)
         self.stream = stream
+        self._n = 0
 
     def __call__(self, x, g, first=1, last=1, xl=0.0, xr=0.0):
+        self._n = x.numel()
         rc = self._fn(C.c_int64(x.numel()), C.c_void_p(x.data_ptr()), C.c_void_p(g.data_ptr()), _p(self._f),
                       self.stream, first, last, self._cr(xl), self._cr(xr), C.c_void_p(self.scratch.data_ptr()))
         if rc != 0:
             raise LbfgsbB200Error("rosenbrock kernel failed: " + last_error())
         return self._f[0]
+
+    def enqueue(self, halo_dev):
+        """An objective for DeviceProblem.minimize_graph (float64, whole problem on one GPU): kernels only, f stays on the
+        device.  halo_dev: two zeros on the device (the neighbours' values of a shard; unused here)."""
+        def fg(xp, gp, fdev, stream):
+            rc = lib().lbfgsb_problem_rosenbrock_halo_f64(C.c_int64(self._n), C.c_void_p(xp), C.c_void_p(gp), C.c_void_p(fdev),
+                                                          C.c_void_p(stream), 1, 1, C.c_void_p(halo_dev.data_ptr()),
+                                                          C.c_void_p(self.scratch.data_ptr()))
+            if rc != 0:
+                raise LbfgsbB200Error("rosenbrock kernel failed")
+        return fg
 
     def shard_async(self, x, g, first, last, halo_dev, f_part_dev):
         """Shard evaluation without a host round trip (float64): xl, xr from halo_dev[0..1], partial f -> f_part_dev."""

@@ -103,7 +103,8 @@ struct DevState {
     int col, head, itail, iupdat, iter, nfgv, nskip, ifun, iback, iword;
     int updatd, prjctd, cnstnd, boxed, wrk, bnded;
     int brackt, stage;            // dcsrch isave(1:2)
-    int m, pad0;
+    int m;
+    int gstage;                   // device-resident iteration (Engine::minimize_graph): which call ran last, 1 FG_LNSRCH entry, 2 NEW_X entry
     i64 n, nintol, nseg, nfree, nact, nenter, nleave, nbreak, nfreec, nbdd, errk;
     i64 ibkmin;                   // variable index (0-based) of the smallest breakpoint
     i64 ibd;                      // subsm backtrack: variable index of the binding bound

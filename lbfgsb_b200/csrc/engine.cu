@@ -113,6 +113,15 @@ __global__ void __launch_bounds__(256) k_publish(const unsigned* src, unsigned* 
     if (threadIdx.x == 0) *flag_host = seq;
 }
 
+// the same from inside a CUDA graph: the sequence number lives on the device (kernel arguments of a graph are fixed)
+__global__ void __launch_bounds__(256) k_publish_g(const unsigned* src, unsigned* dst_host, int words, volatile unsigned long long* flag_host,
+                                                   unsigned long long* counter) {
+    for (int q = threadIdx.x; q < words; q += blockDim.x) dst_host[q] = src[q];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) { const unsigned long long v = *counter + 1; *counter = v; *flag_host = v; }
+}
+
 struct EngineBase {
     virtual ~EngineBase() {}
     int real_kind;
@@ -322,6 +331,7 @@ struct Engine : EngineBase {
     ~Engine() {
         for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
         for (void* p : allocs) cudaFree(p);
+        if (iter_graph) cudaGraphExecDestroy(iter_graph);
         for (DynBuf* d : {&dw_send, &dw_recv, &dw_k0, &dw_k1, &dw_v0, &dw_v1, &tie_k, &tie_v, &tie_kall, &tie_vall}) if (d->p) cudaFree(d->p);
         if (fg_host) cudaFreeHost(fg_host);
         if (s_host) cudaFreeHost(s_host);
@@ -996,6 +1006,9 @@ struct Engine : EngineBase {
             return enqueue_body(from);
         }
         if (s_host->restart) {
+            // lnsrlb met an ascent direction at its first entry (:2247-2253) after the subspace pass had stepped
+            // speculatively: x = t again before the iteration restarts (s_restart_body clears the flag)
+            if (s_host->do_unstep) { begin(F_LS_STEP); k_ls_step<T><<<LG>>>(w); end(F_LS_STEP); }
             begin(F_SCALAR); s_restart_body<T><<<1, 32, 0, stream>>>(w); end(F_SCALAR);
             return enqueue_body();
         }
@@ -1012,6 +1025,96 @@ struct Engine : EngineBase {
         return true;
     }
     i64 fast_pauses = 0;
+
+    // ---- device-resident iteration: the caller's loop as one CUDA graph per step (kernels_dense.cuh g_ls_trial / g_head) ----
+    // Graph = [objective kernels -> g, f_dev] [k_ls_trial, g_ls_trial: FG_LNSRCH entry] [g_head .. f_tail: NEW_X entry, fast
+    // pipeline] [k_ls_step: the next trial point] [k_publish_g].  One launch and one read-back per step; whatever the fast
+    // pipeline does not cover (pause, restart, restore) is finished by the general pipeline on the host, as in call().
+    cudaGraphExec_t iter_graph = nullptr;
+    unsigned long long* pub_count_dev = nullptr;
+    unsigned long long pub_count = 0;
+    T* f_dev = nullptr;
+    i64 graph_launches_per_step = 0, graph_steps = 0;
+    template <typename FGE>
+    bool build_iter_graph(FGE fg, void* user, int max_iter, int max_fg) {
+        if (iter_graph) { cudaGraphExecDestroy(iter_graph); iter_graph = nullptr; }
+        if (!pub_count_dev) {
+            if (!dalloc(&pub_count_dev, 8) || !dalloc(&f_dev, sizeof(T))) return false;
+            CK(cudaMemsetAsync(pub_count_dev, 0, 8, stream));
+            pub_count = 0;
+        }
+        w.bp_hint = 0;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+        const i64 l0 = launches;
+        int rc = fg(user, n, w.x, w.g, f_dev, (void*)stream);
+        k_ls_trial<T><<<LG>>>(w);
+        g_ls_trial<T><<<LS>>>(w, dist(), f_dev);
+        g_head<T><<<1, 32, 0, stream>>>(w, 1, max_iter, max_fg);
+        MTFUSED(launch_update_classify);
+        f_ucf<T><<<LS>>>(w, dist(), mt);
+        MTFUSED(launch_formk_cmprlb_gf);
+        f_mid<T><<<LS>>>(w, dist(), mt, n_global);
+        MTFUSED(launch_subsm_lsinit);
+        f_tail<T><<<LS>>>(w, dist());
+        k_ls_step<T><<<LG>>>(w);
+        k_publish_g<<<1, 256, 0, stream>>>((const unsigned*)s_dev, (unsigned*)s_host, (int)(header_bytes / 4), pub_flag + 1, pub_count_dev);
+        (void)l0;
+        graph_launches_per_step = 11;
+        cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+        if (rc != 0 || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            set_error("the objective callback could not be captured in a CUDA graph (%s)", rc != 0 ? "callback failed" : cudaGetErrorString(ce));
+            return false;
+        }
+        ce = cudaGraphInstantiate(&iter_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); iter_graph = nullptr; return false; }
+        return true;
+    }
+    // one step of the device-resident loop; the state block is current in s_host afterwards
+    bool graph_step() {
+        CK(cudaGraphLaunch(iter_graph, stream));
+        launches += graph_launches_per_step; graph_steps++;
+        pub_count++;
+        volatile unsigned long long* fl = pub_flag + 1;
+        unsigned spins = 0;
+        while (*fl != pub_count) {
+            if ((++spins & 0x3fff) == 0) {
+                cudaError_t q = cudaStreamQuery(stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) { set_error("CUDA error %s in the iteration graph", cudaGetErrorString(q)); return false; }
+                if (q == cudaSuccess && *fl != pub_count) { set_error("the state block was not published by the iteration graph (internal error)"); return false; }
+            }
+        }
+        syncs++;
+        // what call() does after its read-back, for the call that ran last inside the graph
+        for (auto& mk : marks) pool.push_back(mk.e);
+        marks.clear();
+        walked_now = false; body_ran = false;
+        if (s_host->gstage == 2) {
+            if (s_host->pause != PAUSE_NONE) {
+                const int from = s_host->pause;
+                fast_pauses++;
+                s_resume<T><<<1, 32, 0, stream>>>(w); launches++;
+                if (!enqueue_body(from)) return false;
+            } else if (s_host->restart) {
+                s_restart_body<T><<<1, 32, 0, stream>>>(w); launches++;
+                if (!enqueue_body()) return false;
+            }
+        } else {
+            if (s_host->do_restore) {
+                k_restore<T><<<LG>>>(w); launches++;
+                CK(cudaStreamSynchronize(stream));
+            }
+            if (s_host->restart) {
+                s_restart_body<T><<<1, 32, 0, stream>>>(w); launches++;
+                if (!enqueue_body()) return false;
+            }
+        }
+        resolve_phases();
+        return check_launch();
+    }
 
     bool check_launch() {
         cudaError_t e = cudaGetLastError();
@@ -1381,6 +1484,70 @@ static int minimize_impl(lbfgsb_dev_t* h, T* x, const T* l, const T* u, const in
             }
         } else break;
     }
+    if (pre60(task, "CONV")) return 0;
+    if (pre60(task, "ABNO")) return 1;
+    return 2;
+}
+
+// The same loop kept on the device: the objective callback only ENQUEUES work on the given stream and leaves f in device
+// memory, so that one iteration step -- objective, FG_LNSRCH entry, NEW_X entry -- is captured once as a CUDA graph and
+// replayed with one launch and one read-back of the state header per step (Engine::build_iter_graph / graph_step).
+// START and FG_START, the STOP of a limit, and whatever leaves the fast pipeline's common path go through setulb as usual.
+template <typename T, typename FGE>
+static int minimize_graph_impl(lbfgsb_dev_t* h, T* x, const T* l, const T* u, const int32_t* nbd, FGE fg, void* user, T factr, T pgtol,
+                               int32_t max_iter, int32_t max_fg, T* f, T* g, char* task, char* csave, int32_t* lsave,
+                               int32_t* isave, T* dsave) {
+    Engine<T>* e = (Engine<T>*)h;
+    if (!e || e->real_kind != (int)sizeof(T) || !fg) { put60(task, "ERROR: INVALID LBFGSB_B200 HANDLE"); return 2; }
+    const int32_t iprint = -1;
+    T* fd = nullptr;
+    auto eval_host = [&]() -> bool {   // one evaluation outside the graph: f comes back to the host
+        if (!fd) { if (cudaMalloc((void**)&fd, sizeof(T)) != cudaSuccess) return false; }
+        if (fg(user, e->n, x, g, fd, (void*)e->stream) != 0) return false;
+        if (cudaMemcpyAsync(f, fd, sizeof(T), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) return false;
+        return cudaStreamSynchronize(e->stream) == cudaSuccess;
+    };
+    auto fail = [&]() {
+        put60(task, "STOP: THE OBJECTIVE CALLBACK FAILED");
+        setulb_dev_impl<T>(h, x, l, u, nbd, f, g, &factr, &pgtol, task, &iprint, csave, lsave, isave, dsave);
+        if (fd) cudaFree(fd);
+        return 2;
+    };
+    put60(task, "START");
+    bool graph_ok = false, graph_tried = false;
+    for (;;) {
+        setulb_dev_impl<T>(h, x, l, u, nbd, f, g, &factr, &pgtol, task, &iprint, csave, lsave, isave, dsave);
+        // the device-resident loop takes over whenever the state asks for a line-search evaluation
+        if (pre60(task, "FG_LN") && e->fast && e->R == 1 && e->s_host->cnstnd) {
+            if (!graph_tried) {
+                graph_tried = true;
+                e->w.x = x; e->w.l = l; e->w.u = u; e->w.nbd = nbd; e->w.g = g;
+                graph_ok = e->build_iter_graph(fg, user, max_iter, max_fg);
+            }
+            if (graph_ok) {
+                e->w.x = x; e->w.l = l; e->w.u = u; e->w.nbd = nbd; e->w.g = g; e->w.bp_hint = 0;
+                bool ok = true;
+                while (ok && e->s_host->task == TK_FG_LNSRCH) ok = e->graph_step();
+                if (!ok) { put60(task, "ERROR: CUDA FAILURE (see lbfgsb_b200_last_error)"); if (fd) cudaFree(fd); return 2; }
+                *f = e->s_host->f;
+                export_state<T>(e, task, csave, lsave, isave, dsave);
+            }
+        }
+        if (pre60(task, "FG")) {
+            if (!eval_host()) return fail();
+        } else if (pre60(task, "NEW_X")) {
+            const char* stop = nullptr;
+            if (max_fg > 0 && isave[33] >= max_fg) stop = "STOP: TOTAL NO. of f AND g EVALUATIONS EXCEEDS LIMIT";   // driver2.f90:176
+            if (max_iter > 0 && isave[29] >= max_iter) stop = "STOP: TOTAL NO. of ITERATIONS REACHED LIMIT";
+            if (stop) {
+                put60(task, stop);
+                setulb_dev_impl<T>(h, x, l, u, nbd, f, g, &factr, &pgtol, task, &iprint, csave, lsave, isave, dsave);
+                if (fd) cudaFree(fd);
+                return 0;
+            }
+        } else break;
+    }
+    if (fd) cudaFree(fd);
     if (pre60(task, "CONV")) return 0;
     if (pre60(task, "ABNO")) return 1;
     return 2;
@@ -2098,6 +2265,24 @@ int lbfgsb_minimize_dev_f32(lbfgsb_dev_t* h, float* x, const float* l, const flo
                             void* user, float factr, float pgtol, int32_t max_iter, int32_t max_fg, int32_t iprint, float* f,
                             float* g, char* task, char* csave, int32_t* lsave, int32_t* isave, float* dsave) {
     return minimize_impl<float>(h, x, l, u, nbd, fg, user, factr, pgtol, max_iter, max_fg, iprint, f, g, task, csave, lsave, isave, dsave);
+}
+
+int lbfgsb_minimize_graph_dev_f64(lbfgsb_dev_t* h, double* x, const double* l, const double* u, const int32_t* nbd, lbfgsb_fg_enqueue_f64 fg,
+                                  void* user, double factr, double pgtol, int32_t max_iter, int32_t max_fg, double* f, double* g,
+                                  char* task, char* csave, int32_t* lsave, int32_t* isave, double* dsave) {
+    return minimize_graph_impl<double>(h, x, l, u, nbd, fg, user, factr, pgtol, max_iter, max_fg, f, g, task, csave, lsave, isave, dsave);
+}
+int lbfgsb_minimize_graph_dev_f32(lbfgsb_dev_t* h, float* x, const float* l, const float* u, const int32_t* nbd, lbfgsb_fg_enqueue_f32 fg,
+                                  void* user, float factr, float pgtol, int32_t max_iter, int32_t max_fg, float* f, float* g,
+                                  char* task, char* csave, int32_t* lsave, int32_t* isave, float* dsave) {
+    return minimize_graph_impl<float>(h, x, l, u, nbd, fg, user, factr, pgtol, max_iter, max_fg, f, g, task, csave, lsave, isave, dsave);
+}
+int lbfgsb_dev_graph_stats(lbfgsb_dev_t* h, int64_t* graph_steps, int64_t* launches_per_step) {
+    EngineBase* b = (EngineBase*)h;
+    if (!b) return 1;
+    if (b->real_kind == 8) { Engine<double>* e = (Engine<double>*)b; *graph_steps = e->graph_steps; *launches_per_step = e->graph_launches_per_step; }
+    else { Engine<float>* e = (Engine<float>*)b; *graph_steps = e->graph_steps; *launches_per_step = e->graph_launches_per_step; }
+    return 0;
 }
 
 int lbfgsb_dev_nccl_unique_id(void* id128) {

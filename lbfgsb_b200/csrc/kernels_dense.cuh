@@ -1026,6 +1026,35 @@ __global__ void f_head(Wk<T> w, T f, int fused_supported) {
     t0_newx_tests<T>(w.s, fused_supported);
 }
 
+// ===========================================================================
+// Device-resident iteration (Engine::minimize_graph): one CUDA graph holds the caller's objective kernels, the FG_LNSRCH
+// entry and the NEW_X entry of the fast pipeline.  The two entry kernels below open their setulb call only if the state
+// block asks for exactly that call -- what the caller's loop (test/driver1.f90:263-292) decides from `task` on the host --
+// and take f from device memory; otherwise everything enqueued behind them returns at once.
+// ===========================================================================
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) g_ls_trial(Wk<T> w, Dist<T> dist, const T* f_dev) {
+    __shared__ Red<T> red;
+    DevState<T>* s = w.s;
+    if (s->task != TK_FG_LNSRCH) return;
+    site_reduce<T>(w, dist, site_lstrial(), &red);
+    if (threadIdx.x != 0) return;
+    t0_call_begin<T>(s, *f_dev);
+    s->gstage = 1;
+    t0_ls_trial<T>(s, red);
+}
+// NEW_X entry, unless the caller's limits say STOP (test/driver2.f90:174-181: the host then issues it through setulb)
+template <typename T>
+__global__ void g_head(Wk<T> w, int fused_supported, int max_iter, int max_fg) {
+    if (threadIdx.x != 0) return;
+    DevState<T>* s = w.s;
+    const bool limit = (max_iter > 0 && s->iter >= max_iter) || (max_fg > 0 && s->nfgv >= max_fg);
+    if (s->task != TK_NEW_X || limit) { s->go = 0; return; }   // (a restart of the line search left go = 1: the host resumes it)
+    t0_call_begin<T>(s, s->f);
+    s->gstage = 2;
+    t0_newx_tests<T>(s, fused_supported);
+}
+
 // s_update_dense + s_cauchy + s_freev(phase 0 with fuse_gf).
 template <typename T>
 __global__ void __launch_bounds__(LB_SCALAR_THREADS) f_ucf(Wk<T> w, Dist<T> dist, int mt) {

@@ -112,3 +112,33 @@ def test_checkpoint_resume_continues_bit_identically(tmp_path):
     with pytest.raises(lbfgsb_b200.LbfgsbB200Error):
         c.checkpoint_read(path)
     c.close()
+
+
+@pytest.mark.parametrize("n,m,factr,pgtol,max_iter", [(30000, 7, 1e7, 1e-5, 0), (1000, 10, 0.0, 0.0, 40), (200001, 5, 0.0, 0.0, 25)])
+def test_minimize_graph_keeps_the_loop_on_the_device_and_matches_the_caller_loop(n, m, factr, pgtol, max_iter):
+    """lbfgsb_minimize_graph_dev_f64: one CUDA-graph launch per iteration step (objective + FG_LNSRCH entry + NEW_X entry),
+    everything off the common path handed to the general pipeline -- final x, f, isave(22:44) and the task equal to the
+    caller-driven loop bit for bit (the first iterations of these problems walk breakpoints and move variables in and out of
+    the free set, later ones run as graph launches only)."""
+    import torch
+    import lbfgsb_b200
+    fg = lbfgsb_b200.RosenbrockDevice(np.float64)
+    x, l, u, nbd, g = _problem(n)
+    a = lbfgsb_b200.DeviceProblem(n, m, np.float64)
+    if max_iter:
+        rc = a.minimize(x, l, u, nbd, g, fg, factr, pgtol, max_iter=max_iter)
+    else:
+        _loop(a, fg, x, l, u, nbd, g, factr, pgtol, 10 ** 9)
+    x2, l, u, nbd, g2 = _problem(n)
+    b = lbfgsb_b200.DeviceProblem(n, m, np.float64)
+    fg2 = lbfgsb_b200.RosenbrockDevice(np.float64)
+    fg2._n = n
+    halo = torch.zeros(2, dtype=torch.float64, device="cuda")
+    rc = b.minimize_graph(x2, l, u, nbd, g2, fg2.enqueue(halo), factr, pgtol, max_iter=max_iter)
+    assert rc == 0 and b.task_str() == a.task_str()
+    assert float(a.f[0]).hex() == float(b.f[0]).hex()
+    assert list(a.isave[21:44]) == list(b.isave[21:44])
+    assert torch.equal(x, x2)
+    steps, per = b.graph_stats()
+    assert steps >= int(b.isave[29]) // 2 and per > 0, (steps, per, int(b.isave[29]))
+    a.close(); b.close()

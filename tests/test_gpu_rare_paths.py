@@ -152,3 +152,35 @@ def test_ascent_direction_restart_withdraws_speculative_step_f32():
         cols = [r["col"] for r in gpu[0]]
         gpu_restarts += any(b < a for a, b in zip(cols, cols[1:]))
     assert gpu_restarts >= 1, "no GPU run restarted from an ascent direction: the branch is no longer covered on the device"
+
+
+def test_fast_and_general_pipelines_agree_through_ascent_restarts():
+    """The fast NEW_X pipeline (merged scalar kernels, one read-back) against the general one (LBFGSB_B200_NO_FAST=1) on
+    the REAL32 problems above, whose runs restart from an ascent direction after a speculative step (x = t must be put
+    back before the iteration restarts): every iterate bit for bit, and the final x."""
+    import os
+    import lbfgsb_b200
+    restarts = 0
+    for n, m, l_odd, x0 in F32_ASCENT_CASES + [(3001, 20, 1.0, 5.0), (50001, 10, 1.0, 5.0), (4000, 20, 1.0, 5.0)]:
+        runs = []
+        for no_fast in ("0", "1"):
+            old = os.environ.get("LBFGSB_B200_NO_FAST")
+            os.environ["LBFGSB_B200_NO_FAST"] = no_fast
+            try:
+                x, l, u, nbd = H.rosenbrock_problem(n, dtype=np.float32, l_odd=l_odd, x0=x0)
+                runs.append(H.run_driver(lbfgsb_b200.HostSetulb(np.float32), O.rosenbrock_fg, n, m, x, l, u, nbd, 0.0, 0.0,
+                                         stop=H.iteration_budget_stop(120)))
+            finally:
+                if old is None:
+                    del os.environ["LBFGSB_B200_NO_FAST"]
+                else:
+                    os.environ["LBFGSB_B200_NO_FAST"] = old
+        a, b = runs
+        assert a[1] == b[1] and len(a[0]) == len(b[0]), (n, m, x0, a[1], b[1], len(a[0]), len(b[0]))
+        for ra, rb in zip(a[0], b[0]):
+            for k in H.TRACE_FIELDS:
+                assert ra[k] == rb[k], (n, m, x0, k, ra, rb)
+        assert np.array_equal(a[2], b[2])
+        cols = [r["col"] for r in a[0]]
+        restarts += any(q < p for p, q in zip(cols, cols[1:]))
+    assert restarts >= 1, "no run restarted: the branch is not covered"
