@@ -32,6 +32,7 @@ module lbfgsb_module
    public :: setulb, setulb_dev
    public :: lbfgsb_dev_create, lbfgsb_dev_destroy, lbfgsb_host_release
    public :: lbfgsb_dev_set_tie_limit, lbfgsb_dev_checkpoint_write, lbfgsb_dev_checkpoint_read
+   public :: lbfgsb_minimize_graph_dev
    public :: lbfgsb_batch_create, lbfgsb_batch_destroy, setulb_batch_dev, lbfgsb_batch_counts, lbfgsb_batch_get_iwhere
 
    interface
@@ -109,6 +110,27 @@ module lbfgsb_module
          character(kind=c_char), intent(in) :: path(*)
          integer(c_int) :: rc
       end function lbfgsb_dev_checkpoint_read
+
+      !> The caller's loop kept on the device (one CUDA-graph launch per iteration step): fg is a C function pointer
+      !> int fg(void* user, int64_t n, const real* x_dev, real* g_dev, real* f_dev, void* cuda_stream) that only enqueues
+      !> kernels and leaves f in device memory (c_funloc of a bind(C) procedure).
+#ifdef REAL32
+      function lbfgsb_minimize_graph_dev(h, x, l, u, nbd, fg, user, factr, pgtol, max_iter, max_fg, f, g, task, csave, &
+                                         lsave, isave, dsave) result(rc) bind(C, name='lbfgsb_minimize_graph_dev_f32')
+#else
+      function lbfgsb_minimize_graph_dev(h, x, l, u, nbd, fg, user, factr, pgtol, max_iter, max_fg, f, g, task, csave, &
+                                         lsave, isave, dsave) result(rc) bind(C, name='lbfgsb_minimize_graph_dev_f64')
+#endif
+         import :: c_int32_t, c_char, c_ptr, c_funptr, c_int, wp
+         type(c_ptr), value :: h, x, l, u, nbd, g, user
+         type(c_funptr), value :: fg
+         real(wp), value :: factr, pgtol
+         integer(c_int32_t), value :: max_iter, max_fg
+         real(wp), intent(inout) :: f, dsave(29)
+         character(kind=c_char), intent(inout) :: task(60), csave(60)
+         integer(c_int32_t), intent(inout) :: lsave(4), isave(44)
+         integer(c_int) :: rc
+      end function lbfgsb_minimize_graph_dev
 
       !> Batched small problems: nprob independent problems of the same n and m, one call advances every problem from
       !> its own task to its next return point (the caller's loop of test/driver1.f90:263-292, many times over).

@@ -438,7 +438,7 @@ class RosenbrockDevice:
     def __call__(self, x, g, first=1, last=1, xl=0.0, xr=0.0):
         self._n = x.numel()
         rc = self._fn(C.c_int64(x.numel()), C.c_void_p(x.data_ptr()), C.c_void_p(g.data_ptr()), _p(self._f),
-                      self.stream, first, last, self._cr(xl), self._cr(xr), C.c_void_p(self.scratch.data_ptr()))
+                      C.c_void_p(self.stream), first, last, self._cr(xl), self._cr(xr), C.c_void_p(self.scratch.data_ptr()))
         if rc != 0:
             raise LbfgsbB200Error("rosenbrock kernel failed: " + last_error())
         return self._f[0]
@@ -458,7 +458,7 @@ class RosenbrockDevice:
         """Shard evaluation without a host round trip (float64): xl, xr from halo_dev[0..1], partial f -> f_part_dev."""
         rc = lib().lbfgsb_problem_rosenbrock_halo_f64(
             C.c_int64(x.numel()), C.c_void_p(x.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(f_part_dev.data_ptr()),
-            self.stream, C.c_int32(first), C.c_int32(last), C.c_void_p(halo_dev.data_ptr()), C.c_void_p(self.scratch.data_ptr()))
+            C.c_void_p(self.stream), C.c_int32(first), C.c_int32(last), C.c_void_p(halo_dev.data_ptr()), C.c_void_p(self.scratch.data_ptr()))
         if rc != 0:
             raise LbfgsbB200Error("rosenbrock kernel failed")
 
@@ -479,7 +479,7 @@ class QuadraticDevice:
 
     def __call__(self, x, g, offset=0, xl=0.0, xr=0.0):
         rc = self._fn(C.c_int64(x.numel()), C.c_void_p(x.data_ptr()), C.c_void_p(g.data_ptr()), _p(self._f),
-                      self.stream, C.c_int64(offset), C.c_uint64(self.seed), self._cr(xl), self._cr(xr),
+                      C.c_void_p(self.stream), C.c_int64(offset), C.c_uint64(self.seed), self._cr(xl), self._cr(xr),
                       C.c_void_p(self.scratch.data_ptr()))
         if rc != 0:
             raise LbfgsbB200Error("quadratic kernel failed: " + last_error())
@@ -488,7 +488,7 @@ class QuadraticDevice:
     def shard_async(self, x, g, offset, halo_dev, f_part_dev):
         rc = lib().lbfgsb_problem_quadratic_halo_f64(
             C.c_int64(x.numel()), C.c_void_p(x.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(f_part_dev.data_ptr()),
-            self.stream, C.c_int64(offset), C.c_uint64(self.seed), C.c_void_p(halo_dev.data_ptr()),
+            C.c_void_p(self.stream), C.c_int64(offset), C.c_uint64(self.seed), C.c_void_p(halo_dev.data_ptr()),
             C.c_void_p(self.scratch.data_ptr()))
         if rc != 0:
             raise LbfgsbB200Error("quadratic kernel failed")

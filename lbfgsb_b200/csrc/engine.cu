@@ -170,7 +170,7 @@ struct Engine : EngineBase {
     // breakpoint walks tend to come in runs of iterations: after an iteration that needed one, cauchy's per-variable pass of
     // the next iteration also stores every breakpoint and xcp = x (Wk::bp_hint), and the walk's first pass reads 8 bytes
     // per variable instead of recomputing them from x, g, l, u, nbd, iwhere
-    bool walked_prev = false, walked_now = false, body_ran = false, bp_hint_ok = true;
+    bool walked_prev = false, walked_now = false, body_ran = false, bp_hint_ok = true, walk_gf_ok = true;
     bool started = false;            // this workspace has seen task = 'START' (or a checkpoint of a started run)
 
     // records over peer memory (kernels_dense.cuh: P2PBuf)
@@ -258,7 +258,7 @@ struct Engine : EngineBase {
         fast = fused;   // the fast NEW_X pipeline is built from the fused passes
         if (const char* e = getenv("LBFGSB_B200_NO_FAST")) { if (e[0] == '1') fast = false; }
         if (const char* e = getenv("LBFGSB_B200_NO_TIMERS")) { if (e[0] == '1') timers = false; }
-        if (const char* e = getenv("LBFGSB_B200_NO_BP_HINT")) { if (e[0] == '1') bp_hint_ok = false; }
+        if (const char* e = getenv("LBFGSB_B200_NO_BP_HINT")) { if (e[0] == '1') { bp_hint_ok = false; walk_gf_ok = false; } }
         if (!(mt == 5 ? set_smem_attrs<5>() : (mt == 10 ? set_smem_attrs<10>() : set_smem_attrs<20>()))) return false;
         for (int q = 0; q < F_COUNT; ++q) { fam_ms[q] = 0; fam_calls[q] = 0; }
         if (st) stream = st;
@@ -468,10 +468,13 @@ struct Engine : EngineBase {
         if constexpr (fused_passes_ok<T, MT>()) k_update_classify<T, MT><<<LBFGSB_GRID, LB_TMA_THREADS, smem_update_classify<T, MT>(), stream>>>(w);
     }
     template <int MT> void launch_formk_cmprlb() {
-        if constexpr (fused_passes_ok<T, MT>()) k_formk_cmprlb<T, MT, false><<<LBFGSB_GRID, LB_TMA_THREADS, smem_formk_cmprlb<T, MT>(), stream>>>(w);
+        if constexpr (fused_passes_ok<T, MT>()) k_formk_cmprlb<T, MT, 0><<<LBFGSB_GRID, LB_TMA_THREADS, smem_formk_cmprlb<T, MT>(), stream>>>(w);
     }
     template <int MT> void launch_formk_cmprlb_gf() {
-        if constexpr (fused_passes_ok<T, MT>()) k_formk_cmprlb<T, MT, true><<<LBFGSB_GRID, LB_TMA_THREADS, smem_formk_cmprlb<T, MT>(), stream>>>(w);
+        if constexpr (fused_passes_ok<T, MT>()) k_formk_cmprlb<T, MT, 1><<<LBFGSB_GRID, LB_TMA_THREADS, smem_formk_cmprlb<T, MT>(), stream>>>(w);
+    }
+    template <int MT> void launch_formk_cmprlb_gf2() {
+        if constexpr (fused_passes_ok<T, MT>()) k_formk_cmprlb<T, MT, 2><<<LBFGSB_GRID, LB_TMA_THREADS, smem_formk_cmprlb<T, MT>(), stream>>>(w);
     }
     template <int MT> void launch_subsm_lsinit() {
         if constexpr (fused_passes_ok<T, MT>()) k_subsm_lsinit<T, MT, 0><<<LBFGSB_GRID, LB_TMA_THREADS, smem_subsm<T, MT>(), stream>>>(w);
@@ -490,8 +493,9 @@ struct Engine : EngineBase {
         CK(cudaFuncSetAttribute(k_subsm_step<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_subsm<T, MT>()));
         if constexpr (fused_passes_ok<T, MT>()) {
             CK(cudaFuncSetAttribute(k_update_classify<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_update_classify<T, MT>()));
-            CK(cudaFuncSetAttribute(k_formk_cmprlb<T, MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk_cmprlb<T, MT>()));
-            CK(cudaFuncSetAttribute(k_formk_cmprlb<T, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk_cmprlb<T, MT>()));
+            CK(cudaFuncSetAttribute(k_formk_cmprlb<T, MT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk_cmprlb<T, MT>()));
+            CK(cudaFuncSetAttribute(k_formk_cmprlb<T, MT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk_cmprlb<T, MT>()));
+            CK(cudaFuncSetAttribute(k_formk_cmprlb<T, MT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_formk_cmprlb<T, MT>()));
             CK(cudaFuncSetAttribute(k_subsm_lsinit<T, MT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_subsm<T, MT>()));
             CK(cudaFuncSetAttribute(k_subsm_lsinit<T, MT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_subsm<T, MT>()));
         }
@@ -888,6 +892,7 @@ struct Engine : EngineBase {
         body_ran = true;
         for (;;) {
             bool gf = false;   // cauchy's tail and freev run inside k_formk_cmprlb (decided by s_cauchy)
+            bool gf2 = false;  // ... after a breakpoint walk (s_walk_gf)
             if (from <= PAUSE_CLASSIFY) {
                 phase(PH_CAUCHY);
                 begin(F_CLASSIFY); MTCALL(k_cauchy_classify, smem_classify, w); end(F_CLASSIFY);
@@ -900,6 +905,9 @@ struct Engine : EngineBase {
                     if (s_host->go && s_host->in_body && s_host->need_walk) {
                         walked_now = true;
                         if (!enqueue_walk_rounds()) return false;   // (its first count pass writes xcp and the breakpoints)
+                        // the walk has closed: a = M c, and the cauchy tail + freev move into k_formk_cmprlb (fuse_gf = 2) --
+                        // unless that product fails, which the host does not wait to learn: both variants are enqueued
+                        if (fused && walk_gf_ok) { begin(F_SCALAR); s_walk_gf<T><<<LS>>>(w, 1); end(F_SCALAR); gf2 = true; }
                     }
                     gf = fused && s_host->go && s_host->in_body && s_host->fuse_gf;
                 }
@@ -907,17 +915,18 @@ struct Engine : EngineBase {
             if (from <= PAUSE_GCP_FREEV) {
                 phase(PH_SUBSPACE);
                 if (!gf) {
-                    begin(F_GCP_FREEV); k_gcp_freev<T><<<LG>>>(w); end(F_GCP_FREEV);
+                    begin(F_GCP_FREEV); k_gcp_freev<T><<<LG>>>(w); end(F_GCP_FREEV);   // (returns at once under fuse_gf = 2)
                     if (!site(site_freev())) return false;
                 }
                 begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global, 0); end(F_SCALAR);
                 if (fused) {
                     begin(F_FORMK_CMPRLB);
-                    if (gf) MTFUSED(launch_formk_cmprlb_gf); else MTFUSED(launch_formk_cmprlb);
+                    if (gf) MTFUSED(launch_formk_cmprlb_gf);
+                    else { if (gf2) { MTFUSED(launch_formk_cmprlb_gf2); launches++; } MTFUSED(launch_formk_cmprlb); }
                     end(F_FORMK_CMPRLB);
                 }
                 else { begin(F_FORMK_GRAM); MTCALL(k_formk_gram, smem_formk, w); end(F_FORMK_GRAM); }
-                if (gf) {
+                if (gf || gf2) {
                     if (!site(site_freev())) return false;
                     begin(F_SCALAR); s_freev<T><<<LS>>>(w, dist(), n_global, 1); end(F_SCALAR);
                 }

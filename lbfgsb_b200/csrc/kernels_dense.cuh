@@ -465,7 +465,7 @@ template <typename T> __device__ inline void w_freev(DevState<T>* s, const Red<T
     const int lane = threadIdx.x & 31;
     int need_a = 0;
     if (lane == 0) {
-        if (gf) s->lazy_z = 1;   // k_formk_cmprlb did not store xcp (state bit 2 tells where d = -g)
+        if (s->fuse_gf == 1) s->lazy_z = 1;   // k_formk_cmprlb did not store xcp (state bit 2 tells where d = -g)
         if (have) {
             s->nintol = s->nintol + s->nseg;
             s->nfree = red.iv[0];
@@ -827,6 +827,22 @@ __global__ void __launch_bounds__(LB_SCALAR_THREADS) s_cauchy(Wk<T> w, Dist<T> d
     __syncthreads();
     if (threadIdx.x >= 32) return;
     w_cauchy<T>(s, red, mt, ssy, swt, fused_supported);
+}
+
+// After a breakpoint walk has closed: c is final, so cmprlb's a = M c (:1569) can be formed here as s_cauchy forms it when
+// no walk is needed, and the tail of cauchy and freev then run inside k_formk_cmprlb as well (fuse_gf = 2: the Cauchy point
+// starts from the stored xcp, which holds the bounds of the variables the walk fixed).
+template <typename T>
+__global__ void __launch_bounds__(LB_SCALAR_THREADS) s_walk_gf(Wk<T> w, int fused_supported) {
+    __shared__ T ssy[LB_MMAX * LB_MMAX], swt[LB_MMAX * LB_MMAX];
+    DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk || !s->walk_closed || s->cauchy_mode != 0) return;
+    if (!fused_supported || s->col <= 0 || !s->cnstnd || s->fuse_gf) return;
+    stage_in<T>(ssy, s->sy, s->m * s->m); stage_in<T>(swt, s->wt, s->m * s->m);
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int info = wdense::bmv<T>(s->m, ssy, swt, s->col, s->c, s->a);
+    if (info == 0 && (threadIdx.x & 31) == 0) s->fuse_gf = 2;
 }
 
 template <typename T>

@@ -613,7 +613,7 @@ template <typename T, int MT> constexpr unsigned smem_update_classify() { return
 // on sy, wt and c and is therefore computed before this pass (s_freev).
 // part : as k_formk_gram (written when the Gram row is needed)     part2 : as k_cmprlb_wv
 // ---------------------------------------------------------------------------
-template <typename T, int MT, bool GF>
+template <typename T, int MT, int GF>
 __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
     constexpr int VEC = Real<T>::VEC;
     constexpr int SUBT = SubT<T, MT>::v;
@@ -626,11 +626,13 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
     __shared__ i64 smi[LBFGSB_BLOCK / 32];
     const DevState<T>* s = w.s;
     if (!s->go || s->pause || !s->in_body || !s->do_subspace) return;
-    // GF: the tail of cauchy (xcp = x + tsum*d, :1515) and freev (:1980-2059) are part of this pass; the flags
+    // GF != 0: the tail of cauchy (xcp = xcp + tsum*d, :1515) and freev (:1980-2059) are part of this pass; the flags
     // do_subspace / do_formk are then s_freev's tentative values (the counts are only known after this pass).
-    // The host launches the instantiation that matches the device flag (it has read fuse_gf back by then).
-    constexpr bool gf = GF;
-    if ((s->fuse_gf != 0) != GF) return;
+    // GF = 1: no breakpoint walk ran, xcp = x is implied and the Cauchy point is not stored either (lazy_z);
+    // GF = 2: after a walk -- xcp holds the bounds of the variables the walk fixed, and the Cauchy point is stored.
+    // The host launches the instantiation(s) that can match the device flag fuse_gf.
+    constexpr bool gf = GF != 0;
+    if (s->fuse_gf != GF) return;
     const bool gram = s->do_formk && s->updatd;
     const i64 n = w.n;
     const int col = s->col, head0 = s->head - 1;
@@ -640,12 +642,12 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
     const bool axpy = tsum != (T)0;            // daxpy early-out (:49-50)
     const bool cnt = (s->iter > 0 && s->cnstnd);
     constexpr unsigned OG = 0, OX = G::REAL_SLOT, OZ = 2 * G::REAL_SLOT;
-    constexpr unsigned OW = (gf ? 2u : 3u) * G::REAL_SLOT;
+    constexpr unsigned OW = (GF == 1 ? 2u : 3u) * G::REAL_SLOT;
     if (threadIdx.x == 0) {
         pipe_begin(&ps);
         pipe_add(&ps, w.g, sizeof(T), G::REAL_SLOT);
         pipe_add(&ps, w.x, sizeof(T), G::REAL_SLOT);
-        if (!gf) pipe_add(&ps, w.z, sizeof(T), G::REAL_SLOT);
+        if (GF != 1) pipe_add(&ps, w.z, sizeof(T), G::REAL_SLOT);
         pipe_add_w<T>(&ps, w, head0, col, G::REAL_SLOT);
         pipe_add(&ps, w.state, 1, G::BYTE_SLOT);
         if (gf) pipe_add(&ps, w.iwhere, 4, G::INT_SLOT);
@@ -683,6 +685,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
             lds_int<T>(sb, oiw, lt, iw);
             T z[VEC], x[VEC], g[VEC];
             lds_real<T>(sb, OG, lt, g); lds_real<T>(sb, OX, lt, x);
+            if (GF == 2) lds_real<T>(sb, OZ, lt, z);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 const bool inr = base + v < n;
@@ -694,10 +697,12 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
                 // from x and g by the subspace pass, and is not stored here (lazy_z)
                 st[v] = (f ? 1 : 0) | ((cnt ? old : (f ? 1 : 0)) << 1) | ((iw[v] == 0 || iw[v] == -1) ? 4 : 0);
                 fr[v] = f; any |= f;
-                z[v] = axpy ? (x[v] + tsum * cauchy_dir<T>(iw[v], g[v])) : x[v];
+                const T z0 = (GF == 2) ? z[v] : x[v];
+                z[v] = axpy ? (z0 + tsum * cauchy_dir<T>(iw[v], g[v])) : z0;
                 r[v] = ucv ? -g[v] : (-theta * (z[v] - x[v]) - g[v]);
             }
             stvb<T>(w.state, base, n, st);
+            if (GF == 2 && axpy) stv<T>(w.z, base, n, z);   // the Cauchy point (:1515), read by the subspace pass
             if (!any && !gramv) return;
         } else {
 #pragma unroll
@@ -799,7 +804,7 @@ __global__ void __launch_bounds__(LB_TMA_THREADS, 1) k_formk_cmprlb(Wk<T> w) {
         }
     }
 }
-template <typename T, int MT> constexpr unsigned smem_formk_cmprlb() { return pipe_smem_bytes<T, SubT<T, MT>::v>(3 + 2 * MT, 0, 1); }
+template <typename T, int MT> constexpr unsigned smem_formk_cmprlb() { return pipe_smem_bytes<T, SubT<T, MT>::v>(3 + 2 * MT, 1, 1); }
 
 // ---------------------------------------------------------------------------
 // k_subsm_step fused with k_ls_init: the subspace pass has z (the Newton point), x, g, l, u, nbd of every

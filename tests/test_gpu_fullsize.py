@@ -61,6 +61,56 @@ def test_config3_full_size_iteration_properties():
     prob.close()
 
 
+def test_config3_full_size_trace_matches_the_oracle():
+    """BASELINE.json configs[2] at its full size against the oracle itself: tests/golden/config3_n1e8_trace.json holds the
+    oracle's first iterates at n = 1e8, m = 10 in device-order summation mode (tests/golden/make_golden_config3.py; the same
+    script checks that the oracle's reference-order run has the identical discrete trace and stores the drift of f).
+    Every discrete field and the active-set hash equal at every iterate; f and |proj g| within 1e-10 relative for the
+    first 10 iterates, 1e-6 after."""
+    import json
+    import os
+    import torch
+    import lbfgsb_b200
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config3_n1e8_trace.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/config3_n1e8_trace.json has not been recorded")
+    gold = json.load(open(path))
+    _need(60)
+    n, m = gold["n"], gold["m"]
+    dev = torch.device("cuda")
+    x = torch.full((n,), 3.0, dtype=torch.float64, device=dev)
+    l = torch.full((n,), -100.0, dtype=torch.float64, device=dev)
+    l[0::2] = gold["l_odd"]
+    u = torch.full((n,), 100.0, dtype=torch.float64, device=dev)
+    nbd = torch.full((n,), 2, dtype=torch.int32, device=dev)
+    g = torch.zeros_like(x)
+    prob = lbfgsb_b200.DeviceProblem(n, m, np.float64)
+    fg = lbfgsb_b200.RosenbrockDevice(np.float64)
+    rows = gold["iterates"]
+    k = 0
+    while k < len(rows):
+        prob.setulb_dev(x, l, u, nbd, g, 0.0, 0.0)
+        t = prob.task_str()
+        if t[:2] == "FG":
+            prob.f[0] = fg(x, g)
+        elif t[:5] == "NEW_X":
+            b = rows[k]
+            h, c = prob.active_set_hash()
+            a = {"iter": int(prob.isave[29]), "nfgv": int(prob.isave[33]), "nseg": int(prob.isave[32]), "nact": int(prob.isave[38]),
+                 "nfree": int(prob.isave[37]), "nenter": int(prob.isave[40]), "nleave": int(n + 1 - prob.isave[39]),
+                 "iword": int(prob.isave[36]), "iback": int(prob.isave[24]), "col": int(prob.isave[27]), "nskip": int(prob.isave[25]),
+                 "hash": h, "hcount": c}
+            for key, v in a.items():
+                assert v == b[key], (key, k, a, {q: b[q] for q in a})
+            tol = 1e-10 if b["iter"] <= 10 else 1e-6
+            assert abs(float(prob.f[0]) - b["f"]) <= tol * abs(b["f"]), (k, float(prob.f[0]), b["f"])
+            assert abs(float(prob.dsave[12]) - b["sbgnrm"]) <= 100 * tol * abs(b["sbgnrm"]), (k, float(prob.dsave[12]), b["sbgnrm"])
+            k += 1
+        else:
+            raise AssertionError("unexpected task " + t)
+    prob.close()
+
+
 def test_full_size_fixed_shape_sum_and_sort():
     import torch
     import lbfgsb_b200
