@@ -269,6 +269,9 @@ int lbfgsb_test_sum_f64(int64_t n, const double* a, const double* b, double* out
 int lbfgsb_test_sum_f32(int64_t n, const float* a, const float* b, float* out);
 int lbfgsb_test_sort_f64(int64_t n, const double* t_dev, int32_t* order_out_dev, double* sorted_out_dev);
 /* hpsolb (:2079-2157) replayed on the device: heap built over t(1..n), popped n times; order_out = iorder of the pops */
+/* host-only: the engine's host-thread heap replay (long breakpoint lists, sharded workspaces) on t_host[nb] (> 0, variable
+ * order): the variables whose breakpoint equals tk in the reference's order (:1384-1397, hpsolb :2079-2157) */
+int lbfgsb_test_host_heap_group_f64(int64_t nb, const double* t_host, double tk, int32_t* group_out, int64_t* group_count);
 int lbfgsb_test_heap_order_f64(int64_t n, const double* t_dev, int32_t* order_out_dev);
 /* formk's entering/leaving corrections (src/lbfgsb.f90:1801-1851) on their own.  ws_dev, wy_dev: m columns of ldw reals;
  * state_dev: one byte per variable, bit 0 = free now, bit 1 = free before (rows with the two bits different are listed);

@@ -2536,6 +2536,25 @@ int lbfgsb_test_sort_f64(int64_t n, const double* t, int32_t* order_out, double*
     cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(cnt); cudaFree(ctl);
     return e != cudaSuccess || cudaGetLastError() != cudaSuccess;
 }
+// The host thread's heap replay on its own (no GPU): t_host = the breakpoints of a cauchy call in variable order; out = the
+// variables whose breakpoint equals tk, in the order in which the reference takes them (the first minimum before the heap
+// exists, :1384-1397, the others as hpsolb pops them, :2079-2157).
+int lbfgsb_test_host_heap_group_f64(int64_t nb, const double* t_host, double tk, int32_t* group_out, int64_t* group_count) {
+    if (nb <= 0 || !t_host || !group_out || !group_count) return 1;
+    typedef unsigned long long K;
+    std::vector<K> hk((size_t)nb); std::vector<int> hv((size_t)nb);
+    int vmin = 0;
+    for (int64_t i = 0; i < nb; ++i) {
+        memcpy(&hk[(size_t)i], &t_host[i], 8); hv[(size_t)i] = (int)i;
+        if (t_host[i] < t_host[vmin]) vmin = (int)i;   // strict <: lowest index among ties (:1310)
+    }
+    K kk; memcpy(&kk, &tk, 8);
+    std::vector<K> gk; std::vector<int> gv;
+    Engine<double>::heap_group_order<K>(kk, hk, hv, vmin, gk, gv);
+    for (size_t i = 0; i < gv.size(); ++i) group_out[i] = gv[i];
+    *group_count = (int64_t)gv.size();
+    return 0;
+}
 int lbfgsb_test_heap_order_f64(int64_t n, const double* t, int32_t* order_out) {
     unsigned long long* k; int* v;
     if (n <= 0) return 1;

@@ -108,3 +108,40 @@ def test_product_does_not_import_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, fn)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liblbfgsb_oracle" not in src, fn
+
+
+def test_host_heap_replay_takes_ties_in_the_reference_order():
+    """The engine's host-thread heap replay (Engine::heap_group_order; used for long breakpoint lists and, on every rank,
+    for sharded workspaces) against the oracle's verbatim hpsolb driven as cauchy drives it (src/lbfgsb.f90:1384-1401,
+    2079-2157): the members of a group of equal breakpoints come out in the same order.  Host code only: runs without a GPU."""
+    import ctypes as C
+    import lbfgsb_b200
+    from oracle import oracle_py as O
+    L = lbfgsb_b200.lib()
+    L.lbfgsb_test_host_heap_group_f64.argtypes = [C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    for nb, distinct in ((1, 1), (2, 1), (9, 2), (100, 3), (1000, 1), (4097, 7), (60000, 11), (60000, 60000)):
+        vals = np.sort(rng.uniform(0.1, 5.0, distinct))
+        t = vals[rng.integers(0, distinct, nb)].astype(np.float64)
+        for tk in set([float(t.min()), float(np.median(t)), float(t.max())]):
+            out = np.empty(nb, dtype=np.int32)
+            cnt = C.c_int64(0)
+            assert L.lbfgsb_test_host_heap_group_f64(nb, t.ctypes.data_as(C.c_void_p), tk, out.ctypes.data_as(C.c_void_p), C.byref(cnt)) == 0
+            got = list(out[:cnt.value])
+            # the reference: first minimum (lowest index among ties) taken before the heap exists, replaced by the last
+            # entry; then hpsolb builds the heap on its first call and pops the least member into t(nleft) on every call
+            tt = t.copy(); io = np.arange(nb, dtype=np.int32)
+            ibp = int(np.argmin(tt))
+            ref = [ibp] if tt[ibp] == tk else []
+            if ibp != nb - 1:
+                tt[ibp] = tt[nb - 1]; io[ibp] = io[nb - 1]
+            nleft, k = nb - 1, 0
+            while nleft > 0:
+                O.lib().oracle_hpsolb_f64(C.c_int64(nleft), tt.ctypes.data_as(C.c_void_p), io.ctypes.data_as(C.c_void_p), C.c_int64(0 if k == 0 else 1))
+                v, var = tt[nleft - 1], int(io[nleft - 1])
+                nleft -= 1; k += 1
+                if v > tk:
+                    break
+                if v == tk:
+                    ref.append(var)
+            assert got == ref, (nb, distinct, tk, got[:10], ref[:10])
