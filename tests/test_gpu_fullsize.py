@@ -65,8 +65,11 @@ def test_config3_full_size_trace_matches_the_oracle():
     """BASELINE.json configs[2] at its full size against the oracle itself: tests/golden/config3_n1e8_trace.json holds the
     oracle's first iterates at n = 1e8, m = 10 in device-order summation mode (tests/golden/make_golden_config3.py; the same
     script checks that the oracle's reference-order run has the identical discrete trace and stores the drift of f).
-    Every discrete field and the active-set hash equal at every iterate; f and |proj g| within 1e-10 relative for the
-    first 10 iterates, 1e-6 after."""
+    Every discrete field and the active-set hash must be equal at every iterate.  f is the CALLER's sum: the oracle's
+    driver adds the 1e8 terms of the objective serially like test/driver1.f90:274-289, the device objective kernel in the
+    fixed tree shape, and the two differ by up to n * eps ~ 1e-8 relative before the engine has done anything (2e-9 at the
+    first iterate) -- so f is gated at 5e-8 here (at the sizes where the serial sum is itself accurate, the other parity
+    tests hold 1e-10), |proj g| (a maximum over single components) at 1e-6."""
     import json
     import os
     import torch
@@ -88,6 +91,7 @@ def test_config3_full_size_trace_matches_the_oracle():
     fg = lbfgsb_b200.RosenbrockDevice(np.float64)
     rows = gold["iterates"]
     k = 0
+    worst_f = worst_pg = 0.0
     while k < len(rows):
         prob.setulb_dev(x, l, u, nbd, g, 0.0, 0.0)
         t = prob.task_str()
@@ -102,12 +106,14 @@ def test_config3_full_size_trace_matches_the_oracle():
                  "hash": h, "hcount": c}
             for key, v in a.items():
                 assert v == b[key], (key, k, a, {q: b[q] for q in a})
-            tol = 1e-10 if b["iter"] <= 10 else 1e-6
-            assert abs(float(prob.f[0]) - b["f"]) <= tol * abs(b["f"]), (k, float(prob.f[0]), b["f"])
-            assert abs(float(prob.dsave[12]) - b["sbgnrm"]) <= 100 * tol * abs(b["sbgnrm"]), (k, float(prob.dsave[12]), b["sbgnrm"])
+            worst_f = max(worst_f, abs(float(prob.f[0]) - b["f"]) / abs(b["f"]))
+            worst_pg = max(worst_pg, abs(float(prob.dsave[12]) - b["sbgnrm"]) / abs(b["sbgnrm"]))
+            assert abs(float(prob.f[0]) - b["f"]) <= 5e-8 * abs(b["f"]), (k, float(prob.f[0]), b["f"])
+            assert abs(float(prob.dsave[12]) - b["sbgnrm"]) <= 1e-6 * abs(b["sbgnrm"]), (k, float(prob.dsave[12]), b["sbgnrm"])
             k += 1
         else:
             raise AssertionError("unexpected task " + t)
+    print("config 3 at n = 1e8: %d iterates, discrete trace and active-set hash equal to the oracle's; worst relative difference of f %.2e, of |proj g| %.2e" % (k, worst_f, worst_pg))
     prob.close()
 
 
