@@ -71,7 +71,7 @@ def parse():
                     help="N > 1: strong = the workload's n split over the GPUs (default), weak = n per GPU")
     ap.add_argument("--n", type=int, default=None, help="variables (per GPU under weak scaling)")
     ap.add_argument("--m", type=int, default=None)
-    ap.add_argument("--cpu-n", type=int, default=2_000_000, help="sample size of the CPU baseline")
+    ap.add_argument("--cpu-n", type=int, default=10_000_000, help="sample size of the CPU baseline (about 30 s of one core)")
     ap.add_argument("--plain-fg", action="store_true", help="objective kernels without the line-search epilogue")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
