@@ -315,3 +315,55 @@ __global__ void __launch_bounds__(256) k_dw_fix(Wk<T> w, WalkBuf<T> b, const DwC
         w.r[var] = (T)-1;   // no breakpoint any more (cauchy_walk.cuh: the stored breakpoints)
     }
 }
+
+// ---------------------------------------------------------------------------
+// Small rounds (at most LB_RW_MAX breakpoints over all ranks -- the usual case: the search passes a few hundred).
+// The sample sort above costs a hundred small launches, R all-gathers and two host read-backs whatever the size.
+// Instead every rank all-gathers ALL records of the round (cap per rank, padded) and runs the single-GPU scans over the
+// whole list redundantly: concatenated in rank order and stably sorted by key the list is the global (t, index) order,
+// the scans are those of cauchy_walk.cuh on the same operands in the same order on every rank, and each rank fixes
+// those of its own variables that were passed.
+// ---------------------------------------------------------------------------
+#define LB_RW_MAX 4096
+// this rank's count of the round into its RoundRec (all-gathered next)
+template <typename T>
+__global__ void k_rw_count(Wk<T> w, WalkBuf<T> b, RoundRec* out) {
+    if (threadIdx.x != 0) return;
+    out->count = b.ctl->count; out->rem = 0; out->kmin = 0; out->pad = 0;
+}
+// sort keys of the gathered records: rank q's first count_q records of its block of `cap`, in rank order
+template <typename T>
+__global__ void __launch_bounds__(256) k_rw_keys(const T* rec, int rs, i64 cap, const RoundRec* all, int R,
+                                                 typename Real<T>::key_t* keys, int* vals, SortCtl* ctl) {
+    i64 off = 0;
+    for (int q = 0; q < R; ++q) {
+        const i64 c = all[q].count;
+        for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < c; i += (i64)gridDim.x * blockDim.x) {
+            const i64 r = (i64)q * cap + i;
+            keys[off + i] = KeyBits<T>::to(rec[r * rs]);
+            vals[off + i] = (int)r;
+        }
+        off += c;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->count = off; ctl->cur = 0; ctl->skip = 0; }
+}
+// fix this rank's variables among the first walk_fixn entries of the global sorted list (:1424-1434):
+// record number q * cap + i is entry i of rank q's local sorted list
+template <typename T>
+__global__ void __launch_bounds__(256) k_rw_fix(Wk<T> w, WalkBuf<T> local, WalkBuf<T> global, i64 cap, int rank) {
+    const DevState<T>* s = w.s;
+    if (!s->go || !s->in_body || !s->need_walk) return;
+    const i64 J = s->walk_fixn;
+    const int* gv = cur_vals<T>(global);
+    const int* lv = cur_vals<T>(local);
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < J; j += (i64)gridDim.x * blockDim.x) {
+        const i64 r = gv[j];
+        if (r / cap != rank) continue;
+        const int var = lv[r % cap];
+        const T dl = cauchy_dir<T>(w.iwhere[var], w.g[var]);
+        if (dl > (T)0) { w.z[var] = w.u[var]; w.iwhere[var] = 2; }
+        else { w.z[var] = w.l[var]; w.iwhere[var] = 1; }
+        w.r[var] = (T)-1;
+    }
+}
+

@@ -258,6 +258,7 @@ struct Engine : EngineBase {
         fast = fused;   // the fast NEW_X pipeline is built from the fused passes
         if (const char* e = getenv("LBFGSB_B200_NO_FAST")) { if (e[0] == '1') fast = false; }
         if (const char* e = getenv("LBFGSB_B200_NO_TIMERS")) { if (e[0] == '1') timers = false; }
+        if (const char* e = getenv("LBFGSB_B200_NO_SMALL_ROUNDS")) { if (e[0] == '1') small_rounds = false; }
         if (const char* e = getenv("LBFGSB_B200_NO_BP_HINT")) { if (e[0] == '1') { bp_hint_ok = false; walk_gf_ok = false; } }
         if (!(mt == 5 ? set_smem_attrs<5>() : (mt == 10 ? set_smem_attrs<10>() : set_smem_attrs<20>()))) return false;
         for (int q = 0; q < F_COUNT; ++q) { fam_ms[q] = 0; fam_calls[q] = 0; }
@@ -786,9 +787,51 @@ struct Engine : EngineBase {
             launches += 4;
         }
     }
+    // a small round on a sharded problem (cauchy_walk_dist.cuh "Small rounds"): every rank scans the whole gathered list
+    bool small_rounds = true;
+    bool round_scan_gathered(i64 total) {
+        typedef typename Real<T>::key_t K;
+        const int col = s_host->col;
+        const int rs = 3 + 2 * col;
+        const i64 cap = (total + 63) / 64 * 64;   // >= every rank's count of the round
+        if (!ensure(dw_send, sizeof(T) * (size_t)cap * rs) || !ensure(dw_recv, sizeof(T) * (size_t)cap * rs * R)) return false;
+        if (!ensure(dw_k0, sizeof(K) * (size_t)total) || !ensure(dw_k1, sizeof(K) * (size_t)total) ||
+            !ensure(dw_v0, 4 * (size_t)total) || !ensure(dw_v1, 4 * (size_t)total)) return false;
+        begin(F_WALK_SCAN);
+        k_rw_count<T><<<1, 32, 0, stream>>>(w, wb, rr_local); launches++;
+        if (!allgather(rr_local, rr_all, sizeof(RoundRec))) return false;
+        T* send = (T*)dw_send.p; T* recv = (T*)dw_recv.p;
+        k_dw_pack<T><<<LBFGSB_GRID, 256, 0, stream>>>(w, wb, send, rs); launches++;
+        if (!allgather(send, recv, sizeof(T) * (size_t)cap * rs)) return false;
+        WalkBuf<T> wd = wb;
+        wd.k0 = (K*)dw_k0.p; wd.k1 = (K*)dw_k1.p; wd.v0 = (int*)dw_v0.p; wd.v1 = (int*)dw_v1.p; wd.ctl = ctl_d;
+        k_rw_keys<T><<<32, 256, 0, stream>>>(recv, rs, cap, rr_all, R, wd.k0, wd.v0, ctl_d); launches++;
+        enqueue_sort(wd.k0, wd.k1, wd.v0, wd.v1, ctl_d, total);
+        for (i64 start = 0; start < total; start += wd.cap) {
+            const i64 len = (total - start < wd.cap) ? (total - start) : wd.cap;
+            const i64 nblk = (len + LB_WB - 1) / LB_WB;
+            CK(cudaMemsetAsync(jmin, 0xff, 8, stream));
+            k_dw_gather<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wd, recv, rs, start, len);
+            k_walk_scan_vec<T><<<1, 1024, 0, stream>>>(w, wd, nblk, tmpAB);
+            k_walk_dots<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wd, start, len);
+            k_walk_scan_f2<T><<<1, 32, 0, stream>>>(w, wd, nblk, tmpF);
+            k_walk_f2<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wd, start, len);
+            k_walk_scan_f1<T><<<1, 32, 0, stream>>>(w, wd, nblk, tmpF);
+            k_walk_test<T><<<(unsigned)nblk, LB_WB, 0, stream>>>(w, wd, start, len, jmin);
+            k_walk_chunk_end<T><<<1, 32, 0, stream>>>(w, wd, start, len, tmpAB, tmpF, jmin);
+            launches += 8;
+        }
+        k_walk_round_end<T><<<1, LB_WB, 0, stream>>>(w, wd, n_global, 1);
+        end(F_WALK_SCAN, 1);
+        begin(F_WALK_FIX);
+        k_rw_fix<T><<<64, 256, 0, stream>>>(w, wb, wd, cap, rank);
+        end(F_WALK_FIX);
+        return true;
+    }
     // one round on a sharded problem: this rank's breakpoints of the round are sorted in wb
     bool round_scan_sharded() {
         typedef typename Real<T>::key_t K;
+        if (small_rounds && s_host->walk_rcount > 0 && s_host->walk_rcount <= LB_RW_MAX) return round_scan_gathered(s_host->walk_rcount);
         const int S = LB_DW_SAMPLES;
         // 2. splitters from regular samples
         begin(F_WALK_SCAN);
