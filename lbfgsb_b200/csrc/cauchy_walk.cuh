@@ -347,6 +347,26 @@ __global__ void __launch_bounds__(256) k_rs_scatter(K* k0, K* k1, int* v0, int* 
 
 __global__ void k_rs_flip(SortCtl* ctl) { if (threadIdx.x == 0 && !ctl->skip) ctl->cur ^= 1; }
 
+// Short lists (the usual round: a few hundred breakpoints) in ONE launch instead of the 4 x sizeof(key) launches of the LSD
+// sort: every item's position is its rank -- the number of items with a smaller key, or an equal key and a smaller
+// position in the input -- counted against the keys held in shared memory.  Stable by construction: the same order as
+// the radix sort.  In: buffer ctl->cur (0); out: the other buffer, ctl->cur = 1.
+#define LB_SMALL_SORT_MAX 4096
+template <typename K>
+__global__ void __launch_bounds__(1024) k_small_sort(const K* k0, K* k1, const int* v0, int* v1, SortCtl* ctl) {
+    __shared__ K sk[LB_SMALL_SORT_MAX];
+    const int n = (int)ctl->count;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = k0[i];
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const K ke = sk[e];
+        int rank = 0;
+        for (int f = 0; f < n; ++f) { const K kf = sk[f]; rank += (kf < ke || (kf == ke && f < e)) ? 1 : 0; }
+        k1[rank] = ke; v1[rank] = v0[e];
+    }
+    if (threadIdx.x == 0) { ctl->cur = 1; ctl->skip = 0; }
+}
+
 // ---------------------------------------------------------------------------
 // Walk scratch (one chunk of sorted breakpoints)
 // ---------------------------------------------------------------------------

@@ -258,7 +258,7 @@ struct Engine : EngineBase {
         fast = fused;   // the fast NEW_X pipeline is built from the fused passes
         if (const char* e = getenv("LBFGSB_B200_NO_FAST")) { if (e[0] == '1') fast = false; }
         if (const char* e = getenv("LBFGSB_B200_NO_TIMERS")) { if (e[0] == '1') timers = false; }
-        if (const char* e = getenv("LBFGSB_B200_NO_SMALL_ROUNDS")) { if (e[0] == '1') small_rounds = false; }
+        if (const char* e = getenv("LBFGSB_B200_NO_SMALL_ROUNDS")) { if (e[0] == '1') { small_rounds = false; small_sort = false; } }
         if (const char* e = getenv("LBFGSB_B200_NO_BP_HINT")) { if (e[0] == '1') { bp_hint_ok = false; walk_gf_ok = false; } }
         if (!(mt == 5 ? set_smem_attrs<5>() : (mt == 10 ? set_smem_attrs<10>() : set_smem_attrs<20>()))) return false;
         for (int q = 0; q < F_COUNT; ++q) { fam_ms[q] = 0; fam_calls[q] = 0; }
@@ -778,6 +778,10 @@ struct Engine : EngineBase {
     }
     void enqueue_sort(typename Real<T>::key_t* k0, typename Real<T>::key_t* k1, int* v0, int* v1, SortCtl* ctl, i64 count) {
         typedef typename Real<T>::key_t K;
+        if (count <= LB_SMALL_SORT_MAX && small_sort) {   // (count = ctl->count: the callers pass what the device holds)
+            k_small_sort<K><<<1, 1024, 0, stream>>>(k0, k1, v0, v1, ctl); launches++;
+            return;
+        }
         const int nblk = sort_blocks(count);
         for (int pass = 0; pass < (int)sizeof(K); ++pass) {
             k_rs_hist<K><<<nblk, 256, 0, stream>>>(k0, k1, ctl, pass * 8, rs_counts);
@@ -788,7 +792,7 @@ struct Engine : EngineBase {
         }
     }
     // a small round on a sharded problem (cauchy_walk_dist.cuh "Small rounds"): every rank scans the whole gathered list
-    bool small_rounds = true;
+    bool small_rounds = true, small_sort = true;
     bool round_scan_gathered(i64 total) {
         typedef typename Real<T>::key_t K;
         const int col = s_host->col;
