@@ -160,6 +160,21 @@ __global__ void __launch_bounds__(LBFGSB_BLOCK) k_el_count(Wk<T> w, int* tile_co
     }
 }
 
+// Exclusive scan of counts[0..ntiles) into offsets by ONE block: thread t owns the contiguous run of ceil(ntiles / B)
+// entries, sums it, the block scans the B run totals once (three barriers in all, whatever ntiles), and every thread
+// writes its run's offsets.  Returns the total to every thread.  smem: 33 entries.
+__device__ __forceinline__ i64 block_scan_runs(const int* counts, i64* offsets, i64 ntiles, i64* smem) {
+    const i64 per = (ntiles + blockDim.x - 1) / blockDim.x;
+    const i64 a = (i64)threadIdx.x * per;
+    const i64 b = (a + per < ntiles) ? a + per : ntiles;
+    i64 run = 0;
+    for (i64 i = a; i < b; ++i) run += (i64)counts[i];
+    i64 tot;
+    i64 ex = block_excl_scan<i64>(run, smem, tot);
+    for (i64 i = a; i < b; ++i) { offsets[i] = ex; ex += (i64)counts[i]; }
+    return tot;
+}
+
 // exclusive scan of tile_counts -> offsets; total -> ctl->count.  One block of 1024.
 template <typename T>
 __global__ void __launch_bounds__(1024) k_tile_scan(Wk<T> w, int mode, const int* counts, i64* offsets, i64 ntiles,
@@ -169,15 +184,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(Wk<T> w, int mode, const int
     if ((mode == 0 || mode == 2) && !s->need_walk) return;
     if (mode == 1 && !s->do_delta) return;
     __shared__ i64 sm[33];
-    i64 carry = 0;
-    for (i64 b0 = 0; b0 < ntiles; b0 += 1024) {
-        const i64 i = b0 + threadIdx.x;
-        i64 v = (i < ntiles) ? (i64)counts[i] : 0;
-        i64 tot;
-        i64 ex = block_excl_scan<i64>(v, sm, tot);
-        if (i < ntiles) offsets[i] = carry + ex;
-        carry += tot;
-    }
+    const i64 carry = block_scan_runs(counts, offsets, ntiles, sm);
     if (threadIdx.x == 0) { ctl->count = carry; ctl->cur = 0; ctl->skip = 0; }
 }
 
@@ -777,15 +784,7 @@ __global__ void __launch_bounds__(1024) k_walk_round_local(Wk<T> w, const int* c
     DevState<T>* s = w.s;
     if (!s->go || !s->in_body || !s->need_walk || s->walk_closed) return;
     __shared__ i64 sm[33];
-    i64 carry = 0;
-    for (i64 b0 = 0; b0 < ntiles; b0 += 1024) {
-        const i64 i = b0 + threadIdx.x;
-        i64 v = (i < ntiles) ? (i64)counts[i] : 0;
-        i64 tot;
-        i64 ex = block_excl_scan<i64>(v, sm, tot);
-        if (i < ntiles) offsets[i] = carry + ex;
-        carry += tot;
-    }
+    const i64 carry = block_scan_runs(counts, offsets, ntiles, sm);
     if (threadIdx.x < 32) {
         const i64 rem = final_isum_warp(LB_SLOT(w.ipart, 0));
         const i64 km = final_imin_warp(LB_SLOT(w.ipart, 1));
