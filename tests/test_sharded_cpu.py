@@ -84,6 +84,20 @@ def test_library_exports_every_declared_symbol():
     assert L.lbfgsb_b200_version() >= 100
 
 
+def test_fortran_module_binds_only_exported_symbols():
+    """fortran/lbfgsb_b200_module.F90 cannot be compiled in this image (no Fortran compiler): at least every
+    bind(C, name='...') of its interface block must name a symbol that the library exports and the header declares."""
+    import lbfgsb_b200
+    src = open(os.path.join(ROOT, "fortran", "lbfgsb_b200_module.F90")).read()
+    hdr = open(os.path.join(ROOT, "include", "lbfgsb_b200.h")).read()
+    names = sorted(set(re.findall(r"bind\(C,\s*name='([A-Za-z0-9_]+)'\)", src)))
+    assert len(names) >= 12
+    L = lbfgsb_b200.lib()
+    for nm in names:
+        assert hasattr(L, nm), nm
+        assert re.search(r"\b%s\s*\(" % nm, hdr), nm
+
+
 def test_no_cpu_path_without_a_gpu():
     """Without a CUDA device the host twin must refuse (task = 'ERROR: NO CUDA DEVICE ...'), never compute."""
     import torch
