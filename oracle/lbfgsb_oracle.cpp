@@ -67,22 +67,29 @@ static T device_order_sum(i64 n, F term) {
     const i64 tile = (i64)LBFGSB_BLOCK * VEC * UNROLL;
     const i64 ntiles = (n + tile - 1) / tile;
     std::vector<T> block_partial(LBFGSB_GRID, (T)0);
-    std::vector<T> lane(LBFGSB_BLOCK);
-    for (int b = 0; b < LBFGSB_GRID; ++b) {
-        if ((i64)b >= ntiles) { block_partial[b] = (T)0; continue; }
-        for (int t = 0; t < LBFGSB_BLOCK; ++t) {
-            T acc = (T)0;
-            for (i64 tl = b; tl < ntiles; tl += LBFGSB_GRID) {
-                for (int k = 0; k < UNROLL; ++k) {
-                    i64 base = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC) + (i64)t * VEC;
-                    for (int v = 0; v < VEC; ++v) {
-                        i64 i = base + v;
-                        if (i < n) acc = acc + term(i);
-                    }
+    // The accumulators of all GRID x BLOCK threads are kept side by side and the elements are visited in MEMORY order:
+    // a given thread still meets its own elements in the order tile, k, v -- the order of the kernels -- so every
+    // accumulator receives the same additions in the same order as in a thread-by-thread replay, at a fraction of the
+    // cache misses (n = 1e8: seconds instead of minutes per sum).
+    const i64 nblk = ntiles < (i64)LBFGSB_GRID ? ntiles : (i64)LBFGSB_GRID;
+    std::vector<T> acc((size_t)nblk * LBFGSB_BLOCK, (T)0);
+    for (i64 tl = 0; tl < ntiles; ++tl) {
+        T* a = acc.data() + (size_t)(tl % LBFGSB_GRID) * LBFGSB_BLOCK;
+        for (int k = 0; k < UNROLL; ++k) {
+            const i64 base0 = tl * tile + (i64)k * (LBFGSB_BLOCK * VEC);
+            if (base0 >= n) break;
+            for (int t = 0; t < LBFGSB_BLOCK; ++t) {
+                const i64 base = base0 + (i64)t * VEC;
+                for (int v = 0; v < VEC; ++v) {
+                    const i64 i = base + v;
+                    if (i < n) a[t] = a[t] + term(i);
                 }
             }
-            lane[t] = acc;
         }
+    }
+    for (int b = 0; b < LBFGSB_GRID; ++b) {
+        if ((i64)b >= ntiles) { block_partial[b] = (T)0; continue; }
+        const T* lane = acc.data() + (size_t)b * LBFGSB_BLOCK;
         // warp butterflies
         T warp_sum[LBFGSB_BLOCK / 32];
         for (int w = 0; w < LBFGSB_BLOCK / 32; ++w) {
