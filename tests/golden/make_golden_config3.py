@@ -3,8 +3,7 @@ Rosenbrock with the odd lower bound at 1.1, factr = pgtol = 0) into tests/golden
 
 The oracle (oracle/lbfgsb_oracle.cpp, 64-bit offsets) runs in device-order summation mode -- the mode the GPU is gated
 against -- and, with --reference-order, in the reference's own order; the discrete trace of the two is identical
-(checked here) and the drift of f between them is stored next to the trace.  About 25 GB of host memory and several
-minutes per mode on one core; run once, the JSON is committed and tests/test_gpu_fullsize.py compares the GPU with it.
+(checked here) and the drift of f between them is stored next to the trace.  About 25 GB of host memory, 14 min (device order) + 5 min (reference order) on one core; run once, the JSON is committed and tests/test_gpu_fullsize.py compares the GPU with it.
 
     python tests/golden/make_golden_config3.py [iterations=16] [--reference-order]
 """
